@@ -1,0 +1,167 @@
+/*
+ * epialleler_b200 -- C ABI of the B200-native cytosine-report hot path.
+ *
+ * This is the drop-in boundary: what the reference's three `.Call` routines for this path
+ * would bind instead of their CPU loops.  Plain C, plain pointers and sizes; no C++/torch/R
+ * types cross it.  All functions return EA_OK (0) or a negative EA_ERR_* code;
+ * ea_last_error() gives the message (thread-local).  The library must be called from one
+ * host thread per handle; it never calls back into the caller except through `ea_poll_fn`.
+ *
+ * Reference interface each entry point replaces (paths relative to BBCG/epialleleR):
+ *
+ *   ea_pack / ea_pack_blob   the `bam.data` object: data.table {rname,strand,start,templid} + attr
+ *                            "seqxm_xptr" -> std::vector<std::string>
+ *                            (src/rcpp_read_bam.cpp:45,61-69,166-189; R/internal.R:193-195)
+ *   ea_threshold_reads       rcpp_threshold_reads   src/rcpp_threshold_reads.cpp:15-74
+ *                                                   src/RcppExports.cpp:234-251, R/RcppExports.R:64-66
+ *   ea_get_xm_beta           rcpp_get_xm_beta       src/rcpp_get_xm_beta.cpp:10-43
+ *                                                   src/RcppExports.cpp:97-109,  R/RcppExports.R:28-30
+ *   ea_cx_report             rcpp_cx_report         src/rcpp_cx_report.cpp:34-159
+ *                                                   src/RcppExports.cpp:39-51,   R/RcppExports.R:12-14
+ *   ea_cytosine_report       the body of generateCytosineReport after preprocessBam:
+ *                            .thresholdReads + .getCytosineReport fused into one pass over XM
+ *                            (R/generateCytosineReport.R:181-201; R/internal.R:439-456,486-500)
+ *
+ * Data contract (identical to the reference's):
+ *   - rows are sorted by (rname, start)  [R/internal.R:195]; unsorted input is rejected
+ *     (the reference documents "PRE-SORTED DATASET IS A REQUIREMENT", src/rcpp_cx_report.cpp:19);
+ *   - strings are one byte per reference position, low nibble = methylation-call code
+ *     ((c+2)>>2)&15 of the XM character (src/epialleleR.h:15-28), high nibble = base (ignored here);
+ *   - templid[x] indexes the strings (file order); nrow must equal the number of strings for the
+ *     per-read calls, as in the reference (src/rcpp_threshold_reads.cpp:27-28);
+ *   - low-nibble codes outside {2,5,6,7,10,11,12,13,14,15} cannot be produced by the reference's
+ *     readers; the packer rejects them (EA_ERR_DOMAIN) instead of emulating the reference's
+ *     undefined counter aliasing for them.
+ */
+#ifndef EPIALLELER_B200_H
+#define EPIALLELER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EA_OK 0
+#define EA_ERR_ARG (-1)      /* bad argument (null pointer, negative size, templid out of range ...) */
+#define EA_ERR_CUDA (-2)     /* CUDA runtime failure (message has the cudaError string) */
+#define EA_ERR_UNSORTED (-3) /* rows not sorted by (rname, start) */
+#define EA_ERR_DOMAIN (-4)   /* a string holds a low-nibble code the reference's readers never emit */
+#define EA_ERR_NODEVICE (-5) /* no CUDA device: there is NO CPU fallback */
+#define EA_ERR_INTERRUPT (-6)/* the poll callback asked to stop */
+#define EA_ERR_STATE (-7)    /* call order (e.g. fetch before report) */
+
+typedef struct ea_handle ea_handle;
+
+/* Optional interrupt poll (the reference polls Rcpp::checkUserInterrupt every 2^16..2^20 rows,
+ * src/rcpp_cx_report.cpp:110).  Return non-zero to abort; checked between kernel launches. */
+typedef int (*ea_poll_fn)(void);
+
+int ea_version(void);
+const char* ea_last_error(void);
+int ea_device_count(void);
+void ea_set_poll(ea_poll_fn fn);
+
+/* ---- packer: host bam.data -> device-resident CSR (row order) ------------------------------ */
+
+/* str[i]/len[i]: the i-th string of the reference's std::vector<std::string> (file order). */
+int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+            int64_t nrow, const uint8_t* const* str, const int64_t* len, int64_t nstr, int device,
+            ea_handle** out);
+
+/* Same, strings given as one blob + nstr+1 offsets (file order).  When templid is the identity
+ * the blob is copied to the device as is (no host gather). */
+int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                 int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device,
+                 ea_handle** out);
+
+/* Adopt CSR arrays that already live on `device` in ROW order (d_off: nrow+1 int64, d_strand: 1|2 as
+ * uint8).  The handle takes ownership iff take_ownership != 0 (pointers must come from cudaMalloc). */
+int ea_attach_device(int32_t* d_rname, uint8_t* d_strand, int32_t* d_start, uint8_t* d_data, int64_t* d_off,
+                     int64_t nrow, int device, int take_ownership, ea_handle** out);
+
+void ea_free(ea_handle* h);
+
+int64_t ea_nrow(const ea_handle* h);
+int64_t ea_nbytes(const ea_handle* h); /* sum of string lengths */
+int ea_device(const ea_handle* h);
+
+/* ---- the three reference routines ----------------------------------------------------------- */
+
+/* pass_out: nrow bytes, 1 = read passes.  Letter strings exactly as the reference takes them
+ * (ooctx_* may be empty; a letter repeated in one string counts twice, as in the reference). */
+int ea_threshold_reads(ea_handle* h, const char* ctx_meth, const char* ctx_unmeth, const char* ooctx_meth,
+                       const char* ooctx_unmeth, uint32_t min_n_ctx, double min_ctx_meth_frac,
+                       double max_ooctx_meth_frac, uint8_t* pass_out);
+
+int ea_get_xm_beta(ea_handle* h, const char* ctx_meth, const char* ctx_unmeth, double* beta_out);
+
+/* pass: nrow bytes (0 = FALSE, anything else incl. R's NA = TRUE), or NULL for all TRUE.
+ * Two-phase: this call computes the report on the device and returns the row count; the caller
+ * allocates six int32 columns of that length and calls ea_cx_report_fetch (any column may be NULL). */
+int ea_cx_report(ea_handle* h, const uint8_t* pass, const char* ctx, int64_t* nrow_out);
+int ea_cx_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* pos, int32_t* context,
+                       int32_t* meth, int32_t* unmeth);
+
+/* ---- fused generateCytosineReport body ------------------------------------------------------- */
+
+typedef struct ea_report_params {
+  int32_t threshold_reads;      /* 0: pass = all TRUE (R/generateCytosineReport.R:194) */
+  const char* ctx_meth;         /* the four threshold letter sets (R/internal.R:54-65) */
+  const char* ctx_unmeth;
+  const char* ooctx_meth;
+  const char* ooctx_unmeth;
+  uint32_t min_n_ctx;           /* min.context.sites */
+  double min_ctx_meth_frac;     /* min.context.beta */
+  double max_ooctx_meth_frac;   /* max.outofcontext.beta */
+  const char* report_ctx;       /* ctx.meth letters of report.context, e.g. "Z" or "ZXH" */
+} ea_report_params;
+
+/* One pass over the XM bytes: per-read pass flags and the report.  pass_out may be NULL.
+ * Rows are fetched with ea_cx_report_fetch. */
+int ea_cytosine_report(ea_handle* h, const ea_report_params* p, uint8_t* pass_out, int64_t* nrow_out);
+
+/* ---- measurement hooks (device-resident, no host copies; used by bench.py) ------------------- */
+
+typedef struct ea_timing {
+  float total_ms;        /* CUDA-event time of the whole device pipeline of the call */
+  float kernel_ms[8];    /* per-stage times, see ea_stage_name() */
+  int32_t n_launches;    /* kernels launched by the call */
+  int64_t n_rows;        /* report rows produced */
+  int64_t n_pass;        /* reads that passed */
+  int64_t alg_bytes;     /* algorithmic bytes of the call: sum(L) + 14 N + 24 R (13 N unthresholded) */
+} ea_timing;
+
+/* mode 0: fused kernel; mode 1: threshold kernel + report kernel (two passes over XM). */
+int ea_cytosine_report_device(ea_handle* h, const ea_report_params* p, int mode, ea_timing* t);
+const char* ea_stage_name(int i);
+/* Write `bytes` bytes of scratch on the handle's device (L2 flush between timed iterations). */
+int ea_flush_l2(ea_handle* h, int64_t bytes);
+
+/* ---- deterministic synthetic reads (same generator on host and device) ----------------------- */
+
+#define EA_SYNTH_MAX_CHR 32
+typedef struct ea_synth_cfg {
+  uint64_t seed;
+  int64_t n_reads;          /* rows of the WHOLE data set */
+  int32_t n_chr;
+  int32_t len_min, len_max; /* read length uniform in [len_min, len_max] */
+  int32_t n_islands;        /* 0: reads tile each chromosome uniformly; >0: target islands */
+  int32_t island_len;
+  int32_t reserved;
+  int64_t chr_len[EA_SYNTH_MAX_CHR];
+} ea_synth_cfg;
+
+/* Generate rows [row_begin, row_end) of the data set directly in device memory and pack them. */
+int ea_synth_device(const ea_synth_cfg* cfg, int64_t row_begin, int64_t row_end, int device, ea_handle** out);
+/* Same rows on the host (CPU baseline / parity inputs): caller-allocated arrays; blob sized by a first
+ * call with blob == NULL that only fills off[] (row_end-row_begin+1 entries). */
+int ea_synth_host(const ea_synth_cfg* cfg, int64_t row_begin, int64_t row_end, int32_t* rname, int32_t* strand,
+                  int32_t* start, int64_t* off, uint8_t* blob);
+/* Copy a handle's CSR back to the host (used to build host inputs for the end-to-end timing). */
+int ea_export_host(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* start, int64_t* off, uint8_t* blob);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPIALLELER_B200_H */

@@ -1,0 +1,232 @@
+/* TEST INFRASTRUCTURE ONLY -- not part of the product path.
+ *
+ * Plain-C restatement ("port") of the reference's cytosine-report hot path.  It is the
+ * checker the GPU tests compare against on the GPU box (where /root/reference is absent);
+ * tests/test_oracle.py pins it against the reference's own golden constants and against
+ * the reference's unmodified sources compiled into oracle/_ref (see oracle/Makefile).
+ * Parity status: PINNED (goldens of inst/unitTests/test_generateCytosineReport.R:32-60,
+ * :117-156, :215-233, test_generateBedReport.R:22-35, test_simulateBam.R:55-89 all hold).
+ *
+ * What each function follows:
+ *   code_of()               ctx_to_idx            /root/reference/src/epialleleR.h:28
+ *   nibble_hist()           per-read 16-bin count /root/reference/src/rcpp_threshold_reads.cpp:32-37
+ *   port_threshold_reads()  pass/fail chain       /root/reference/src/rcpp_threshold_reads.cpp:27-71
+ *   port_get_xm_beta()      per-read beta         /root/reference/src/rcpp_get_xm_beta.cpp:18-40
+ *   port_cx_report()        aggregation + flush   /root/reference/src/rcpp_cx_report.cpp:58-131
+ *
+ * The data structure is deliberately NOT the reference's (sorted flat_map of 32-int arrays):
+ * an open-addressing hash keyed by position plus a key sort at flush time.  Semantics kept:
+ * flush when start > max_pos or rname changes, stale last-position carry-over after an
+ * all-'-' read, NA pass == TRUE, rows emitted in ascending position, '+' before '-'.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef struct {
+  long n, nstr;
+  int *rname, *strand, *start, *templid;
+  uint8_t* blob;
+  int64_t* off;
+  /* last report */
+  long nrow, cap;
+  int* col[6];
+} PortBam;
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static unsigned code_of(unsigned c) { return ((c + 2u) >> 2) & 15u; }
+
+static int* dup_i(const int* p, long n) {
+  int* r = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  if (n > 0) memcpy(r, p, sizeof(int) * (size_t)n);
+  return r;
+}
+
+void* port_bam_new(long n, const int* rname, const int* strand, const int* start, const int* templid, long nstr,
+                   const uint8_t* blob, const int64_t* off) {
+  PortBam* b = (PortBam*)calloc(1, sizeof(PortBam));
+  b->n = n;
+  b->nstr = nstr;
+  b->rname = dup_i(rname, n);
+  b->strand = dup_i(strand, n);
+  b->start = dup_i(start, n);
+  b->templid = dup_i(templid, n);
+  int64_t total = off[nstr];
+  b->blob = (uint8_t*)malloc((size_t)(total > 0 ? total : 1));
+  if (total > 0) memcpy(b->blob, blob, (size_t)total);
+  b->off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nstr + 1));
+  memcpy(b->off, off, sizeof(int64_t) * (size_t)(nstr + 1));
+  return b;
+}
+
+void port_bam_free(void* h) {
+  PortBam* b = (PortBam*)h;
+  if (!b) return;
+  free(b->rname); free(b->strand); free(b->start); free(b->templid); free(b->blob); free(b->off);
+  for (int c = 0; c < 6; c++) free(b->col[c]);
+  free(b);
+}
+
+static void nibble_hist(const PortBam* b, long x, unsigned hist[16]) {
+  memset(hist, 0, 16 * sizeof(unsigned));
+  long t = b->templid[x];
+  const uint8_t* s = b->blob + b->off[t];
+  int64_t len = b->off[t + 1] - b->off[t];
+  for (int64_t i = 0; i < len; i++) hist[s[i] & 15u]++;
+}
+
+static unsigned letters_sum(const unsigned hist[16], const char* letters) {
+  unsigned s = 0; /* one term per LETTER, so repeated letters count twice, as in the reference */
+  for (const unsigned char* p = (const unsigned char*)letters; *p; p++) s += hist[code_of(*p)];
+  return s;
+}
+
+double port_threshold_reads(void* h, const char* ctx_meth, const char* ctx_unmeth, const char* ooctx_meth,
+                            const char* ooctx_unmeth, unsigned min_n_ctx, double min_beta, double max_oo_beta,
+                            uint8_t* pass_out) {
+  PortBam* b = (PortBam*)h;
+  double t0 = now_s();
+  unsigned hist[16];
+  for (long x = 0; x < b->nstr; x++) {
+    pass_out[x] = 0;
+    nibble_hist(b, x, hist);
+    unsigned m = letters_sum(hist, ctx_meth);
+    if (m == 0) continue;
+    unsigned all = m + letters_sum(hist, ctx_unmeth);
+    if (all < min_n_ctx) continue;
+    if ((double)m / all < min_beta) continue;
+    unsigned om = letters_sum(hist, ooctx_meth);
+    if (om > 0) {
+      unsigned oall = om + letters_sum(hist, ooctx_unmeth);
+      if ((double)om / oall > max_oo_beta) continue;
+    }
+    pass_out[x] = 1;
+  }
+  return now_s() - t0;
+}
+
+double port_get_xm_beta(void* h, const char* ctx_meth, const char* ctx_unmeth, double* beta_out) {
+  PortBam* b = (PortBam*)h;
+  double t0 = now_s();
+  unsigned hist[16];
+  for (long x = 0; x < b->nstr; x++) {
+    nibble_hist(b, x, hist);
+    unsigned m = letters_sum(hist, ctx_meth);
+    unsigned all = m + letters_sum(hist, ctx_unmeth);
+    if (all == 0) all = 1;
+    beta_out[x] = (double)m / all;
+  }
+  return now_s() - t0;
+}
+
+/* ---- position-keyed counters: open addressing, linear probing ---- */
+typedef struct { int64_t key; int cnt[32]; } Slot;
+typedef struct { Slot* s; size_t cap, used; } PosMap;
+
+static void pm_init(PosMap* m, size_t cap) {
+  m->cap = cap; m->used = 0;
+  m->s = (Slot*)malloc(sizeof(Slot) * cap);
+  for (size_t i = 0; i < cap; i++) m->s[i].key = -1;
+}
+static size_t pm_hash(int64_t k, size_t cap) { return (size_t)((uint64_t)k * 0x9E3779B97F4A7C15ull >> 20) & (cap - 1); }
+static Slot* pm_get(PosMap* m, int64_t key);
+static void pm_grow(PosMap* m) {
+  PosMap n; pm_init(&n, m->cap * 2);
+  for (size_t i = 0; i < m->cap; i++) if (m->s[i].key >= 0) { Slot* d = pm_get(&n, m->s[i].key); memcpy(d->cnt, m->s[i].cnt, sizeof d->cnt); }
+  free(m->s); *m = n;
+}
+static Slot* pm_get(PosMap* m, int64_t key) {
+  if ((m->used + 1) * 4 > m->cap * 3) pm_grow(m);
+  size_t i = pm_hash(key, m->cap);
+  for (;;) {
+    if (m->s[i].key == key) return &m->s[i];
+    if (m->s[i].key < 0) { m->s[i].key = key; memset(m->s[i].cnt, 0, sizeof m->s[i].cnt); m->used++; return &m->s[i]; }
+    i = (i + 1) & (m->cap - 1);
+  }
+}
+static int cmp_i64(const void* a, const void* b) { int64_t x = *(const int64_t*)a, y = *(const int64_t*)b; return (x > y) - (x < y); }
+
+static void emit(PortBam* b, int rname, int strand, int pos, int ctx, int meth, int unmeth) {
+  if (b->nrow == b->cap) {
+    b->cap = b->cap ? b->cap * 2 : 1024;
+    for (int c = 0; c < 6; c++) b->col[c] = (int*)realloc(b->col[c], sizeof(int) * (size_t)b->cap);
+  }
+  int v[6] = {rname, strand, pos, ctx, meth, unmeth};
+  for (int c = 0; c < 6; c++) b->col[c][b->nrow] = v[c];
+  b->nrow++;
+}
+
+static void flush(PortBam* b, PosMap* m, int rname, const unsigned want[16]) {
+  if (m->used) {
+    int64_t* keys = (int64_t*)malloc(sizeof(int64_t) * m->used);
+    size_t k = 0;
+    for (size_t i = 0; i < m->cap; i++) if (m->s[i].key >= 0) keys[k++] = m->s[i].key;
+    qsort(keys, k, sizeof(int64_t), cmp_i64);
+    for (size_t i = 0; i < k; i++) {
+      Slot* s = pm_get(m, keys[i]);
+      for (int st = 0; st < 2; st++) {
+        const int* v = s->cnt + 16 * st;
+        int cov = v[9];
+        if (cov == 0) continue;
+        int half = cov / 2, ctx;
+        if (v[12] > half) continue;
+        else if (v[2] + v[10] > half) ctx = 2;
+        else if (v[6] + v[14] > half) ctx = 6;
+        else if (v[7] + v[15] > half) ctx = 7;
+        else continue;
+        if (want[ctx]) emit(b, rname, st + 1, (int)keys[i], ctx, v[ctx], v[ctx | 8]);
+      }
+    }
+    free(keys);
+    for (size_t i = 0; i < m->cap; i++) m->s[i].key = -1;
+    m->used = 0;
+  }
+}
+
+long port_cx_report(void* h, const int* pass, const char* ctx, double* seconds) {
+  PortBam* b = (PortBam*)h;
+  double t0 = now_s();
+  unsigned want[16] = {0};
+  for (const unsigned char* p = (const unsigned char*)ctx; *p; p++) want[code_of(*p)] = 1;
+  b->nrow = 0;
+  PosMap m; pm_init(&m, 1 << 12);
+  int cur_rname = 0, max_pos = 0, last_pos = 0;
+  for (long x = 0; x < b->n; x++) {
+    int st = b->start[x];
+    if (st > max_pos || b->rname[x] != cur_rname) {
+      flush(b, &m, cur_rname, want);
+      max_pos = 0;
+      cur_rname = b->rname[x];
+    }
+    int shift = (b->strand[x] - 1) << 4;
+    unsigned lower = (!pass[x]) ? 8u : 0u;
+    long t = b->templid[x];
+    const uint8_t* s = b->blob + b->off[t];
+    int64_t len = b->off[t + 1] - b->off[t];
+    for (int64_t i = 0; i < len; i++) {
+      unsigned idx = (s[i] & 15u) | lower;
+      if (idx == 11) continue;
+      last_pos = st + (int)i;
+      Slot* sl = pm_get(&m, (int64_t)(uint64_t)(int64_t)last_pos & 0x7FFFFFFFFFFFFFFFll);
+      sl->cnt[idx + shift]++;
+      sl->cnt[9 + shift]++;
+    }
+    if (max_pos < last_pos) max_pos = last_pos; /* last_pos may be stale after an all-'-' read */
+  }
+  flush(b, &m, cur_rname, want);
+  free(m.s);
+  if (seconds) *seconds = now_s() - t0;
+  return b->nrow;
+}
+
+void port_cx_fetch(void* h, int* rname, int* strand, int* pos, int* context, int* meth, int* unmeth) {
+  PortBam* b = (PortBam*)h;
+  int* dst[6] = {rname, strand, pos, context, meth, unmeth};
+  for (int c = 0; c < 6; c++) if (b->nrow) memcpy(dst[c], b->col[c], sizeof(int) * (size_t)b->nrow);
+}

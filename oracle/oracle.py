@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE ONLY -- not part of the product path.
+
+ctypes front-ends for the two CPU checkers:
+
+* ``RefCpu``  -- the reference's own three hot-path C++ sources compiled unmodified
+  (oracle/_ref/libepiref.so, built by oracle/Makefile from /root/reference/src).
+* ``PortCpu`` -- the independent plain-C restatement oracle/cx_oracle.c
+  (oracle/_build/liboracle.so).
+
+Both expose the same three calls, named like the reference's Rcpp exports
+(/root/reference/R/RcppExports.R:12-14,28-30,64-66):
+``rcpp_threshold_reads``, ``rcpp_get_xm_beta``, ``rcpp_cx_report``.
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libepiref.so")
+PORT_SO = os.path.join(HERE, "_build", "liboracle.so")
+
+# context name -> the four letter sets (/root/reference/R/internal.R:54-65)
+CONTEXT_TO_BASES = {
+    "CG": ("Z", "z", "XH", "xh"),
+    "CHG": ("X", "x", "ZH", "zh"),
+    "CHH": ("H", "h", "ZX", "zx"),
+    "CxG": ("ZX", "zx", "H", "h"),
+    "CX": ("ZXH", "zxh", "", ""),
+}
+
+
+def build(which=("port", "ref")):
+    """(Re)build the checkers.  'ref' needs /root/reference; absent there, a prebuilt .so is used."""
+    for w in which:
+        if w == "ref" and not os.path.isdir("/root/reference/src"):
+            continue
+        subprocess.run(["make", "-s", "-C", HERE, w], check=True)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class _Cpu:
+    PREFIX = ""
+    SO = ""
+
+    def __init__(self, bam):
+        """bam: anything with rname/strand/start/templid int32 arrays and .blob() (file-order strings)."""
+        if not os.path.exists(self.SO):
+            build((self.KIND,))
+        self.lib = C.CDLL(self.SO)
+        L, px = self.lib, self.PREFIX
+        getattr(L, px + "bam_new").restype = C.c_void_p
+        getattr(L, px + "bam_new").argtypes = [C.c_long] + [C.POINTER(C.c_int)] * 4 + [C.c_long, C.POINTER(C.c_uint8), C.POINTER(C.c_int64)]
+        getattr(L, px + "bam_free").argtypes = [C.c_void_p]
+        getattr(L, px + "threshold_reads").restype = C.c_double
+        getattr(L, px + "threshold_reads").argtypes = [C.c_void_p] + [C.c_char_p] * 4 + [C.c_uint, C.c_double, C.c_double, C.POINTER(C.c_uint8)]
+        getattr(L, px + "get_xm_beta").restype = C.c_double
+        getattr(L, px + "get_xm_beta").argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
+        getattr(L, px + "cx_report").restype = C.c_long
+        getattr(L, px + "cx_report").argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.POINTER(C.c_double)]
+        getattr(L, px + "cx_fetch").argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 6
+        self.n = int(bam.rname.shape[0])
+        data, off = bam.blob()
+        self.nstr = int(off.shape[0] - 1)
+        cols = [np.ascontiguousarray(getattr(bam, k), dtype=np.int32) for k in ("rname", "strand", "start", "templid")]
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        if data.shape[0] == 0:
+            data = np.zeros(1, np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        self.h = getattr(L, px + "bam_new")(self.n, *[_p(c, C.c_int) for c in cols], self.nstr, _p(data, C.c_uint8), _p(off, C.c_int64))
+        self.last_seconds = 0.0
+
+    def close(self):
+        if getattr(self, "h", None):
+            getattr(self.lib, self.PREFIX + "bam_free")(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def rcpp_threshold_reads(self, ctx_meth, ctx_unmeth, ooctx_meth, ooctx_unmeth, min_n_ctx, min_ctx_meth_frac, max_ooctx_meth_frac):
+        out = np.zeros(max(self.nstr, 1), np.uint8)
+        self.last_seconds = getattr(self.lib, self.PREFIX + "threshold_reads")(
+            self.h, ctx_meth.encode(), ctx_unmeth.encode(), ooctx_meth.encode(), ooctx_unmeth.encode(),
+            C.c_uint(min_n_ctx & 0xFFFFFFFF), float(min_ctx_meth_frac), float(max_ooctx_meth_frac), _p(out, C.c_uint8))
+        return out[:self.nstr].astype(bool)
+
+    def rcpp_get_xm_beta(self, ctx_meth, ctx_unmeth):
+        out = np.zeros(max(self.nstr, 1), np.float64)
+        self.last_seconds = getattr(self.lib, self.PREFIX + "get_xm_beta")(self.h, ctx_meth.encode(), ctx_unmeth.encode(), _p(out, C.c_double))
+        return out[:self.nstr]
+
+    def rcpp_cx_report(self, pass_, ctx):
+        """pass_: bool/int array of nrow (None = all TRUE).  Returns dict of six int32 columns."""
+        if pass_ is None:
+            pv = np.ones(max(self.n, 1), np.int32)
+        else:
+            pv = np.ascontiguousarray(np.asarray(pass_).astype(np.int32))
+            if pv.shape[0] == 0:
+                pv = np.ones(1, np.int32)
+        sec = C.c_double(0)
+        nrow = getattr(self.lib, self.PREFIX + "cx_report")(self.h, _p(pv, C.c_int), ctx.encode(), C.byref(sec))
+        self.last_seconds = sec.value
+        cols = [np.zeros(max(nrow, 1), np.int32) for _ in range(6)]
+        getattr(self.lib, self.PREFIX + "cx_fetch")(self.h, *[_p(c, C.c_int) for c in cols])
+        names = ("rname", "strand", "pos", "context", "meth", "unmeth")
+        return {k: c[:nrow] for k, c in zip(names, cols)}
+
+    # reference-level glue (R/generateCytosineReport.R:164-208, R/internal.R:439-456,486-500)
+    def generateCytosineReport(self, threshold_reads=True, threshold_context="CG", min_context_sites=2,
+                               min_context_beta=0.5, max_outofcontext_beta=0.1, report_context=None):
+        report_context = report_context or threshold_context
+        seconds = 0.0
+        if threshold_reads:
+            b = CONTEXT_TO_BASES[threshold_context]
+            pass_ = self.rcpp_threshold_reads(b[0], b[1], b[2], b[3], min_context_sites, min_context_beta, max_outofcontext_beta)
+            seconds += self.last_seconds
+        else:
+            pass_ = np.ones(self.n, bool)
+        rep = self.rcpp_cx_report(pass_, CONTEXT_TO_BASES[report_context][0])
+        self.last_seconds += seconds
+        return pass_, rep
+
+
+class RefCpu(_Cpu):
+    PREFIX = "ref_"
+    SO = REF_SO
+    KIND = "ref"
+
+
+class PortCpu(_Cpu):
+    PREFIX = "port_"
+    SO = PORT_SO
+    KIND = "port"

@@ -1,0 +1,110 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product path.
+//
+// C-callable driver around the reference's own, UNMODIFIED hot-path functions
+//   rcpp_threshold_reads  (/root/reference/src/rcpp_threshold_reads.cpp:15)
+//   rcpp_get_xm_beta      (/root/reference/src/rcpp_get_xm_beta.cpp:10)
+//   rcpp_cx_report        (/root/reference/src/rcpp_cx_report.cpp:34)
+// which oracle/Makefile compiles from where they lie into oracle/_ref/.
+// Used (a) to validate oracle/cx_oracle.c and the CUDA path, and (b) as the
+// CPU baseline ("kind":"reference") in bench.py.  Timings returned here cover
+// only the reference function call, never the marshalling around it.
+#include <Rcpp.h>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+std::vector<bool> rcpp_threshold_reads(Rcpp::DataFrame& df, const std::string ctx_meth,
+                                       const std::string ctx_unmeth, const std::string ooctx_meth,
+                                       const std::string ooctx_unmeth, const unsigned int min_n_ctx,
+                                       const double min_ctx_meth_frac, const double max_ooctx_meth_frac);
+std::vector<double> rcpp_get_xm_beta(Rcpp::DataFrame& df, const std::string ctx_meth,
+                                     const std::string ctx_unmeth);
+Rcpp::DataFrame rcpp_cx_report(Rcpp::DataFrame& df, Rcpp::LogicalVector& pass, const std::string ctx);
+
+namespace {
+struct RefBam {
+  Rcpp::DataFrame df;
+  std::vector<std::string>* seqxm = nullptr;
+  long n = 0;
+  // last report
+  std::shared_ptr<std::vector<int>> cols[6];
+};
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+extern "C" {
+
+// Build the reference's bam.data: four int columns + the seqxm string vector
+// (strings given as one byte blob + nstr+1 offsets, in FILE order = templid).
+void* ref_bam_new(long n, const int* rname, const int* strand, const int* start, const int* templid,
+                  long nstr, const uint8_t* blob, const int64_t* off) {
+  RefBam* b = new RefBam;
+  b->n = n;
+  b->df.set_column("rname", std::make_shared<std::vector<int>>(rname, rname + n));
+  b->df.set_column("strand", std::make_shared<std::vector<int>>(strand, strand + n));
+  b->df.set_column("start", std::make_shared<std::vector<int>>(start, start + n));
+  b->df.set_column("templid", std::make_shared<std::vector<int>>(templid, templid + n));
+  b->seqxm = new std::vector<std::string>;
+  b->seqxm->reserve(static_cast<size_t>(nstr));
+  for (long i = 0; i < nstr; i++)
+    b->seqxm->emplace_back(reinterpret_cast<const char*>(blob) + off[i], static_cast<size_t>(off[i + 1] - off[i]));
+  b->df.attr("seqxm_xptr") = static_cast<SEXP>(b->seqxm);
+  return b;
+}
+
+void ref_bam_free(void* h) {
+  RefBam* b = static_cast<RefBam*>(h);
+  if (!b) return;
+  delete b->seqxm;
+  delete b;
+}
+
+// pass_out: nstr bytes (the reference sizes its result by the number of strings).
+double ref_threshold_reads(void* h, const char* ctx_meth, const char* ctx_unmeth, const char* ooctx_meth,
+                           const char* ooctx_unmeth, unsigned int min_n_ctx, double min_beta, double max_oo_beta,
+                           uint8_t* pass_out) {
+  RefBam* b = static_cast<RefBam*>(h);
+  double t0 = now_s();
+  std::vector<bool> r = rcpp_threshold_reads(b->df, ctx_meth, ctx_unmeth, ooctx_meth, ooctx_unmeth, min_n_ctx,
+                                             min_beta, max_oo_beta);
+  double t1 = now_s();
+  for (size_t i = 0; i < r.size(); i++) pass_out[i] = r[i] ? 1 : 0;
+  return t1 - t0;
+}
+
+double ref_get_xm_beta(void* h, const char* ctx_meth, const char* ctx_unmeth, double* beta_out) {
+  RefBam* b = static_cast<RefBam*>(h);
+  double t0 = now_s();
+  std::vector<double> r = rcpp_get_xm_beta(b->df, ctx_meth, ctx_unmeth);
+  double t1 = now_s();
+  std::memcpy(beta_out, r.data(), r.size() * sizeof(double));
+  return t1 - t0;
+}
+
+// pass: n ints (R logical encoding: 0 FALSE, non-zero TRUE, INT_MIN = NA).
+// Returns the number of report rows; fetch them with ref_cx_fetch.
+long ref_cx_report(void* h, const int* pass, const char* ctx, double* seconds) {
+  RefBam* b = static_cast<RefBam*>(h);
+  Rcpp::LogicalVector pv(std::make_shared<std::vector<int>>(pass, pass + b->n));
+  double t0 = now_s();
+  Rcpp::DataFrame res = rcpp_cx_report(b->df, pv, ctx);
+  double t1 = now_s();
+  if (seconds) *seconds = t1 - t0;
+  static const char* names[6] = {"rname", "strand", "pos", "context", "meth", "unmeth"};
+  for (int c = 0; c < 6; c++) b->cols[c] = res[names[c]].shared();
+  return static_cast<long>(b->cols[0]->size());
+}
+
+void ref_cx_fetch(void* h, int* rname, int* strand, int* pos, int* context, int* meth, int* unmeth) {
+  RefBam* b = static_cast<RefBam*>(h);
+  int* dst[6] = {rname, strand, pos, context, meth, unmeth};
+  for (int c = 0; c < 6; c++)
+    if (b->cols[c] && !b->cols[c]->empty())
+      std::memcpy(dst[c], b->cols[c]->data(), b->cols[c]->size() * sizeof(int));
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+"""Regenerates tests/golden/*.npz.  Run in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Inputs : the reference's bundled fixture BAMs (/root/reference/inst/extdata), decoded to the
+         reference's ``bam.data`` layout by oracle/bamdata.py (no HTSlib/R here).
+Outputs: for every case in CASES, the per-read pass flags / betas and the six report columns
+         produced by the REFERENCE'S OWN, UNMODIFIED C++ (oracle/_ref/libepiref.so, compiled by
+         oracle/Makefile from /root/reference/src).  These are the committed golden vectors the
+         CPU and GPU parity tests compare against on machines where /root/reference is absent.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.bamdata import read_bam  # noqa: E402
+from oracle.oracle import CONTEXT_TO_BASES, RefCpu, build  # noqa: E402
+
+EXT = "/root/reference/inst/extdata/"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+FIXTURES = {
+    "amplicon000meth": (EXT + "amplicon000meth.bam", {}),
+    "amplicon010meth": (EXT + "amplicon010meth.bam", {}),
+    "amplicon100meth": (EXT + "amplicon100meth.bam", {}),
+    "capture": (EXT + "capture.bam", {}),
+    "capture_q30_bq20": (EXT + "capture.bam", dict(min_mapq=30, min_baseq=20)),
+    "capture_trim": (EXT + "capture.bam", dict(trim=(3, 5))),
+    "dragen_se": (EXT + "test/dragen-se-unsort-xg-xm.bam", {}),
+    "dragen_pe": (EXT + "test/dragen-pe-namesort-xg-xm.bam", {}),
+}
+
+# (name, threshold_reads, threshold_context, min_sites, min_beta, max_oo_beta, report_context)
+CASES = [
+    ("cg_default", True, "CG", 2, 0.5, 0.1, "CG"),
+    ("cx_nothr", False, "CG", 2, 0.5, 0.1, "CX"),
+    ("cg_thr_cx_rep", True, "CG", 2, 0.5, 0.1, "CX"),
+    ("chg_thr_cxg_rep", True, "CHG", 1, 0.3, 0.5, "CxG"),
+    ("chh_thr_chh_rep", True, "CHH", 3, 0.1, 0.9, "CHH"),
+    ("cxg_thr_chg_rep", True, "CxG", 2, 0.25, 0.2, "CHG"),
+    ("cx_thr_cg_rep", True, "CX", 5, 0.05, 0.1, "CG"),
+    ("cg_zero_thresholds", True, "CG", 0, 0.0, 1.0, "CG"),
+]
+BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh")]
+
+
+def main():
+    build(("ref",))
+    for name, (path, kw) in FIXTURES.items():
+        bam = read_bam(path, **kw)
+        blob, off = bam.blob()
+        out = dict(rname=bam.rname, strand=bam.strand, start=bam.start, templid=bam.templid, blob=blob, off=off,
+                   levels=np.array(bam.rname_levels))
+        ref = RefCpu(bam)
+        for cname, thr, tctx, ms, mb, mo, rctx in CASES:
+            p, rep = ref.generateCytosineReport(thr, tctx, ms, mb, mo, rctx)
+            out[cname + ".pass"] = p.astype(np.uint8)
+            for k, v in rep.items():
+                out[cname + "." + k] = v
+        for bname, m, u in BETAS:
+            out[bname] = ref.rcpp_get_xm_beta(m, u)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(name, bam.nrow, int(off[-1]), {c[0]: int(out[c[0] + ".pos"].shape[0]) for c in CASES})
+
+
+if __name__ == "__main__":
+    main()
