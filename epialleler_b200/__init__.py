@@ -1,0 +1,10 @@
+"""epialleler_b200 -- B200-native cytosine-report hot path of BBCG/epialleleR.
+
+Host-side mirror of the reference's interface for this path (same names and argument meaning):
+``preprocessBam`` (pass-through of already preprocessed reads), ``generateCytosineReport`` and the
+three Rcpp routines ``rcpp_threshold_reads``, ``rcpp_get_xm_beta``, ``rcpp_cx_report``; all compute
+runs in hand-written sm_100a kernels behind the C ABI of include/epialleler_b200.h.
+"""
+from .api import (BamData, CONTEXT_TO_BASES, generateCytosineReport, preprocessBam, rcpp_cx_report,  # noqa: F401
+                  rcpp_get_xm_beta, rcpp_threshold_reads, synth_config, synth_device, synth_host)
+from ._native import EaError  # noqa: F401

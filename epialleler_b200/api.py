@@ -1,0 +1,284 @@
+"""Host-side mirror of the reference's R/Rcpp interface for the cytosine-report path.
+
+Names, argument order/meaning and error behaviour follow the reference (file:line cited per
+function); the bodies only marshal numpy arrays across the C ABI (epialleler_b200/_native.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip as _gzip
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+# R/internal.R:54-65 -- context name -> (ctx.meth, ctx.unmeth, ooctx.meth, ooctx.unmeth)
+CONTEXT_TO_BASES = {
+    "CG": ("Z", "z", "XH", "xh"),
+    "CHG": ("X", "x", "ZH", "zh"),
+    "CHH": ("H", "h", "ZX", "zx"),
+    "CxG": ("ZX", "zx", "H", "h"),
+    "CX": ("ZXH", "zxh", "", ""),
+}
+CONTEXT_LEVELS = ("NA1", "CHH", "NA3", "NA4", "NA5", "CHG", "CG")  # src/rcpp_cx_report.cpp:150-152
+STRAND_LEVELS = ("+", "-")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class BamData:
+    """The reference's ``bam.data``: four int columns in (rname,start) order plus the packed SEQ|XM
+    strings in file order (src/rcpp_read_bam.cpp:166-189, R/internal.R:193-195).  The device-resident
+    packed copy is created on first use and kept on the object, like the reference keeps its
+    ``seqxm_xptr`` external pointer on the data.table (pack once, many reports)."""
+
+    def __init__(self, rname, strand, start, templid, seqxm_blob, seqxm_off, rname_levels: Sequence[str] = (), device: int = 0):
+        self.rname = np.ascontiguousarray(rname, dtype=np.int32)
+        self.strand = np.ascontiguousarray(strand, dtype=np.int32)
+        self.start = np.ascontiguousarray(start, dtype=np.int32)
+        self.templid = np.ascontiguousarray(templid, dtype=np.int32)
+        self._blob = np.ascontiguousarray(seqxm_blob, dtype=np.uint8)
+        self._off = np.ascontiguousarray(seqxm_off, dtype=np.int64)
+        self.rname_levels = list(rname_levels)
+        self.device = device
+        self._h = None
+        n = self.rname.shape[0]
+        if not (self.strand.shape[0] == self.start.shape[0] == self.templid.shape[0] == n):
+            raise ValueError("rname/strand/start/templid must have the same length")
+
+    @classmethod
+    def from_strings(cls, rname, strand, start, templid, seqxm: Sequence[bytes], rname_levels=(), device=0):
+        lens = np.fromiter((len(s) for s in seqxm), dtype=np.int64, count=len(seqxm))
+        off = np.zeros(len(seqxm) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        blob = np.frombuffer(b"".join(seqxm), dtype=np.uint8) if len(seqxm) else np.zeros(0, np.uint8)
+        return cls(rname, strand, start, templid, blob, off, rname_levels, device)
+
+    @property
+    def nrow(self) -> int:
+        return int(self.rname.shape[0])
+
+    @property
+    def nstr(self) -> int:
+        return int(self._off.shape[0] - 1)
+
+    def blob(self):
+        return self._blob, self._off
+
+    # -- device handle ------------------------------------------------------------------------
+    def handle(self):
+        if self._h is None:
+            L = N.lib()
+            h = C.c_void_p()
+            blob = self._blob if self._blob.shape[0] else np.zeros(1, np.uint8)
+            N.check(L.ea_pack_blob(_p(self.rname, C.c_int32), _p(self.strand, C.c_int32), _p(self.start, C.c_int32),
+                                   _p(self.templid, C.c_int32), self.nrow, _p(blob, C.c_uint8), _p(self._off, C.c_int64),
+                                   self.nstr, self.device, C.byref(h)))
+            self._h = h
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            N.lib().ea_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBam:
+    """A bam.data that only exists on the device (synthetic reads); same calls as BamData."""
+
+    def __init__(self, h, device):
+        self._h = h
+        self.device = device
+        self.rname_levels = []
+
+    def handle(self):
+        return self._h
+
+    @property
+    def nrow(self):
+        return int(N.lib().ea_nrow(self._h))
+
+    @property
+    def nstr(self):
+        return self.nrow
+
+    @property
+    def nbytes(self):
+        return int(N.lib().ea_nbytes(self._h))
+
+    def to_host(self) -> BamData:
+        L = N.lib()
+        n = self.nrow
+        rn, st, sa = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+        off = np.zeros(n + 1, np.int64)
+        blob = np.zeros(max(self.nbytes, 1), np.uint8)
+        N.check(L.ea_export_host(self._h, _p(rn, C.c_int32), _p(st, C.c_int32), _p(sa, C.c_int32), _p(off, C.c_int64), _p(blob, C.c_uint8)))
+        return BamData(rn[:n], st[:n], sa[:n], np.arange(n, dtype=np.int32), blob[:self.nbytes], off, device=self.device)
+
+    def close(self):
+        if self._h is not None:
+            N.lib().ea_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def preprocessBam(bam_file, **kwargs):
+    """R/preprocessBam.R:197-237.  Already preprocessed reads pass through unchanged; decoding a BAM
+    file stays on the host with HTSlib (BASELINE.json north_star) and is not part of this package."""
+    if isinstance(bam_file, (BamData, DeviceBam)):
+        return bam_file
+    raise NotImplementedError("BAM decoding (HTSlib) is outside the B200 hot path: pass preprocessed reads "
+                              "(BamData) as the reference allows (R/preprocessBam.R:226-235)")
+
+
+def _check_nrow(df):
+    # the reference sizes its result by the number of strings and indexes templid by row
+    # (src/rcpp_threshold_reads.cpp:27-33): anything else is out of contract
+    if df.nrow != df.nstr:
+        raise ValueError("nrow(bam) must equal the number of seqxm strings")
+
+
+def rcpp_threshold_reads(df, ctx_meth, ctx_unmeth, ooctx_meth, ooctx_unmeth, min_n_ctx, min_ctx_meth_frac, max_ooctx_meth_frac):
+    """src/rcpp_threshold_reads.cpp:15-74 -> logical vector, TRUE for reads passing the thresholds."""
+    _check_nrow(df)
+    L = N.lib()
+    out = np.zeros(max(df.nrow, 1), np.uint8)
+    N.check(L.ea_threshold_reads(df.handle(), ctx_meth.encode(), ctx_unmeth.encode(), ooctx_meth.encode(), ooctx_unmeth.encode(),
+                                 int(min_n_ctx) & 0xFFFFFFFF, float(min_ctx_meth_frac), float(max_ooctx_meth_frac), _p(out, C.c_uint8)))
+    return out[:df.nrow].astype(bool)
+
+
+def rcpp_get_xm_beta(df, ctx_meth, ctx_unmeth):
+    """src/rcpp_get_xm_beta.cpp:10-43 -> per-read average beta (double)."""
+    _check_nrow(df)
+    L = N.lib()
+    out = np.zeros(max(df.nrow, 1), np.float64)
+    N.check(L.ea_get_xm_beta(df.handle(), ctx_meth.encode(), ctx_unmeth.encode(), _p(out, C.c_double)))
+    return out[:df.nrow]
+
+
+def _fetch_report(df, nrow):
+    L = N.lib()
+    cols = [np.zeros(max(nrow, 1), np.int32) for _ in range(6)]
+    N.check(L.ea_cx_report_fetch(df.handle(), *[_p(c, C.c_int32) for c in cols]))
+    names = ("rname", "strand", "pos", "context", "meth", "unmeth")
+    rep = {k: c[:nrow] for k, c in zip(names, cols)}
+    rep["levels"] = {"rname": list(df.rname_levels), "strand": list(STRAND_LEVELS), "context": list(CONTEXT_LEVELS)}
+    return rep
+
+
+def rcpp_cx_report(df, pass_, ctx):
+    """src/rcpp_cx_report.cpp:34-159 -> six integer columns (rname, strand, pos, context, meth, unmeth),
+    factor levels under "levels".  pass_: logical vector of nrow (None/NA = TRUE)."""
+    L = N.lib()
+    nrow = C.c_int64(0)
+    if pass_ is None:
+        pp = None
+    else:
+        pv = np.ascontiguousarray(np.asarray(pass_) != 0, dtype=np.uint8)
+        if pv.shape[0] != df.nrow:
+            raise ValueError("length(pass) must equal nrow(bam)")
+        pp = _p(pv if pv.shape[0] else np.zeros(1, np.uint8), C.c_uint8)
+    N.check(L.ea_cx_report(df.handle(), pp, ctx.encode(), C.byref(nrow)))
+    return _fetch_report(df, nrow.value)
+
+
+def _match_arg(value, choices, name):
+    if isinstance(value, (list, tuple)):
+        value = value[0]
+    if value not in choices:
+        raise ValueError("'%s' should be one of %s" % (name, ", ".join('"%s"' % c for c in choices)))
+    return value
+
+
+def _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, report_context):
+    b = CONTEXT_TO_BASES[threshold_context]
+    keep = [s.encode() for s in b] + [CONTEXT_TO_BASES[report_context][0].encode()]
+    p = N.ReportParams(1 if threshold_reads else 0, keep[0], keep[1], keep[2], keep[3], int(min_context_sites) & 0xFFFFFFFF,
+                       float(min_context_beta), float(max_outofcontext_beta), keep[4])
+    p._keep = keep
+    return p
+
+
+def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshold_context="CG", min_context_sites=2,
+                           min_context_beta=0.5, max_outofcontext_beta=0.1, report_context=None, gzip=False,
+                           verbose=False, return_pass=False, **kwargs):
+    """R/generateCytosineReport.R:164-208.  Thresholding and aggregation run as ONE fused pass over the
+    XM bytes (ea_cytosine_report).  Returns the report (dict of columns), or writes a TSV like the
+    reference's .writeReport (R/internal.R:274-287) when report_file is given."""
+    contexts = tuple(CONTEXT_TO_BASES)
+    threshold_context = _match_arg(threshold_context, contexts, "threshold.context")
+    report_context = _match_arg(report_context if report_context is not None else threshold_context, contexts, "report.context")
+    bam = preprocessBam(bam, **kwargs)
+    L = N.lib()
+    p = _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, report_context)
+    nrow = C.c_int64(0)
+    pass_out = np.zeros(max(bam.nrow, 1), np.uint8) if return_pass else None
+    N.check(L.ea_cytosine_report(bam.handle(), C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow)))
+    rep = _fetch_report(bam, nrow.value)
+    if report_file is not None:
+        _write_report(rep, report_file, gzip)
+        return None
+    if return_pass:
+        return pass_out[:bam.nrow].astype(bool), rep
+    return rep
+
+
+def _write_report(rep, path, gz):
+    lv = rep["levels"]
+    opener = (lambda p: _gzip.open(p, "wt")) if gz else (lambda p: open(p, "w"))
+    with opener(path) as fh:
+        fh.write("rname\tstrand\tpos\tcontext\tmeth\tunmeth\n")
+        for i in range(rep["pos"].shape[0]):
+            rn = rep["rname"][i]
+            name = lv["rname"][rn - 1] if 0 < rn <= len(lv["rname"]) else str(rn)
+            fh.write("%s\t%s\t%d\t%s\t%d\t%d\n" % (name, STRAND_LEVELS[rep["strand"][i] - 1], rep["pos"][i],
+                                                  CONTEXT_LEVELS[rep["context"][i] - 1], rep["meth"][i], rep["unmeth"][i]))
+
+
+# ---- deterministic synthetic reads (bench / parity at BASELINE.json sizes) -----------------------
+def synth_config(seed, n_reads, chr_len, len_min, len_max=None, n_islands=0, island_len=0):
+    cfg = N.SynthCfg()
+    cfg.seed = seed
+    cfg.n_reads = n_reads
+    cfg.n_chr = len(chr_len)
+    cfg.len_min = len_min
+    cfg.len_max = len_max if len_max is not None else len_min
+    cfg.n_islands = n_islands
+    cfg.island_len = island_len
+    for i, v in enumerate(chr_len):
+        cfg.chr_len[i] = v
+    return cfg
+
+
+def synth_device(cfg, row_begin=0, row_end=None, device=0) -> DeviceBam:
+    L = N.lib()
+    h = C.c_void_p()
+    N.check(L.ea_synth_device(C.byref(cfg), row_begin, cfg.n_reads if row_end is None else row_end, device, C.byref(h)))
+    return DeviceBam(h, device)
+
+
+def synth_host(cfg, row_begin=0, row_end=None) -> BamData:
+    L = N.lib()
+    row_end = cfg.n_reads if row_end is None else row_end
+    n = row_end - row_begin
+    rn, st, sa = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+    off = np.zeros(n + 1, np.int64)
+    N.check(L.ea_synth_host(C.byref(cfg), row_begin, row_end, _p(rn, C.c_int32), _p(st, C.c_int32), _p(sa, C.c_int32), _p(off, C.c_int64), None))
+    blob = np.zeros(max(int(off[-1]), 1), np.uint8)
+    N.check(L.ea_synth_host(C.byref(cfg), row_begin, row_end, None, None, None, _p(off, C.c_int64), _p(blob, C.c_uint8)))
+    return BamData(rn[:n], st[:n], sa[:n], np.arange(n, dtype=np.int32), blob[:int(off[-1])], off)

@@ -1,0 +1,1098 @@
+// C-ABI implementation (include/epialleler_b200.h): packer, window index, kernel dispatch.
+// There is no CPU compute path in this file: without a CUDA device every entry point fails with
+// EA_ERR_NODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/epialleler_b200.h"
+#include "kernels.cuh"
+#include "synth.h"
+
+namespace {
+
+thread_local std::string g_err;
+ea_poll_fn g_poll = nullptr;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(EA_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define POLL()                                                                   \
+  do {                                                                           \
+    if (g_poll && g_poll()) return fail(EA_ERR_INTERRUPT, "interrupted by caller"); \
+  } while (0)
+
+template <class T>
+int dmalloc(T** p, size_t n) {
+  *p = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+  return EA_OK;
+}
+
+struct WinIndex {
+  int S = 0;
+  int32_t n = 0;
+  int32_t *rname = nullptr, *pos0 = nullptr, *lo = nullptr, *hi = nullptr;
+  long long *w_base = nullptr, *w_dst = nullptr;
+  int32_t* w_cnt = nullptr;
+  int32_t max_rows = 0;  // largest hi-lo
+  void release() {
+    cudaFree(rname); cudaFree(pos0); cudaFree(lo); cudaFree(hi); cudaFree(w_base); cudaFree(w_dst); cudaFree(w_cnt);
+    *this = WinIndex();
+  }
+};
+
+}  // namespace
+
+struct ea_handle {
+  int device = 0;
+  int64_t n = 0;
+  int64_t nbytes = 0;   // sum of true lengths
+  int64_t npadded = 0;  // bytes of the padded data array
+  int32_t max_len = 0;
+  bool owns = true;
+  int32_t* d_rname = nullptr;
+  uint8_t* d_strand = nullptr;
+  int32_t* d_start = nullptr;
+  int32_t* d_len = nullptr;
+  int64_t* d_off = nullptr;
+  uint8_t* d_data = nullptr;
+  uint64_t* d_maxend = nullptr;  // per row: rname<<32 | prefix max of row ends
+  WinIndex idx[2];               // S = 4096 and S = 2048
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10] = {};
+  // per-call state
+  uint8_t* d_pass = nullptr;
+  double* d_beta = nullptr;
+  unsigned long long* d_counters = nullptr;  // [0] row cursor, [1] n_pass
+  int4* d_scratch = nullptr;
+  int32_t* d_cols[6] = {};
+  int64_t cap_rows = 0;
+  int64_t n_rows = -1;
+  int32_t report_n_launches = 0;
+  void* d_flush = nullptr;
+  int64_t flush_bytes = 0;
+  int sm_count = 148;
+};
+
+namespace {
+
+using namespace ea;
+
+Csr csr_of(const ea_handle* h) {
+  Csr c;
+  c.data = h->d_data; c.off = h->d_off; c.len = h->d_len; c.start = h->d_start; c.strand = h->d_strand;
+  c.rname = h->d_rname; c.n = h->n;
+  return c;
+}
+
+int pick_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(EA_ERR_NODEVICE, "no CUDA device available: epialleler_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(EA_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  CU(cudaSetDevice(device));
+  return EA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack-time kernels
+// ---------------------------------------------------------------------------------------------
+enum { F_UNSORTED = 1, F_DOMAIN = 2, F_TEMPLID = 4, F_NEGSTART = 8, F_STRAND = 16, F_TOOLONG = 32 };
+
+__global__ void k_lens_from_templid(const int64_t* __restrict__ soff, const int32_t* __restrict__ templid, int64_t n,
+                                    int64_t nstr, int32_t* __restrict__ len, int64_t* __restrict__ padded,
+                                    unsigned* flags) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int64_t t = templid ? templid[r] : r;
+  int64_t l = 0;
+  if (t < 0 || t >= nstr) atomicOr(flags, F_TEMPLID);
+  else l = soff[t + 1] - soff[t];
+  if (l < 0 || l > 0x7FFFFFF0ll) { atomicOr(flags, F_TOOLONG); l = 0; }
+  len[r] = (int32_t)l;
+  padded[r] = (l + 15) & ~15ll;
+}
+
+// one warp per row: tight source string -> 16-byte aligned, 0x0B-padded destination row
+__global__ void k_repack(const uint8_t* __restrict__ blob, const int64_t* __restrict__ soff,
+                         const int32_t* __restrict__ templid, int64_t n, const int64_t* __restrict__ doff,
+                         const int32_t* __restrict__ len, uint8_t* __restrict__ dst) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += n_warps) {
+    const int64_t t = templid ? templid[r] : r;
+    const uint8_t* src = blob + soff[t];
+    const int l = len[r];
+    uint8_t* d = dst + doff[r];
+    const int nch = (l + 15) >> 4;
+    for (int c = lane; c < nch; c += 32) {
+      uint32_t w[4] = {0x0B0B0B0Bu, 0x0B0B0B0Bu, 0x0B0B0B0Bu, 0x0B0B0B0Bu};
+      const int b0 = c * 16;
+      const int m = min(16, l - b0);
+      for (int i = 0; i < m; i++) {
+        const uint32_t v = src[b0 + i];
+        w[i >> 2] = (w[i >> 2] & ~(0xFFu << ((i & 3) * 8))) | (v << ((i & 3) * 8));
+      }
+      *reinterpret_cast<uint4*>(d + b0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+__global__ void k_unpad(const uint8_t* __restrict__ data, const int64_t* __restrict__ doff, const int32_t* __restrict__ len,
+                        const int64_t* __restrict__ toff, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += n_warps) {
+    const uint8_t* s = data + doff[r];
+    uint8_t* d = out + toff[r];
+    const int l = len[r];
+    for (int i = lane; i < l; i += 32) d[i] = s[i];
+  }
+}
+
+__global__ void k_strand_u8(const int32_t* __restrict__ s32, int64_t n, uint8_t* __restrict__ s8, unsigned* flags) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int v = s32[r];
+  if (v != 1 && v != 2) atomicOr(flags, F_STRAND);
+  s8[r] = (uint8_t)v;
+}
+
+__global__ void k_len_i64(const int32_t* __restrict__ len, int64_t n, int64_t* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) out[r] = len[r];
+}
+
+// validation + row-end keys.  key = rname<<32 | (start+len) (0 for empty rows, so they never extend coverage)
+__global__ void k_row_keys(Csr csr, uint64_t* __restrict__ key, int32_t* __restrict__ max_len, unsigned* flags) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= csr.n) return;
+  const int32_t rn = csr.rname[r], st = csr.start[r], l = csr.len[r];
+  unsigned f = 0;
+  if (st < 0 || rn < 0) f |= F_NEGSTART;
+  if ((int64_t)st + l > 0x7FFFFFF0ll) f |= F_TOOLONG;
+  if (csr.strand[r] != 1 && csr.strand[r] != 2) f |= F_STRAND;
+  if (r > 0) {
+    const int32_t prn = csr.rname[r - 1], pst = csr.start[r - 1];
+    if (prn > rn || (prn == rn && pst > st)) f |= F_UNSORTED;
+  }
+  if (f) atomicOr(flags, f);
+  key[r] = ((uint64_t)(uint32_t)rn << 32) | (uint32_t)(l > 0 ? st + l : 0);
+  atomicMax(max_len, l);
+}
+
+// every low nibble must be one of {2,5,6,7,10,11,12,13,14,15}
+__global__ void k_validate_domain(const uint8_t* __restrict__ data, int64_t n_chunks, unsigned* flags) {
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = i0; i < n_chunks; i += stride) {
+    const uint4 v = *reinterpret_cast<const uint4*>(data + i * 16);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) bad |= !((0xFCE4u >> ((w[k] >> (8 * b)) & 15u)) & 1u);
+  }
+  if (bad) atomicOr(flags, F_DOMAIN);
+}
+
+// windows newly opened by row r (rows are sorted, so they are the ones beyond the furthest end so far)
+__device__ __forceinline__ void new_windows(const Csr& csr, const uint64_t* maxend, int64_t r, int S, int& first, int& count) {
+  const int32_t l = csr.len[r];
+  first = 0; count = 0;
+  if (l <= 0) return;
+  const int32_t st = csr.start[r];
+  const int fw = st / S, lw = (st + l - 1) / S;
+  int prev_lw = -1;
+  if (r > 0) {
+    const uint64_t m = maxend[r - 1];
+    const int32_t pe = (int32_t)(uint32_t)m;
+    if ((int32_t)(m >> 32) == csr.rname[r] && pe > 0) prev_lw = (pe - 1) / S;
+  }
+  first = max(fw, prev_lw + 1);
+  count = max(0, lw - first + 1);
+}
+
+__global__ void k_count_windows(Csr csr, const uint64_t* __restrict__ maxend, int S, int32_t* __restrict__ cnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= csr.n) return;
+  int first, count;
+  new_windows(csr, maxend, r, S, first, count);
+  cnt[r] = count;
+}
+
+__global__ void k_fill_windows(Csr csr, const uint64_t* __restrict__ maxend, int S, const int32_t* __restrict__ woff,
+                               int32_t* __restrict__ w_rname, int32_t* __restrict__ w_pos0) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= csr.n) return;
+  int first, count;
+  new_windows(csr, maxend, r, S, first, count);
+  const int32_t base = woff[r], rn = csr.rname[r];
+  for (int k = 0; k < count; k++) {
+    w_rname[base + k] = rn;
+    w_pos0[base + k] = (first + k) * S;
+  }
+}
+
+__global__ void k_window_rows(Csr csr, const uint64_t* __restrict__ maxend, int S, int32_t n_win,
+                              const int32_t* __restrict__ w_rname, const int32_t* __restrict__ w_pos0,
+                              int32_t* __restrict__ w_lo, int32_t* __restrict__ w_hi, int32_t* max_rows) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_win) return;
+  const uint64_t rn = (uint64_t)(uint32_t)w_rname[w] << 32;
+  const uint32_t p0 = (uint32_t)w_pos0[w];
+  // hi: first row with (rname,start) >= (rn, p0+S)
+  const uint64_t khi = rn | (uint64_t)(p0 + (uint32_t)S);
+  int64_t a = 0, b = csr.n;
+  while (a < b) {
+    const int64_t m = (a + b) >> 1;
+    const uint64_t k = ((uint64_t)(uint32_t)csr.rname[m] << 32) | (uint32_t)csr.start[m];
+    if (k < khi) a = m + 1; else b = m;
+  }
+  const int64_t hi = a;
+  // lo: first row whose running furthest end (same chromosome) reaches beyond p0
+  const uint64_t klo = rn | (uint64_t)p0;
+  a = 0; b = hi;
+  while (a < b) {
+    const int64_t m = (a + b) >> 1;
+    if (maxend[m] <= klo) a = m + 1; else b = m;
+  }
+  w_lo[w] = (int32_t)a;
+  w_hi[w] = (int32_t)hi;
+  atomicMax(max_rows, (int32_t)(hi - a));
+}
+
+struct MaxU64 {
+  __host__ __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const { return a > b ? a : b; }
+};
+
+int grid_for(int64_t n, int threads) { return (int)std::min<int64_t>((n + threads - 1) / threads, 1 << 30); }
+
+int flags_error(unsigned f) {
+  if (f & F_TEMPLID) return fail(EA_ERR_ARG, "templid out of range (the reference's seqxm->at() would throw std::out_of_range)");
+  if (f & F_TOOLONG) return fail(EA_ERR_ARG, "string length / end position does not fit 31 bits");
+  if (f & F_NEGSTART) return fail(EA_ERR_ARG, "negative start or rname");
+  if (f & F_STRAND) return fail(EA_ERR_ARG, "strand must be 1 ('+') or 2 ('-')");
+  if (f & F_UNSORTED) return fail(EA_ERR_UNSORTED, "rows are not sorted by (rname, start): pre-sorted input is a requirement (rcpp_cx_report.cpp:19)");
+  if (f & F_DOMAIN) return fail(EA_ERR_DOMAIN, "a string holds a methylation-call code the reference's readers never emit (valid low nibbles: 2,5,6,7,10..15)");
+  return EA_OK;
+}
+
+// Common tail of every constructor: validation, row-end keys, stream/events.
+int finish_handle(ea_handle* h) {
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  int rc;
+  if ((rc = dmalloc(&h->d_counters, 4))) return rc;
+  if ((rc = dmalloc(&h->d_maxend, (size_t)h->n))) return rc;
+  unsigned* d_flags; int32_t* d_maxlen;
+  if ((rc = dmalloc(&d_flags, 1))) return rc;
+  if ((rc = dmalloc(&d_maxlen, 1))) return rc;
+  CU(cudaMemsetAsync(d_flags, 0, 4, h->stream));
+  CU(cudaMemsetAsync(d_maxlen, 0, 4, h->stream));
+  if (h->n > 0) {
+    k_row_keys<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, d_maxlen, d_flags);
+    const int64_t n_chunks = h->npadded / 16;
+    if (n_chunks > 0) k_validate_domain<<<(int)std::min<int64_t>((n_chunks + 255) / 256, h->sm_count * 32), 256, 0, h->stream>>>(h->d_data, n_chunks, d_flags);
+    size_t tb = 0;
+    CU(cub::DeviceScan::InclusiveScan(nullptr, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
+    void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+    CU(cub::DeviceScan::InclusiveScan(tmp, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp);
+  }
+  unsigned f = 0;
+  CU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&h->max_len, d_maxlen, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(d_flags); cudaFree(d_maxlen);
+  CU(cudaGetLastError());
+  return flags_error(f);
+}
+
+int build_index(ea_handle* h, int S, WinIndex** out) {
+  WinIndex* ix = &h->idx[S == 4096 ? 0 : 1];
+  *out = ix;
+  if (ix->S == S) return EA_OK;
+  ix->release();
+  ix->S = S;
+  if (h->n == 0) return EA_OK;
+  int rc;
+  int32_t *d_cnt, *d_woff, *d_max;
+  if ((rc = dmalloc(&d_cnt, (size_t)h->n))) return rc;
+  if ((rc = dmalloc(&d_woff, (size_t)h->n))) return rc;
+  if ((rc = dmalloc(&d_max, 1))) return rc;
+  k_count_windows<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, S, d_cnt);
+  size_t tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt, d_woff, (int)h->n, h->stream));
+  void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_cnt, d_woff, (int)h->n, h->stream));
+  int32_t last_off = 0, last_cnt = 0;
+  CU(cudaMemcpyAsync(&last_off, d_woff + h->n - 1, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&last_cnt, d_cnt + h->n - 1, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(tmp);
+  ix->n = last_off + last_cnt;
+  if ((rc = dmalloc(&ix->rname, (size_t)ix->n))) return rc;
+  if ((rc = dmalloc(&ix->pos0, (size_t)ix->n))) return rc;
+  if ((rc = dmalloc(&ix->lo, (size_t)ix->n))) return rc;
+  if ((rc = dmalloc(&ix->hi, (size_t)ix->n))) return rc;
+  if ((rc = dmalloc(&ix->w_base, (size_t)ix->n))) return rc;
+  if ((rc = dmalloc(&ix->w_dst, (size_t)ix->n))) return rc;
+  if ((rc = dmalloc(&ix->w_cnt, (size_t)ix->n))) return rc;
+  CU(cudaMemsetAsync(d_max, 0, 4, h->stream));
+  if (ix->n > 0) {
+    k_fill_windows<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, S, d_woff, ix->rname, ix->pos0);
+    k_window_rows<<<grid_for(ix->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, S, ix->n, ix->rname, ix->pos0, ix->lo, ix->hi, d_max);
+  }
+  CU(cudaMemcpyAsync(&ix->max_rows, d_max, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(d_cnt); cudaFree(d_woff); cudaFree(d_max);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// letter sets
+// ---------------------------------------------------------------------------------------------
+inline unsigned code_of(unsigned char c) { return ((c + 2u) >> 2) & 15u; }  // src/epialleleR.h:28
+
+struct ThresholdSpec {
+  int tctx = TC_NONE;  // named context, or -1 for the generic kernel
+  LetterWeights lw;
+};
+
+void parse_threshold_letters(const char* m, const char* u, const char* om, const char* ou, ThresholdSpec* s) {
+  const char* sets[4] = {m ? m : "", u ? u : "", om ? om : "", ou ? ou : ""};
+  memset(&s->lw, 0, sizeof s->lw);
+  unsigned mask[4] = {0, 0, 0, 0};
+  bool multi = false;
+  for (int k = 0; k < 4; k++)
+    for (const unsigned char* p = (const unsigned char*)sets[k]; *p; p++) {
+      const unsigned c = code_of(*p);
+      if (s->lw.w[k][c] == 255) continue;
+      if (s->lw.w[k][c]++) multi = true;
+      mask[k] |= 1u << c;
+    }
+  s->tctx = -1;
+  if (multi) return;
+  const unsigned Z = 1u << 7, X = 1u << 6, H = 1u << 2, z = 1u << 15, x = 1u << 14, hh = 1u << 10;
+  struct { int t; unsigned m, u, om, ou; } named[5] = {
+      {TC_CG, Z, z, X | H, x | hh}, {TC_CHG, X, x, Z | H, z | hh}, {TC_CHH, H, hh, Z | X, z | x},
+      {TC_CXG, Z | X, z | x, H, hh}, {TC_CX, Z | X | H, z | x | hh, 0, 0}};
+  for (auto& nm : named)
+    if (mask[0] == nm.m && mask[1] == nm.u && mask[2] == nm.om && mask[3] == nm.ou) s->tctx = nm.t;
+}
+
+// beta only looks at the in-context sets; out-of-context ones of the named context are harmless
+void parse_beta_letters(const char* m, const char* u, ThresholdSpec* s) {
+  parse_threshold_letters(m, u, "", "", s);
+  if (s->tctx >= 0) return;
+  static const char* oo[5][2] = {{"XH", "xh"}, {"ZH", "zh"}, {"ZX", "zx"}, {"H", "h"}, {"", ""}};
+  for (int k = 0; k < 5; k++) {
+    ThresholdSpec t;
+    parse_threshold_letters(m, u, oo[k][0], oo[k][1], &t);
+    if (t.tctx >= 0) { *s = t; return; }
+  }
+}
+
+int want_of(const char* ctx) {
+  int w = 0;
+  for (const unsigned char* p = (const unsigned char*)(ctx ? ctx : ""); *p; p++) {
+    const unsigned c = code_of(*p);
+    if (c == 2) w |= W_CHH;
+    if (c == 6) w |= W_CHG;
+    if (c == 7) w |= W_CG;
+  }
+  return w;
+}
+
+int group_lanes(const ea_handle* h) {
+  const int nch = (h->max_len + 15) / 16;
+  return std::max(1, std::min(32, nch));
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+template <int TCTX>
+void launch_threshold_t(ea_handle* h, const ThrParams& tp, uint8_t* pass, double* beta, unsigned long long* n_pass) {
+  const int g = group_lanes(h);
+  const int rpw = 32 / g;
+  const int64_t warps_needed = (h->n + rpw - 1) / rpw;
+  const int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)h->sm_count * 16);
+  k_threshold<TCTX><<<std::max(blocks, 1), 256, 0, h->stream>>>(csr_of(h), tp, g, pass, beta, n_pass);
+}
+
+int launch_threshold(ea_handle* h, const ThresholdSpec& spec, const ThrParams& tp, uint8_t* pass, double* beta,
+                     unsigned long long* n_pass) {
+  if (h->n == 0) return EA_OK;
+  if (spec.tctx < 0 || h->max_len > 65535) {
+    k_threshold_generic<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), spec.lw, tp, pass, beta, n_pass);
+  } else {
+    switch (spec.tctx) {
+      case TC_CG: launch_threshold_t<TC_CG>(h, tp, pass, beta, n_pass); break;
+      case TC_CHG: launch_threshold_t<TC_CHG>(h, tp, pass, beta, n_pass); break;
+      case TC_CHH: launch_threshold_t<TC_CHH>(h, tp, pass, beta, n_pass); break;
+      case TC_CXG: launch_threshold_t<TC_CXG>(h, tp, pass, beta, n_pass); break;
+      default: launch_threshold_t<TC_CX>(h, tp, pass, beta, n_pass); break;
+    }
+  }
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+template <int WANT>
+size_t window_smem(int S, bool wide) {
+  return sizeof(int32_t) * 2 * (S + 4) + (wide ? 8 : 4) * (size_t)n_ctx<WANT>() * 2 * S;
+}
+
+template <int TCTX, int WANT, typename CT, bool FUSED>
+int launch_window_t(ea_handle* h, const WinIndex& ix, const ThrParams& tp, const uint8_t* pass_in, uint8_t* pass_out,
+                    const ReportOut& out) {
+  const size_t smem = window_smem<WANT>(ix.S, sizeof(CT) == 8);
+  auto kern = k_window<TCTX, WANT, CT, FUSED>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
+  kern<<<grid, kThreads, smem, h->stream>>>(csr_of(h), wt, tp, pass_in, pass_out, group_lanes(h), out);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+template <int WANT>
+int launch_window_w(ea_handle* h, const WinIndex& ix, int tctx_fused, bool wide, const ThrParams& tp,
+                    const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  typedef unsigned long long u64;
+  if (tctx_fused < 0) {
+    return wide ? launch_window_t<TC_NONE, WANT, u64, false>(h, ix, tp, pass_in, pass_out, out)
+                : launch_window_t<TC_NONE, WANT, uint32_t, false>(h, ix, tp, pass_in, pass_out, out);
+  }
+  switch (tctx_fused) {
+    case TC_CG: return launch_window_t<TC_CG, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+    case TC_CHG: return launch_window_t<TC_CHG, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+    case TC_CHH: return launch_window_t<TC_CHH, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+    case TC_CXG: return launch_window_t<TC_CXG, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+    default: return launch_window_t<TC_CX, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+  }
+}
+
+int launch_window(ea_handle* h, const WinIndex& ix, int want, int tctx_fused, bool wide, const ThrParams& tp,
+                  const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (want) {
+    case 1: return launch_window_w<1>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+    case 2: return launch_window_w<2>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+    case 3: return launch_window_w<3>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+    case 4: return launch_window_w<4>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+    case 5: return launch_window_w<5>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+    case 6: return launch_window_w<6>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+    default: return launch_window_w<7>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+  }
+}
+
+int ensure_pass(ea_handle* h) {
+  if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
+  return EA_OK;
+}
+
+int ensure_rows(ea_handle* h, int64_t cap) {
+  if (cap <= h->cap_rows) return EA_OK;
+  cudaFree(h->d_scratch); h->d_scratch = nullptr;
+  for (auto& c : h->d_cols) { cudaFree(c); c = nullptr; }
+  h->cap_rows = 0;
+  int rc;
+  if ((rc = dmalloc(&h->d_scratch, (size_t)cap))) return rc;
+  for (auto& c : h->d_cols)
+    if ((rc = dmalloc(&c, (size_t)cap))) return rc;
+  h->cap_rows = cap;
+  return EA_OK;
+}
+
+struct ReportPlan {
+  int want = 0;
+  bool threshold = false;
+  ThresholdSpec spec;
+  ThrParams tp{};
+  int mode = 0;  // 0 fused, 1 two-pass
+};
+
+// The device pipeline of one report: (threshold) -> window kernel -> window scan -> ordered gather.
+// pass_in_dev: device pass flags for the unthresholded/explicit-pass case (may be null = all TRUE).
+int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, ea_timing* tm) {
+  int rc;
+  h->n_rows = -1;
+  if (tm) memset(tm, 0, sizeof *tm);
+  const int nc = ((rp.want >> 0) & 1) + ((rp.want >> 1) & 1) + ((rp.want >> 2) & 1);
+  const int S = nc <= 1 ? 4096 : 2048;
+  WinIndex* ix = nullptr;
+  if (rp.want) { if ((rc = build_index(h, S, &ix))) return rc; }
+  if (rp.threshold && (rc = ensure_pass(h))) return rc;
+  const bool wide = ix && ix->max_rows > 65535;
+  const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
+  const bool fused = can_fuse && rp.mode == 0;
+  if (h->cap_rows == 0 && (rc = ensure_rows(h, h->nbytes / 24 + 4096))) return rc;
+
+  for (int attempt = 0; attempt < 2; attempt++) {
+    int launches = 0;
+    CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    const uint8_t* pass_for_window = pass_in_dev;
+    if (rp.threshold) {
+      if (fused || h->n == 0) {
+        CU(cudaMemsetAsync(h->d_pass, 0, (size_t)std::max<int64_t>(h->n, 1), h->stream));  // empty rows keep FALSE
+      } else {
+        if ((rc = launch_threshold(h, rp.spec, rp.tp, h->d_pass, nullptr, h->d_counters + 1))) return rc;
+        launches++;
+      }
+      pass_for_window = h->d_pass;
+    }
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    POLL();
+    if (rp.want && ix->n > 0) {
+      ReportOut out;
+      out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
+      out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
+      if ((rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out))) return rc;
+      launches++;
+      CU(cudaEventRecord(h->ev[2], h->stream));
+      k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
+      ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
+      k_gather_rows<<<std::max(1, std::min(ix->n / 4 + 1, h->sm_count * 16)), 128, 0, h->stream>>>(
+          h->d_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, cols);
+      launches += 2;
+      CU(cudaGetLastError());
+    } else {
+      CU(cudaEventRecord(h->ev[2], h->stream));
+    }
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    unsigned long long counters[2] = {0, 0};
+    CU(cudaMemcpyAsync(counters, h->d_counters, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->report_n_launches = launches;
+    if ((int64_t)counters[0] > h->cap_rows) {  // scratch too small: grow to the exact size and redo
+      if (attempt == 1) return fail(EA_ERR_STATE, "report row capacity exceeded twice");
+      if ((rc = ensure_rows(h, (int64_t)counters[0] + 1024))) return rc;
+      continue;
+    }
+    h->n_rows = (int64_t)counters[0];
+    if (tm) {
+      CU(cudaEventElapsedTime(&tm->total_ms, h->ev[0], h->ev[3]));
+      CU(cudaEventElapsedTime(&tm->kernel_ms[0], h->ev[0], h->ev[1]));
+      CU(cudaEventElapsedTime(&tm->kernel_ms[1], h->ev[1], h->ev[2]));
+      CU(cudaEventElapsedTime(&tm->kernel_ms[2], h->ev[2], h->ev[3]));
+      tm->n_launches = launches;
+      tm->n_rows = h->n_rows;
+      tm->n_pass = rp.threshold ? (int64_t)counters[1] : h->n;
+      tm->alg_bytes = h->nbytes + (rp.threshold ? 14 : 13) * h->n + 24 * h->n_rows;
+    }
+    return EA_OK;
+  }
+  return EA_OK;
+}
+
+int make_plan_from_params(const ea_report_params* p, int mode, ReportPlan* rp) {
+  if (!p) return fail(EA_ERR_ARG, "null params");
+  rp->want = want_of(p->report_ctx);
+  rp->threshold = p->threshold_reads != 0;
+  rp->mode = mode;
+  if (rp->threshold) {
+    if (!p->ctx_meth || !p->ctx_unmeth) return fail(EA_ERR_ARG, "ctx_meth/ctx_unmeth must be non-null");
+    parse_threshold_letters(p->ctx_meth, p->ctx_unmeth, p->ooctx_meth, p->ooctx_unmeth, &rp->spec);
+    rp->tp.min_n = p->min_n_ctx; rp->tp.min_beta = p->min_ctx_meth_frac; rp->tp.max_oo = p->max_ooctx_meth_frac;
+  }
+  return EA_OK;
+}
+
+int adopt_and_finish(ea_handle* h, ea_handle** out) {
+  const int rc = finish_handle(h);
+  if (rc != EA_OK) { ea_free(h); return rc; }
+  *out = h;
+  return EA_OK;
+}
+
+// Build the padded CSR from a tight device blob (file order) + per-row metadata already on the device.
+int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_soff, int64_t nstr,
+                          const int32_t* d_templid /* null = identity */) {
+  int rc;
+  unsigned* d_flags; int64_t* d_padded;
+  if ((rc = dmalloc(&d_flags, 1))) return rc;
+  if ((rc = dmalloc(&d_padded, (size_t)h->n + 1))) return rc;
+  if ((rc = dmalloc(&h->d_len, (size_t)h->n))) return rc;
+  if ((rc = dmalloc(&h->d_off, (size_t)h->n + 1))) return rc;
+  CU(cudaMemset(d_flags, 0, 4));
+  CU(cudaMemset(d_padded, 0, sizeof(int64_t) * (size_t)(h->n + 1)));
+  if (h->n > 0) k_lens_from_templid<<<grid_for(h->n, 256), 256>>>(d_soff, d_templid, h->n, nstr, h->d_len, d_padded, d_flags);
+  size_t tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_padded, h->d_off, (int)(h->n + 1)));
+  void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_padded, h->d_off, (int)(h->n + 1)));
+  unsigned f = 0;
+  CU(cudaMemcpy(&f, d_flags, 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&h->npadded, h->d_off + h->n, 8, cudaMemcpyDeviceToHost));
+  cudaFree(tmp);
+  if (f) { cudaFree(d_flags); cudaFree(d_padded); return flags_error(f); }
+  // true byte total
+  {
+    int64_t* d_l64; int64_t* d_sum;
+    if ((rc = dmalloc(&d_l64, (size_t)h->n))) return rc;
+    if ((rc = dmalloc(&d_sum, 1))) return rc;
+    if (h->n > 0) k_len_i64<<<grid_for(h->n, 256), 256>>>(h->d_len, h->n, d_l64);
+    size_t tb2 = 0;
+    CU(cub::DeviceReduce::Sum(nullptr, tb2, d_l64, d_sum, (int)h->n));
+    void* tmp2; CU(cudaMalloc(&tmp2, std::max<size_t>(tb2, 1)));
+    CU(cub::DeviceReduce::Sum(tmp2, tb2, d_l64, d_sum, (int)h->n));
+    CU(cudaMemcpy(&h->nbytes, d_sum, 8, cudaMemcpyDeviceToHost));
+    cudaFree(tmp2); cudaFree(d_l64); cudaFree(d_sum);
+  }
+  if ((rc = dmalloc(&h->d_data, (size_t)h->npadded + 16))) return rc;
+  if (h->n > 0) k_repack<<<std::max(1, std::min(grid_for(h->n * 32, 256), h->sm_count * 32)), 256>>>(d_blob, d_soff, d_templid, h->n, h->d_off, h->d_len, h->d_data);
+  CU(cudaDeviceSynchronize());
+  cudaFree(d_flags); cudaFree(d_padded);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+__global__ void k_synth_rows(easynth::Plan plan, int64_t row_begin, int64_t n, int32_t* rname, uint8_t* strand,
+                             int32_t* start, int32_t* len, int64_t* padded) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const easynth::RowInfo r = easynth::row_info(plan, row_begin + i);
+  rname[i] = r.rname; strand[i] = (uint8_t)r.strand; start[i] = r.start; len[i] = r.len;
+  padded[i] = (r.len + 15) & ~15;
+}
+
+// one thread per 16-byte chunk of the padded data
+__global__ void k_synth_bytes(easynth::Plan plan, int64_t row_begin, int64_t n, const int64_t* __restrict__ off,
+                              uint8_t* __restrict__ data, int uniform_chunks) {
+  const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_chunks = off[n] >> 4;
+  if (chunk >= n_chunks) return;
+  int64_t r;
+  if (uniform_chunks > 0) {
+    r = chunk / uniform_chunks;
+  } else {  // last row with off[r] <= chunk*16
+    int64_t a = 0, b = n;
+    const int64_t target = chunk << 4;
+    while (b - a > 1) {
+      const int64_t m = (a + b) >> 1;
+      if (off[m] <= target) a = m; else b = m;
+    }
+    r = a;
+  }
+  const easynth::RowInfo ri = easynth::row_info(plan, row_begin + r);
+  const int j0 = (int)((chunk << 4) - off[r]);
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int j = j0 + 4 * k + b;
+      const uint32_t byte = j < ri.len ? easynth::read_byte(plan, row_begin + r, ri, j) : 0x0Bu;
+      v |= byte << (8 * b);
+    }
+    w[k] = v;
+  }
+  *reinterpret_cast<uint4*>(data + (chunk << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int ea_version(void) { return 100; }
+const char* ea_last_error(void) { return g_err.c_str(); }
+int ea_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+void ea_set_poll(ea_poll_fn fn) { g_poll = fn; }
+
+void ea_free(ea_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->owns) {
+    cudaFree(h->d_rname); cudaFree(h->d_strand); cudaFree(h->d_start); cudaFree(h->d_off); cudaFree(h->d_data);
+  }
+  cudaFree(h->d_len);
+  cudaFree(h->d_maxend);
+  h->idx[0].release(); h->idx[1].release();
+  cudaFree(h->d_pass); cudaFree(h->d_beta); cudaFree(h->d_counters); cudaFree(h->d_scratch); cudaFree(h->d_flush);
+  for (auto& c : h->d_cols) cudaFree(c);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int64_t ea_nrow(const ea_handle* h) { return h ? h->n : -1; }
+int64_t ea_nbytes(const ea_handle* h) { return h ? h->nbytes : -1; }
+int ea_device(const ea_handle* h) { return h ? h->device : -1; }
+
+int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                 int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out) {
+  if (!out) return fail(EA_ERR_ARG, "null out");
+  *out = nullptr;
+  if (nrow < 0 || nstr < 0 || nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row/string count");
+  if (nrow > 0 && (!rname || !strand || !start || !off)) return fail(EA_ERR_ARG, "null column");
+  if (nstr > 0 && !off) return fail(EA_ERR_ARG, "null offsets");
+  int rc;
+  if ((rc = pick_device(device))) return rc;
+  const int64_t total = nstr > 0 ? off[nstr] : 0;
+  if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
+  ea_handle* h = new ea_handle;
+  h->device = device; h->n = nrow;
+  int32_t *d_strand32 = nullptr, *d_templid = nullptr; int64_t* d_soff = nullptr; uint8_t* d_blob = nullptr;
+  unsigned* d_flags = nullptr;
+  auto cleanup = [&]() { cudaFree(d_strand32); cudaFree(d_templid); cudaFree(d_soff); cudaFree(d_blob); cudaFree(d_flags); };
+#define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); ea_free(h); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  TRY(dmalloc(&h->d_rname, (size_t)nrow));
+  TRY(dmalloc(&h->d_start, (size_t)nrow));
+  TRY(dmalloc(&h->d_strand, (size_t)nrow));
+  TRY(dmalloc(&d_strand32, (size_t)nrow));
+  TRY(dmalloc(&d_soff, (size_t)nstr + 1));
+  TRY(dmalloc(&d_blob, (size_t)total + 16));
+  TRY(dmalloc(&d_flags, 1));
+  TRYCU(cudaMemset(d_flags, 0, 4));
+  bool identity = templid == nullptr;
+  if (templid && nrow == nstr) {
+    identity = true;
+    for (int64_t i = 0; i < nrow; i++) if (templid[i] != i) { identity = false; break; }
+  }
+  if (nrow > 0) {
+    TRYCU(cudaMemcpy(h->d_rname, rname, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(h->d_start, start, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(d_strand32, strand, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
+    k_strand_u8<<<grid_for(nrow, 256), 256>>>(d_strand32, nrow, h->d_strand, d_flags);
+    if (!identity) {
+      TRY(dmalloc(&d_templid, (size_t)nrow));
+      TRYCU(cudaMemcpy(d_templid, templid, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
+    }
+  }
+  if (nstr > 0) TRYCU(cudaMemcpy(d_soff, off, 8 * (size_t)(nstr + 1), cudaMemcpyHostToDevice));
+  else TRYCU(cudaMemset(d_soff, 0, 8));
+  if (total > 0) TRYCU(cudaMemcpy(d_blob, blob, (size_t)total, cudaMemcpyHostToDevice));
+  unsigned f = 0;
+  TRYCU(cudaMemcpy(&f, d_flags, 4, cudaMemcpyDeviceToHost));
+  if (f) { cleanup(); ea_free(h); return flags_error(f); }
+  TRY(pack_from_device_blob(h, d_blob, d_soff, nstr, identity ? nullptr : d_templid));
+  cleanup();
+#undef TRY
+#undef TRYCU
+  return adopt_and_finish(h, out);
+}
+
+int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
+            const uint8_t* const* str, const int64_t* len, int64_t nstr, int device, ea_handle** out) {
+  if (!out) return fail(EA_ERR_ARG, "null out");
+  *out = nullptr;
+  if (nstr < 0 || (nstr > 0 && (!str || !len))) return fail(EA_ERR_ARG, "bad string table");
+  // gather the scattered strings (std::vector<std::string> in the reference) into one pinned blob
+  std::vector<int64_t> off((size_t)nstr + 1, 0);
+  for (int64_t i = 0; i < nstr; i++) {
+    if (len[i] < 0) return fail(EA_ERR_ARG, "negative string length");
+    off[(size_t)i + 1] = off[(size_t)i] + len[i];
+  }
+  const int64_t total = off[(size_t)nstr];
+  int rc;
+  if ((rc = pick_device(device))) return rc;
+  uint8_t* blob = nullptr;
+  if (cudaMallocHost(reinterpret_cast<void**>(&blob), (size_t)std::max<int64_t>(total, 1)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(EA_ERR_CUDA, "cudaMallocHost(%lld) failed", (long long)total);
+  }
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, total / (8 << 20) + 1}));
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      for (int64_t i = nstr * t / nt; i < nstr * (t + 1) / nt; i++)
+        if (len[i]) memcpy(blob + off[(size_t)i], str[i], (size_t)len[i]);
+    });
+  for (auto& x : th) x.join();
+  rc = ea_pack_blob(rname, strand, start, templid, nrow, blob, off.data(), nstr, device, out);
+  cudaFreeHost(blob);
+  return rc;
+}
+
+int ea_attach_device(int32_t* d_rname, uint8_t* d_strand, int32_t* d_start, uint8_t* d_data, int64_t* d_off,
+                     int64_t nrow, int device, int take_ownership, ea_handle** out) {
+  if (!out) return fail(EA_ERR_ARG, "null out");
+  *out = nullptr;
+  if (nrow < 0 || nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row count");
+  if (nrow > 0 && (!d_rname || !d_strand || !d_start || !d_data || !d_off)) return fail(EA_ERR_ARG, "null device pointer");
+  int rc;
+  if ((rc = pick_device(device))) return rc;
+  ea_handle* h = new ea_handle;
+  h->device = device; h->n = nrow;
+  // the caller's CSR is tight; rows are re-laid out into the padded form, metadata is copied
+  if ((rc = dmalloc(&h->d_rname, (size_t)nrow)) || (rc = dmalloc(&h->d_start, (size_t)nrow)) || (rc = dmalloc(&h->d_strand, (size_t)nrow))) { ea_free(h); return rc; }
+  if (nrow > 0) {
+    cudaMemcpy(h->d_rname, d_rname, 4 * (size_t)nrow, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(h->d_start, d_start, 4 * (size_t)nrow, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(h->d_strand, d_strand, (size_t)nrow, cudaMemcpyDeviceToDevice);
+  }
+  int64_t zero = 0; int64_t* d_soff = d_off;
+  if (nrow == 0) { if ((rc = dmalloc(&d_soff, 1))) { ea_free(h); return rc; } cudaMemcpy(d_soff, &zero, 8, cudaMemcpyHostToDevice); }
+  rc = pack_from_device_blob(h, d_data, d_soff, nrow, nullptr);
+  if (nrow == 0) cudaFree(d_soff);
+  if (rc != EA_OK) { ea_free(h); return rc; }
+  if (take_ownership) { cudaFree(d_rname); cudaFree(d_strand); cudaFree(d_start); cudaFree(d_data); cudaFree(d_off); }
+  return adopt_and_finish(h, out);
+}
+
+int ea_threshold_reads(ea_handle* h, const char* ctx_meth, const char* ctx_unmeth, const char* ooctx_meth,
+                       const char* ooctx_unmeth, uint32_t min_n_ctx, double min_ctx_meth_frac,
+                       double max_ooctx_meth_frac, uint8_t* pass_out) {
+  if (!h || !ctx_meth || !ctx_unmeth || (h->n > 0 && !pass_out)) return fail(EA_ERR_ARG, "null argument");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  if ((rc = ensure_pass(h))) return rc;
+  ThresholdSpec spec;
+  parse_threshold_letters(ctx_meth, ctx_unmeth, ooctx_meth, ooctx_unmeth, &spec);
+  ThrParams tp{min_n_ctx, min_ctx_meth_frac, max_ooctx_meth_frac};
+  CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
+  if ((rc = launch_threshold(h, spec, tp, h->d_pass, nullptr, h->d_counters + 1))) return rc;
+  if (h->n > 0) CU(cudaMemcpyAsync(pass_out, h->d_pass, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return EA_OK;
+}
+
+int ea_get_xm_beta(ea_handle* h, const char* ctx_meth, const char* ctx_unmeth, double* beta_out) {
+  if (!h || !ctx_meth || !ctx_unmeth || (h->n > 0 && !beta_out)) return fail(EA_ERR_ARG, "null argument");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  if (!h->d_beta && (rc = dmalloc(&h->d_beta, (size_t)h->n))) return rc;
+  ThresholdSpec spec;
+  parse_beta_letters(ctx_meth, ctx_unmeth, &spec);
+  ThrParams tp{0, 0.0, 0.0};
+  if ((rc = launch_threshold(h, spec, tp, nullptr, h->d_beta, nullptr))) return rc;
+  if (h->n > 0) CU(cudaMemcpyAsync(beta_out, h->d_beta, 8 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return EA_OK;
+}
+
+int ea_cx_report(ea_handle* h, const uint8_t* pass, const char* ctx, int64_t* nrow_out) {
+  if (!h || !ctx || !nrow_out) return fail(EA_ERR_ARG, "null argument");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  const uint8_t* d_pass_in = nullptr;
+  if (pass && h->n > 0) {
+    if ((rc = ensure_pass(h))) return rc;
+    CU(cudaMemcpyAsync(h->d_pass, pass, (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    d_pass_in = h->d_pass;
+  }
+  ReportPlan rp;
+  rp.want = want_of(ctx);
+  rp.threshold = false;
+  rp.mode = 1;
+  if ((rc = run_report(h, rp, d_pass_in, nullptr))) return rc;
+  *nrow_out = h->n_rows;
+  return EA_OK;
+}
+
+int ea_cx_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* pos, int32_t* context, int32_t* meth,
+                       int32_t* unmeth) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  if (h->n_rows < 0) return fail(EA_ERR_STATE, "no report has been computed on this handle");
+  CU(cudaSetDevice(h->device));
+  int32_t* dst[6] = {rname, strand, pos, context, meth, unmeth};
+  if (h->n_rows > 0)
+    for (int c = 0; c < 6; c++)
+      if (dst[c]) CU(cudaMemcpyAsync(dst[c], h->d_cols[c], 4 * (size_t)h->n_rows, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return EA_OK;
+}
+
+int ea_cytosine_report(ea_handle* h, const ea_report_params* p, uint8_t* pass_out, int64_t* nrow_out) {
+  if (!h || !nrow_out) return fail(EA_ERR_ARG, "null argument");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  ReportPlan rp;
+  if ((rc = make_plan_from_params(p, 0, &rp))) return rc;
+  if ((rc = run_report(h, rp, nullptr, nullptr))) return rc;
+  if (pass_out && h->n > 0) {
+    if (rp.threshold) CU(cudaMemcpyAsync(pass_out, h->d_pass, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    else memset(pass_out, 1, (size_t)h->n);
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  *nrow_out = h->n_rows;
+  return EA_OK;
+}
+
+int ea_cytosine_report_device(ea_handle* h, const ea_report_params* p, int mode, ea_timing* t) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  ReportPlan rp;
+  if ((rc = make_plan_from_params(p, mode, &rp))) return rc;
+  return run_report(h, rp, nullptr, t);
+}
+
+const char* ea_stage_name(int i) {
+  static const char* names[3] = {"threshold", "window", "scan+gather"};
+  return (i >= 0 && i < 3) ? names[i] : "";
+}
+
+int ea_flush_l2(ea_handle* h, int64_t bytes) {
+  if (!h || bytes <= 0) return fail(EA_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(h->device));
+  if (h->flush_bytes < bytes) {
+    cudaFree(h->d_flush); h->d_flush = nullptr; h->flush_bytes = 0;
+    CU(cudaMalloc(&h->d_flush, (size_t)bytes));
+    h->flush_bytes = bytes;
+  }
+  CU(cudaMemsetAsync(h->d_flush, 0x5A, (size_t)bytes, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return EA_OK;
+}
+
+int ea_synth_device(const ea_synth_cfg* cfg, int64_t row_begin, int64_t row_end, int device, ea_handle** out) {
+  if (!out) return fail(EA_ERR_ARG, "null out");
+  *out = nullptr;
+  easynth::Plan plan;
+  if (easynth::make_plan(cfg, &plan)) return fail(EA_ERR_ARG, "bad synthetic configuration");
+  if (row_begin < 0 || row_end < row_begin || row_end > plan.n_reads || row_end - row_begin > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row range");
+  int rc;
+  if ((rc = pick_device(device))) return rc;
+  ea_handle* h = new ea_handle;
+  h->device = device; h->n = row_end - row_begin;
+  const int64_t n = h->n;
+  int64_t* d_padded = nullptr;
+#define TRY(x) do { rc = (x); if (rc != EA_OK) { cudaFree(d_padded); ea_free(h); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaFree(d_padded); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  TRY(dmalloc(&h->d_rname, (size_t)n)); TRY(dmalloc(&h->d_start, (size_t)n)); TRY(dmalloc(&h->d_strand, (size_t)n));
+  TRY(dmalloc(&h->d_len, (size_t)n)); TRY(dmalloc(&h->d_off, (size_t)n + 1)); TRY(dmalloc(&d_padded, (size_t)n + 1));
+  TRYCU(cudaMemset(d_padded, 0, 8 * (size_t)(n + 1)));
+  if (n > 0) k_synth_rows<<<grid_for(n, 256), 256>>>(plan, row_begin, n, h->d_rname, h->d_strand, h->d_start, h->d_len, d_padded);
+  size_t tb = 0;
+  TRYCU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_padded, h->d_off, (int)(n + 1)));
+  void* tmp; TRYCU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+  TRYCU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_padded, h->d_off, (int)(n + 1)));
+  TRYCU(cudaMemcpy(&h->npadded, h->d_off + n, 8, cudaMemcpyDeviceToHost));
+  cudaFree(tmp);
+  {
+    int64_t* d_l64; int64_t* d_sum;
+    TRY(dmalloc(&d_l64, (size_t)n)); TRY(dmalloc(&d_sum, 1));
+    if (n > 0) k_len_i64<<<grid_for(n, 256), 256>>>(h->d_len, n, d_l64);
+    size_t tb2 = 0;
+    TRYCU(cub::DeviceReduce::Sum(nullptr, tb2, d_l64, d_sum, (int)n));
+    void* tmp2; TRYCU(cudaMalloc(&tmp2, std::max<size_t>(tb2, 1)));
+    TRYCU(cub::DeviceReduce::Sum(tmp2, tb2, d_l64, d_sum, (int)n));
+    TRYCU(cudaMemcpy(&h->nbytes, d_sum, 8, cudaMemcpyDeviceToHost));
+    cudaFree(tmp2); cudaFree(d_l64); cudaFree(d_sum);
+  }
+  TRY(dmalloc(&h->d_data, (size_t)h->npadded + 16));
+  const int64_t n_chunks = h->npadded / 16;
+  const int uniform = plan.len_min == plan.len_max ? (plan.len_min + 15) / 16 : 0;
+  if (n_chunks > 0) k_synth_bytes<<<grid_for(n_chunks, 256), 256>>>(plan, row_begin, n, h->d_off, h->d_data, uniform);
+  TRYCU(cudaDeviceSynchronize());
+  cudaFree(d_padded); d_padded = nullptr;
+#undef TRY
+#undef TRYCU
+  return adopt_and_finish(h, out);
+}
+
+int ea_synth_host(const ea_synth_cfg* cfg, int64_t row_begin, int64_t row_end, int32_t* rname, int32_t* strand,
+                  int32_t* start, int64_t* off, uint8_t* blob) {
+  easynth::Plan plan;
+  if (easynth::make_plan(cfg, &plan)) return fail(EA_ERR_ARG, "bad synthetic configuration");
+  if (row_begin < 0 || row_end < row_begin || row_end > plan.n_reads || !off) return fail(EA_ERR_ARG, "bad row range");
+  const int64_t n = row_end - row_begin;
+  off[0] = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const easynth::RowInfo r = easynth::row_info(plan, row_begin + i);
+    if (rname) rname[i] = r.rname;
+    if (strand) strand[i] = r.strand;
+    if (start) start[i] = r.start;
+    off[i + 1] = off[i] + r.len;
+  }
+  if (!blob) return EA_OK;
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)std::thread::hardware_concurrency(), n / 4096 + 1));
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      for (int64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+        const easynth::RowInfo r = easynth::row_info(plan, row_begin + i);
+        uint8_t* d = blob + off[i];
+        for (int j = 0; j < r.len; j++) d[j] = easynth::read_byte(plan, row_begin + i, r, j);
+      }
+    });
+  for (auto& x : th) x.join();
+  return EA_OK;
+}
+
+int ea_export_host(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* start, int64_t* off, uint8_t* blob) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  if (n == 0) { if (off) off[0] = 0; return EA_OK; }
+  int rc;
+  if (rname) CU(cudaMemcpy(rname, h->d_rname, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  if (start) CU(cudaMemcpy(start, h->d_start, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  if (strand) {
+    std::vector<uint8_t> s8((size_t)n);
+    CU(cudaMemcpy(s8.data(), h->d_strand, (size_t)n, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; i++) strand[i] = s8[(size_t)i];
+  }
+  if (off || blob) {
+    int64_t *d_l64, *d_toff;
+    if ((rc = dmalloc(&d_l64, (size_t)n + 1))) return rc;
+    if ((rc = dmalloc(&d_toff, (size_t)n + 1))) return rc;
+    CU(cudaMemset(d_l64, 0, 8 * (size_t)(n + 1)));
+    k_len_i64<<<grid_for(n, 256), 256>>>(h->d_len, n, d_l64);
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_l64, d_toff, (int)(n + 1)));
+    void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+    CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_l64, d_toff, (int)(n + 1)));
+    if (off) CU(cudaMemcpy(off, d_toff, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost));
+    if (blob && h->nbytes > 0) {
+      uint8_t* d_tight;
+      if ((rc = dmalloc(&d_tight, (size_t)h->nbytes))) return rc;
+      k_unpad<<<std::max(1, std::min(grid_for(n * 32, 256), h->sm_count * 32)), 256>>>(h->d_data, h->d_off, h->d_len, d_toff, n, d_tight);
+      CU(cudaMemcpy(blob, d_tight, (size_t)h->nbytes, cudaMemcpyDeviceToHost));
+      cudaFree(d_tight);
+    }
+    cudaFree(tmp); cudaFree(d_l64); cudaFree(d_toff);
+  }
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+}  // extern "C"

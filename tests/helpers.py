@@ -1,0 +1,93 @@
+"""Shared test helpers: golden fixtures, KAT inputs, comparison utilities."""
+import glob
+import os
+
+import numpy as np
+
+from epialleler_b200 import BamData
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COLS = ("rname", "strand", "pos", "context", "meth", "unmeth")
+
+# must match tests/golden/make_golden.py
+CASES = [
+    ("cg_default", True, "CG", 2, 0.5, 0.1, "CG"),
+    ("cx_nothr", False, "CG", 2, 0.5, 0.1, "CX"),
+    ("cg_thr_cx_rep", True, "CG", 2, 0.5, 0.1, "CX"),
+    ("chg_thr_cxg_rep", True, "CHG", 1, 0.3, 0.5, "CxG"),
+    ("chh_thr_chh_rep", True, "CHH", 3, 0.1, 0.9, "CHH"),
+    ("cxg_thr_chg_rep", True, "CxG", 2, 0.25, 0.2, "CHG"),
+    ("cx_thr_cg_rep", True, "CX", 5, 0.05, 0.1, "CG"),
+    ("cg_zero_thresholds", True, "CG", 0, 0.0, 1.0, "CG"),
+]
+BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh")]
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    bam = BamData(z["rname"], z["strand"], z["start"], z["templid"], z["blob"], z["off"], [str(s) for s in z["levels"]])
+    return bam, z
+
+
+def ctx_to_idx(c):
+    return ((ord(c) + 2) >> 2) & 15
+
+
+def bam_from_xm(rows, high_nibble=0x10):
+    """rows = [(rname, strand, start, "XM text")] in file order -> BamData sorted like R/internal.R:195."""
+    rn = np.asarray([r[0] for r in rows], dtype=np.int32).reshape(-1)
+    st = np.asarray([r[1] for r in rows], dtype=np.int32).reshape(-1)
+    sa = np.asarray([r[2] for r in rows], dtype=np.int32).reshape(-1)
+    seqxm = [bytes((high_nibble & 0xF0) | ctx_to_idx(ch) for ch in r[3]) for r in rows]
+    order = np.lexsort((sa, rn)) if len(rows) else np.zeros(0, np.int64)
+    return BamData.from_strings(rn[order], st[order], sa[order], np.arange(len(rows), dtype=np.int32)[order], seqxm)
+
+
+def report_tuples(rep):
+    return list(zip(*[rep[k].tolist() for k in COLS]))
+
+
+def assert_report_equal(got, want, what=""):
+    for k in COLS:
+        g, w = np.asarray(got[k]), np.asarray(want[k])
+        assert g.shape == w.shape, "%s: %s has %d rows, expected %d" % (what, k, g.shape[0], w.shape[0])
+        if not np.array_equal(g, w):
+            i = int(np.nonzero(g != w)[0][0])
+            raise AssertionError("%s: column %s differs first at row %d: got %s want %s (row got=%s want=%s)" % (
+                what, k, i, g[i], w[i], [int(got[c][i]) for c in COLS], [int(want[c][i]) for c in COLS]))
+
+
+# ---- BAM-free known-answer tests (C-1: R/generateCytosineReport.R:16-54,
+#      C-2: inst/unitTests/test_simulateBam.R:55-72, C-4: test_simulateBam.R:74-89) ------------------
+KAT_C1_ROWS = [(1, 1, 1, "...Z..x.h..x..h."), (1, 1, 1, "...Z..z.h..x..h."), (1, 1, 1, "...Z..z.h..X..h."), (1, 1, 1, "...Z..z.h..z-.h.")]
+KAT_C1_PASS = [0, 1, 0, 0]
+KAT_C1_BETA = [1.0, 0.5, 0.5, 1.0 / 3.0]
+KAT_C1_THR_ZXH = [(1, 1, 4, 7, 1, 3), (1, 1, 7, 7, 0, 3), (1, 1, 9, 2, 0, 4), (1, 1, 12, 6, 0, 3), (1, 1, 15, 2, 0, 4)]
+KAT_C1_NOTHR_ZXH = [(1, 1, 4, 7, 4, 0), (1, 1, 7, 7, 0, 3), (1, 1, 9, 2, 0, 4), (1, 1, 12, 6, 1, 2), (1, 1, 15, 2, 0, 4)]
+
+KAT_C2_ROWS = [(1, 1 if i % 2 else 2, i, "ZZZzzZZZ" if i % 2 else "ZZzzzzZZ") for i in range(1, 7)]
+KAT_C2_Z = [(1, 1, 1, 7, 1, 0), (1, 1, 2, 7, 1, 0), (1, 2, 2, 7, 1, 0), (1, 1, 3, 7, 2, 0), (1, 2, 3, 7, 1, 0), (1, 1, 4, 7, 1, 1),
+            (1, 2, 4, 7, 1, 1), (1, 1, 5, 7, 2, 1), (1, 2, 5, 7, 1, 1), (1, 1, 6, 7, 2, 1), (1, 2, 6, 7, 1, 2), (1, 1, 7, 7, 2, 1),
+            (1, 2, 7, 7, 1, 2), (1, 1, 8, 7, 2, 1), (1, 2, 8, 7, 1, 2), (1, 1, 9, 7, 1, 1), (1, 2, 9, 7, 1, 2), (1, 1, 10, 7, 2, 0),
+            (1, 2, 10, 7, 1, 1), (1, 1, 11, 7, 1, 0), (1, 2, 11, 7, 1, 1), (1, 1, 12, 7, 1, 0), (1, 2, 12, 7, 1, 0), (1, 2, 13, 7, 1, 0)]
+
+KAT_C3_ROWS = [(1, 1, 10, "Zz"), (1, 1, 11, "-Z"), (1, 2, 11, "hH"), (2, 1, 5, "-----"), (2, 1, 6, "z.z"), (2, 1, 7, "U.Z"),
+               (2, 2, 7, "xXx"), (2, 2, 8, "Xh")]
+KAT_C3_PASS = [1, 0, 0, 0, 0, 0, 0, 0]
+KAT_C3_NOTHR_ZXH = [(1, 1, 10, 7, 1, 0), (1, 1, 11, 7, 0, 1), (1, 2, 11, 2, 0, 1), (1, 1, 12, 7, 1, 0), (1, 2, 12, 2, 1, 0),
+                    (2, 1, 6, 7, 0, 1), (2, 2, 7, 6, 0, 1), (2, 2, 8, 6, 2, 0), (2, 1, 9, 7, 1, 0)]
+KAT_C3_THR_ZX = [(1, 1, 10, 7, 1, 0), (1, 1, 11, 7, 0, 1), (1, 1, 12, 7, 0, 1), (2, 1, 6, 7, 0, 1), (2, 2, 7, 6, 0, 1),
+                 (2, 2, 8, 6, 0, 2), (2, 1, 9, 7, 0, 1)]
+
+
+def kat_c4_rows():
+    rows = [(1, 1, 1, "ZZZZZZZZZZ")]
+    for i in range(999):
+        s = ["z"] * 10
+        s[i % 10] = "Z"
+        rows.append((1, 1, 1, "".join(s)))
+    return rows

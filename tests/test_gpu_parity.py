@@ -1,0 +1,183 @@
+"""GPU parity tests: the CUDA path through the C ABI against the committed golden vectors (outputs of
+the reference's own compiled C++) and against the CPU oracle on seeded synthetic reads.  Bit-exact:
+identical pass flags, identical betas (IEEE double), identical integer report rows in identical order."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import epialleler_b200 as ea
+from epialleler_b200 import _native as N
+from helpers import (BETAS, CASES, COLS, KAT_C1_BETA, KAT_C1_NOTHR_ZXH, KAT_C1_PASS, KAT_C1_ROWS, KAT_C1_THR_ZXH, KAT_C2_ROWS,
+                     KAT_C2_Z, KAT_C3_NOTHR_ZXH, KAT_C3_PASS, KAT_C3_ROWS, KAT_C3_THR_ZX, assert_report_equal, bam_from_xm,
+                     golden_names, kat_c4_rows, load_golden, report_tuples)
+from oracle.oracle import CONTEXT_TO_BASES, PortCpu
+
+pytestmark = pytest.mark.gpu
+CG = ("Z", "z", "XH", "xh", 2, 0.5, 0.1)
+
+
+def two_pass(bam, thr, tctx, ms, mb, mo, rctx):
+    """The reference's own call sequence: rcpp_threshold_reads then rcpp_cx_report."""
+    if thr:
+        p = ea.rcpp_threshold_reads(bam, *CONTEXT_TO_BASES[tctx], ms, mb, mo)
+    else:
+        p = np.ones(bam.nrow, bool)
+    return p, ea.rcpp_cx_report(bam, p, CONTEXT_TO_BASES[rctx][0])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_vectors_two_pass_and_fused(name):
+    bam, z = load_golden(name)
+    for cname, thr, tctx, ms, mb, mo, rctx in CASES:
+        want = {k: z[cname + "." + k] for k in COLS}
+        p, rep = two_pass(bam, thr, tctx, ms, mb, mo, rctx)
+        assert np.array_equal(p.astype(np.uint8), z[cname + ".pass"]), (name, cname, "two-pass flags")
+        assert_report_equal(rep, want, "%s/%s two-pass" % (name, cname))
+        p2, rep2 = ea.generateCytosineReport(bam, threshold_reads=thr, threshold_context=tctx, min_context_sites=ms,
+                                             min_context_beta=mb, max_outofcontext_beta=mo, report_context=rctx, return_pass=True)
+        assert np.array_equal(p2.astype(np.uint8), z[cname + ".pass"]), (name, cname, "fused flags")
+        assert_report_equal(rep2, want, "%s/%s fused" % (name, cname))
+    for bname, m, u in BETAS:
+        assert np.array_equal(ea.rcpp_get_xm_beta(bam, m, u), z[bname]), (name, bname)
+    bam.close()
+
+
+def test_known_answer_tests():
+    b = bam_from_xm(KAT_C1_ROWS)
+    p = ea.rcpp_threshold_reads(b, *CG)
+    assert p.astype(int).tolist() == KAT_C1_PASS
+    assert ea.rcpp_get_xm_beta(b, "Z", "z").tolist() == KAT_C1_BETA
+    assert report_tuples(ea.rcpp_cx_report(b, p, "ZXH")) == KAT_C1_THR_ZXH
+    assert report_tuples(ea.rcpp_cx_report(b, None, "ZXH")) == KAT_C1_NOTHR_ZXH
+    assert report_tuples(ea.generateCytosineReport(b, report_context="CX")) == KAT_C1_THR_ZXH
+
+    b = bam_from_xm(KAT_C2_ROWS)
+    p = ea.rcpp_threshold_reads(b, *CG)
+    assert p.all()
+    assert report_tuples(ea.rcpp_cx_report(b, p, "Z")) == KAT_C2_Z
+    assert report_tuples(ea.generateCytosineReport(b)) == KAT_C2_Z
+
+    b = bam_from_xm(KAT_C3_ROWS)
+    p = ea.rcpp_threshold_reads(b, *CG)
+    assert p.astype(int).tolist() == KAT_C3_PASS
+    assert report_tuples(ea.rcpp_cx_report(b, None, "ZXH")) == KAT_C3_NOTHR_ZXH
+    assert report_tuples(ea.rcpp_cx_report(b, p, "ZX")) == KAT_C3_THR_ZX
+    assert report_tuples(ea.generateCytosineReport(b, report_context="CxG")) == KAT_C3_THR_ZX
+
+    b = bam_from_xm(kat_c4_rows())
+    p, rep = ea.generateCytosineReport(b, return_pass=True)
+    assert p.sum() == 1 and p[0]
+    assert (rep["pos"].shape[0], rep["meth"].sum(), rep["unmeth"].sum()) == (10, 10, 9990)
+
+
+SYNTH = {
+    "wgbs150": dict(seed=20261018, n_reads=40000, chr_len=[200000], len_min=150),
+    "pe_merged": dict(seed=5, n_reads=20000, chr_len=[150000, 90000, 40000], len_min=150, len_max=450),
+    "capture_islands": dict(seed=20261019, n_reads=60000, chr_len=[400000, 300000], len_min=100, len_max=417, n_islands=12, island_len=2000),
+    "long_reads": dict(seed=20261020, n_reads=300, chr_len=[900000, 500000], len_min=10000, len_max=30000),
+    "tiny_reads": dict(seed=9, n_reads=30000, chr_len=[30000], len_min=1, len_max=40),
+    "deep_amplicon": dict(seed=11, n_reads=70000, chr_len=[20000], len_min=120, len_max=260, n_islands=1, island_len=600),
+}
+SYNTH_CASES = [(True, "CG", 2, 0.5, 0.1, "CG"), (False, "CG", 2, 0.5, 0.1, "CX"), (True, "CHH", 1, 0.02, 0.9, "CxG"),
+               (True, "CX", 3, 0.04, 0.1, "CHG")]
+
+
+@pytest.mark.parametrize("shape", sorted(SYNTH))
+def test_synthetic_reads_against_oracle(shape):
+    cfg = ea.synth_config(**SYNTH[shape])
+    host = ea.synth_host(cfg)
+    dev = ea.synth_device(cfg)
+    # the device generator and the host generator are the same function
+    back = dev.to_host()
+    assert np.array_equal(back.blob()[1], host.blob()[1]) and np.array_equal(back.blob()[0], host.blob()[0])
+    assert np.array_equal(back.start, host.start) and np.array_equal(back.strand, host.strand) and np.array_equal(back.rname, host.rname)
+    oracle = PortCpu(host)
+    for thr, tctx, ms, mb, mo, rctx in SYNTH_CASES:
+        want_p, want = oracle.generateCytosineReport(thr, tctx, ms, mb, mo, rctx)
+        assert want["pos"].shape[0] > 0
+        for bam in (host, dev):  # packed from host buffers / generated in HBM
+            p, rep = ea.generateCytosineReport(bam, threshold_reads=thr, threshold_context=tctx, min_context_sites=ms, min_context_beta=mb,
+                                               max_outofcontext_beta=mo, report_context=rctx, return_pass=True)
+            assert np.array_equal(p, want_p), (shape, tctx, "fused flags")
+            assert_report_equal(rep, want, "%s fused %s/%s" % (shape, tctx, rctx))
+        p, rep = two_pass(host, thr, tctx, ms, mb, mo, rctx)
+        assert np.array_equal(p, want_p)
+        assert_report_equal(rep, want, "%s two-pass %s/%s" % (shape, tctx, rctx))
+    assert np.array_equal(ea.rcpp_get_xm_beta(host, "ZX", "zx"), oracle.rcpp_get_xm_beta("ZX", "zx"))
+    host.close(); dev.close()
+
+
+def test_unusual_letter_sets_use_the_generic_kernel():
+    cfg = ea.synth_config(3, 5000, [40000], 90, 200)
+    host = ea.synth_host(cfg)
+    o = PortCpu(host)
+    for letters in (("ZZ", "z", "X", "x"), ("Z", "zx", "", ""), ("ZU", "zu", "H", "h."), ("Z-", "z", "XH", "xh"), ("z", "Z", "xh", "XH")):
+        assert np.array_equal(ea.rcpp_threshold_reads(host, *letters, 2, 0.5, 0.1), o.rcpp_threshold_reads(*letters, 2, 0.5, 0.1)), letters
+        assert np.array_equal(ea.rcpp_get_xm_beta(host, letters[0], letters[1]), o.rcpp_get_xm_beta(letters[0], letters[1])), letters
+    # report letters other than Z/X/H select nothing; lower-case never selects (src/rcpp_cx_report.cpp:88-91)
+    for ctx in ("", "zxh", "U.", "Zz", "hX"):
+        assert_report_equal(ea.rcpp_cx_report(host, None, ctx), o.rcpp_cx_report(None, ctx), ctx)
+
+
+def test_threshold_edge_values():
+    cfg = ea.synth_config(4, 8000, [50000], 150)
+    host = ea.synth_host(cfg)
+    o = PortCpu(host)
+    for ms, mb, mo in ((0, 0.0, 0.0), (1, 1.0, 1.0), (2, 0.3, 0.3), (4, 1.0 / 3.0, 0.1), (2, float("nan"), 0.1), (2, 0.5, float("nan")),
+                       (2**32 - 1, 0.5, 0.1), (2, -1.0, 2.0), (3, 0.1 + 0.2, 1e-300)):
+        got = ea.rcpp_threshold_reads(host, "Z", "z", "XH", "xh", ms, mb, mo)
+        assert np.array_equal(got, o.rcpp_threshold_reads("Z", "z", "XH", "xh", ms, mb, mo)), (ms, mb, mo)
+        p, _ = ea.generateCytosineReport(host, min_context_sites=ms, min_context_beta=mb, max_outofcontext_beta=mo, return_pass=True)
+        assert np.array_equal(p, got), (ms, mb, mo, "fused")
+
+
+def test_empty_and_degenerate_inputs():
+    empty = ea.BamData.from_strings([], [], [], [], [])
+    assert ea.rcpp_threshold_reads(empty, *CG).shape == (0,)
+    assert ea.rcpp_cx_report(empty, None, "ZXH")["pos"].shape == (0,)
+    assert ea.generateCytosineReport(empty)["pos"].shape == (0,)
+    # empty strings, a single byte, an all-'-' read, NA-like pass values
+    rows = [(1, 1, 5, ""), (1, 2, 5, "Z"), (1, 1, 6, "----"), (2, 1, 1, "zZ"), (2, 1, 4000, "Z" * 33), (2, 2, 8191, "xXh"), (3, 1, 4096, "ZzZ")]
+    b = bam_from_xm(rows)
+    o = PortCpu(b)
+    assert np.array_equal(ea.rcpp_threshold_reads(b, *CG), o.rcpp_threshold_reads(*CG))
+    for ctx in ("Z", "ZXH", "X"):
+        assert_report_equal(ea.rcpp_cx_report(b, None, ctx), o.rcpp_cx_report(None, ctx), ctx)
+        pv = np.array([1, 0, 2, -2147483648, 0, 1, 1])
+        assert_report_equal(ea.rcpp_cx_report(b, pv, ctx), o.rcpp_cx_report(pv, ctx), ctx + " pass")
+    for rctx in ("CG", "CX"):
+        p, rep = ea.generateCytosineReport(b, report_context=rctx, min_context_sites=1, return_pass=True)
+        wp, want = o.generateCytosineReport(True, "CG", 1, 0.5, 0.1, rctx)
+        assert np.array_equal(p, wp)
+        assert_report_equal(rep, want, rctx)
+
+
+def test_invalid_inputs_are_rejected():
+    with pytest.raises(ea.EaError) as e:  # unsorted rows
+        ea.BamData.from_strings([1, 1], [1, 1], [10, 5], [0, 1], [b"\x17", b"\x17"]).handle()
+    assert e.value.code == -3
+    with pytest.raises(ea.EaError) as e:  # low nibble 0 is not a methylation-call code
+        ea.BamData.from_strings([1], [1], [1], [0], [b"\x10"]).handle()
+    assert e.value.code == -4
+    with pytest.raises(ea.EaError) as e:  # templid out of range
+        ea.BamData.from_strings([1], [1], [1], [3], [b"\x17"]).handle()
+    assert e.value.code == -1
+
+
+def test_string_pointer_packer_matches_blob_packer():
+    bam, z = load_golden("amplicon010meth")
+    L = N.lib()
+    blob, off = bam.blob()
+    strs = [blob[off[i]:off[i + 1]].tobytes() for i in range(bam.nstr)]
+    keep = [C.create_string_buffer(s, len(s)) for s in strs]
+    ptrs = (C.c_void_p * len(strs))(*[C.addressof(k) for k in keep])
+    lens = np.array([len(s) for s in strs], np.int64)
+    h = C.c_void_p()
+    N.check(L.ea_pack(bam.rname.ctypes.data_as(C.POINTER(C.c_int32)), bam.strand.ctypes.data_as(C.POINTER(C.c_int32)),
+                      bam.start.ctypes.data_as(C.POINTER(C.c_int32)), bam.templid.ctypes.data_as(C.POINTER(C.c_int32)), bam.nrow,
+                      ptrs, lens.ctypes.data_as(C.POINTER(C.c_int64)), len(strs), 0, C.byref(h)))
+    out = np.zeros(bam.nrow, np.uint8)
+    N.check(L.ea_threshold_reads(h, b"Z", b"z", b"XH", b"xh", 2, 0.5, 0.1, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    assert np.array_equal(out, z["cg_default.pass"])
+    L.ea_free(h)

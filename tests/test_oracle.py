@@ -1,0 +1,112 @@
+"""CPU-only: pins the oracles.  The C restatement (oracle/cx_oracle.c) and, where it could be built,
+the reference's own compiled sources (oracle/_ref) must reproduce (a) the constants the reference's
+RUnit tests assert, (b) the committed golden vectors, (c) the BAM-free known-answer tests."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (BETAS, CASES, KAT_C1_BETA, KAT_C1_NOTHR_ZXH, KAT_C1_PASS, KAT_C1_ROWS, KAT_C1_THR_ZXH, KAT_C2_ROWS,
+                     KAT_C2_Z, KAT_C3_NOTHR_ZXH, KAT_C3_PASS, KAT_C3_ROWS, KAT_C3_THR_ZX, assert_report_equal, bam_from_xm,
+                     golden_names, kat_c4_rows, load_golden, report_tuples)
+from oracle.oracle import REF_SO, PortCpu, RefCpu
+
+ORACLES = [PortCpu] + ([RefCpu] if os.path.exists(REF_SO) or os.path.isdir("/root/reference/src") else [])
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_golden_vectors(oracle, name):
+    bam, z = load_golden(name)
+    o = oracle(bam)
+    for cname, thr, tctx, ms, mb, mo, rctx in CASES:
+        p, rep = o.generateCytosineReport(thr, tctx, ms, mb, mo, rctx)
+        assert np.array_equal(p.astype(np.uint8), z[cname + ".pass"]), (name, cname)
+        assert_report_equal(rep, {k: z[cname + "." + k] for k in rep}, "%s/%s" % (name, cname))
+    for bname, m, u in BETAS:
+        assert np.array_equal(o.rcpp_get_xm_beta(m, u), z[bname])
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_reference_runit_constants_capture(oracle):
+    # inst/unitTests/test_generateCytosineReport.R:7-60
+    bam, _ = load_golden("capture")
+    o = oracle(bam)
+    _, cg = o.generateCytosineReport()
+    _, cx = o.generateCytosineReport(threshold_reads=False, report_context="CX")
+    assert cg["pos"].shape[0] == 15408 and cx["pos"].shape[0] == 97186
+    assert (cg["meth"].sum(), cg["unmeth"].sum()) == (4974, 15245)
+    assert (cx["meth"].sum(), cx["unmeth"].sum()) == (6051, 125903)
+    assert np.bincount(cx["strand"]).tolist()[1:] == [48517, 48669]
+    assert [int((cx["context"] == c).sum()) for c in (2, 6, 7)] == [58292, 23486, 15408]
+    key = cx["rname"].astype(np.int64) << 32 | cx["pos"]
+    for s in (1, 2):  # no duplicated (rname,pos) within a strand
+        k = key[cx["strand"] == s]
+        assert np.unique(k).shape[0] == k.shape[0]
+    # :117-156 (min.mapq=30, min.baseq=20)
+    bamq, _ = load_golden("capture_q30_bq20")
+    oq = oracle(bamq)
+    _, cgq = oq.generateCytosineReport()
+    _, cxq = oq.generateCytosineReport(threshold_reads=False, report_context="CX")
+    assert (cgq["pos"].shape[0], cgq["meth"].sum(), cgq["unmeth"].sum()) == (15197, 4830, 15062)
+    assert (cxq["pos"].shape[0], cxq["meth"].sum(), cxq["unmeth"].sum()) == (96151, 5873, 124333)
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_reference_runit_constants_single_end_and_amplicon(oracle):
+    # inst/unitTests/test_generateCytosineReport.R:215-233
+    bam, _ = load_golden("dragen_se")
+    _, cx = oracle(bam).generateCytosineReport(threshold_reads=False, report_context="CX")
+    assert cx["pos"].shape[0] == 3236
+    assert [int((cx["context"] == c).sum()) for c in (2, 6, 7)] == [2165, 802, 269]
+    assert (cx["meth"].sum(), cx["unmeth"].sum()) == (355, 3599)
+    # config 1: amplicon010meth, defaults; pass count pinned by test_generateBedReport.R:22-35 (48 = 13+7+5+9+14)
+    amp, _ = load_golden("amplicon010meth")
+    p, cg = oracle(amp).generateCytosineReport()
+    assert (amp.nrow, int(amp.blob()[1][-1]), int(p.sum())) == (500, 190455, 48)
+    assert (cg["pos"].shape[0], cg["meth"].sum(), cg["unmeth"].sum()) == (478, 632, 6449)
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_known_answer_tests(oracle):
+    cg = ("Z", "z", "XH", "xh", 2, 0.5, 0.1)
+    o = oracle(bam_from_xm(KAT_C1_ROWS))
+    p = o.rcpp_threshold_reads(*cg)
+    assert p.astype(int).tolist() == KAT_C1_PASS
+    assert o.rcpp_get_xm_beta("Z", "z").tolist() == KAT_C1_BETA
+    assert report_tuples(o.rcpp_cx_report(p, "ZXH")) == KAT_C1_THR_ZXH
+    assert report_tuples(o.rcpp_cx_report(None, "ZXH")) == KAT_C1_NOTHR_ZXH
+
+    o = oracle(bam_from_xm(KAT_C2_ROWS))
+    p = o.rcpp_threshold_reads(*cg)
+    assert p.all()
+    rep = o.rcpp_cx_report(p, "Z")
+    assert report_tuples(rep) == KAT_C2_Z and report_tuples(o.rcpp_cx_report(None, "Z")) == KAT_C2_Z
+    assert (rep["pos"].shape[0], rep["meth"].sum(), rep["unmeth"].sum()) == (24, 30, 18)
+
+    o = oracle(bam_from_xm(KAT_C3_ROWS))
+    p = o.rcpp_threshold_reads(*cg)
+    assert p.astype(int).tolist() == KAT_C3_PASS
+    assert report_tuples(o.rcpp_cx_report(None, "ZXH")) == KAT_C3_NOTHR_ZXH
+    assert report_tuples(o.rcpp_cx_report(p, "ZX")) == KAT_C3_THR_ZX
+
+    o = oracle(bam_from_xm(kat_c4_rows()))
+    p = o.rcpp_threshold_reads(*cg)
+    assert p.sum() == 1 and p[0]
+    rep = o.rcpp_cx_report(p, "Z")
+    assert (rep["pos"].shape[0], rep["meth"].sum(), rep["unmeth"].sum()) == (10, 10, 9990)
+
+
+def test_port_matches_reference_on_synthetic_reads():
+    if RefCpu not in ORACLES:
+        pytest.skip("reference sources not available here")
+    from epialleler_b200 import synth_config, synth_host
+    for cfg in (synth_config(7, 4000, [60000], 150), synth_config(8, 3000, [50000, 30000], 40, 300, n_islands=6, island_len=900)):
+        bam = synth_host(cfg)
+        a, b = PortCpu(bam), RefCpu(bam)
+        for thr, tctx, rctx in ((True, "CG", "CG"), (False, "CG", "CX"), (True, "CHH", "CxG")):
+            pa, ra = a.generateCytosineReport(thr, tctx, 2, 0.5, 0.1, rctx)
+            pb, rb = b.generateCytosineReport(thr, tctx, 2, 0.5, 0.1, rctx)
+            assert np.array_equal(pa, pb)
+            assert_report_equal(ra, rb)
+            assert ra["pos"].shape[0] > 0
