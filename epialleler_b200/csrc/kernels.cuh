@@ -542,13 +542,15 @@ struct ReportCols { int32_t *rname, *strand, *pos, *ctx, *meth, *unmeth; };
 
 __global__ void __launch_bounds__(128)
 k_gather_rows(const int4* __restrict__ scratch, const long long* __restrict__ w_base, const long long* __restrict__ w_dst,
-              const int32_t* __restrict__ w_cnt, const int32_t* __restrict__ w_rname, int n_win, ReportCols out) {
+              const int32_t* __restrict__ w_cnt, const int32_t* __restrict__ w_rname, int n_win, long long cap,
+              ReportCols out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int w = warp; w < n_win; w += n_warps) {
     const int cnt = w_cnt[w];
     if (!cnt) continue;
     const long long src = w_base[w], dst = w_dst[w];
+    if (src + cnt > cap || dst + cnt > cap) continue;  // capacity overflow: the host grows the buffers and reruns
     const int rn = w_rname[w];
     for (int i = lane; i < cnt; i += 32) {
       const int4 v = scratch[src + i];

@@ -590,7 +590,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
       k_gather_rows<<<std::max(1, std::min(ix->n / 4 + 1, h->sm_count * 16)), 128, 0, h->stream>>>(
-          h->d_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, cols);
+          h->d_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, h->cap_rows, cols);
       launches += 2;
       CU(cudaGetLastError());
     } else {

@@ -1,0 +1,99 @@
+"""Range partitioning of coordinate-sorted reads over ranks (one process per GPU).
+
+The path shards with NO data-path collective: thresholding is per read, aggregation
+is per (rname,pos), and rows are sorted by (rname,start), so a contiguous genomic range is a
+contiguous row range.  A cut that falls inside continuous coverage is handled by a HALO: the few
+rows that start before the cut but reach past it are packed on both neighbours, and every rank keeps
+only the report rows whose (rname,pos) lies in the range it owns.  The only exchange is the
+all-gather of per-rank row counts that places each rank's rows in the concatenated report.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+
+
+@dataclass
+class Shard:
+    rank: int
+    row_lo: int      # first row packed on this rank (halo included)
+    own_lo: int      # rows [own_lo, own_hi) are the ones whose pass flags this rank reports
+    own_hi: int
+    key_lo: int      # report rows with key_lo <= (rname<<32|pos) < key_hi belong to this rank
+    key_hi: int
+
+
+KEY_MIN, KEY_MAX = 0, (1 << 62)
+
+
+def _key(rname, pos):
+    return (np.asarray(rname, dtype=np.int64) << 32) | np.asarray(pos, dtype=np.int64)
+
+
+def plan_shards(rname, start, length, world: int, weights=None) -> List[Shard]:
+    """Split sorted rows into `world` contiguous ranges of about equal weight (bytes by default).
+
+    rname/start/length: per-row arrays (length = string length).  Cuts are snapped to the first row
+    of a run of equal (rname,start) so that all rows starting at or after a cut position are on the
+    right of it."""
+    rname = np.asarray(rname, dtype=np.int64)
+    start = np.asarray(start, dtype=np.int64)
+    length = np.asarray(length, dtype=np.int64)
+    n = rname.shape[0]
+    keys = _key(rname, start)
+    w = length if weights is None else np.asarray(weights, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(w)])
+    ends = start + length
+    # furthest end so far within the chromosome (rows are sorted by rname, so the combined key is monotone)
+    maxend = np.maximum.accumulate((rname << 32) | np.where(length > 0, ends, 0))
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r // world
+        c = int(np.searchsorted(cum, target, side="left"))
+        c = min(max(c, cuts[-1]), n)
+        if c < n:
+            c = int(np.searchsorted(keys, keys[c], side="left"))  # snap to the first row with that (rname,start)
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(n)
+    shards = []
+    for r in range(world):
+        own_lo, own_hi = cuts[r], cuts[r + 1]
+        key_lo = KEY_MIN if r == 0 or own_lo >= n else int(keys[own_lo])
+        key_hi = KEY_MAX if r == world - 1 or own_hi >= n else int(keys[own_hi])
+        if r > 0 and own_lo < n:
+            # halo: earlier rows of the same chromosome that reach past the cut position
+            row_lo = int(np.searchsorted(maxend[:own_lo], key_lo, side="right"))
+        else:
+            row_lo = own_lo
+        if own_lo >= n:  # nothing left for this rank
+            row_lo, key_lo, key_hi = n, KEY_MAX, KEY_MAX
+        shards.append(Shard(r, row_lo, own_lo, own_hi, key_lo, key_hi))
+    # later empty shards must not steal the open-ended range of the last non-empty one
+    for r in range(world - 1):
+        if shards[r + 1].own_lo >= n and shards[r].own_lo < n:
+            shards[r].key_hi = KEY_MAX
+    return shards
+
+
+def filter_report(rep: dict, shard: Shard) -> dict:
+    """Keep the report rows this rank owns."""
+    k = _key(rep["rname"], rep["pos"])
+    m = (k >= shard.key_lo) & (k < shard.key_hi)
+    out = {c: (v[m] if isinstance(v, np.ndarray) else v) for c, v in rep.items()}
+    return out
+
+
+def merge_reports(parts: List[dict]) -> dict:
+    """Concatenate per-rank reports in rank order (= genomic order)."""
+    cols = ("rname", "strand", "pos", "context", "meth", "unmeth")
+    return {c: np.concatenate([p[c] for p in parts]) if parts else np.zeros(0, np.int32) for c in cols}
+
+
+def slice_bam(bam, shard: Shard):
+    """Rows [row_lo, own_hi) of a host BamData as a new BamData (strings stay shared)."""
+    from .api import BamData
+    sl = slice(shard.row_lo, shard.own_hi)
+    blob, off = bam.blob()
+    return BamData(bam.rname[sl], bam.strand[sl], bam.start[sl], bam.templid[sl], blob, off, bam.rname_levels, bam.device)
