@@ -16,12 +16,14 @@
 
 #include "../../include/epialleler_b200.h"
 #include "kernels.cuh"
+#include "window_tpr.cuh"
 #include "synth.h"
 
 namespace {
 
 thread_local std::string g_err;
 ea_poll_fn g_poll = nullptr;
+int g_kernel_policy = 0;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -522,6 +524,66 @@ int launch_window(ea_handle* h, const WinIndex& ix, int want, int tctx_fused, bo
   }
 }
 
+// ---- thread-per-row TMA kernel (short reads, moderate depth) ----
+struct TprPlan { bool ok = false; int tile_bytes = 0; int max_span = 0; };
+
+TprPlan plan_tpr(const ea_handle* h, const WinIndex& ix) {
+  TprPlan t;
+  if (h->n == 0 || ix.n == 0) return t;
+  const int max_pad = (h->max_len + 15) & ~15;
+  const int64_t avg_pad = (h->npadded + h->n - 1) / h->n;
+  if (max_pad > 8192 || ix.max_rows > 8192) return t;  // long reads / deep windows: lane-group kernel
+  int64_t tb = (32 * avg_pad + 127) & ~127ll;
+  tb = std::min<int64_t>(std::max<int64_t>({tb, 4096, (int64_t)((max_pad + 127) & ~127)}), 8192);
+  if (tb * 32 < 8 * avg_pad * 32) {}  // (tiles hold >= 8 rows on average by construction of the bounds above)
+  if (avg_pad * 8 > tb) return t;      // fewer than 8 rows per tile: thread-per-row would idle most lanes
+  t.ok = true; t.tile_bytes = (int)tb; t.max_span = max_pad;
+  return t;
+}
+
+template <int TCTX, int WANT, bool FUSED>
+int launch_tpr_t(ea_handle* h, const WinIndex& ix, const TprPlan& tp, const ThrParams& thr, const uint8_t* pass_in,
+                 uint8_t* pass_out, const ReportOut& out) {
+  constexpr int NC = n_ctx<WANT>();
+  constexpr int S = NC == 1 ? 4096 : 2048;
+  if (ix.S != S) return fail(EA_ERR_STATE, "window size mismatch");
+  const size_t smem = sizeof(uint32_t) * NC * 2 * S + (size_t)kTprWarps * tp.tile_bytes;
+  auto kern = k_window_tpr<TCTX, WANT, FUSED>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 96));
+  kern<<<grid, kTprThreads, smem, h->stream>>>(csr_of(h), wt, thr, pass_in, pass_out, tp.tile_bytes, tp.max_span, out);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+template <int WANT>
+int launch_tpr_w(ea_handle* h, const WinIndex& ix, const TprPlan& tp, int tctx_fused, const ThrParams& thr,
+                 const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (tctx_fused) {
+    case TC_CG: return launch_tpr_t<TC_CG, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
+    case TC_CHG: return launch_tpr_t<TC_CHG, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
+    case TC_CHH: return launch_tpr_t<TC_CHH, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
+    case TC_CXG: return launch_tpr_t<TC_CXG, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
+    case TC_CX: return launch_tpr_t<TC_CX, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
+    default: return launch_tpr_t<TC_NONE, WANT, false>(h, ix, tp, thr, pass_in, pass_out, out);
+  }
+}
+
+int launch_tpr(ea_handle* h, const WinIndex& ix, const TprPlan& tp, int want, int tctx_fused, const ThrParams& thr,
+               const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (want) {
+    case 1: return launch_tpr_w<1>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+    case 2: return launch_tpr_w<2>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+    case 3: return launch_tpr_w<3>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+    case 4: return launch_tpr_w<4>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+    case 5: return launch_tpr_w<5>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+    case 6: return launch_tpr_w<6>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+    default: return launch_tpr_w<7>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+  }
+}
+
 int ensure_pass(ea_handle* h) {
   if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
   return EA_OK;
@@ -545,7 +607,8 @@ struct ReportPlan {
   bool threshold = false;
   ThresholdSpec spec;
   ThrParams tp{};
-  int mode = 0;  // 0 fused, 1 two-pass
+  int mode = 0;    // 0 fused, 1 two-pass
+  int kernel = 0;  // 0 auto (thread-per-row TMA kernel when the data allow it), 1 force the lane-group kernel
 };
 
 // The device pipeline of one report: (threshold) -> window kernel -> window scan -> ordered gather.
@@ -584,7 +647,10 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      if ((rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out))) return rc;
+      const TprPlan tpr = (wide || rp.kernel == 1 || g_kernel_policy == 1) ? TprPlan() : plan_tpr(h, *ix);
+      if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
+      if (rc) return rc;
       launches++;
       CU(cudaEventRecord(h->ev[2], h->stream));
       k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
@@ -626,7 +692,8 @@ int make_plan_from_params(const ea_report_params* p, int mode, ReportPlan* rp) {
   if (!p) return fail(EA_ERR_ARG, "null params");
   rp->want = want_of(p->report_ctx);
   rp->threshold = p->threshold_reads != 0;
-  rp->mode = mode;
+  rp->mode = mode & 1;
+  rp->kernel = (mode >> 1) & 1;
   if (rp->threshold) {
     if (!p->ctx_meth || !p->ctx_unmeth) return fail(EA_ERR_ARG, "ctx_meth/ctx_unmeth must be non-null");
     parse_threshold_letters(p->ctx_meth, p->ctx_unmeth, p->ooctx_meth, p->ooctx_unmeth, &rp->spec);
@@ -743,6 +810,7 @@ int ea_device_count(void) {
   return n;
 }
 void ea_set_poll(ea_poll_fn fn) { g_poll = fn; }
+int ea_set_kernel_policy(int policy) { const int old = g_kernel_policy; g_kernel_policy = policy; return old; }
 
 void ea_free(ea_handle* h) {
   if (!h) return;

@@ -61,6 +61,9 @@ int ea_version(void);
 const char* ea_last_error(void);
 int ea_device_count(void);
 void ea_set_poll(ea_poll_fn fn);
+/* Kernel choice for the report: 0 automatic (default), 1 always the general lane-group window kernel.
+ * Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
+int ea_set_kernel_policy(int policy);
 
 /* ---- packer: host bam.data -> device-resident CSR (row order) ------------------------------ */
 
@@ -132,7 +135,8 @@ typedef struct ea_timing {
   int64_t alg_bytes;     /* algorithmic bytes of the call: sum(L) + 14 N + 24 R (13 N unthresholded) */
 } ea_timing;
 
-/* mode 0: fused kernel; mode 1: threshold kernel + report kernel (two passes over XM). */
+/* mode bit0: 0 fused kernel, 1 threshold kernel + report kernel (two passes over XM);
+ * mode bit1: 0 automatic kernel choice, 1 force the general lane-group window kernel (A/B measurements). */
 int ea_cytosine_report_device(ea_handle* h, const ea_report_params* p, int mode, ea_timing* t);
 const char* ea_stage_name(int i);
 /* Write `bytes` bytes of scratch on the handle's device (L2 flush between timed iterations). */

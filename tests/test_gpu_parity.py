@@ -17,6 +17,15 @@ pytestmark = pytest.mark.gpu
 CG = ("Z", "z", "XH", "xh", 2, 0.5, 0.1)
 
 
+@pytest.fixture(params=["auto", "lane-group"], autouse=True)
+def kernel_policy(request):
+    """Every parity test runs twice: with the automatic kernel choice (thread-per-row TMA kernel for short
+    reads) and with the general lane-group window kernel forced."""
+    old = N.lib().ea_set_kernel_policy(1 if request.param == "lane-group" else 0)
+    yield request.param
+    N.lib().ea_set_kernel_policy(old)
+
+
 def two_pass(bam, thr, tctx, ms, mb, mo, rctx):
     """The reference's own call sequence: rcpp_threshold_reads then rcpp_cx_report."""
     if thr:
