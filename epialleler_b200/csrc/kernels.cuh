@@ -2,9 +2,11 @@
 //
 // Device data layout ("padded CSR", built by the packer in pack.cu):
 //   data   : every read's packed SEQ|XM string, rows in (rname,start) order, each row starting on a
-//            16-byte boundary and padded to a multiple of 16 bytes with 0x0B ('-': code 11, which the
-//            reference neither counts nor covers, src/rcpp_cx_report.cpp:122).  One 16-byte "chunk"
-//            is the unit a lane loads (LDG.128 / TMA-able), so no edge masking is ever needed.
+//            16-byte boundary and padded to a multiple of 16 bytes with code 3 (a low nibble the
+//            reference's readers never emit; it belongs to no class below, so no edge masking is ever
+//            needed).  The LAST pad byte carries the pad count in its high nibble (0x03 | n<<4), which
+//            gives the true row end without reading len[].  One 16-byte "chunk" is the unit a lane
+//            loads (LDG.128 / one TMA bulk copy per tile of rows).
 //   off    : int64[n+1] byte offsets of the padded rows;  len : int32[n] true lengths
 //   start  : int32[n] 1-based reference position of byte 0;  strand : uint8[n] 1 '+', 2 '-'
 //   rname  : int32[n] chromosome factor code
@@ -56,7 +58,10 @@ __device__ __forceinline__ uint4 ldg_chunk(const uint8_t* p) {
   return v;
 }
 
+constexpr uint32_t kPadByte = 0x03u;
+
 struct Planes {
+  uint32_t last;            // raw bytes 12..15 of the chunk (byte 15 of a row's last chunk holds the pad count)
   uint32_t P0, P1;          // nibble-packed codes
   uint32_t A0, B0, C0, D0;  // bit planes of P0 aligned at bit 0 of every nibble (B0 masked)
   uint32_t A1, B1, C1, D1;  // bit planes of P1 aligned at bit 1 of every nibble (B1 masked)
@@ -65,11 +70,15 @@ struct Planes {
 // Merged indicator layout: bit i <-> nibble t=i>>2 of P(i&1); chunk byte = 8*(i&1) + 4*(t&1) + (t>>1).
 __device__ __forceinline__ void make_planes(const uint4& v, Planes& p) {
   const uint32_t M = 0x0F0F0F0Fu;
+  p.last = v.w;
   p.P0 = (v.x & M) | ((v.y << 4) & ~M);
   p.P1 = (v.z & M) | ((v.w << 4) & ~M);
   p.A0 = p.P0;       p.B0 = (p.P0 >> 1) & kNib0; p.C0 = p.P0 >> 2; p.D0 = p.P0 >> 3;
   p.A1 = p.P1 << 1;  p.B1 = p.P1 & kNib1;        p.C1 = p.P1 >> 1; p.D1 = p.P1 >> 2;
 }
+
+// number of pad bytes at the end of a row, read from its last chunk
+__device__ __forceinline__ int pad_count(const Planes& p) { return ((p.last >> 24) & 15u) == kPadByte ? (int)(p.last >> 28) : 0; }
 
 // every class below contains the (masked) B plane positively, so results are clean indicator masks
 __device__ __forceinline__ uint32_t cls_cg(uint32_t A, uint32_t B, uint32_t C) { return A & B & C; }
@@ -202,10 +211,12 @@ __device__ __forceinline__ void push_chunk(const Planes& p, const WinSmem<CT>& w
       }
     }
   }
-  const int qe = rel + 16;
-  if (qe < S) {
-    if (end16 && !is_last) atomicAdd(&covd[max(qe, 0)], 1);
-    if (!end16 && is_last) atomicAdd(&covd[max(qe, 0)], -1);
+  if (!is_last) {
+    const int qe = rel + 16;
+    if (end16 && qe < S) atomicAdd(&covd[max(qe, 0)], 1);
+  } else if (!end16) {  // row end = true end (a '-' run reaching the end has already closed the coverage)
+    const int qe = rel + 16 - pad_count(p);
+    if (qe < S) atomicAdd(&covd[max(qe, 0)], -1);
   }
 }
 

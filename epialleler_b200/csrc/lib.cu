@@ -140,7 +140,7 @@ __global__ void k_lens_from_templid(const int64_t* __restrict__ soff, const int3
   padded[r] = (l + 15) & ~15ll;
 }
 
-// one warp per row: tight source string -> 16-byte aligned, 0x0B-padded destination row
+// one warp per row: tight source string -> 16-byte aligned destination row padded with code 3 (kernels.cuh)
 __global__ void k_repack(const uint8_t* __restrict__ blob, const int64_t* __restrict__ soff,
                          const int32_t* __restrict__ templid, int64_t n, const int64_t* __restrict__ doff,
                          const int32_t* __restrict__ len, uint8_t* __restrict__ dst) {
@@ -154,9 +154,10 @@ __global__ void k_repack(const uint8_t* __restrict__ blob, const int64_t* __rest
     uint8_t* d = dst + doff[r];
     const int nch = (l + 15) >> 4;
     for (int c = lane; c < nch; c += 32) {
-      uint32_t w[4] = {0x0B0B0B0Bu, 0x0B0B0B0Bu, 0x0B0B0B0Bu, 0x0B0B0B0Bu};
+      uint32_t w[4] = {0x03030303u, 0x03030303u, 0x03030303u, 0x03030303u};
       const int b0 = c * 16;
       const int m = min(16, l - b0);
+      if (m < 16) w[3] |= (uint32_t)(16 - m) << 28;  // last pad byte carries the pad count
       for (int i = 0; i < m; i++) {
         const uint32_t v = src[b0 + i];
         w[i >> 2] = (w[i >> 2] & ~(0xFFu << ((i & 3) * 8))) | (v << ((i & 3) * 8));
@@ -210,19 +211,25 @@ __global__ void k_row_keys(Csr csr, uint64_t* __restrict__ key, int32_t* __restr
   atomicMax(max_len, l);
 }
 
-// every low nibble must be one of {2,5,6,7,10,11,12,13,14,15}
-__global__ void k_validate_domain(const uint8_t* __restrict__ data, int64_t n_chunks, unsigned* flags) {
+// every low nibble of the caller's strings must be one of {2,5,6,7,10,11,12,13,14,15}
+// (runs on the tight source blob, 16 bytes per thread step; head/tail bytes one by one)
+__global__ void k_validate_domain(const uint8_t* __restrict__ blob, int64_t n_bytes, unsigned* flags) {
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t head = min(n_bytes, (int64_t)((16 - (reinterpret_cast<uintptr_t>(blob) & 15)) & 15));
+  const int64_t n_chunks = (n_bytes - head) / 16;
   bool bad = false;
   for (int64_t i = i0; i < n_chunks; i += stride) {
-    const uint4 v = *reinterpret_cast<const uint4*>(data + i * 16);
+    const uint4 v = *reinterpret_cast<const uint4*>(blob + head + i * 16);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++)
 #pragma unroll
       for (int b = 0; b < 4; b++) bad |= !((0xFCE4u >> ((w[k] >> (8 * b)) & 15u)) & 1u);
   }
+  if (i0 < head) bad |= !((0xFCE4u >> (blob[i0] & 15u)) & 1u);
+  const int64_t tail0 = head + n_chunks * 16;
+  if (tail0 + i0 < n_bytes && i0 < 16) bad |= !((0xFCE4u >> (blob[tail0 + i0] & 15u)) & 1u);
   if (bad) atomicOr(flags, F_DOMAIN);
 }
 
@@ -325,8 +332,6 @@ int finish_handle(ea_handle* h) {
   CU(cudaMemsetAsync(d_maxlen, 0, 4, h->stream));
   if (h->n > 0) {
     k_row_keys<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, d_maxlen, d_flags);
-    const int64_t n_chunks = h->npadded / 16;
-    if (n_chunks > 0) k_validate_domain<<<(int)std::min<int64_t>((n_chunks + 255) / 256, h->sm_count * 32), 256, 0, h->stream>>>(h->d_data, n_chunks, d_flags);
     size_t tb = 0;
     CU(cub::DeviceScan::InclusiveScan(nullptr, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
     void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
@@ -525,19 +530,19 @@ int launch_window(ea_handle* h, const WinIndex& ix, int want, int tctx_fused, bo
 }
 
 // ---- thread-per-row TMA kernel (short reads, moderate depth) ----
-struct TprPlan { bool ok = false; int tile_bytes = 0; int max_span = 0; };
+struct TprPlan { bool ok = false; int tile_bytes = 0; };
 
 TprPlan plan_tpr(const ea_handle* h, const WinIndex& ix) {
   TprPlan t;
   if (h->n == 0 || ix.n == 0) return t;
   const int max_pad = (h->max_len + 15) & ~15;
   const int64_t avg_pad = (h->npadded + h->n - 1) / h->n;
-  if (max_pad > 8192 || ix.max_rows > 8192) return t;  // long reads / deep windows: lane-group kernel
+  if (max_pad > 8192 || ix.max_rows > 32767) return t;  // long reads / very deep windows: lane-group kernel
   int64_t tb = (32 * avg_pad + 127) & ~127ll;
   tb = std::min<int64_t>(std::max<int64_t>({tb, 4096, (int64_t)((max_pad + 127) & ~127)}), 8192);
   if (tb * 32 < 8 * avg_pad * 32) {}  // (tiles hold >= 8 rows on average by construction of the bounds above)
   if (avg_pad * 8 > tb) return t;      // fewer than 8 rows per tile: thread-per-row would idle most lanes
-  t.ok = true; t.tile_bytes = (int)tb; t.max_span = max_pad;
+  t.ok = true; t.tile_bytes = (int)tb;
   return t;
 }
 
@@ -545,15 +550,15 @@ template <int TCTX, int WANT, bool FUSED>
 int launch_tpr_t(ea_handle* h, const WinIndex& ix, const TprPlan& tp, const ThrParams& thr, const uint8_t* pass_in,
                  uint8_t* pass_out, const ReportOut& out) {
   constexpr int NC = n_ctx<WANT>();
-  constexpr int S = NC == 1 ? 4096 : 2048;
+  constexpr int S = 2048;
   if (ix.S != S) return fail(EA_ERR_STATE, "window size mismatch");
-  const size_t smem = sizeof(uint32_t) * NC * 2 * S + (size_t)kTprWarps * tp.tile_bytes;
-  auto kern = k_window_tpr<TCTX, WANT, FUSED>;
+  const size_t smem = sizeof(uint32_t) * (NC * 2 * S + 2 * (S + 4)) + (size_t)kTprWarps * tp.tile_bytes;
+  auto kern = k_window_tpr<TCTX, WANT, FUSED, S>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WinTable wt;
   wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
   const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 96));
-  kern<<<grid, kTprThreads, smem, h->stream>>>(csr_of(h), wt, thr, pass_in, pass_out, tp.tile_bytes, tp.max_span, out);
+  kern<<<grid, kTprThreads, smem, h->stream>>>(csr_of(h), wt, thr, pass_in, pass_out, tp.tile_bytes, out);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -618,9 +623,14 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   h->n_rows = -1;
   if (tm) memset(tm, 0, sizeof *tm);
   const int nc = ((rp.want >> 0) & 1) + ((rp.want >> 1) & 1) + ((rp.want >> 2) & 1);
-  const int S = nc <= 1 ? 4096 : 2048;
   WinIndex* ix = nullptr;
-  if (rp.want) { if ((rc = build_index(h, S, &ix))) return rc; }
+  TprPlan tpr;
+  if (rp.want) {
+    // short reads: thread-per-row TMA kernel on 2048-position windows; otherwise the lane-group kernel
+    if ((rc = build_index(h, 2048, &ix))) return rc;
+    if (rp.kernel != 1 && g_kernel_policy != 1) tpr = plan_tpr(h, *ix);
+    if (!tpr.ok && nc <= 1 && (rc = build_index(h, 4096, &ix))) return rc;
+  }
   if (rp.threshold && (rc = ensure_pass(h))) return rc;
   const bool wide = ix && ix->max_rows > 65535;
   const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
@@ -647,7 +657,6 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      const TprPlan tpr = (wide || rp.kernel == 1 || g_kernel_policy == 1) ? TprPlan() : plan_tpr(h, *ix);
       if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
       if (rc) return rc;
@@ -721,6 +730,11 @@ int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_
   CU(cudaMemset(d_flags, 0, 4));
   CU(cudaMemset(d_padded, 0, sizeof(int64_t) * (size_t)(h->n + 1)));
   if (h->n > 0) k_lens_from_templid<<<grid_for(h->n, 256), 256>>>(d_soff, d_templid, h->n, nstr, h->d_len, d_padded, d_flags);
+  {  // domain check on the caller's bytes (all strings, referenced or not)
+    int64_t total = 0;
+    CU(cudaMemcpy(&total, d_soff + nstr, 8, cudaMemcpyDeviceToHost));
+    if (total > 0) k_validate_domain<<<(int)std::min<int64_t>((total / 16 + 256) / 256, 148 * 32), 256>>>(d_blob, total, d_flags);
+  }
   size_t tb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_padded, h->d_off, (int)(h->n + 1)));
   void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
@@ -787,7 +801,8 @@ __global__ void k_synth_bytes(easynth::Plan plan, int64_t row_begin, int64_t n, 
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const int j = j0 + 4 * k + b;
-      const uint32_t byte = j < ri.len ? easynth::read_byte(plan, row_begin + r, ri, j) : 0x0Bu;
+      uint32_t byte = j < ri.len ? easynth::read_byte(plan, row_begin + r, ri, j) : 0x03u;
+      if (4 * k + b == 15 && j >= ri.len) byte |= (uint32_t)(j0 + 16 - ri.len) << 4;  // pad count in the last pad byte
       v |= byte << (8 * b);
     }
     w[k] = v;

@@ -7,15 +7,16 @@
 //     aligned byte range of the CSR) into shared memory with ONE cp.async.bulk (TMA) completed on a
 //     warp-private mbarrier, then every lane walks its own row with LDS.128: no shuffles, row
 //     metadata loads are coalesced over 32 rows, the IEEE-double pass chain runs for 32 rows at once;
-//   * only cytosine calls of the requested contexts become shared-memory atomics ({total, methylated
-//     of passing reads} packed in one 32-bit word per (context, strand, position));
-//   * coverage is NOT accumulated: by SURVEY.md 8a invariant 3 a row exists iff total_ctx >
-//     floor(cov/2), so cov is only needed where total_ctx > 0.  Those few candidates (~2% of the
-//     positions for a CpG report) are compacted in position order and every thread PULLS the
-//     coverage of one candidate from the rows that cover it (rows are sorted, so they are a short
-//     contiguous range), counting bytes whose code is not 11 ('-' and the 0x0B padding).
-// Preconditions (checked by the host dispatcher): every padded row fits a tile, at most 65535
-// candidate rows per window, moderate depth (the pull walks depth x max_len/avg_len rows).
+//   * ONE sweep over the row does everything that does not depend on the pass flag: class counts for
+//     the thresholds, {total calls} of the requested contexts and coverage deltas (row start/end,
+//     '-' runs) as shared-memory atomics.  By SURVEY.md 8a invariant 4 only the methylated count
+//     depends on `pass`, so after the flag is known the few passing rows (~10%) get a
+//     warp-cooperative fix-up: the 32 lanes take one chunk each of such a row and add its
+//     methylated calls;
+//   * the finalize touches shared memory only: vectorised prefix sum of the coverage deltas, row
+//     detection (total_ctx > floor(cov/2), src/rcpp_cx_report.cpp:62-72), ordered compaction.
+// Preconditions (checked by the host dispatcher): every padded row fits a tile, at most 32767 rows
+// overlap a window (16-bit packed counters).
 #pragma once
 #include "kernels.cuh"
 
@@ -79,37 +80,111 @@ __device__ __forceinline__ int block_exscan_n(int v, int* total, int* s_warp /* 
   return s_warp[warp] + inc - v;
 }
 
-// push the requested-context calls of one chunk; rel = window-relative position of the chunk's byte 0
-template <int WANT>
-__device__ __forceinline__ void push_calls(const Planes& p, uint32_t* __restrict__ tm, int S, int strand0, int rel, bool pass) {
-  uint32_t cand = cls_want<WANT>(p.A0, p.B0, p.C0) | cls_want<WANT>(p.A1, p.B1, p.C1);
-  while (cand) {
-    const int i = __ffs(cand) - 1;
-    cand &= cand - 1u;
-    const int q = rel + ((i & 1) << 3) + (i & 4) + (i >> 3);
+
+// position (byte index within the chunk) of merged-indicator bit i
+__device__ __forceinline__ int bit_pos(int i) { return ((i & 1) << 3) + (i & 4) + (i >> 3); }
+
+// Events of one chunk.  tms = tm + strand*S (per-context stride 2*S), cv = coverage words of the strand.
+// A coverage word packs two 16-bit fields that are decoded at the end: low = running-coverage DELTA
+// (+1 row start, -1 row end, -1/+1 around long '-' runs; modular arithmetic keeps it exact), high =
+// number of isolated '-' bytes at the position.  cov(p) = prefix_sum(low)(p) - high(p).
+// Returns the merged mask of methylated requested-context calls of the chunk.
+template <int WANT, bool WITH_METH>
+__device__ __forceinline__ uint32_t push_events(const Planes& p, uint32_t* __restrict__ tms, int32_t* __restrict__ cv, int S,
+                                                 int rel, bool pass, bool first_in_win, bool is_last) {
+  constexpr int NC = n_ctx<WANT>();
+  const uint32_t c0 = cls_want<WANT>(p.A0, p.B0, p.C0), c1 = cls_want<WANT>(p.A1, p.B1, p.C1);
+  const uint32_t cand = c0 | c1;
+  const uint32_t methc = (c0 & ~p.D0) | (c1 & ~p.D1);                               // methylated calls among them
+  const uint32_t E = (p.A0 & p.B0 & ~p.C0 & p.D0) | (p.A1 & p.B1 & ~p.C1 & p.D1);   // code 11 bytes
+  if (first_in_win) atomicAdd(&cv[max(rel, 0)], 1);
+  for (uint32_t m = cand; m;) {
+    const int i = __ffs(m) - 1;
+    const uint32_t bit = m & (0u - m);
+    m ^= bit;
+    const int q = rel + bit_pos(i);
     if ((unsigned)q < (unsigned)S) {
-      const uint32_t code = (((i & 1) ? p.P1 : p.P0) >> (i & 28)) & 15u;
-      const int slot = n_ctx<WANT>() == 1 ? 0 : slot_of<WANT>(code & 7u);
-      atomicAdd(&tm[(slot * 2 + strand0) * S + q], (pass && code < 8u) ? 0x10001u : 1u);
+      int slot = 0;
+      if (NC > 1) slot = slot_of<WANT>(((((i & 1) ? p.P1 : p.P0) >> (i & 28)) & 7u));
+      uint32_t inc = 1u;
+      if (WITH_METH && pass && (methc & bit)) inc = 0x10001u;
+      atomicAdd(&tms[slot * 2 * S + q], inc);
     }
   }
+  if (E) {
+    if (__popc(E) <= 2) {  // isolated '-' bytes: one count each
+      for (uint32_t m = E; m;) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1u;
+        const int q = rel + bit_pos(i);
+        if ((unsigned)q < (unsigned)S) atomicAdd(&cv[q], 0x10000);
+      }
+    } else {               // runs (mate gaps): -1 where a run starts, +1 right after it ends
+      const uint32_t prev = (E << 8) | ((E >> 20) & 0x30u) | ((E >> 27) & 0x2u);  // "byte before me is 11"
+      const uint32_t starts = E & ~prev;
+      for (uint32_t m = starts | (prev & ~E); m;) {
+        const int i = __ffs(m) - 1;
+        const uint32_t bit = m & (0u - m);
+        m ^= bit;
+        const int q = rel + bit_pos(i);
+        if (q < S) atomicAdd(&cv[max(q, 0)], (starts & bit) ? -1 : 1);
+      }
+      if (((E >> 29) & 1u) && rel + 16 < S) atomicAdd(&cv[max(rel + 16, 0)], 1);  // run reaches the chunk end
+    }
+  }
+  if (is_last) {
+    const int qe = rel + 16 - pad_count(p);
+    if (qe < S) atomicAdd(&cv[max(qe, 0)], -1);
+  }
+  return methc;
 }
 
-template <int TCTX, int WANT, bool FUSED>
-__global__ void __launch_bounds__(kTprThreads, 2)
+template <int NWARPS>
+__device__ __forceinline__ long long block_exscan64_n(long long v, long long* total, long long* s_warp /* NWARPS+1 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const long long x = lane < NWARPS ? s_warp[lane] : 0;
+    long long xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long o = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+      if (lane >= d) xi += o;
+    }
+    if (lane < NWARPS) s_warp[lane] = xi - x;
+    if (lane == NWARPS - 1) s_warp[NWARPS] = xi;
+  }
+  __syncthreads();
+  *total = s_warp[NWARPS];
+  return s_warp[warp] + inc - v;
+}
+
+template <int TCTX, int WANT, bool FUSED, int S>
+__global__ void __launch_bounds__(kTprThreads, 3)
 k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pass_in, uint8_t* __restrict__ pass_out,
-             int tile_bytes, int max_span, ReportOut out) {
+             int tile_bytes, ReportOut out) {
   constexpr int NC = n_ctx<WANT>();
+  constexpr int Sp = S + 4;
+  constexpr int PER = S / kTprThreads;  // positions per thread in the finalize (8 or 16)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[kTprWarps];
+  __shared__ long long s_scan64[kTprWarps + 1];
   __shared__ int s_scan[kTprWarps + 1];
   __shared__ long long s_base;
   __shared__ int s_npass;
 
-  constexpr int S = NC == 1 ? 4096 : 2048;  // == wt.S (host asserts)
-  uint32_t* tm = reinterpret_cast<uint32_t*>(smem_raw);                     // [NC][2][S]
-  unsigned char* tiles = smem_raw + sizeof(uint32_t) * NC * 2 * S;           // [kTprWarps][tile_bytes]; candidate list later
-  uint32_t* list = reinterpret_cast<uint32_t*>(tiles);
+  uint32_t* tm = reinterpret_cast<uint32_t*>(smem_raw);                          // [NC][2][S]
+  int32_t* covd = reinterpret_cast<int32_t*>(smem_raw + sizeof(uint32_t) * NC * 2 * S);  // [2][Sp]
+  unsigned char* tiles = smem_raw + sizeof(uint32_t) * (NC * 2 * S + 2 * Sp);     // [kTprWarps][tile_bytes]
+  constexpr int kZero4 = (NC * 2 * S + 2 * Sp) / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* my_tile = tiles + (size_t)warp * tile_bytes;
   uint64_t* my_bar = &s_bar[warp];
@@ -120,10 +195,8 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
   __syncthreads();
 
   for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
-    // generic-proxy writes of the previous window (candidate list) must be ordered before this window's TMA writes
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    for (int i = threadIdx.x; i < NC * 2 * S / 4; i += kTprThreads) reinterpret_cast<uint4*>(tm)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < kZero4; i += kTprThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) s_npass = 0;
     __syncthreads();
 
@@ -157,34 +230,67 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
           mbar_wait(my_bar, phase);
           phase ^= 1u;
         }
-        if (valid && lane >= first && lane < first + k) {
-          const int nch = (int)((o1 - o0) >> 4);
-          const unsigned char* row = my_tile + (int)(o0 - of);
-          const int rel0 = start - w0;
-          const bool overlaps = rel0 + nch * 16 > 0;
-          if (overlaps) {
-            bool pass = true;
-            if (FUSED) {
-              uint32_t c0 = 0, c1 = 0;
-              for (int c = 0; c < nch; c++) {
-                Planes p;
-                make_planes(*reinterpret_cast<const uint4*>(row + c * 16), p);
-                count_chunk<TCTX>(p, c0, c1);
-              }
-              pass = eval_pass(c0 >> 16, c0 & 0xFFFFu, c1 >> 16, c1 & 0xFFFFu, thr);
-              if (rel0 >= 0) {  // the window that holds the row's start owns its flag
-                pass_out[r] = pass ? 1 : 0;
-                if (pass) atomicAdd(&s_npass, 1);
-              }
-            } else {
-              pass = pass_in ? (pass_in[r] != 0) : true;
+        const bool mine = valid && lane >= first && lane < first + k;
+        const int nch = mine ? (int)((o1 - o0) >> 4) : 0;
+        const int row_off = (int)(o0 - of);
+        const int rel0 = start - w0;
+        const bool overlaps = mine && rel0 + nch * 16 > 0;
+        const int c_first = rel0 >= 0 ? 0 : ((-rel0) >> 4);
+        const int c_end = rel0 + nch * 16 > S ? ((S - rel0 + 15) >> 4) : nch;
+        bool pass = true, fix = false;
+        if (overlaps) {
+          const unsigned char* row = my_tile + row_off;
+          int32_t* cv = covd + strand0 * Sp;
+          uint32_t* tms = tm + strand0 * S;
+          if (FUSED) {
+            uint32_t c0 = 0, c1 = 0, anym = 0;
+            for (int c = 0; c < nch; c++) {
+              Planes p;
+              make_planes(*reinterpret_cast<const uint4*>(row + c * 16), p);
+              count_chunk<TCTX>(p, c0, c1);
+              if (c >= c_first && c < c_end) anym |= push_events<WANT, false>(p, tms, cv, S, rel0 + c * 16, false, c == c_first, c == nch - 1);
             }
-            const int c_first = rel0 >= 0 ? 0 : ((-rel0) >> 4);
-            const int c_end = rel0 + nch * 16 > S ? ((S - rel0 + 15) >> 4) : nch;
+            pass = eval_pass(c0 >> 16, c0 & 0xFFFFu, c1 >> 16, c1 & 0xFFFFu, thr);
+            if (rel0 >= 0) {  // the window that holds the row's start owns its flag
+              pass_out[r] = pass ? 1 : 0;
+              if (pass) atomicAdd(&s_npass, 1);
+            }
+            fix = pass && anym;
+          } else {
+            pass = pass_in ? (pass_in[r] != 0) : true;
             for (int c = c_first; c < c_end; c++) {
               Planes p;
               make_planes(*reinterpret_cast<const uint4*>(row + c * 16), p);
-              push_calls<WANT>(p, tm, S, strand0, rel0 + c * 16, pass);
+              push_events<WANT, true>(p, tms, cv, S, rel0 + c * 16, pass, c == c_first, c == nch - 1);
+            }
+          }
+        }
+        if (FUSED) {
+          // methylated calls of passing rows: the warp takes one such row at a time, one chunk per lane
+          uint32_t todo = __ballot_sync(0xFFFFFFFFu, fix);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int f_off = __shfl_sync(0xFFFFFFFFu, row_off, src);
+            const int f_rel = __shfl_sync(0xFFFFFFFFu, rel0, src);
+            const int f_cf = __shfl_sync(0xFFFFFFFFu, c_first, src);
+            const int f_ce = __shfl_sync(0xFFFFFFFFu, c_end, src);
+            const int f_st = __shfl_sync(0xFFFFFFFFu, strand0, src);
+            for (int c = f_cf + lane; c < f_ce; c += 32) {
+              Planes p;
+              make_planes(*reinterpret_cast<const uint4*>(my_tile + f_off + c * 16), p);
+              uint32_t mm = (cls_want<WANT>(p.A0, p.B0, p.C0) & ~p.D0) | (cls_want<WANT>(p.A1, p.B1, p.C1) & ~p.D1);
+              const int rel = f_rel + c * 16;
+              while (mm) {
+                const int i = __ffs(mm) - 1;
+                mm &= mm - 1u;
+                const int q = rel + ((i & 1) << 3) + (i & 4) + (i >> 3);
+                if ((unsigned)q < (unsigned)S) {
+                  int slot = 0;
+                  if (NC > 1) slot = slot_of<WANT>(((((i & 1) ? p.P1 : p.P0) >> (i & 28)) & 7u));
+                  atomicAdd(&tm[(slot * 2 + f_st) * S + q], 0x10000u);
+                }
+              }
             }
           }
         }
@@ -194,10 +300,31 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
     }
     __syncthreads();
 
-    // ---------------- candidates: (pos,strand) with any requested-context call, in position order ----------------
-    constexpr int PER = S / kTprThreads;  // positions per thread
+    // ---------------- finalize: coverage prefix sum, row detection, ordered compaction ----------------
     const int q0 = threadIdx.x * PER;
-    uint32_t nz = 0;  // bit 2k+s
+    int cov[2][PER];
+    long long packed = 0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      int run = 0;
+#pragma unroll
+      for (int v4 = 0; v4 < PER / 4; v4++) {
+        const int4 d = *reinterpret_cast<const int4*>(&covd[s * Sp + q0 + v4 * 4]);
+        const int w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int lo16 = (int)(short)w[j];            // coverage delta
+          run += lo16;
+          cov[s][v4 * 4 + j] = run - ((w[j] - lo16) >> 16);  // minus the '-' bytes at this position (prefix added later)
+        }
+      }
+      packed += (long long)(run + (1 << 20)) << (32 * s);  // biased so both halves stay non-negative
+    }
+    long long tot64;
+    const long long ex = block_exscan64_n<kTprWarps>(packed, &tot64, s_scan64);
+    const int bias = (int)threadIdx.x << 20;
+    const int pre0 = (int)(ex & 0xFFFFFFFFll) - bias, pre1 = (int)(ex >> 32) - bias;
+    uint32_t flags = 0;  // bit 2k+s: (q0+k, strand s) is a report row
 #pragma unroll
     for (int s = 0; s < 2; s++)
 #pragma unroll
@@ -205,59 +332,17 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
 #pragma unroll
         for (int v4 = 0; v4 < PER / 4; v4++) {
           const uint4 v = *reinterpret_cast<const uint4*>(&tm[(c * 2 + s) * S + q0 + v4 * 4]);
-          if (v.x) nz |= 1u << (2 * (v4 * 4 + 0) + s);
-          if (v.y) nz |= 1u << (2 * (v4 * 4 + 1) + s);
-          if (v.z) nz |= 1u << (2 * (v4 * 4 + 2) + s);
-          if (v.w) nz |= 1u << (2 * (v4 * 4 + 3) + s);
-        }
-    int n_cand;
-    int my = block_exscan_n<kTprWarps>(__popc(nz), &n_cand, s_scan);
-    // (the tiles are dead now: the list aliases them; capacity S*2 entries <= tile area, checked by the host)
-    for (uint32_t m = nz; m; m &= m - 1u) {
-      const int b = __ffs(m) - 1;
-      list[my++] = (uint32_t)(q0 + (b >> 1)) | ((uint32_t)(b & 1) << 16);
-    }
-    __syncthreads();
-
-    // ---------------- pull the coverage of every candidate from the rows covering it ----------------
-    for (int idx = threadIdx.x; idx < n_cand; idx += kTprThreads) {
-      const uint32_t e = list[idx];
-      const int q = e & 0xFFFF, s = (e >> 16) & 1;
-      const int p = w0 + q;
-      int a = lo, b = hi;  // first row with start > p
-      while (a < b) {
-        const int m = (a + b) >> 1;
-        if (__ldg(&csr.start[m]) <= p) a = m + 1; else b = m;
-      }
-      uint32_t cov = 0;
-      for (int r = a - 1; r >= lo; r--) {
-        const int st = __ldg(&csr.start[r]);
-        if (st <= p - max_span) break;
-        if (__ldg(&csr.strand[r]) - 1 != s) continue;
-        const long long ro = __ldg(&csr.off[r]);
-        const int d = p - st;
-        if (d < (int)(__ldg(&csr.off[r + 1]) - ro)) cov += ((__ldg(&csr.data[ro + d]) & 15u) != 11u);
-      }
-      const uint32_t half = cov >> 1;
-      uint32_t res = e;
-      int slot = 0;
+          if (v.x | v.y | v.z | v.w) {
+            const uint32_t t[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int cc = 0; cc < 3; cc++) {
-        if (!((WANT >> cc) & 1)) continue;
-        if ((tm[(slot * 2 + s) * S + q] & 0xFFFFu) > half) res |= (uint32_t)(slot + 1) << 20 | (uint32_t)(cc == 0 ? 2 : (cc == 1 ? 6 : 7)) << 24;
-        slot++;
-      }
-      list[idx] = res;
-    }
-    __syncthreads();
-
-    // ---------------- ordered emission ----------------
-    const int chunk = (n_cand + kTprThreads - 1) / kTprThreads;
-    const int i0 = min(n_cand, (int)threadIdx.x * chunk), i1 = min(n_cand, i0 + chunk);
-    int mine = 0;
-    for (int i = i0; i < i1; i++) mine += (list[i] >> 20) != 0;
+            for (int j = 0; j < 4; j++) {
+              const uint32_t half = (uint32_t)(cov[s][v4 * 4 + j] + (s ? pre1 : pre0)) >> 1;
+              if ((t[j] & 0xFFFFu) > half) flags |= 1u << (2 * (v4 * 4 + j) + s);
+            }
+          }
+        }
     int nrows_total;
-    int my_off = block_exscan_n<kTprWarps>(mine, &nrows_total, s_scan);
+    const int my_off = block_exscan_n<kTprWarps>(__popc(flags), &nrows_total, s_scan);
     if (threadIdx.x == 0) {
       const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
       s_base = (long long)bb;
@@ -267,15 +352,24 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
     }
     __syncthreads();
     const long long wbase = s_base;
-    if (mine && wbase + nrows_total <= out.cap) {
+    if (flags && wbase + nrows_total <= out.cap) {
       long long dst = wbase + my_off;
-      for (int i = i0; i < i1; i++) {
-        const uint32_t e = list[i];
-        if (!(e >> 20)) continue;
-        const int q = e & 0xFFFF, s = (e >> 16) & 1, slot = (int)((e >> 20) & 15u) - 1, code = (int)(e >> 24);
-        const uint32_t v = tm[(slot * 2 + s) * S + q];
-        out.scratch[dst++] = make_int4(w0 + q, (s + 1) | (code << 8), (int)(v >> 16), (int)((v & 0xFFFFu) - (v >> 16)));
-      }
+#pragma unroll
+      for (int k = 0; k < PER; k++)
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          if (!((flags >> (2 * k + s)) & 1u)) continue;
+          const uint32_t half = (uint32_t)(cov[s][k] + (s ? pre1 : pre0)) >> 1;
+          int code = 0; uint32_t val = 0; int slot = 0;
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            if (!((WANT >> cc) & 1)) continue;
+            const uint32_t v = tm[(slot * 2 + s) * S + q0 + k];
+            if ((v & 0xFFFFu) > half) { code = cc == 0 ? 2 : (cc == 1 ? 6 : 7); val = v; }
+            slot++;
+          }
+          out.scratch[dst++] = make_int4(w0 + q0 + k, (s + 1) | (code << 8), (int)(val >> 16), (int)((val & 0xFFFFu) - (val >> 16)));
+        }
     }
   }
 }
