@@ -92,8 +92,21 @@ def merge_reports(parts: List[dict]) -> dict:
 
 
 def slice_bam(bam, shard: Shard):
-    """Rows [row_lo, own_hi) of a host BamData as a new BamData (strings stay shared)."""
+    """Rows [row_lo, own_hi) of a host BamData as a self-contained BamData: its strings are gathered in row
+    order (templid = 0..n-1), so nrow equals the number of strings as the per-read routines require."""
     from .api import BamData
     sl = slice(shard.row_lo, shard.own_hi)
     blob, off = bam.blob()
-    return BamData(bam.rname[sl], bam.strand[sl], bam.start[sl], bam.templid[sl], blob, off, bam.rname_levels, bam.device)
+    tid = bam.templid[sl].astype(np.int64)
+    lens = off[tid + 1] - off[tid]
+    new_off = np.zeros(tid.shape[0] + 1, dtype=np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    # gather: byte i of the new blob comes from off[tid[row]] + (i - new_off[row])
+    if tid.shape[0]:
+        row_of = np.repeat(np.arange(tid.shape[0]), lens)
+        src = off[tid][row_of] + (np.arange(int(new_off[-1])) - new_off[:-1][row_of])
+        new_blob = blob[src]
+    else:
+        new_blob = np.zeros(0, np.uint8)
+    return BamData(bam.rname[sl], bam.strand[sl], bam.start[sl], np.arange(tid.shape[0], dtype=np.int32), new_blob, new_off,
+                   bam.rname_levels, bam.device)

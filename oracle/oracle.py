@@ -84,7 +84,14 @@ class _Cpu:
 
     __del__ = close
 
+    def _check_per_read(self):
+        # the reference loops over the strings and indexes templid by the same counter
+        # (src/rcpp_threshold_reads.cpp:27-33): nrow != nstr is out of contract (and out of bounds)
+        if self.n != self.nstr:
+            raise ValueError("nrow(bam) must equal the number of seqxm strings")
+
     def rcpp_threshold_reads(self, ctx_meth, ctx_unmeth, ooctx_meth, ooctx_unmeth, min_n_ctx, min_ctx_meth_frac, max_ooctx_meth_frac):
+        self._check_per_read()
         out = np.zeros(max(self.nstr, 1), np.uint8)
         self.last_seconds = getattr(self.lib, self.PREFIX + "threshold_reads")(
             self.h, ctx_meth.encode(), ctx_unmeth.encode(), ooctx_meth.encode(), ooctx_unmeth.encode(),
@@ -92,6 +99,7 @@ class _Cpu:
         return out[:self.nstr].astype(bool)
 
     def rcpp_get_xm_beta(self, ctx_meth, ctx_unmeth):
+        self._check_per_read()
         out = np.zeros(max(self.nstr, 1), np.float64)
         self.last_seconds = getattr(self.lib, self.PREFIX + "get_xm_beta")(self.h, ctx_meth.encode(), ctx_unmeth.encode(), _p(out, C.c_double))
         return out[:self.nstr]

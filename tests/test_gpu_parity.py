@@ -190,3 +190,23 @@ def test_string_pointer_packer_matches_blob_packer():
     N.check(L.ea_threshold_reads(h, b"Z", b"z", b"XH", b"xh", 2, 0.5, 0.1, out.ctypes.data_as(C.POINTER(C.c_uint8))))
     assert np.array_equal(out, z["cg_default.pass"])
     L.ea_free(h)
+
+
+def test_range_sharded_gpu_equals_whole():
+    """The N>1 data path on one GPU: every rank's shard (halo included) through the CUDA kernels, ownership
+    filter, concatenation == the unsharded oracle report."""
+    from epialleler_b200.distributed import shard_report
+    from epialleler_b200.shard import merge_reports
+    for cfg, kw in ((ea.synth_config(41, 30000, [120000], 150), dict()),
+                    (ea.synth_config(42, 20000, [60000, 50000], 80, 420), dict(threshold_reads=False, report_context="CX")),
+                    (ea.synth_config(43, 30000, [80000], 100, 300, n_islands=3, island_len=1500), dict(threshold_context="CxG", report_context="CHG"))):
+        host = ea.synth_host(cfg)
+        want_pass, want = PortCpu(host).generateCytosineReport(kw.get("threshold_reads", True), kw.get("threshold_context", "CG"), 2, 0.5, 0.1,
+                                                               kw.get("report_context") or kw.get("threshold_context", "CG"))
+        for world in (2, 3, 8):
+            parts, passes = [], []
+            for r in range(world):
+                _, own_pass, rep = shard_report(host, r, world, **kw)
+                parts.append(rep); passes.append(own_pass)
+            assert np.array_equal(np.concatenate(passes), want_pass), (world, kw)
+            assert_report_equal(merge_reports(parts), want, "world=%d" % world)
