@@ -243,7 +243,7 @@ def run_ours(args):
                            "what": "ea_pack_blob (H2D + device repack + validation + window index) + fused report + D2H of pass flags and rows + free"}
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     dev.close()
     if world > 1:
         dist.destroy_process_group()
@@ -291,16 +291,29 @@ def run_reference(args):
     s = float(np.mean(secs))
     v = rows / s
     sample = "each step = first %d rows of the workload (single-threaded reference; %d host cores present)" % (rows, os.cpu_count())
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "configs[1]: synthetic WGBS, %d reads x %d bp per GPU, CpG report, threshold.reads=TRUE; bounded sample" % (args.reads, READ_LEN)},
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "xm_gbs": float(host.blob()[1][-1]) / 1e9 / s}), flush=True)
+        "xm_gbs": float(host.blob()[1][-1]) / 1e9 / s})
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL banners, warnings)
+    was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -317,6 +330,7 @@ def main():
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:  # convenience: relaunch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        os.dup2(_REAL_STDOUT, 1)
         raise SystemExit(subprocess.call(cmd))
     run_ours(args)
 

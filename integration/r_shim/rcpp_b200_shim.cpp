@@ -1,0 +1,112 @@
+// Reference-side binding of the B200 library (SOURCE ONLY: R, Rcpp and a GPU-enabled R build are not
+// available in the build image, so this file has never been compiled; the same C ABI is exercised
+// from Python/ctypes by the test-suite).
+//
+// Drop this file into the reference's src/ in place of rcpp_threshold_reads.cpp, rcpp_get_xm_beta.cpp
+// and rcpp_cx_report.cpp, add `PKG_LIBS += -L$(EA_B200_LIB) -lepialleler_b200` and
+// `PKG_CPPFLAGS += -I$(EA_B200_INCLUDE)` to src/Makevars, and re-run Rcpp::compileAttributes():
+// the three exported R closures (R/RcppExports.R:12-14,28-30,64-66) and the registered native
+// symbols (src/RcppExports.cpp:253-271) keep their names, arity and argument meaning.
+#include <Rcpp.h>
+#include <epialleler_b200.h>
+
+namespace {
+
+void ea_check(int rc) {
+  if (rc != EA_OK) Rcpp::stop("epialleler_b200: %s", ea_last_error());
+}
+
+int poll_interrupt() {           // Rcpp::checkUserInterrupt() throws; the C ABI wants a flag
+  try { Rcpp::checkUserInterrupt(); } catch (...) { return 1; }
+  return 0;
+}
+
+struct Handle {
+  ea_handle* h = nullptr;
+  ~Handle() { ea_free(h); }
+};
+
+// The device-resident packed copy hangs on the data.frame as a second external pointer, next to the
+// reference's "seqxm_xptr" (src/rcpp_read_bam.cpp:185): pack once, reuse across reports.
+ea_handle* handle_of(Rcpp::DataFrame& df) {
+  if (df.hasAttribute("b200_xptr")) {
+    Rcpp::XPtr<Handle> p((SEXP)df.attr("b200_xptr"));
+    if (p->h && ea_nrow(p->h) == df.nrows()) return p->h;
+  }
+  Rcpp::XPtr<std::vector<std::string>> seqxm((SEXP)df.attr("seqxm_xptr"));
+  Rcpp::IntegerVector rname = df["rname"], strand = df["strand"], start = df["start"], templid = df["templid"];
+  std::vector<const uint8_t*> str(seqxm->size());
+  std::vector<int64_t> len(seqxm->size());
+  for (size_t i = 0; i < seqxm->size(); i++) {
+    str[i] = reinterpret_cast<const uint8_t*>((*seqxm)[i].data());
+    len[i] = static_cast<int64_t>((*seqxm)[i].size());
+  }
+  ea_set_poll(poll_interrupt);
+  Handle* hd = new Handle;
+  ea_check(ea_pack(rname.begin(), strand.begin(), start.begin(), templid.begin(), df.nrows(), str.data(), len.data(),
+                   static_cast<int64_t>(str.size()), /*device=*/0, &hd->h));
+  df.attr("b200_xptr") = Rcpp::XPtr<Handle>(hd, true);
+  return hd->h;
+}
+
+Rcpp::DataFrame wrap_report(ea_handle* h, int64_t n, Rcpp::DataFrame& df) {
+  Rcpp::IntegerVector rname(n), strand(n), pos(n), context(n), meth(n), unmeth(n);
+  ea_check(ea_cx_report_fetch(h, rname.begin(), strand.begin(), pos.begin(), context.begin(), meth.begin(), unmeth.begin()));
+  Rcpp::IntegerVector in_rname = df["rname"], in_strand = df["strand"];
+  rname.attr("class") = "factor";   rname.attr("levels") = in_rname.attr("levels");     // src/rcpp_cx_report.cpp:142-148
+  strand.attr("class") = "factor";  strand.attr("levels") = in_strand.attr("levels");
+  context.attr("class") = "factor";
+  context.attr("levels") = Rcpp::CharacterVector::create("NA1", "CHH", "NA3", "NA4", "NA5", "CHG", "CG");  // :150-155
+  return Rcpp::DataFrame::create(Rcpp::Named("rname") = rname, Rcpp::Named("strand") = strand, Rcpp::Named("pos") = pos,
+                                 Rcpp::Named("context") = context, Rcpp::Named("meth") = meth, Rcpp::Named("unmeth") = unmeth);
+}
+
+}  // namespace
+
+// [[Rcpp::export("rcpp_threshold_reads")]]
+std::vector<bool> rcpp_threshold_reads(Rcpp::DataFrame& df, const std::string ctx_meth, const std::string ctx_unmeth,
+                                       const std::string ooctx_meth, const std::string ooctx_unmeth, const unsigned int min_n_ctx,
+                                       const double min_ctx_meth_frac, const double max_ooctx_meth_frac) {
+  ea_handle* h = handle_of(df);
+  std::vector<uint8_t> flags(static_cast<size_t>(ea_nrow(h)) + 1);
+  ea_check(ea_threshold_reads(h, ctx_meth.c_str(), ctx_unmeth.c_str(), ooctx_meth.c_str(), ooctx_unmeth.c_str(), min_n_ctx,
+                              min_ctx_meth_frac, max_ooctx_meth_frac, flags.data()));
+  return std::vector<bool>(flags.begin(), flags.end() - 1);
+}
+
+// [[Rcpp::export("rcpp_get_xm_beta")]]
+std::vector<double> rcpp_get_xm_beta(Rcpp::DataFrame& df, const std::string ctx_meth, const std::string ctx_unmeth) {
+  ea_handle* h = handle_of(df);
+  std::vector<double> beta(static_cast<size_t>(ea_nrow(h)));
+  ea_check(ea_get_xm_beta(h, ctx_meth.c_str(), ctx_unmeth.c_str(), beta.data()));
+  return beta;
+}
+
+// [[Rcpp::export("rcpp_cx_report")]]
+Rcpp::DataFrame rcpp_cx_report(Rcpp::DataFrame& df, Rcpp::LogicalVector& pass, const std::string ctx) {
+  ea_handle* h = handle_of(df);
+  std::vector<uint8_t> flags(pass.size());
+  for (R_xlen_t i = 0; i < pass.size(); i++) flags[i] = pass[i] != 0;  // NA_LOGICAL counts as TRUE (src/rcpp_cx_report.cpp:118)
+  int64_t n = 0;
+  ea_check(ea_cx_report(h, flags.data(), ctx.c_str(), &n));
+  return wrap_report(h, n, df);
+}
+
+// Optional fourth entry: the fused body of generateCytosineReport (R/generateCytosineReport.R:181-201),
+// one pass over the XM bytes instead of two.  R side:
+//   cx.report <- rcpp_cytosine_report_fused(bam, threshold.reads, ctx.meth, ctx.unmeth, ooctx.meth, ooctx.unmeth,
+//                                            min.context.sites, min.context.beta, max.outofcontext.beta, report.ctx)
+// [[Rcpp::export("rcpp_cytosine_report_fused")]]
+Rcpp::DataFrame rcpp_cytosine_report_fused(Rcpp::DataFrame& df, const bool threshold_reads, const std::string ctx_meth,
+                                           const std::string ctx_unmeth, const std::string ooctx_meth, const std::string ooctx_unmeth,
+                                           const unsigned int min_n_ctx, const double min_ctx_meth_frac,
+                                           const double max_ooctx_meth_frac, const std::string report_ctx) {
+  ea_handle* h = handle_of(df);
+  ea_report_params p;
+  p.threshold_reads = threshold_reads; p.ctx_meth = ctx_meth.c_str(); p.ctx_unmeth = ctx_unmeth.c_str();
+  p.ooctx_meth = ooctx_meth.c_str(); p.ooctx_unmeth = ooctx_unmeth.c_str(); p.min_n_ctx = min_n_ctx;
+  p.min_ctx_meth_frac = min_ctx_meth_frac; p.max_ooctx_meth_frac = max_ooctx_meth_frac; p.report_ctx = report_ctx.c_str();
+  int64_t n = 0;
+  ea_check(ea_cytosine_report(h, &p, nullptr, &n));
+  return wrap_report(h, n, df);
+}
