@@ -84,49 +84,48 @@ __device__ __forceinline__ int block_exscan_n(int v, int* total, int* s_warp /* 
 // position (byte index within the chunk) of merged-indicator bit i
 __device__ __forceinline__ int bit_pos(int i) { return ((i & 1) << 3) + (i & 4) + (i >> 3); }
 
-// Events of one chunk.  tms = tm + strand*S (per-context stride 2*S), cv = coverage words of the strand.
-// A coverage word packs two 16-bit fields that are decoded at the end: low = running-coverage DELTA
-// (+1 row start, -1 row end, -1/+1 around long '-' runs; modular arithmetic keeps it exact), high =
-// number of isolated '-' bytes at the position.  cov(p) = prefix_sum(low)(p) - high(p).
-// Returns the merged mask of methylated requested-context calls of the chunk.
-template <int WANT, bool WITH_METH>
-__device__ __forceinline__ uint32_t push_events(const Planes& p, uint32_t* __restrict__ tms, int32_t* __restrict__ cv, int S,
-                                                 int rel, bool pass, bool first_in_win, bool is_last) {
-  constexpr int NC = n_ctx<WANT>();
-  const uint32_t c0 = cls_want<WANT>(p.A0, p.B0, p.C0), c1 = cls_want<WANT>(p.A1, p.B1, p.C1);
-  const uint32_t cand = c0 | c1;
-  const uint32_t methc = (c0 & ~p.D0) | (c1 & ~p.D1);                               // methylated calls among them
-  const uint32_t E = (p.A0 & p.B0 & ~p.C0 & p.D0) | (p.A1 & p.B1 & ~p.C1 & p.D1);   // code 11 bytes
-  if (first_in_win) atomicAdd(&cv[max(rel, 0)], 1);
-  for (uint32_t m = cand; m;) {
-    const int i = __ffs(m) - 1;
-    const uint32_t bit = m & (0u - m);
+// One shared-memory atomic per set bit of m: t[q] += 1 (+ 0x10000 when the bit is also in `meth`).
+// The first bit is straight-line code (almost every warp step has some lane with an event), the rest loop.
+__device__ __forceinline__ void push_mask(uint32_t m, uint32_t meth, uint32_t* __restrict__ t, int rel, int S) {
+  if (m) {
+    uint32_t bit = m & (0u - m);
+    int q = rel + bit_pos(__ffs(m) - 1);
+    if ((unsigned)q < (unsigned)S) atomicAdd(&t[q], (meth & bit) ? 0x10001u : 1u);
     m ^= bit;
-    const int q = rel + bit_pos(i);
-    if ((unsigned)q < (unsigned)S) {
-      int slot = 0;
-      if (NC > 1) slot = slot_of<WANT>(((((i & 1) ? p.P1 : p.P0) >> (i & 28)) & 7u));
-      uint32_t inc = 1u;
-      if (WITH_METH && pass && (methc & bit)) inc = 0x10001u;
-      atomicAdd(&tms[slot * 2 * S + q], inc);
+    while (m) {
+      bit = m & (0u - m);
+      q = rel + bit_pos(__ffs(m) - 1);
+      if ((unsigned)q < (unsigned)S) atomicAdd(&t[q], (meth & bit) ? 0x10001u : 1u);
+      m ^= bit;
     }
   }
+}
+
+// Coverage events of one chunk (independent of the pass flag).  cv = coverage words of the row's strand.
+// A coverage word packs two 16-bit fields that are decoded at the end: low = running-coverage DELTA
+// (+1 row start, -1 true row end, -1/+1 around long '-' runs; two's-complement arithmetic keeps the
+// packed sum exact), high = number of isolated '-' bytes at the position.
+// cov(p) = prefix_sum(low)(p) - high(p).
+__device__ __forceinline__ void push_cov(const Planes& p, int32_t* __restrict__ cv, int S, int rel, bool first_in_win, bool is_last) {
+  const uint32_t E = (p.A0 & p.B0 & ~p.C0 & p.D0) | (p.A1 & p.B1 & ~p.C1 & p.D1);  // code 11 bytes
+  if (first_in_win) atomicAdd(&cv[max(rel, 0)], 1);
   if (E) {
     if (__popc(E) <= 2) {  // isolated '-' bytes: one count each
-      for (uint32_t m = E; m;) {
-        const int i = __ffs(m) - 1;
-        m &= m - 1u;
-        const int q = rel + bit_pos(i);
+      uint32_t m = E;
+      int q = rel + bit_pos(__ffs(m) - 1);
+      if ((unsigned)q < (unsigned)S) atomicAdd(&cv[q], 0x10000);
+      m &= m - 1u;
+      if (m) {
+        q = rel + bit_pos(__ffs(m) - 1);
         if ((unsigned)q < (unsigned)S) atomicAdd(&cv[q], 0x10000);
       }
     } else {               // runs (mate gaps): -1 where a run starts, +1 right after it ends
       const uint32_t prev = (E << 8) | ((E >> 20) & 0x30u) | ((E >> 27) & 0x2u);  // "byte before me is 11"
       const uint32_t starts = E & ~prev;
       for (uint32_t m = starts | (prev & ~E); m;) {
-        const int i = __ffs(m) - 1;
         const uint32_t bit = m & (0u - m);
+        const int q = rel + bit_pos(__ffs(m) - 1);
         m ^= bit;
-        const int q = rel + bit_pos(i);
         if (q < S) atomicAdd(&cv[max(q, 0)], (starts & bit) ? -1 : 1);
       }
       if (((E >> 29) & 1u) && rel + 16 < S) atomicAdd(&cv[max(rel + 16, 0)], 1);  // run reaches the chunk end
@@ -136,7 +135,27 @@ __device__ __forceinline__ uint32_t push_events(const Planes& p, uint32_t* __res
     const int qe = rel + 16 - pad_count(p);
     if (qe < S) atomicAdd(&cv[max(qe, 0)], -1);
   }
-  return methc;
+}
+
+// requested-context call masks of a chunk, one per context slot (order CHH, CHG, CG among the requested),
+// plus the methylated ones; merged indicator layout
+template <int WANT>
+__device__ __forceinline__ uint4 call_masks(const Planes& p) {
+  uint32_t m[3] = {0u, 0u, 0u};
+  int slot = 0;
+  uint32_t meth = 0;
+  if (WANT & W_CHH) { const uint32_t a = cls_chh(p.A0, p.B0, p.C0), b = cls_chh(p.A1, p.B1, p.C1); m[slot++] = a | b; meth |= (a & ~p.D0) | (b & ~p.D1); }
+  if (WANT & W_CHG) { const uint32_t a = cls_chg(p.A0, p.B0, p.C0), b = cls_chg(p.A1, p.B1, p.C1); m[slot++] = a | b; meth |= (a & ~p.D0) | (b & ~p.D1); }
+  if (WANT & W_CG) { const uint32_t a = cls_cg(p.A0, p.B0, p.C0), b = cls_cg(p.A1, p.B1, p.C1); m[slot++] = a | b; meth |= (a & ~p.D0) | (b & ~p.D1); }
+  return make_uint4(m[0], m[1], m[2], meth);
+}
+
+template <int WANT>
+__device__ __forceinline__ void push_calls(const uint4& cm, uint32_t meth_if_pass, uint32_t* __restrict__ tms, int S, int rel) {
+  constexpr int NC = n_ctx<WANT>();
+  push_mask(cm.x, meth_if_pass, tms, rel, S);
+  if (NC > 1) push_mask(cm.y, meth_if_pass, tms + 2 * S, rel, S);
+  if (NC > 2) push_mask(cm.z, meth_if_pass, tms + 4 * S, rel, S);
 }
 
 template <int NWARPS>
@@ -237,63 +256,51 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
         const bool overlaps = mine && rel0 + nch * 16 > 0;
         const int c_first = rel0 >= 0 ? 0 : ((-rel0) >> 4);
         const int c_end = rel0 + nch * 16 > S ? ((S - rel0 + 15) >> 4) : nch;
-        bool pass = true, fix = false;
         if (overlaps) {
-          const unsigned char* row = my_tile + row_off;
+          unsigned char* row = my_tile + row_off;
           int32_t* cv = covd + strand0 * Sp;
           uint32_t* tms = tm + strand0 * S;
           if (FUSED) {
-            uint32_t c0 = 0, c1 = 0, anym = 0;
+            // sweep 1: class counts, coverage events; the call masks replace the chunk in place
+            uint32_t c0 = 0, c1 = 0;
             for (int c = 0; c < nch; c++) {
               Planes p;
               make_planes(*reinterpret_cast<const uint4*>(row + c * 16), p);
               count_chunk<TCTX>(p, c0, c1);
-              if (c >= c_first && c < c_end) anym |= push_events<WANT, false>(p, tms, cv, S, rel0 + c * 16, false, c == c_first, c == nch - 1);
+              if (c >= c_first && c < c_end) {
+                push_cov(p, cv, S, rel0 + c * 16, c == c_first, c == nch - 1);
+                const uint4 cm = call_masks<WANT>(p);
+                if (NC == 1) *reinterpret_cast<uint2*>(row + c * 16) = make_uint2(cm.x, cm.w);
+                else *reinterpret_cast<uint4*>(row + c * 16) = cm;
+              }
             }
-            pass = eval_pass(c0 >> 16, c0 & 0xFFFFu, c1 >> 16, c1 & 0xFFFFu, thr);
+            const bool pass = eval_pass(c0 >> 16, c0 & 0xFFFFu, c1 >> 16, c1 & 0xFFFFu, thr);
             if (rel0 >= 0) {  // the window that holds the row's start owns its flag
               pass_out[r] = pass ? 1 : 0;
               if (pass) atomicAdd(&s_npass, 1);
             }
-            fix = pass && anym;
+            // sweep 2: the calls, now that the flag is known ({total, methylated-of-passing} in one atomic)
+            const uint32_t pm = pass ? 0xFFFFFFFFu : 0u;
+            for (int c = c_first; c < c_end; c++) {
+              uint4 cm;
+              if (NC == 1) { const uint2 v = *reinterpret_cast<const uint2*>(row + c * 16); cm = make_uint4(v.x, 0u, 0u, v.y); }
+              else cm = *reinterpret_cast<const uint4*>(row + c * 16);
+              push_calls<WANT>(cm, cm.w & pm, tms, S, rel0 + c * 16);
+            }
           } else {
-            pass = pass_in ? (pass_in[r] != 0) : true;
+            const bool pass = pass_in ? (pass_in[r] != 0) : true;
+            const uint32_t pm = pass ? 0xFFFFFFFFu : 0u;
             for (int c = c_first; c < c_end; c++) {
               Planes p;
               make_planes(*reinterpret_cast<const uint4*>(row + c * 16), p);
-              push_events<WANT, true>(p, tms, cv, S, rel0 + c * 16, pass, c == c_first, c == nch - 1);
+              push_cov(p, cv, S, rel0 + c * 16, c == c_first, c == nch - 1);
+              const uint4 cm = call_masks<WANT>(p);
+              push_calls<WANT>(cm, cm.w & pm, tms, S, rel0 + c * 16);
             }
           }
         }
-        if (FUSED) {
-          // methylated calls of passing rows: the warp takes one such row at a time, one chunk per lane
-          uint32_t todo = __ballot_sync(0xFFFFFFFFu, fix);
-          while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const int f_off = __shfl_sync(0xFFFFFFFFu, row_off, src);
-            const int f_rel = __shfl_sync(0xFFFFFFFFu, rel0, src);
-            const int f_cf = __shfl_sync(0xFFFFFFFFu, c_first, src);
-            const int f_ce = __shfl_sync(0xFFFFFFFFu, c_end, src);
-            const int f_st = __shfl_sync(0xFFFFFFFFu, strand0, src);
-            for (int c = f_cf + lane; c < f_ce; c += 32) {
-              Planes p;
-              make_planes(*reinterpret_cast<const uint4*>(my_tile + f_off + c * 16), p);
-              uint32_t mm = (cls_want<WANT>(p.A0, p.B0, p.C0) & ~p.D0) | (cls_want<WANT>(p.A1, p.B1, p.C1) & ~p.D1);
-              const int rel = f_rel + c * 16;
-              while (mm) {
-                const int i = __ffs(mm) - 1;
-                mm &= mm - 1u;
-                const int q = rel + ((i & 1) << 3) + (i & 4) + (i >> 3);
-                if ((unsigned)q < (unsigned)S) {
-                  int slot = 0;
-                  if (NC > 1) slot = slot_of<WANT>(((((i & 1) ? p.P1 : p.P0) >> (i & 28)) & 7u));
-                  atomicAdd(&tm[(slot * 2 + f_st) * S + q], 0x10000u);
-                }
-              }
-            }
-          }
-        }
+        // the rows were overwritten in place (generic proxy): order those writes before the next TMA into this tile
+        if (FUSED) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         first += k;
       }
