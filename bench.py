@@ -130,6 +130,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = N.lib()
+    L.ea_set_kernel_policy(args.policy)
     cfg = synth_cfg(ea, world, args.reads)
     row_lo, own_lo, own_hi = shard_rows(ea, cfg, rank, world)
     dev = ea.synth_device(cfg, row_lo, own_hi, device=local)
@@ -322,6 +323,7 @@ def main():
     ap.add_argument("--reads", type=int, default=READS_PER_GPU, help="reads per GPU (default: BASELINE configs[1])")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000)
     ap.add_argument("--ref-rows", type=int, default=500_000)
+    ap.add_argument("--policy", type=int, default=0, help="kernel policy for A/B runs: 0 automatic, 1 lane-group, 2 thread-per-row TMA")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -9,6 +9,7 @@
 //            loads (LDG.128 / one TMA bulk copy per tile of rows).
 //   off    : int64[n+1] byte offsets of the padded rows;  len : int32[n] true lengths
 //   start  : int32[n] 1-based reference position of byte 0;  strand : uint8[n] 1 '+', 2 '-'
+//   sp     : uint8[n] strand '-' flag (bit 0) | pad bytes of the row << 4 (true length without len[])
 //   rname  : int32[n] chromosome factor code
 //   windows: the covered part of every chromosome cut into windows of S positions; per window the
 //            contiguous row range [lo,hi) that can overlap it (rows are sorted, so it is contiguous).
@@ -40,6 +41,7 @@ struct Csr {
   const int32_t* len;
   const int32_t* start;
   const uint8_t* strand;
+  const uint8_t* sp;  // per row: strand '-' (bit 0) | pad bytes of the padded row << 4
   const int32_t* rname;
   int64_t n;
 };

@@ -17,6 +17,7 @@
 #include "../../include/epialleler_b200.h"
 #include "kernels.cuh"
 #include "window_tpr.cuh"
+#include "window_cpl.cuh"
 #include "synth.h"
 
 namespace {
@@ -77,6 +78,7 @@ struct ea_handle {
   bool owns = true;
   int32_t* d_rname = nullptr;
   uint8_t* d_strand = nullptr;
+  uint8_t* d_sp = nullptr;       // strand '-' flag | pad count << 4 (window_cpl.cuh)
   int32_t* d_start = nullptr;
   int32_t* d_len = nullptr;
   int64_t* d_off = nullptr;
@@ -105,7 +107,7 @@ using namespace ea;
 
 Csr csr_of(const ea_handle* h) {
   Csr c;
-  c.data = h->d_data; c.off = h->d_off; c.len = h->d_len; c.start = h->d_start; c.strand = h->d_strand;
+  c.data = h->d_data; c.off = h->d_off; c.len = h->d_len; c.start = h->d_start; c.strand = h->d_strand; c.sp = h->d_sp;
   c.rname = h->d_rname; c.n = h->n;
   return c;
 }
@@ -194,7 +196,7 @@ __global__ void k_len_i64(const int32_t* __restrict__ len, int64_t n, int64_t* _
 }
 
 // validation + row-end keys.  key = rname<<32 | (start+len) (0 for empty rows, so they never extend coverage)
-__global__ void k_row_keys(Csr csr, uint64_t* __restrict__ key, int32_t* __restrict__ max_len, unsigned* flags) {
+__global__ void k_row_keys(Csr csr, uint64_t* __restrict__ key, uint8_t* __restrict__ sp, int32_t* __restrict__ max_len, unsigned* flags) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= csr.n) return;
   const int32_t rn = csr.rname[r], st = csr.start[r], l = csr.len[r];
@@ -208,6 +210,7 @@ __global__ void k_row_keys(Csr csr, uint64_t* __restrict__ key, int32_t* __restr
   }
   if (f) atomicOr(flags, f);
   key[r] = ((uint64_t)(uint32_t)rn << 32) | (uint32_t)(l > 0 ? st + l : 0);
+  sp[r] = (uint8_t)((csr.strand[r] == 2 ? 1 : 0) | (((16 - (l & 15)) & 15) << 4));
   atomicMax(max_len, l);
 }
 
@@ -325,13 +328,14 @@ int finish_handle(ea_handle* h) {
   int rc;
   if ((rc = dmalloc(&h->d_counters, 4))) return rc;
   if ((rc = dmalloc(&h->d_maxend, (size_t)h->n))) return rc;
+  if ((rc = dmalloc(&h->d_sp, (size_t)h->n))) return rc;
   unsigned* d_flags; int32_t* d_maxlen;
   if ((rc = dmalloc(&d_flags, 1))) return rc;
   if ((rc = dmalloc(&d_maxlen, 1))) return rc;
   CU(cudaMemsetAsync(d_flags, 0, 4, h->stream));
   CU(cudaMemsetAsync(d_maxlen, 0, 4, h->stream));
   if (h->n > 0) {
-    k_row_keys<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, d_maxlen, d_flags);
+    k_row_keys<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, h->d_sp, d_maxlen, d_flags);
     size_t tb = 0;
     CU(cub::DeviceScan::InclusiveScan(nullptr, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
     void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
@@ -589,6 +593,67 @@ int launch_tpr(ea_handle* h, const WinIndex& ix, const TprPlan& tp, int want, in
   }
 }
 
+// ---- chunk-per-lane kernel (reads up to 1 KB, moderate depth): window_cpl.cuh ----
+struct CplPlan { bool ok = false; int rpt = 0; int tc = 0; size_t smem = 0; };
+
+CplPlan plan_cpl(const ea_handle* h, const WinIndex& ix, int nc, bool fused) {
+  CplPlan t;
+  if (h->n == 0 || ix.n == 0 || ix.S != 2048) return t;
+  const int max_nch = (h->max_len + 15) >> 4;
+  if (max_nch < 1 || max_nch > 64 || ix.max_rows > 32767) return t;  // long reads / very deep windows: lane-group kernel
+  const int avg_nch = (int)((h->npadded / 16 + h->n - 1) / h->n);
+  int tc = std::min(640, std::max(320, 32 * std::max(avg_nch, 1)));  // chunks per tile
+  tc = std::max(tc, max_nch);
+  tc = (tc + 31) & ~31;
+  t.rpt = std::min(32, tc / max_nch);
+  t.tc = tc;
+  const int mw = fused ? (nc == 3 ? 2 : 1) : 0;
+  t.smem = sizeof(uint32_t) * ((size_t)(nc + 1) * 2 * (kGuardLo + 2048 + kGuardHi) + (size_t)kCplWarps * (1 + mw) * tc);
+  t.ok = t.smem <= 200u * 1024u;
+  return t;
+}
+
+template <int TCTX, int WANT, bool FUSED>
+int launch_cpl_t(ea_handle* h, const WinIndex& ix, const CplPlan& cp, const ThrParams& thr, const uint8_t* pass_in,
+                 uint8_t* pass_out, const ReportOut& out) {
+  constexpr int S = 2048;
+  if (ix.S != S) return fail(EA_ERR_STATE, "window size mismatch");
+  auto kern = k_window_cpl<TCTX, WANT, FUSED, S>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem));
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
+  kern<<<grid, kCplThreads, cp.smem, h->stream>>>(csr_of(h), wt, thr, pass_in, pass_out, cp.rpt, cp.tc, out);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+template <int WANT>
+int launch_cpl_w(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int tctx_fused, const ThrParams& thr,
+                 const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (tctx_fused) {
+    case TC_CG: return launch_cpl_t<TC_CG, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
+    case TC_CHG: return launch_cpl_t<TC_CHG, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
+    case TC_CHH: return launch_cpl_t<TC_CHH, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
+    case TC_CXG: return launch_cpl_t<TC_CXG, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
+    case TC_CX: return launch_cpl_t<TC_CX, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
+    default: return launch_cpl_t<TC_NONE, WANT, false>(h, ix, cp, thr, pass_in, pass_out, out);
+  }
+}
+
+int launch_cpl(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int want, int tctx_fused, const ThrParams& thr,
+               const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (want) {
+    case 1: return launch_cpl_w<1>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+    case 2: return launch_cpl_w<2>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+    case 3: return launch_cpl_w<3>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+    case 4: return launch_cpl_w<4>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+    case 5: return launch_cpl_w<5>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+    case 6: return launch_cpl_w<6>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+    default: return launch_cpl_w<7>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+  }
+}
+
 int ensure_pass(ea_handle* h) {
   if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
   return EA_OK;
@@ -625,16 +690,23 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   const int nc = ((rp.want >> 0) & 1) + ((rp.want >> 1) & 1) + ((rp.want >> 2) & 1);
   WinIndex* ix = nullptr;
   TprPlan tpr;
-  if (rp.want) {
-    // short reads: thread-per-row TMA kernel on 2048-position windows; otherwise the lane-group kernel
-    if ((rc = build_index(h, 2048, &ix))) return rc;
-    if (rp.kernel != 1 && g_kernel_policy != 1) tpr = plan_tpr(h, *ix);
-    if (!tpr.ok && nc <= 1 && (rc = build_index(h, 4096, &ix))) return rc;
-  }
+  CplPlan cpl;
+  // kernel policy: 0 automatic (chunk-per-lane kernel when the data allow it, else the lane-group kernel),
+  // 1 force the general lane-group kernel, 2 prefer the thread-per-row TMA kernel (A/B measurements)
+  const int policy = rp.kernel == 1 ? 1 : g_kernel_policy;
+  if (rp.want && (rc = build_index(h, 2048, &ix))) return rc;
   if (rp.threshold && (rc = ensure_pass(h))) return rc;
-  const bool wide = ix && ix->max_rows > 65535;
+  bool wide = ix && ix->max_rows > 65535;
   const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
   const bool fused = can_fuse && rp.mode == 0;
+  if (rp.want) {
+    if (policy == 0) cpl = plan_cpl(h, *ix, nc, fused);
+    if (policy == 2) tpr = plan_tpr(h, *ix);
+    if (!cpl.ok && !tpr.ok && nc <= 1) {
+      if ((rc = build_index(h, 4096, &ix))) return rc;
+      wide = ix->max_rows > 65535;
+    }
+  }
   if (h->cap_rows == 0 && (rc = ensure_rows(h, h->nbytes / 24 + 4096))) return rc;
 
   for (int attempt = 0; attempt < 2; attempt++) {
@@ -657,7 +729,8 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      if (cpl.ok) rc = launch_cpl(h, *ix, cpl, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
       if (rc) return rc;
       launches++;
@@ -836,6 +909,7 @@ void ea_free(ea_handle* h) {
   }
   cudaFree(h->d_len);
   cudaFree(h->d_maxend);
+  cudaFree(h->d_sp);
   h->idx[0].release(); h->idx[1].release();
   cudaFree(h->d_pass); cudaFree(h->d_beta); cudaFree(h->d_counters); cudaFree(h->d_scratch); cudaFree(h->d_flush);
   for (auto& c : h->d_cols) cudaFree(c);

@@ -17,11 +17,11 @@ pytestmark = pytest.mark.gpu
 CG = ("Z", "z", "XH", "xh", 2, 0.5, 0.1)
 
 
-@pytest.fixture(params=["auto", "lane-group"], autouse=True)
+@pytest.fixture(params=["auto", "lane-group", "thread-per-row"], autouse=True)
 def kernel_policy(request):
-    """Every parity test runs twice: with the automatic kernel choice (thread-per-row TMA kernel for short
-    reads) and with the general lane-group window kernel forced."""
-    old = N.lib().ea_set_kernel_policy(1 if request.param == "lane-group" else 0)
+    """Every parity test runs three times: with the automatic kernel choice (chunk-per-lane kernel for reads
+    up to 1 KB), with the general lane-group window kernel forced, and with the thread-per-row TMA kernel."""
+    old = N.lib().ea_set_kernel_policy({"auto": 0, "lane-group": 1, "thread-per-row": 2}[request.param])
     yield request.param
     N.lib().ea_set_kernel_policy(old)
 
