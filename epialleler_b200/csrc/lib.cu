@@ -91,6 +91,7 @@ struct ea_handle {
   uint8_t* d_pass = nullptr;
   double* d_beta = nullptr;
   unsigned long long* d_counters = nullptr;  // [0] row cursor, [1] n_pass
+  uint16_t* d_thr_tables = nullptr;          // 2 x kThrTable integer thresholds of the pass/fail chain (window_cpl.cuh)
   int4* d_scratch = nullptr;
   int32_t* d_cols[6] = {};
   int64_t cap_rows = 0;
@@ -513,23 +514,28 @@ int launch_window_w(ea_handle* h, const WinIndex& ix, int tctx_fused, bool wide,
   }
   switch (tctx_fused) {
     case TC_CG: return launch_window_t<TC_CG, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+#ifndef EA_FAST_BUILD
     case TC_CHG: return launch_window_t<TC_CHG, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
     case TC_CHH: return launch_window_t<TC_CHH, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
     case TC_CXG: return launch_window_t<TC_CXG, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
-    default: return launch_window_t<TC_CX, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+    case TC_CX: return launch_window_t<TC_CX, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
+#endif
+    default: return launch_window_t<TC_CG, WANT, uint32_t, true>(h, ix, tp, pass_in, pass_out, out);
   }
 }
 
 int launch_window(ea_handle* h, const WinIndex& ix, int want, int tctx_fused, bool wide, const ThrParams& tp,
                   const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
   switch (want) {
+#ifndef EA_FAST_BUILD
     case 1: return launch_window_w<1>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
     case 2: return launch_window_w<2>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
     case 3: return launch_window_w<3>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
-    case 4: return launch_window_w<4>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
     case 5: return launch_window_w<5>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
     case 6: return launch_window_w<6>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
-    default: return launch_window_w<7>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+    case 7: return launch_window_w<7>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+#endif
+    default: return launch_window_w<4>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
   }
 }
 
@@ -572,10 +578,12 @@ int launch_tpr_w(ea_handle* h, const WinIndex& ix, const TprPlan& tp, int tctx_f
                  const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
   switch (tctx_fused) {
     case TC_CG: return launch_tpr_t<TC_CG, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
+#ifndef EA_FAST_BUILD
     case TC_CHG: return launch_tpr_t<TC_CHG, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
     case TC_CHH: return launch_tpr_t<TC_CHH, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
     case TC_CXG: return launch_tpr_t<TC_CXG, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
     case TC_CX: return launch_tpr_t<TC_CX, WANT, true>(h, ix, tp, thr, pass_in, pass_out, out);
+#endif
     default: return launch_tpr_t<TC_NONE, WANT, false>(h, ix, tp, thr, pass_in, pass_out, out);
   }
 }
@@ -583,13 +591,15 @@ int launch_tpr_w(ea_handle* h, const WinIndex& ix, const TprPlan& tp, int tctx_f
 int launch_tpr(ea_handle* h, const WinIndex& ix, const TprPlan& tp, int want, int tctx_fused, const ThrParams& thr,
                const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
   switch (want) {
+#ifndef EA_FAST_BUILD
     case 1: return launch_tpr_w<1>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
     case 2: return launch_tpr_w<2>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
     case 3: return launch_tpr_w<3>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
-    case 4: return launch_tpr_w<4>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
     case 5: return launch_tpr_w<5>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
     case 6: return launch_tpr_w<6>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
-    default: return launch_tpr_w<7>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+    case 7: return launch_tpr_w<7>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_tpr_w<4>(h, ix, tp, tctx_fused, thr, pass_in, pass_out, out);
   }
 }
 
@@ -622,8 +632,15 @@ int launch_cpl_t(ea_handle* h, const WinIndex& ix, const CplPlan& cp, const ThrP
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem));
   WinTable wt;
   wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  ThrTables tb{nullptr, nullptr};
+  if (FUSED) {
+    int rc;
+    if (!h->d_thr_tables && (rc = dmalloc(&h->d_thr_tables, (size_t)2 * kThrTable))) return rc;
+    tb.mmin = h->d_thr_tables; tb.omax = h->d_thr_tables + kThrTable;
+    k_thr_tables<<<(kThrTable + 127) / 128, 128, 0, h->stream>>>(thr, h->d_thr_tables, h->d_thr_tables + kThrTable);
+  }
   const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
-  kern<<<grid, kCplThreads, cp.smem, h->stream>>>(csr_of(h), wt, thr, pass_in, pass_out, cp.rpt, cp.tc, out);
+  kern<<<grid, kCplThreads, cp.smem, h->stream>>>(csr_of(h), wt, thr, tb, pass_in, pass_out, cp.rpt, cp.tc, out);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -633,10 +650,12 @@ int launch_cpl_w(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int tctx_f
                  const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
   switch (tctx_fused) {
     case TC_CG: return launch_cpl_t<TC_CG, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
+#ifndef EA_FAST_BUILD
     case TC_CHG: return launch_cpl_t<TC_CHG, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
     case TC_CHH: return launch_cpl_t<TC_CHH, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
     case TC_CXG: return launch_cpl_t<TC_CXG, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
     case TC_CX: return launch_cpl_t<TC_CX, WANT, true>(h, ix, cp, thr, pass_in, pass_out, out);
+#endif
     default: return launch_cpl_t<TC_NONE, WANT, false>(h, ix, cp, thr, pass_in, pass_out, out);
   }
 }
@@ -644,13 +663,15 @@ int launch_cpl_w(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int tctx_f
 int launch_cpl(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int want, int tctx_fused, const ThrParams& thr,
                const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
   switch (want) {
+#ifndef EA_FAST_BUILD
     case 1: return launch_cpl_w<1>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
     case 2: return launch_cpl_w<2>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
     case 3: return launch_cpl_w<3>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
-    case 4: return launch_cpl_w<4>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
     case 5: return launch_cpl_w<5>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
     case 6: return launch_cpl_w<6>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
-    default: return launch_cpl_w<7>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+    case 7: return launch_cpl_w<7>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_cpl_w<4>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
   }
 }
 
@@ -733,7 +754,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
       if (rc) return rc;
-      launches++;
+      launches += (cpl.ok && fused) ? 2 : 1;  // the chunk-per-lane kernel is preceded by its threshold-table kernel
       CU(cudaEventRecord(h->ev[2], h->stream));
       k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
@@ -911,7 +932,7 @@ void ea_free(ea_handle* h) {
   cudaFree(h->d_maxend);
   cudaFree(h->d_sp);
   h->idx[0].release(); h->idx[1].release();
-  cudaFree(h->d_pass); cudaFree(h->d_beta); cudaFree(h->d_counters); cudaFree(h->d_scratch); cudaFree(h->d_flush);
+  cudaFree(h->d_pass); cudaFree(h->d_beta); cudaFree(h->d_counters); cudaFree(h->d_thr_tables); cudaFree(h->d_scratch); cudaFree(h->d_flush);
   for (auto& c : h->d_cols) cudaFree(c);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
