@@ -547,7 +547,7 @@ TprPlan plan_tpr(const ea_handle* h, const WinIndex& ix) {
   if (h->n == 0 || ix.n == 0) return t;
   const int max_pad = (h->max_len + 15) & ~15;
   const int64_t avg_pad = (h->npadded + h->n - 1) / h->n;
-  if (max_pad > 8192 || ix.max_rows > 32767) return t;  // long reads / very deep windows: lane-group kernel
+  if (max_pad > 512 || ix.max_rows > 32767 || ix.S != 2048) return t;  // long reads / very deep windows: other kernels
   int64_t tb = (32 * avg_pad + 127) & ~127ll;
   tb = std::min<int64_t>(std::max<int64_t>({tb, 4096, (int64_t)((max_pad + 127) & ~127)}), 8192);
   if (tb * 32 < 8 * avg_pad * 32) {}  // (tiles hold >= 8 rows on average by construction of the bounds above)
@@ -556,19 +556,30 @@ TprPlan plan_tpr(const ea_handle* h, const WinIndex& ix) {
   return t;
 }
 
+int thr_tables(ea_handle* h, const ThrParams& thr, ThrTables* tb) {
+  int rc;
+  if (!h->d_thr_tables && (rc = dmalloc(&h->d_thr_tables, (size_t)2 * kThrTable))) return rc;
+  tb->mmin = h->d_thr_tables; tb->omax = h->d_thr_tables + kThrTable;
+  k_thr_tables<<<(kThrTable + 127) / 128, 128, 0, h->stream>>>(thr, h->d_thr_tables, h->d_thr_tables + kThrTable);
+  return EA_OK;
+}
+
 template <int TCTX, int WANT, bool FUSED>
 int launch_tpr_t(ea_handle* h, const WinIndex& ix, const TprPlan& tp, const ThrParams& thr, const uint8_t* pass_in,
                  uint8_t* pass_out, const ReportOut& out) {
   constexpr int NC = n_ctx<WANT>();
   constexpr int S = 2048;
   if (ix.S != S) return fail(EA_ERR_STATE, "window size mismatch");
-  const size_t smem = sizeof(uint32_t) * (NC * 2 * S + 2 * (S + 4)) + (size_t)kTprWarps * tp.tile_bytes;
+  const size_t smem = sizeof(uint32_t) * (size_t)(NC + 1) * 2 * (kGuardLo + S + kGuardHi) + (size_t)kTprWarps * tp.tile_bytes;
   auto kern = k_window_tpr<TCTX, WANT, FUSED, S>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WinTable wt;
   wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  ThrTables tb{nullptr, nullptr};
+  int rc;
+  if (FUSED && (rc = thr_tables(h, thr, &tb))) return rc;
   const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 96));
-  kern<<<grid, kTprThreads, smem, h->stream>>>(csr_of(h), wt, thr, pass_in, pass_out, tp.tile_bytes, out);
+  kern<<<grid, kTprThreads, smem, h->stream>>>(csr_of(h), wt, thr, tb, pass_in, pass_out, tp.tile_bytes, out);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -633,12 +644,8 @@ int launch_cpl_t(ea_handle* h, const WinIndex& ix, const CplPlan& cp, const ThrP
   WinTable wt;
   wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
   ThrTables tb{nullptr, nullptr};
-  if (FUSED) {
-    int rc;
-    if (!h->d_thr_tables && (rc = dmalloc(&h->d_thr_tables, (size_t)2 * kThrTable))) return rc;
-    tb.mmin = h->d_thr_tables; tb.omax = h->d_thr_tables + kThrTable;
-    k_thr_tables<<<(kThrTable + 127) / 128, 128, 0, h->stream>>>(thr, h->d_thr_tables, h->d_thr_tables + kThrTable);
-  }
+  int rc;
+  if (FUSED && (rc = thr_tables(h, thr, &tb))) return rc;
   const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
   kern<<<grid, kCplThreads, cp.smem, h->stream>>>(csr_of(h), wt, thr, tb, pass_in, pass_out, cp.rpt, cp.tc, out);
   CU(cudaGetLastError());
@@ -754,7 +761,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
       if (rc) return rc;
-      launches += (cpl.ok && fused) ? 2 : 1;  // the chunk-per-lane kernel is preceded by its threshold-table kernel
+      launches += ((cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
       CU(cudaEventRecord(h->ev[2], h->stream));
       k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};

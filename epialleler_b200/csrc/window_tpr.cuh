@@ -1,31 +1,30 @@
-// Short-read window kernel: one THREAD per read over TMA-staged tiles.
+// Short-read window kernel, "thread per row over TMA-staged tiles" formulation.
 //
-// Why a second formulation next to k_window (kernels.cuh): with ~150-byte reads the lane-group
-// kernel spends most of its issue slots on per-row overheads that are paid per warp instruction
-// (row metadata, cross-lane reductions, pass evaluation) and on a divergent event loop.  Here
-//   * each warp bulk-copies a tile of up to 32 consecutive padded rows (one contiguous, 16-byte
-//     aligned byte range of the CSR) into shared memory with ONE cp.async.bulk (TMA) completed on a
-//     warp-private mbarrier, then every lane walks its own row with LDS.128: no shuffles, row
-//     metadata loads are coalesced over 32 rows, the IEEE-double pass chain runs for 32 rows at once;
-//   * ONE sweep over the row does everything that does not depend on the pass flag: class counts for
-//     the thresholds, {total calls} of the requested contexts and coverage deltas (row start/end,
-//     '-' runs) as shared-memory atomics.  By SURVEY.md 8a invariant 4 only the methylated count
-//     depends on `pass`, so after the flag is known the few passing rows (~10%) get a
-//     warp-cooperative fix-up: the 32 lanes take one chunk each of such a row and add its
-//     methylated calls;
-//   * the finalize touches shared memory only: vectorised prefix sum of the coverage deltas, row
-//     detection (total_ctx > floor(cov/2), src/rcpp_cx_report.cpp:62-72), ordered compaction.
-// Preconditions (checked by the host dispatcher): every padded row fits a tile, at most 32767 rows
-// overlap a window (16-bit packed counters).
+// One CTA per genomic window of S positions.  Each warp bulk-copies a tile of up to 32 consecutive padded
+// rows (one contiguous, 16-byte aligned byte range of the CSR) into shared memory with ONE cp.async.bulk
+// (TMA) completed on a warp-private mbarrier, then every lane walks ITS OWN row with LDS.128 in a single
+// sweep:
+//   * class counts for the thresholds stay in registers (no cross-lane reduction, no staging of counts);
+//   * everything that does not depend on the pass flag - {total calls} of the requested contexts, '-'
+//     bytes, row start/end coverage deltas - goes to the shared-memory window state as reductions
+//     (win_common.cuh);
+//   * chunks that hold methylated calls of a requested context are remembered in a per-row bit mask and
+//     their call masks overwrite the chunk in place; once the row's flag is known (the reference's
+//     pass/fail chain, src/rcpp_threshold_reads.cpp:39-70, through the exact integer tables of
+//     k_thr_tables), a passing row revisits just those chunks and adds its methylated calls
+//     (SURVEY.md 8a invariant 4: only the methylated count depends on `pass`).
+// Row metadata loads are coalesced over 32 rows, the pass chain runs for 32 rows per instruction.
+// Rows of very different lengths leave lanes idle at the end of a tile; the dispatcher prefers the
+// chunk-per-lane kernel (window_cpl.cuh) for such data.
+// Preconditions (checked by the dispatcher): padded rows <= 512 bytes and <= tile_bytes, at most 32767
+// rows overlap a window.
 #pragma once
-#include "kernels.cuh"
+#include "win_common.cuh"
 
 namespace ea {
 
 constexpr int kTprThreads = 256;
 constexpr int kTprWarps = kTprThreads / 32;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -52,166 +51,35 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
-template <int NWARPS>
-__device__ __forceinline__ int block_exscan_n(int v, int* total, int* s_warp /* NWARPS+1 ints */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-    if (lane >= d) inc += o;
-  }
-  __syncthreads();
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    const int x = lane < NWARPS ? s_warp[lane] : 0;
-    int xi = x;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xFFFFFFFFu, xi, d);
-      if (lane >= d) xi += o;
-    }
-    if (lane < NWARPS) s_warp[lane] = xi - x;
-    if (lane == NWARPS - 1) s_warp[NWARPS] = xi;
-  }
-  __syncthreads();
-  *total = s_warp[NWARPS];
-  return s_warp[warp] + inc - v;
-}
-
-
-// position (byte index within the chunk) of merged-indicator bit i
-__device__ __forceinline__ int bit_pos(int i) { return ((i & 1) << 3) + (i & 4) + (i >> 3); }
-
-// One shared-memory atomic per set bit of m: t[q] += 1 (+ 0x10000 when the bit is also in `meth`).
-// The first bit is straight-line code (almost every warp step has some lane with an event), the rest loop.
-__device__ __forceinline__ void push_mask(uint32_t m, uint32_t meth, uint32_t* __restrict__ t, int rel, int S) {
-  if (m) {
-    uint32_t bit = m & (0u - m);
-    int q = rel + bit_pos(__ffs(m) - 1);
-    if ((unsigned)q < (unsigned)S) atomicAdd(&t[q], (meth & bit) ? 0x10001u : 1u);
-    m ^= bit;
-    while (m) {
-      bit = m & (0u - m);
-      q = rel + bit_pos(__ffs(m) - 1);
-      if ((unsigned)q < (unsigned)S) atomicAdd(&t[q], (meth & bit) ? 0x10001u : 1u);
-      m ^= bit;
-    }
-  }
-}
-
-// Coverage events of one chunk (independent of the pass flag).  cv = coverage words of the row's strand.
-// A coverage word packs two 16-bit fields that are decoded at the end: low = running-coverage DELTA
-// (+1 row start, -1 true row end, -1/+1 around long '-' runs; two's-complement arithmetic keeps the
-// packed sum exact), high = number of isolated '-' bytes at the position.
-// cov(p) = prefix_sum(low)(p) - high(p).
-__device__ __forceinline__ void push_cov(const Planes& p, int32_t* __restrict__ cv, int S, int rel, bool first_in_win, bool is_last) {
-  const uint32_t E = (p.A0 & p.B0 & ~p.C0 & p.D0) | (p.A1 & p.B1 & ~p.C1 & p.D1);  // code 11 bytes
-  if (first_in_win) atomicAdd(&cv[max(rel, 0)], 1);
-  if (E) {
-    if (__popc(E) <= 2) {  // isolated '-' bytes: one count each
-      uint32_t m = E;
-      int q = rel + bit_pos(__ffs(m) - 1);
-      if ((unsigned)q < (unsigned)S) atomicAdd(&cv[q], 0x10000);
-      m &= m - 1u;
-      if (m) {
-        q = rel + bit_pos(__ffs(m) - 1);
-        if ((unsigned)q < (unsigned)S) atomicAdd(&cv[q], 0x10000);
-      }
-    } else {               // runs (mate gaps): -1 where a run starts, +1 right after it ends
-      const uint32_t prev = (E << 8) | ((E >> 20) & 0x30u) | ((E >> 27) & 0x2u);  // "byte before me is 11"
-      const uint32_t starts = E & ~prev;
-      for (uint32_t m = starts | (prev & ~E); m;) {
-        const uint32_t bit = m & (0u - m);
-        const int q = rel + bit_pos(__ffs(m) - 1);
-        m ^= bit;
-        if (q < S) atomicAdd(&cv[max(q, 0)], (starts & bit) ? -1 : 1);
-      }
-      if (((E >> 29) & 1u) && rel + 16 < S) atomicAdd(&cv[max(rel + 16, 0)], 1);  // run reaches the chunk end
-    }
-  }
-  if (is_last) {
-    const int qe = rel + 16 - pad_count(p);
-    if (qe < S) atomicAdd(&cv[max(qe, 0)], -1);
-  }
-}
-
-// requested-context call masks of a chunk, one per context slot (order CHH, CHG, CG among the requested),
-// plus the methylated ones; merged indicator layout
-template <int WANT>
-__device__ __forceinline__ uint4 call_masks(const Planes& p) {
-  uint32_t m[3] = {0u, 0u, 0u};
-  int slot = 0;
-  uint32_t meth = 0;
-  if (WANT & W_CHH) { const uint32_t a = cls_chh(p.A0, p.B0, p.C0), b = cls_chh(p.A1, p.B1, p.C1); m[slot++] = a | b; meth |= (a & ~p.D0) | (b & ~p.D1); }
-  if (WANT & W_CHG) { const uint32_t a = cls_chg(p.A0, p.B0, p.C0), b = cls_chg(p.A1, p.B1, p.C1); m[slot++] = a | b; meth |= (a & ~p.D0) | (b & ~p.D1); }
-  if (WANT & W_CG) { const uint32_t a = cls_cg(p.A0, p.B0, p.C0), b = cls_cg(p.A1, p.B1, p.C1); m[slot++] = a | b; meth |= (a & ~p.D0) | (b & ~p.D1); }
-  return make_uint4(m[0], m[1], m[2], meth);
-}
-
-template <int WANT>
-__device__ __forceinline__ void push_calls(const uint4& cm, uint32_t meth_if_pass, uint32_t* __restrict__ tms, int S, int rel) {
-  constexpr int NC = n_ctx<WANT>();
-  push_mask(cm.x, meth_if_pass, tms, rel, S);
-  if (NC > 1) push_mask(cm.y, meth_if_pass, tms + 2 * S, rel, S);
-  if (NC > 2) push_mask(cm.z, meth_if_pass, tms + 4 * S, rel, S);
-}
-
-template <int NWARPS>
-__device__ __forceinline__ long long block_exscan64_n(long long v, long long* total, long long* s_warp /* NWARPS+1 */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  long long inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-    if (lane >= d) inc += o;
-  }
-  __syncthreads();
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    const long long x = lane < NWARPS ? s_warp[lane] : 0;
-    long long xi = x;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const long long o = __shfl_up_sync(0xFFFFFFFFu, xi, d);
-      if (lane >= d) xi += o;
-    }
-    if (lane < NWARPS) s_warp[lane] = xi - x;
-    if (lane == NWARPS - 1) s_warp[NWARPS] = xi;
-  }
-  __syncthreads();
-  *total = s_warp[NWARPS];
-  return s_warp[warp] + inc - v;
-}
-
 template <int TCTX, int WANT, bool FUSED, int S>
 __global__ void __launch_bounds__(kTprThreads, 3)
-k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pass_in, uint8_t* __restrict__ pass_out,
+k_window_tpr(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* __restrict__ pass_in, uint8_t* __restrict__ pass_out,
              int tile_bytes, ReportOut out) {
   constexpr int NC = n_ctx<WANT>();
-  constexpr int Sp = S + 4;
-  constexpr int PER = S / kTprThreads;  // positions per thread in the finalize (8 or 16)
+  constexpr int SG = kGuardLo + S + kGuardHi;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[kTprWarps];
-  __shared__ long long s_scan64[kTprWarps + 1];
-  __shared__ int s_scan[kTprWarps + 1];
+  __shared__ uint32_t s_scan[kTprWarps + 1];
   __shared__ long long s_base;
   __shared__ int s_npass;
+  __shared__ __align__(4) uint8_t s_bp4[32];
 
-  uint32_t* tm = reinterpret_cast<uint32_t*>(smem_raw);                          // [NC][2][S]
-  int32_t* covd = reinterpret_cast<int32_t*>(smem_raw + sizeof(uint32_t) * NC * 2 * S);  // [2][Sp]
-  unsigned char* tiles = smem_raw + sizeof(uint32_t) * (NC * 2 * S + 2 * Sp);     // [kTprWarps][tile_bytes]
-  constexpr int kZero4 = (NC * 2 * S + 2 * Sp) / 4;
+  uint32_t* const W = reinterpret_cast<uint32_t*>(smem_raw);  // [SG]
+  uint32_t* const D = W + SG;                                 // [SG]
+  uint32_t* const T = D + SG;                                 // [NC][2][SG]
+  constexpr int kZero4 = (NC + 1) * 2 * SG / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* my_tile = tiles + (size_t)warp * tile_bytes;
-  uint64_t* my_bar = &s_bar[warp];
+  unsigned char* const my_tile = smem_raw + sizeof(uint32_t) * (NC + 1) * 2 * SG + (size_t)warp * tile_bytes;
+  uint64_t* const my_bar = &s_bar[warp];
+  const uint32_t w_base = smem_u32(W), d_base = smem_u32(D), t_base = smem_u32(T), bp_tbl = smem_u32(s_bp4);
+  const uint32_t w_floor = w_base + 4u * kGuardLo;
+  const uint32_t tile_addr = smem_u32(my_tile);
   uint32_t phase = 0;
 
+  if (threadIdx.x < 32) s_bp4[threadIdx.x] = (uint8_t)(4 * bit_pos(threadIdx.x));
   if (lane == 0) mbar_init(my_bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
 
   for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
     __syncthreads();
@@ -221,25 +89,30 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
 
     const int w0 = wt.pos0[win];
     const int lo = wt.lo[win], hi = wt.hi[win];
+    // the window's rows are split evenly over the warps, each warp's share into equal tiles of at most 32 rows
+    const int per_warp = (hi - lo + kTprWarps - 1) / kTprWarps;
+    const int my_lo = lo + warp * per_warp, my_hi = min(hi, my_lo + per_warp);
+    const int n_t = (per_warp + 31) >> 5;
+    const int per_tile = n_t ? (per_warp + n_t - 1) / n_t : 0;
+    int npass_w = 0;
 
-    // ---------------- rows: 32 per warp step, staged through shared memory by TMA ----------------
-    for (int base = lo + warp * 32; base < hi; base += kTprWarps * 32) {
+    for (int base = my_lo; base < my_hi; base += per_tile) {
+      const int tend = min(base + per_tile, my_hi);
       const int r = base + lane;
-      const bool valid = r < hi;
-      const int rc = valid ? r : hi;  // off[hi] exists (off has n+1 entries)
-      const long long o0 = csr.off[rc];
-      long long o1 = __shfl_down_sync(0xFFFFFFFFu, o0, 1);
-      if (lane == 31) o1 = valid ? csr.off[r + 1] : o0;
-      int start = 0, strand0 = 0;
-      if (valid) { start = csr.start[r]; strand0 = csr.strand[r] - 1; }
-      const int nvalid = min(32, hi - base);
+      const bool valid = r < tend;
+      const long long o0 = csr.off[valid ? r : tend];
+      long long o1 = __shfl_down_sync(FULL, o0, 1);
+      if (lane == 31) o1 = csr.off[tend];
+      int start = 0, spv = 0;
+      if (valid) { start = csr.start[r]; spv = csr.sp[r]; }
+      const int nvalid = tend - base;
       int first = 0;
       while (first < nvalid) {
-        // rows [first, first+k) of this step whose bytes fit one tile
-        const long long of = __shfl_sync(0xFFFFFFFFu, o0, first);
-        const uint32_t fit = __ballot_sync(0xFFFFFFFFu, valid && lane >= first && (o1 - of) <= (long long)tile_bytes) >> first;
-        const int k = (~fit == 0u) ? 32 : max(1, __ffs(~fit) - 1);  // leading run of fitting rows (>=1 by the dispatcher's precondition)
-        const long long oe = __shfl_sync(0xFFFFFFFFu, o1, first + k - 1);
+        // rows [first, first+k) of this step whose bytes fit one tile (normally all of them)
+        const long long of = __shfl_sync(FULL, o0, first);
+        const uint32_t fit = __ballot_sync(FULL, valid && lane >= first && (o1 - of) <= (long long)tile_bytes) >> first;
+        const int k = (~fit == 0u) ? 32 : max(1, __ffs(~fit) - 1);  // leading run of fitting rows (>= 1 by the dispatcher's precondition)
+        const long long oe = __shfl_sync(FULL, o1, first + k - 1);
         const uint32_t bytes = (uint32_t)(oe - of);
         if (bytes) {
           if (lane == 0) {
@@ -251,133 +124,81 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pa
         }
         const bool mine = valid && lane >= first && lane < first + k;
         const int nch = mine ? (int)((o1 - o0) >> 4) : 0;
-        const int row_off = (int)(o0 - of);
+        const int strand0 = spv & 1;
+        const int len = nch * 16 - (spv >> 4);
         const int rel0 = start - w0;
-        const bool overlaps = mine && rel0 + nch * 16 > 0;
-        const int c_first = rel0 >= 0 ? 0 : ((-rel0) >> 4);
-        const int c_end = rel0 + nch * 16 > S ? ((S - rel0 + 15) >> 4) : nch;
+        const bool overlaps = mine && len > 0 && rel0 + len > 0;  // rel0 < S by construction of hi
         if (overlaps) {
-          unsigned char* row = my_tile + row_off;
-          int32_t* cv = covd + strand0 * Sp;
-          uint32_t* tms = tm + strand0 * S;
-          if (FUSED) {
-            // sweep 1: class counts, coverage events; the call masks replace the chunk in place
-            uint32_t c0 = 0, c1 = 0;
-            for (int c = 0; c < nch; c++) {
-              Planes p;
-              make_planes(*reinterpret_cast<const uint4*>(row + c * 16), p);
-              count_chunk<TCTX>(p, c0, c1);
-              if (c >= c_first && c < c_end) {
-                push_cov(p, cv, S, rel0 + c * 16, c == c_first, c == nch - 1);
-                const uint4 cm = call_masks<WANT>(p);
-                if (NC == 1) *reinterpret_cast<uint2*>(row + c * 16) = make_uint2(cm.x, cm.w);
-                else *reinterpret_cast<uint4*>(row + c * 16) = cm;
+          const uint32_t sinc = strand0 ? 0x10000u : 1u;
+          red_shared(w_floor + 4u * (uint32_t)max(rel0, 0), sinc);
+          const int e = rel0 + len;
+          if (e < S) red_shared(w_floor + 4u * (uint32_t)e, 0u - sinc);
+          const uint32_t row_addr = tile_addr + (uint32_t)(o0 - of);
+          // byte addresses of the row's position 0 in W/D (strand independent) and in T[0][strand0]
+          const uint32_t rel4 = 4u * (uint32_t)(rel0 + kGuardLo);
+          const uint32_t wq = w_base + rel4, dq = d_base + rel4, tq = t_base + 4u * (uint32_t)(strand0 * SG) + rel4;
+          const bool pass_known = FUSED ? false : (pass_in == nullptr || pass_in[r] != 0);
+          uint32_t part = 0, acc_in = 0, acc_out = 0, mb = 0;
+          for (int c = 0; c < nch; c++) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(row_addr + 16u * c));
+            Planes p;
+            make_planes(v, p);
+            uint32_t m[3], meth[3];
+            want_masks<WANT>(p, m, meth);
+            const int rel = rel0 + 16 * c;
+            const bool inwin = (unsigned)(rel + 15) < (unsigned)(S + 15);  // -16 < rel < S
+            if (FUSED) {
+              part += count4<TCTX>(p);
+              if ((c & 7) == 7) {
+                acc_in += (part & 0xFFu) | ((part & 0xFF00u) << 8);
+                acc_out += ((part >> 16) & 0xFFu) | ((part >> 24) << 16);
+                part = 0;
               }
             }
-            const bool pass = eval_pass(c0 >> 16, c0 & 0xFFFFu, c1 >> 16, c1 & 0xFFFFu, thr);
+            if (inwin) {
+              chunk_events<NC, SG>(p, m, (!FUSED && pass_known) ? (meth[0] | meth[1] | meth[2]) : 0u, wq + 64u * c, dq + 64u * c, tq + 64u * c, sinc,
+                                   w_floor, bp_tbl);
+              if (FUSED && (meth[0] | meth[1] | meth[2])) {  // remember the chunk and leave its methylated-call masks in place
+                mb |= 1u << c;
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(row_addr + 16u * c), "r"(meth[0] | (meth[1] << 2)), "r"(meth[2]) : "memory");
+              }
+            }
+          }
+          if (FUSED) {
+            acc_in += (part & 0xFFu) | ((part & 0xFF00u) << 8);
+            acc_out += ((part >> 16) & 0xFFu) | ((part >> 24) << 16);
+            const bool pass = eval_pass_tables(acc_in >> 16, acc_in & 0xFFFFu, acc_out >> 16, acc_out & 0xFFFFu, thr, tbl);
             if (rel0 >= 0) {  // the window that holds the row's start owns its flag
               pass_out[r] = pass ? 1 : 0;
-              if (pass) atomicAdd(&s_npass, 1);
+              npass_w += pass;
             }
-            // sweep 2: the calls, now that the flag is known ({total, methylated-of-passing} in one atomic)
-            const uint32_t pm = pass ? 0xFFFFFFFFu : 0u;
-            for (int c = c_first; c < c_end; c++) {
-              uint4 cm;
-              if (NC == 1) { const uint2 v = *reinterpret_cast<const uint2*>(row + c * 16); cm = make_uint4(v.x, 0u, 0u, v.y); }
-              else cm = *reinterpret_cast<const uint4*>(row + c * 16);
-              push_calls<WANT>(cm, cm.w & pm, tms, S, rel0 + c * 16);
-            }
-          } else {
-            const bool pass = pass_in ? (pass_in[r] != 0) : true;
-            const uint32_t pm = pass ? 0xFFFFFFFFu : 0u;
-            for (int c = c_first; c < c_end; c++) {
-              Planes p;
-              make_planes(*reinterpret_cast<const uint4*>(row + c * 16), p);
-              push_cov(p, cv, S, rel0 + c * 16, c == c_first, c == nch - 1);
-              const uint4 cm = call_masks<WANT>(p);
-              push_calls<WANT>(cm, cm.w & pm, tms, S, rel0 + c * 16);
+            if (pass) {
+              while (mb) {
+                const int c = 31 - __clz(mb);
+                mb ^= 1u << c;
+                uint32_t m01, m2;
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(m01), "=r"(m2) : "r"(row_addr + 16u * c));
+                push_meth(m01 & 0x33333333u, tq + 64u * c, bp_tbl);
+                if (NC > 1) push_meth((m01 >> 2) & 0x33333333u, tq + 64u * c + 2 * SG * 4, bp_tbl);
+                if (NC > 2) push_meth(m2, tq + 64u * c + 4 * SG * 4, bp_tbl);
+              }
             }
           }
         }
-        // the rows were overwritten in place (generic proxy): order those writes before the next TMA into this tile
+        // rows were overwritten in place (generic proxy): order those writes before the next TMA into this tile
         if (FUSED) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         first += k;
       }
     }
+    if (FUSED) {
+      for (int d = 16; d >= 1; d >>= 1) npass_w += __shfl_down_sync(FULL, npass_w, d);
+      if (lane == 0 && npass_w) atomicAdd(&s_npass, npass_w);
+    }
     __syncthreads();
 
-    // ---------------- finalize: coverage prefix sum, row detection, ordered compaction ----------------
-    const int q0 = threadIdx.x * PER;
-    int cov[2][PER];
-    long long packed = 0;
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      int run = 0;
-#pragma unroll
-      for (int v4 = 0; v4 < PER / 4; v4++) {
-        const int4 d = *reinterpret_cast<const int4*>(&covd[s * Sp + q0 + v4 * 4]);
-        const int w[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int lo16 = (int)(short)w[j];            // coverage delta
-          run += lo16;
-          cov[s][v4 * 4 + j] = run - ((w[j] - lo16) >> 16);  // minus the '-' bytes at this position (prefix added later)
-        }
-      }
-      packed += (long long)(run + (1 << 20)) << (32 * s);  // biased so both halves stay non-negative
-    }
-    long long tot64;
-    const long long ex = block_exscan64_n<kTprWarps>(packed, &tot64, s_scan64);
-    const int bias = (int)threadIdx.x << 20;
-    const int pre0 = (int)(ex & 0xFFFFFFFFll) - bias, pre1 = (int)(ex >> 32) - bias;
-    uint32_t flags = 0;  // bit 2k+s: (q0+k, strand s) is a report row
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-      for (int c = 0; c < NC; c++)
-#pragma unroll
-        for (int v4 = 0; v4 < PER / 4; v4++) {
-          const uint4 v = *reinterpret_cast<const uint4*>(&tm[(c * 2 + s) * S + q0 + v4 * 4]);
-          if (v.x | v.y | v.z | v.w) {
-            const uint32_t t[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const uint32_t half = (uint32_t)(cov[s][v4 * 4 + j] + (s ? pre1 : pre0)) >> 1;
-              if ((t[j] & 0xFFFFu) > half) flags |= 1u << (2 * (v4 * 4 + j) + s);
-            }
-          }
-        }
-    int nrows_total;
-    const int my_off = block_exscan_n<kTprWarps>(__popc(flags), &nrows_total, s_scan);
-    if (threadIdx.x == 0) {
-      const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
-      s_base = (long long)bb;
-      out.w_base[win] = (long long)bb;
-      out.w_cnt[win] = nrows_total;
-      if (FUSED && s_npass) atomicAdd(out.n_pass, (unsigned long long)s_npass);
-    }
-    __syncthreads();
-    const long long wbase = s_base;
-    if (flags && wbase + nrows_total <= out.cap) {
-      long long dst = wbase + my_off;
-#pragma unroll
-      for (int k = 0; k < PER; k++)
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          if (!((flags >> (2 * k + s)) & 1u)) continue;
-          const uint32_t half = (uint32_t)(cov[s][k] + (s ? pre1 : pre0)) >> 1;
-          int code = 0; uint32_t val = 0; int slot = 0;
-#pragma unroll
-          for (int cc = 0; cc < 3; cc++) {
-            if (!((WANT >> cc) & 1)) continue;
-            const uint32_t v = tm[(slot * 2 + s) * S + q0 + k];
-            if ((v & 0xFFFFu) > half) { code = cc == 0 ? 2 : (cc == 1 ? 6 : 7); val = v; }
-            slot++;
-          }
-          out.scratch[dst++] = make_int4(w0 + q0 + k, (s + 1) | (code << 8), (int)(val >> 16), (int)((val & 0xFFFFu) - (val >> 16)));
-        }
-    }
+    window_finalize<WANT, S, kTprThreads, FUSED>(W, D, T, w0, win, out, s_scan, &s_base, &s_npass);
   }
 }
 

@@ -3,21 +3,23 @@
 import re, subprocess, sys
 rep = sys.argv[1]
 steps = float(sys.argv[2]) if len(sys.argv) > 2 else 3.35e6
-src = open("epialleler_b200/csrc/window_cpl.cuh").read().split("\n")
-def find(pat):
-    for i, l in enumerate(src, 1):
+FILES = {"window_cpl.cuh": None, "win_common.cuh": None, "window_tpr.cuh": None}
+for f in FILES: FILES[f] = open("epialleler_b200/csrc/" + f).read().split("\n")
+def find(f, pat):
+    for i, l in enumerate(FILES[f], 1):
         if pat in l: return i
     raise KeyError(pat)
-marks = sorted([(find("k_thr_tables(ThrParams"), "thr tables"), (find("bool eval_pass_tables"), "eval_pass"), (find("void red_shared"), "red/lds helpers"),
-         (find("uint32_t block_exscan_u32"), "block scan"), (find("uint32_t count4"), "count4"), (find("void want_masks"), "want_masks"),
-         (find("void chunk_events"), "events: E/runs"), (find("uint32_t ev = m[0]"), "events: loop"), (find("void push_meth"), "push_meth"),
-         (find("k_window_cpl(Csr"), "prologue/zero"), (find("for (int base = lo"), "row phase 1"), (find("const uint8_t* ptr = csr.data"), "chunk body"),
-         (find("if (FUSED) {\n".strip()) if False else find("rows: class counts -> pass flag"), "row phase 2"), (find("for (int d = 16; d >= 1; d >>= 1) npass_w"), "npass"),
-         (find("const int q0 = threadIdx.x * PER"), "finalize")])
+C, K = "win_common.cuh", "window_cpl.cuh"
+marks = {C: sorted([(find(C, "void k_thr_tables"), "thr tables"), (find(C, "bool eval_pass_tables"), "eval_pass"), (find(C, "void red_shared"), "red/lds helpers"),
+         (find(C, "uint32_t block_exscan_u32"), "block scan"), (find(C, "uint32_t count4"), "count4"), (find(C, "void want_masks"), "want_masks"),
+         (find(C, "void chunk_events"), "events: E/runs"), (find(C, "uint32_t ev = m[0]"), "events: loop"), (find(C, "void push_meth"), "push_meth"),
+         (find(C, "void window_finalize"), "finalize")]),
+         K: sorted([(find(K, "k_window_cpl(Csr"), "prologue/zero"), (find(K, "for (int base = my_lo"), "row phase 1"), (find(K, "const uint8_t* ptr = csr.data"), "chunk body"),
+         (find(K, "rows: class counts -> pass flag"), "row phase 2"), (find(K, "for (int d = 16; d >= 1; d >>= 1) npass_w"), "npass/finalize call")])}
 def phase(f, l):
-    if f == "window_cpl.cuh":
-        name = "?"
-        for ln, nm in marks:
+    if f in marks:
+        name = f
+        for ln, nm in marks[f]:
             if l >= ln: name = nm
         return name
     if f == "kernels.cuh":

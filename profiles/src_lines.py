@@ -11,8 +11,10 @@ for r in rows:
     if len(r) == 2: continue
     if r and r[0] == "Line No": hdr = r; ie = hdr.index("Instructions Executed"); sm = hdr.index("# Samples"); th = hdr.index("Thread Instructions Executed"); continue
     if hdr and r and r[0].isdigit():
-        n = int(r[ie] or 0)
-        if n: out.append((n, int(r[sm] or 0), int(r[th] or 0), fname, int(r[0]), r[1]))
+        def num(x):
+            return int(x) if x.strip().isdigit() else 0
+        n = num(r[ie])
+        if n: out.append((n, num(r[sm]), num(r[th]), fname, int(r[0]), r[1]))
 tot = sum(o[0] for o in out); tots = sum(o[1] for o in out)
 print("total warp-instructions %d, stall samples %d" % (tot, tots))
 for n, s, t, f, ln, src in sorted(out, key=lambda o: -o[0])[:top]:
