@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libepialleler_b200.so")
+LIB_PATH = os.environ.get("EA_LIB_PATH") or os.path.join(HERE, "lib", "libepialleler_b200.so")  # override: A/B builds only
 
 EA_SYNTH_MAX_CHR = 32
 

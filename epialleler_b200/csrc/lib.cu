@@ -75,6 +75,7 @@ struct ea_handle {
   int64_t nbytes = 0;   // sum of true lengths
   int64_t npadded = 0;  // bytes of the padded data array
   int32_t max_len = 0;
+  bool rows32 = false;  // every padded row is a multiple of 32 bytes (pairs of chunks can be handled as one unit)
   bool owns = true;
   int32_t* d_rname = nullptr;
   uint8_t* d_strand = nullptr;
@@ -127,7 +128,8 @@ int pick_device(int device) {
 // ---------------------------------------------------------------------------------------------
 // pack-time kernels
 // ---------------------------------------------------------------------------------------------
-enum { F_UNSORTED = 1, F_DOMAIN = 2, F_TEMPLID = 4, F_NEGSTART = 8, F_STRAND = 16, F_TOOLONG = 32 };
+enum { F_UNSORTED = 1, F_DOMAIN = 2, F_TEMPLID = 4, F_NEGSTART = 8, F_STRAND = 16, F_TOOLONG = 32,
+       F_ODDCHUNKS = 64 /* informational: some padded row is not a multiple of 32 bytes */ };
 
 __global__ void k_lens_from_templid(const int64_t* __restrict__ soff, const int32_t* __restrict__ templid, int64_t n,
                                     int64_t nstr, int32_t* __restrict__ len, int64_t* __restrict__ padded,
@@ -209,6 +211,7 @@ __global__ void k_row_keys(Csr csr, uint64_t* __restrict__ key, uint8_t* __restr
     const int32_t prn = csr.rname[r - 1], pst = csr.start[r - 1];
     if (prn > rn || (prn == rn && pst > st)) f |= F_UNSORTED;
   }
+  if (((l + 15) >> 4) & 1) f |= F_ODDCHUNKS;
   if (f) atomicOr(flags, f);
   key[r] = ((uint64_t)(uint32_t)rn << 32) | (uint32_t)(l > 0 ? st + l : 0);
   sp[r] = (uint8_t)((csr.strand[r] == 2 ? 1 : 0) | (((16 - (l & 15)) & 15) << 4));
@@ -350,7 +353,8 @@ int finish_handle(ea_handle* h) {
   CU(cudaStreamSynchronize(h->stream));
   cudaFree(d_flags); cudaFree(d_maxlen);
   CU(cudaGetLastError());
-  return flags_error(f);
+  h->rows32 = !(f & F_ODDCHUNKS);
+  return flags_error(f & ~(unsigned)F_ODDCHUNKS);
 }
 
 int build_index(ea_handle* h, int S, WinIndex** out) {
@@ -615,31 +619,38 @@ int launch_tpr(ea_handle* h, const WinIndex& ix, const TprPlan& tp, int want, in
 }
 
 // ---- chunk-per-lane kernel (reads up to 1 KB, moderate depth): window_cpl.cuh ----
-struct CplPlan { bool ok = false; int rpt = 0; int tc = 0; size_t smem = 0; };
+struct CplPlan { bool ok = false; int ub = 16; int rpt = 0; int tc = 0; size_t smem = 0; };
 
 CplPlan plan_cpl(const ea_handle* h, const WinIndex& ix, int nc, bool fused) {
   CplPlan t;
   if (h->n == 0 || ix.n == 0 || ix.S != 2048) return t;
   const int max_nch = (h->max_len + 15) >> 4;
   if (max_nch < 1 || max_nch > 64 || ix.max_rows > 32767) return t;  // long reads / very deep windows: lane-group kernel
-  const int avg_nch = (int)((h->npadded / 16 + h->n - 1) / h->n);
-  int tc = std::min(640, std::max(320, 32 * std::max(avg_nch, 1)));  // chunks per tile
-  tc = std::max(tc, max_nch);
+#ifdef EA_CPL_FORCE_UB16
+  t.ub = 16;
+#else
+  t.ub = h->rows32 ? 32 : 16;  // unit a lane handles: a pair of chunks when every padded row is a multiple of 32 bytes
+#endif
+  const int cpu = t.ub / 16;
+  const int max_nu = (max_nch + cpu - 1) / cpu;
+  const int avg_nu = (int)((h->npadded / t.ub + h->n - 1) / h->n);
+  int tc = std::min(640 / cpu, std::max(320 / cpu, 32 * std::max(avg_nu, 1)));  // units per tile
+  tc = std::max(tc, max_nu);
   tc = (tc + 31) & ~31;
-  t.rpt = std::min(32, tc / max_nch);
+  t.rpt = std::min(32, tc / max_nu);
   t.tc = tc;
-  const int mw = fused ? (nc == 3 ? 2 : 1) : 0;
+  const int mw = fused ? nc : 0;
   t.smem = sizeof(uint32_t) * ((size_t)(nc + 1) * 2 * (kGuardLo + 2048 + kGuardHi) + (size_t)kCplWarps * (1 + mw) * tc);
   t.ok = t.smem <= 200u * 1024u;
   return t;
 }
 
-template <int TCTX, int WANT, bool FUSED>
-int launch_cpl_t(ea_handle* h, const WinIndex& ix, const CplPlan& cp, const ThrParams& thr, const uint8_t* pass_in,
+template <int TCTX, int WANT, bool FUSED, int UB>
+int launch_cpl_u(ea_handle* h, const WinIndex& ix, const CplPlan& cp, const ThrParams& thr, const uint8_t* pass_in,
                  uint8_t* pass_out, const ReportOut& out) {
   constexpr int S = 2048;
   if (ix.S != S) return fail(EA_ERR_STATE, "window size mismatch");
-  auto kern = k_window_cpl<TCTX, WANT, FUSED, S>;
+  auto kern = k_window_cpl<TCTX, WANT, FUSED, S, UB>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem));
   WinTable wt;
   wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
@@ -650,6 +661,13 @@ int launch_cpl_t(ea_handle* h, const WinIndex& ix, const CplPlan& cp, const ThrP
   kern<<<grid, kCplThreads, cp.smem, h->stream>>>(csr_of(h), wt, thr, tb, pass_in, pass_out, cp.rpt, cp.tc, out);
   CU(cudaGetLastError());
   return EA_OK;
+}
+
+template <int TCTX, int WANT, bool FUSED>
+int launch_cpl_t(ea_handle* h, const WinIndex& ix, const CplPlan& cp, const ThrParams& thr, const uint8_t* pass_in,
+                 uint8_t* pass_out, const ReportOut& out) {
+  if (cp.ub == 32) return launch_cpl_u<TCTX, WANT, FUSED, 32>(h, ix, cp, thr, pass_in, pass_out, out);
+  return launch_cpl_u<TCTX, WANT, FUSED, 16>(h, ix, cp, thr, pass_in, pass_out, out);
 }
 
 template <int WANT>

@@ -14,14 +14,16 @@
 
 namespace ea {
 
-constexpr int kGuardLo = 16;
-constexpr int kGuardHi = 32;
+constexpr int kGuardLo = 32;   // a unit (up to 32 bytes) may start this far before the window
+constexpr int kGuardHi = 48;   // ... and end this far after it (+1 for the delta after a run)
 constexpr int kThrTable = 1025;   // class counts 0..1024 (rows are at most 1024 bytes in these kernels)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // position (byte index within the chunk) of merged-indicator bit i
 __device__ __forceinline__ int bit_pos(int i) { return ((i & 1) << 3) + (i & 4) + (i >> 3); }
+// same for a 32-byte unit: bits 4t, 4t+1 belong to the first chunk, 4t+2, 4t+3 (masks shifted left by 2) to the second
+__device__ __forceinline__ int bit_pos32(int i) { return ((i & 2) << 3) + bit_pos(i & ~2); }
 
 // Integer form of the two IEEE-double comparisons of the pass/fail chain (src/rcpp_threshold_reads.cpp:52-53,66-67).
 // For a fixed denominator the rounded quotient is monotone in the numerator, so each comparison is a threshold on the
@@ -119,15 +121,14 @@ __device__ __forceinline__ void want_masks(const Planes& p, uint32_t (&m)[3], ui
   if (WANT & W_CG) { const uint32_t a = cls_cg(p.A0, p.B0, p.C0), b = cls_cg(p.A1, p.B1, p.C1); m[slot] = a | b; meth[slot] = (a & ~p.D0) | (b & ~p.D1); slot++; }
 }
 
-// Shared-memory events of one in-window chunk.  All addresses are 32-bit shared-space BYTE addresses of the chunk's
-// byte 0: w_addr in W, d_addr in D, t_addr in T[0][strand]; sinc = 1 << 16*strand.  methpass = methylated calls to be
-// counted now (0 in the fused kernel); bp_tbl = table of 4*bit_pos(i).
-template <int NC, int SG>
-__device__ __forceinline__ void chunk_events(const Planes& p, const uint32_t (&m)[3], uint32_t methpass, uint32_t w_addr, uint32_t d_addr,
-                                             uint32_t t_addr, uint32_t sinc, uint32_t w_floor, uint32_t bp_tbl) {
+// '-' bytes (code 11) of one 16-byte chunk.  Isolated ones (at most two per chunk) are returned as a merged-layout mask
+// and counted in D by the caller; longer runs (mate gaps) become coverage deltas in W right here: -1 where a run starts,
+// +1 right after it ends, clamped to the window start.  w_addr = shared BYTE address of the chunk's byte 0 in W,
+// sinc = 1 << 16*strand, bp_tbl = table of 4*position of merged-indicator bit i.
+__device__ __forceinline__ uint32_t dash_events(const Planes& p, uint32_t w_addr, uint32_t sinc, uint32_t w_floor, uint32_t bp_tbl) {
   const uint32_t e0 = p.A0 & p.B0 & ~p.C0, e1 = p.A1 & p.B1 & ~p.C1;
-  uint32_t E = (e0 & p.D0) | (e1 & p.D1);  // code 11 bytes
-  if (__popc(E) > 2) {  // runs (mate gaps): -1 where a run starts, +1 right after it ends; clamped to the window start
+  uint32_t E = (e0 & p.D0) | (e1 & p.D1);
+  if (__popc(E) > 2) {
     const uint32_t prev = (E << 8) | ((E >> 20) & 0x30u) | ((E >> 27) & 0x2u);  // "byte before me is 11"
     const uint32_t starts = E & ~prev;
     for (uint32_t mm = starts | (prev & ~E); mm;) {
@@ -139,6 +140,15 @@ __device__ __forceinline__ void chunk_events(const Planes& p, const uint32_t (&m
     if ((E >> 29) & 1u) red_shared(max(w_addr + 64u, w_floor), sinc);  // the run reaches the chunk end
     E = 0u;
   }
+  return E;
+}
+
+// Shared-memory events of one in-window unit (one chunk, or two chunks with the second one's masks shifted left by 2):
+// m[k] = calls of requested context k, E = isolated '-' bytes, methpass = methylated calls to be counted now (0 in the
+// fused kernels).  d_addr / t_addr = shared BYTE addresses of the unit's byte 0 in D and in T[0][strand].
+template <int NC, int SG>
+__device__ __forceinline__ void unit_events(const uint32_t (&m)[3], uint32_t E, uint32_t methpass, uint32_t d_addr, uint32_t t_addr,
+                                            uint32_t sinc, uint32_t bp_tbl) {
   uint32_t ev = m[0] | m[1] | m[2] | E;
   while (ev) {
     const int i = 31 - __clz(ev);
@@ -152,6 +162,13 @@ __device__ __forceinline__ void chunk_events(const Planes& p, const uint32_t (&m
     if (E & bit) { a = d_addr; v = sinc; }
     red_shared(a + bp4, v);
   }
+}
+
+template <int NC, int SG>
+__device__ __forceinline__ void chunk_events(const Planes& p, const uint32_t (&m)[3], uint32_t methpass, uint32_t w_addr, uint32_t d_addr,
+                                             uint32_t t_addr, uint32_t sinc, uint32_t w_floor, uint32_t bp_tbl) {
+  const uint32_t E = dash_events(p, w_addr, sinc, w_floor, bp_tbl);
+  unit_events<NC, SG>(m, E, methpass, d_addr, t_addr, sinc, bp_tbl);
 }
 
 // methylated calls of a passing row's chunk (fused kernel, after the flag is known)

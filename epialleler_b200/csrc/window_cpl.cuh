@@ -19,6 +19,9 @@
 //           stored, and the few passing rows push their methylated calls (SURVEY.md 8a invariant 4:
 //           only the methylated count depends on `pass`).
 //
+// When every padded row is a multiple of 32 bytes (always true for 150 bp reads) the unit a lane handles is a PAIR
+// of chunks (UB = 32: one 256-bit load, the second chunk's indicator masks shifted left by 2 so that one event loop,
+// one count word and one descriptor serve 32 positions); otherwise UB = 16.
 // No lane ever walks a row serially over data bytes, every global load is coalesced, and the only
 // warp-divergent code is the event loop over the handful of calls in a chunk.
 // The finalize (coverage prefix sum, row test total_ctx > floor(cov/2), ordered compaction;
@@ -34,15 +37,40 @@ namespace ea {
 
 constexpr int kCplThreads = 256;
 constexpr int kCplWarps = kCplThreads / 32;
-constexpr int kCplBatch = 5;      // chunk loads in flight per lane
+// tuning knobs (overridable for A/B builds)
+#ifndef EA_CPL_MINB32
+#define EA_CPL_MINB32 5   // CTAs per SM the 32-byte-unit variant is compiled for (measured: 5 x 8 warps beats 4 and 3)
+#endif
+#ifndef EA_CPL_MINB16
+#define EA_CPL_MINB16 4
+#endif
+#ifndef EA_CPL_BATCH32
+#define EA_CPL_BATCH32 2
+#endif
+#ifndef EA_CPL_BATCH16
+#define EA_CPL_BATCH16 5
+#endif
+#ifndef EA_CPL_EVEN
+#define EA_CPL_EVEN 0     // 1: split a window's rows evenly over the warps (fewer barrier stalls, more partial tiles; measured slower)
+#endif
 
-template <int TCTX, int WANT, bool FUSED, int S>
-__global__ void __launch_bounds__(kCplThreads, 4)
+__device__ __forceinline__ void ldg_unit(const uint8_t* p, uint4& a) { a = ldg_chunk(p); }
+__device__ __forceinline__ void ldg_unit(const uint8_t* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+
+template <int TCTX, int WANT, bool FUSED, int S, int UB>
+__global__ void __launch_bounds__(kCplThreads, UB == 32 ? EA_CPL_MINB32 : EA_CPL_MINB16)
 k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* __restrict__ pass_in, uint8_t* __restrict__ pass_out,
              int rpt, int tc, ReportOut out) {
   constexpr int NC = n_ctx<WANT>();
   constexpr int SG = kGuardLo + S + kGuardHi;
-  constexpr int MW = FUSED ? (NC == 3 ? 2 : 1) : 0;  // mask words per chunk
+  constexpr int MW = FUSED ? NC : 0;              // mask words per unit
+  constexpr int USH = UB == 32 ? 5 : 4;           // log2(unit bytes)
+  constexpr int BATCH = UB == 32 ? EA_CPL_BATCH32 : EA_CPL_BATCH16;  // unit loads in flight per lane
+  constexpr int FLUSH = UB == 32 ? 4 : 8;         // units whose byte-wide class counts can be summed without overflow
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t s_scan[kCplWarps + 1];
@@ -55,13 +83,12 @@ k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   uint32_t* const T = D + SG;                                 // [NC][2][SG]
   constexpr int kZero4 = (NC + 1) * 2 * SG / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* const aux_d = T + NC * 2 * SG + warp * (1 + MW) * tc;  // descriptor, then count word
-  uint32_t* const aux_m = aux_d + tc;                              // methylated-call masks (slots 0,1)
-  uint32_t* const aux_m2 = aux_m + tc;                             // slot 2 (CX reports)
+  uint32_t* const aux_d = T + NC * 2 * SG + warp * (1 + MW) * tc;  // per unit: descriptor, then count word
+  uint32_t* const aux_m = aux_d + tc;                              // [MW][tc] methylated-call masks per requested context
   const uint32_t w_base = smem_u32(W), d_base = smem_u32(D), t_base = smem_u32(T), bp_tbl = smem_u32(s_bp4);
   const uint32_t w_floor = w_base + 4u * kGuardLo;
 
-  if (threadIdx.x < 32) s_bp4[threadIdx.x] = (uint8_t)(4 * bit_pos(threadIdx.x));
+  if (threadIdx.x < 32) s_bp4[threadIdx.x] = (uint8_t)(4 * bit_pos32(threadIdx.x));
 
   for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
     __syncthreads();
@@ -73,13 +100,18 @@ k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
     const int lo = wt.lo[win], hi = wt.hi[win];
     int npass_w = 0;
     // the window's rows are split evenly over the warps, each warp's share into equal tiles of at most rpt rows
+#if EA_CPL_EVEN
     const int per_warp = (hi - lo + kCplWarps - 1) / kCplWarps;
     const int my_lo = lo + warp * per_warp, my_hi = min(hi, my_lo + per_warp);
     const int n_t = (per_warp + rpt - 1) / rpt;
     const int per_tile = n_t ? (per_warp + n_t - 1) / n_t : 1;
+    const int tile_stride = per_tile;
+#else
+    const int my_lo = lo + warp * rpt, my_hi = hi, per_tile = rpt, tile_stride = kCplWarps * rpt;
+#endif
 
-    for (int base = my_lo; base < my_hi; base += per_tile) {
-      // ------------------------------ rows: metadata, coverage deltas, chunk descriptors ------------------------------
+    for (int base = my_lo; base < my_hi; base += tile_stride) {
+      // ------------------------------ rows: metadata, coverage deltas, unit descriptors ------------------------------
       const int tend = min(base + per_tile, my_hi);
       const int r = base + lane;
       const bool valid = r < tend;
@@ -87,19 +119,19 @@ k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
       long long o1 = __shfl_down_sync(FULL, o0, 1);
       if (lane == 31) o1 = csr.off[tend];
       const long long tile_o0 = __shfl_sync(FULL, o0, 0);
-      const int n_chunks = (int)((__shfl_sync(FULL, o1, 31) - tile_o0) >> 4);
+      const int n_units = (int)((__shfl_sync(FULL, o1, 31) - tile_o0) >> USH);
       int start = 0, spv = 0;
       if (valid) { start = csr.start[r]; spv = csr.sp[r]; }
-      const int nch = (int)((o1 - o0) >> 4);
-      const int cbeg = (int)((o0 - tile_o0) >> 4);
+      const int nu = (int)((o1 - o0) >> USH);        // units of this row
+      const int ubeg = (int)((o0 - tile_o0) >> USH);  // its first unit in the tile
       const int strand0 = spv & 1;
-      const int len = nch * 16 - (spv >> 4);
+      const int len = (int)(o1 - o0) - (spv >> 4);
       const int rel0 = start - w0;
       const bool overlaps = valid && len > 0 && rel0 + len > 0;  // rel0 < S by construction of hi
       {
-        // descriptor of chunk c: T-relative word index of its byte 0 (strand0*SG + rel + kGuardLo) when the chunk
+        // descriptor of unit c: T-relative word index of its byte 0 (strand0*SG + rel + kGuardLo) when the unit
         // overlaps the window, else 0; bit 31 = pass flag in the two-pass kernel
-        int rel16 = rel0 + kGuardLo;
+        int relg = rel0 + kGuardLo;
         uint32_t flag = 0u;
         if (overlaps) {
           const uint32_t sinc = strand0 ? 0x10000u : 1u;
@@ -108,44 +140,62 @@ k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
           if (e < S) red_shared(w_floor + 4u * (uint32_t)e, 0u - sinc);
           if (!FUSED && (pass_in == nullptr || pass_in[r] != 0)) flag = 0x80000000u;
         } else {
-          rel16 = -0x40000000;  // never in the window
+          relg = -0x40000000;  // never in the window
         }
-        uint32_t* dst = aux_d + cbeg;
+        uint32_t* dst = aux_d + ubeg;
         const uint32_t sbase = (uint32_t)(strand0 * SG) | flag;
-        for (int c = 0; c < nch; c++) {
-          dst[c] = ((unsigned)(rel16 - 1) < (unsigned)(S + 15)) ? sbase + (uint32_t)rel16 : 0u;
-          rel16 += 16;
+        for (int c = 0; c < nu; c++) {  // in the window: -UB < rel < S
+          dst[c] = ((unsigned)(relg - (kGuardLo - UB) - 1) < (unsigned)(S + UB - 1)) ? sbase + (uint32_t)relg : 0u;
+          relg += UB;
         }
       }
       __syncwarp();
 
-      // ------------------------------ chunks: classification, counts, pass-independent events ------------------------------
-      const uint8_t* ptr = csr.data + tile_o0 + (size_t)lane * 16;
-      for (int j0 = lane; j0 < n_chunks; j0 += 32 * kCplBatch, ptr += 512 * kCplBatch) {
-        uint4 v[kCplBatch];
+      // ------------------------------ units: classification, counts, pass-independent events ------------------------------
+      const uint8_t* ptr = csr.data + tile_o0 + (size_t)lane * UB;
+      for (int j0 = lane; j0 < n_units; j0 += 32 * BATCH, ptr += 32 * UB * BATCH) {
+        uint4 va[BATCH], vb[BATCH];
 #pragma unroll
-        for (int u = 0; u < kCplBatch; u++)
-          if (j0 + 32 * u < n_chunks) v[u] = ldg_chunk(ptr + 512 * u);
+        for (int u = 0; u < BATCH; u++)
+          if (j0 + 32 * u < n_units) {
+            if (UB == 32) ldg_unit(ptr + 32 * UB * u, va[u], vb[u]);
+            else ldg_unit(ptr + 32 * UB * u, va[u]);
+          }
 #pragma unroll
-        for (int u = 0; u < kCplBatch; u++) {
+        for (int u = 0; u < BATCH; u++) {
           const int j = j0 + 32 * u;
-          if (j >= n_chunks) break;
+          if (j >= n_units) break;
           const uint32_t d = aux_d[j];
-          Planes p;
-          make_planes(v[u], p);
-          uint32_t m[3], meth[3];
-          want_masks<WANT>(p, m, meth);
-          const uint32_t ix = d & 0x7FFFFFFFu;  // strand*SG + rel16, 0 = not in the window
+          const uint32_t ix = d & 0x7FFFFFFFu;  // strand*SG + rel + kGuardLo, 0 = not in the window
+          const uint32_t s = ix >= (uint32_t)SG ? 1u : 0u;
+          const uint32_t rel4 = 4u * (ix - s * (uint32_t)SG);
+          const uint32_t sinc = s ? 0x10000u : 1u;
+          uint32_t m[3], meth[3], E = 0u, cnt = 0u;
+          {
+            Planes p;
+            make_planes(va[u], p);
+            want_masks<WANT>(p, m, meth);
+            if (FUSED) cnt = count4<TCTX>(p);
+            if (ix) E = dash_events(p, w_base + rel4, sinc, w_floor, bp_tbl);
+          }
+          if (UB == 32) {
+            Planes p;
+            make_planes(vb[u], p);
+            uint32_t m2[3], meth2[3];
+            want_masks<WANT>(p, m2, meth2);
+            if (FUSED) cnt += count4<TCTX>(p);
+            if (ix) E |= dash_events(p, w_base + rel4 + 64u, sinc, w_floor, bp_tbl) << 2;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { m[k] |= m2[k] << 2; meth[k] |= meth2[k] << 2; }
+          }
           if (ix) {
-            const uint32_t s = ix >= (uint32_t)SG ? 1u : 0u;
-            const uint32_t rel4 = 4u * (ix - s * (uint32_t)SG);
             const uint32_t methpass = FUSED ? 0u : ((d >> 31) ? (meth[0] | meth[1] | meth[2]) : 0u);
-            chunk_events<NC, SG>(p, m, methpass, w_base + rel4, d_base + rel4, t_base + 4u * ix, s ? 0x10000u : 1u, w_floor, bp_tbl);
+            unit_events<NC, SG>(m, E, methpass, d_base + rel4, t_base + 4u * ix, sinc, bp_tbl);
           }
           if (FUSED) {
-            aux_d[j] = count4<TCTX>(p);
-            aux_m[j] = ix ? (meth[0] | (meth[1] << 2)) : 0u;
-            if (NC == 3) aux_m2[j] = ix ? meth[2] : 0u;
+            aux_d[j] = cnt;
+#pragma unroll
+            for (int k = 0; k < NC; k++) aux_m[k * tc + j] = ix ? meth[k] : 0u;
           }
         }
       }
@@ -156,10 +206,10 @@ k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
         bool pass = false;
         if (overlaps) {
           uint32_t acc_in = 0, acc_out = 0;
-          const uint32_t* src = aux_d + cbeg;
-          for (int c0 = 0; c0 < nch; c0 += 8) {  // byte fields hold up to 8 chunks (8 * 16 < 256)
+          const uint32_t* src = aux_d + ubeg;
+          for (int c0 = 0; c0 < nu; c0 += FLUSH) {  // byte-wide fields hold the counts of FLUSH units
             uint32_t part = 0;
-            const int c1 = min(c0 + 8, nch);
+            const int c1 = min(c0 + FLUSH, nu);
             for (int c = c0; c < c1; c++) part += src[c];
             acc_in += (part & 0xFFu) | ((part & 0xFF00u) << 8);
             acc_out += ((part >> 16) & 0xFFu) | ((part >> 24) << 16);
@@ -170,21 +220,17 @@ k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
             npass_w += pass;
           }
         }
-        // methylated calls of the passing rows, one row at a time with a lane per chunk
+        // methylated calls of the passing rows, one row at a time with a lane per unit
         const uint32_t ta = t_base + 4u * (uint32_t)(strand0 * SG + rel0 + kGuardLo);
         for (uint32_t pm = __ballot_sync(FULL, pass); pm; pm &= pm - 1u) {
           const int src_lane = __ffs(pm) - 1;
-          const int cb = __shfl_sync(FULL, cbeg, src_lane), n = __shfl_sync(FULL, nch, src_lane);
+          const int ub = __shfl_sync(FULL, ubeg, src_lane), n = __shfl_sync(FULL, nu, src_lane);
           const uint32_t ta_s = __shfl_sync(FULL, ta, src_lane);
           for (int c = lane; c < n; c += 32) {
-            const uint32_t mm = aux_m[cb + c];
-            if (mm) {
-              push_meth(mm & 0x33333333u, ta_s + 64u * c, bp_tbl);
-              if (NC > 1) push_meth((mm >> 2) & 0x33333333u, ta_s + 64u * c + 2 * SG * 4, bp_tbl);
-            }
-            if (NC > 2) {
-              const uint32_t m2 = aux_m2[cb + c];
-              if (m2) push_meth(m2, ta_s + 64u * c + 4 * SG * 4, bp_tbl);
+#pragma unroll
+            for (int k = 0; k < NC; k++) {
+              const uint32_t mm = aux_m[k * tc + ub + c];
+              if (mm) push_meth(mm, ta_s + 4u * UB * c + k * 2 * SG * 4, bp_tbl);
             }
           }
         }

@@ -77,7 +77,7 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   const uint32_t tile_addr = smem_u32(my_tile);
   uint32_t phase = 0;
 
-  if (threadIdx.x < 32) s_bp4[threadIdx.x] = (uint8_t)(4 * bit_pos(threadIdx.x));
+  if (threadIdx.x < 32) s_bp4[threadIdx.x] = (uint8_t)(4 * bit_pos32(threadIdx.x));
   if (lane == 0) mbar_init(my_bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
