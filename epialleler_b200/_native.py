@@ -51,6 +51,7 @@ SIGNATURES = {
     "ea_device_count": (C.c_int, []),
     "ea_set_poll": (None, [C.c_void_p]),
     "ea_set_kernel_policy": (C.c_int, [C.c_int]),
+    "ea_report_kernel": (C.c_char_p, [_H]),
     "ea_pack": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_void_p), _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
     "ea_pack_blob": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, _U8P, _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
     "ea_attach_device": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.POINTER(_H)]),

@@ -171,9 +171,15 @@ def rcpp_get_xm_beta(df, ctx_meth, ctx_unmeth):
     return out[:df.nrow]
 
 
+def _host_out(n, dtype):
+    """Result buffer for a device->host copy (plain pageable memory: page-locked result buffers were measured and
+    rejected - cudaHostAlloc of a few hundred MB costs more than the pageable copy it would speed up)."""
+    return np.empty(max(int(n), 1), dtype)
+
+
 def _fetch_report(df, nrow):
     L = N.lib()
-    cols = [np.zeros(max(nrow, 1), np.int32) for _ in range(6)]
+    cols = [_host_out(nrow, np.int32) for _ in range(6)]
     N.check(L.ea_cx_report_fetch(df.handle(), *[_p(c, C.c_int32) for c in cols]))
     names = ("rname", "strand", "pos", "context", "meth", "unmeth")
     rep = {k: c[:nrow] for k, c in zip(names, cols)}
@@ -227,14 +233,14 @@ def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshol
     L = N.lib()
     p = _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, report_context)
     nrow = C.c_int64(0)
-    pass_out = np.zeros(max(bam.nrow, 1), np.uint8) if return_pass else None
+    pass_out = _host_out(bam.nrow, np.uint8) if return_pass else None
     N.check(L.ea_cytosine_report(bam.handle(), C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow)))
     rep = _fetch_report(bam, nrow.value)
     if report_file is not None:
         _write_report(rep, report_file, gzip)
         return None
     if return_pass:
-        return pass_out[:bam.nrow].astype(bool), rep
+        return pass_out[:bam.nrow].view(np.bool_), rep  # the library writes 0/1 bytes
     return rep
 
 

@@ -7,6 +7,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <string>
 #include <thread>
 #include <vector>
@@ -46,6 +48,14 @@ int fail(int code, const char* fmt, ...) {
   do {                                                                           \
     if (g_poll && g_poll()) return fail(EA_ERR_INTERRUPT, "interrupted by caller"); \
   } while (0)
+
+// EA_TRACE=1: wall-clock stage marks on stderr (each mark synchronizes the device; diagnostics only)
+struct Trace {
+  bool on; double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit Trace(const char* what) : on(getenv("EA_TRACE") != nullptr), t0(0) { if (on) { cudaDeviceSynchronize(); t0 = now(); fprintf(stderr, "[ea] %s\n", what); } }
+  void mark(const char* stage) { if (on) { cudaDeviceSynchronize(); const double t = now(); fprintf(stderr, "[ea]   %-28s %8.2f ms\n", stage, t - t0); t0 = t; } }
+};
 
 template <class T>
 int dmalloc(T** p, size_t n) {
@@ -98,6 +108,7 @@ struct ea_handle {
   int64_t cap_rows = 0;
   int64_t n_rows = -1;
   int32_t report_n_launches = 0;
+  const char* report_kernel = "";  // which window kernel the last report ran
   void* d_flush = nullptr;
   int64_t flush_bytes = 0;
   int sm_count = 148;
@@ -731,6 +742,7 @@ struct ReportPlan {
 // pass_in_dev: device pass flags for the unthresholded/explicit-pass case (may be null = all TRUE).
 int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, ea_timing* tm) {
   int rc;
+  Trace tr("run_report");
   h->n_rows = -1;
   if (tm) memset(tm, 0, sizeof *tm);
   const int nc = ((rp.want >> 0) & 1) + ((rp.want >> 1) & 1) + ((rp.want >> 2) & 1);
@@ -753,7 +765,9 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       wide = ix->max_rows > 65535;
     }
   }
+  tr.mark("window index");
   if (h->cap_rows == 0 && (rc = ensure_rows(h, h->nbytes / 24 + 4096))) return rc;
+  tr.mark("row buffers");
 
   for (int attempt = 0; attempt < 2; attempt++) {
     int launches = 0;
@@ -775,6 +789,8 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
+      h->report_kernel = cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
+                                : tpr.ok ? "k_window_tpr (thread-per-row over TMA tiles)" : "k_window (lane-group)";
       if (cpl.ok) rc = launch_cpl(h, *ix, cpl, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
@@ -801,6 +817,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       continue;
     }
     h->n_rows = (int64_t)counters[0];
+    tr.mark("kernels");
     if (tm) {
       CU(cudaEventElapsedTime(&tm->total_ms, h->ev[0], h->ev[3]));
       CU(cudaEventElapsedTime(&tm->kernel_ms[0], h->ev[0], h->ev[1]));
@@ -949,6 +966,7 @@ int ea_set_kernel_policy(int policy) { const int old = g_kernel_policy; g_kernel
 void ea_free(ea_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  Trace tr("ea_free");
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->owns) {
     cudaFree(h->d_rname); cudaFree(h->d_strand); cudaFree(h->d_start); cudaFree(h->d_off); cudaFree(h->d_data);
@@ -962,6 +980,7 @@ void ea_free(ea_handle* h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  tr.mark("cudaFree");
 }
 
 int64_t ea_nrow(const ea_handle* h) { return h ? h->n : -1; }
@@ -979,6 +998,7 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
   if ((rc = pick_device(device))) return rc;
   const int64_t total = nstr > 0 ? off[nstr] : 0;
   if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
+  Trace tr("ea_pack_blob");
   ea_handle* h = new ea_handle;
   h->device = device; h->n = nrow;
   int32_t *d_strand32 = nullptr, *d_templid = nullptr; int64_t* d_soff = nullptr; uint8_t* d_blob = nullptr;
@@ -994,11 +1014,9 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
   TRY(dmalloc(&d_blob, (size_t)total + 16));
   TRY(dmalloc(&d_flags, 1));
   TRYCU(cudaMemset(d_flags, 0, 4));
-  bool identity = templid == nullptr;
-  if (templid && nrow == nstr) {
-    identity = true;
-    for (int64_t i = 0; i < nrow; i++) if (templid[i] != i) { identity = false; break; }
-  }
+  tr.mark("cudaMalloc staging");
+  // templid is resolved on the device (k_lens_from_templid / k_repack); no host pass over it
+  const bool identity = templid == nullptr;
   if (nrow > 0) {
     TRYCU(cudaMemcpy(h->d_rname, rname, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(h->d_start, start, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
@@ -1011,15 +1029,21 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
   }
   if (nstr > 0) TRYCU(cudaMemcpy(d_soff, off, 8 * (size_t)(nstr + 1), cudaMemcpyHostToDevice));
   else TRYCU(cudaMemset(d_soff, 0, 8));
+  tr.mark("H2D metadata");
   if (total > 0) TRYCU(cudaMemcpy(d_blob, blob, (size_t)total, cudaMemcpyHostToDevice));
+  tr.mark("H2D blob");
   unsigned f = 0;
   TRYCU(cudaMemcpy(&f, d_flags, 4, cudaMemcpyDeviceToHost));
   if (f) { cleanup(); ea_free(h); return flags_error(f); }
   TRY(pack_from_device_blob(h, d_blob, d_soff, nstr, identity ? nullptr : d_templid));
+  tr.mark("device repack");
   cleanup();
+  tr.mark("free staging");
 #undef TRY
 #undef TRYCU
-  return adopt_and_finish(h, out);
+  rc = adopt_and_finish(h, out);
+  tr.mark("validate + row keys");
+  return rc;
 }
 
 int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
@@ -1135,11 +1159,13 @@ int ea_cx_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* p
   if (!h) return fail(EA_ERR_ARG, "null handle");
   if (h->n_rows < 0) return fail(EA_ERR_STATE, "no report has been computed on this handle");
   CU(cudaSetDevice(h->device));
+  Trace tr("ea_cx_report_fetch");
   int32_t* dst[6] = {rname, strand, pos, context, meth, unmeth};
   if (h->n_rows > 0)
     for (int c = 0; c < 6; c++)
       if (dst[c]) CU(cudaMemcpyAsync(dst[c], h->d_cols[c], 4 * (size_t)h->n_rows, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  tr.mark("D2H rows");
   return EA_OK;
 }
 
@@ -1167,6 +1193,8 @@ int ea_cytosine_report_device(ea_handle* h, const ea_report_params* p, int mode,
   if ((rc = make_plan_from_params(p, mode, &rp))) return rc;
   return run_report(h, rp, nullptr, t);
 }
+
+const char* ea_report_kernel(const ea_handle* h) { return h ? h->report_kernel : ""; }
 
 const char* ea_stage_name(int i) {
   static const char* names[3] = {"threshold", "window", "scan+gather"};

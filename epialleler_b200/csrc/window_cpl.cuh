@@ -50,9 +50,6 @@ constexpr int kCplWarps = kCplThreads / 32;
 #ifndef EA_CPL_BATCH16
 #define EA_CPL_BATCH16 5
 #endif
-#ifndef EA_CPL_EVEN
-#define EA_CPL_EVEN 0     // 1: split a window's rows evenly over the warps (fewer barrier stalls, more partial tiles; measured slower)
-#endif
 
 __device__ __forceinline__ void ldg_unit(const uint8_t* p, uint4& a) { a = ldg_chunk(p); }
 __device__ __forceinline__ void ldg_unit(const uint8_t* p, uint4& a, uint4& b) {
@@ -100,19 +97,19 @@ k_window_cpl(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
     const int lo = wt.lo[win], hi = wt.hi[win];
     int npass_w = 0;
     // the window's rows are split evenly over the warps, each warp's share into equal tiles of at most rpt rows
-#if EA_CPL_EVEN
-    const int per_warp = (hi - lo + kCplWarps - 1) / kCplWarps;
-    const int my_lo = lo + warp * per_warp, my_hi = min(hi, my_lo + per_warp);
-    const int n_t = (per_warp + rpt - 1) / rpt;
-    const int per_tile = n_t ? (per_warp + n_t - 1) / n_t : 1;
-    const int tile_stride = per_tile;
-#else
-    const int my_lo = lo + warp * rpt, my_hi = hi, per_tile = rpt, tile_stride = kCplWarps * rpt;
-#endif
+    // Tiles: full rounds of kCplWarps tiles of rpt rows, then the remaining rows split evenly over the warps, so that
+    // all warps reach the finalize barrier together (n_full rounds + at most one shorter tile each).
+    const int n_rows = hi - lo;
+    const int n_full = n_rows / (kCplWarps * rpt);
+    const int rem_lo = lo + n_full * kCplWarps * rpt;
+    const int rem_tile = (hi - rem_lo + kCplWarps - 1) / kCplWarps;  // <= rpt
 
-    for (int base = my_lo; base < my_hi; base += tile_stride) {
+    for (int t = 0; t <= n_full; t++) {
+      int base, tend;
+      if (t < n_full) { base = lo + (t * kCplWarps + warp) * rpt; tend = base + rpt; }
+      else { base = rem_lo + warp * rem_tile; tend = min(base + rem_tile, hi); }
+      if (base >= tend) break;
       // ------------------------------ rows: metadata, coverage deltas, unit descriptors ------------------------------
-      const int tend = min(base + per_tile, my_hi);
       const int r = base + lane;
       const bool valid = r < tend;
       const long long o0 = csr.off[valid ? r : tend];

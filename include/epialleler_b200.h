@@ -61,8 +61,9 @@ int ea_version(void);
 const char* ea_last_error(void);
 int ea_device_count(void);
 void ea_set_poll(ea_poll_fn fn);
-/* Kernel choice for the report: 0 automatic (default), 1 always the general lane-group window kernel.
- * Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
+/* Kernel choice for the report: 0 automatic (default: the chunk-per-lane kernel for reads up to 1 KB, else the
+ * general lane-group kernel), 1 always the lane-group kernel, 2 prefer the thread-per-row TMA kernel (reads up to
+ * 512 bytes).  Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
 int ea_set_kernel_policy(int policy);
 
 /* ---- packer: host bam.data -> device-resident CSR (row order) ------------------------------ */
@@ -139,6 +140,8 @@ typedef struct ea_timing {
  * mode bit1: 0 automatic kernel choice, 1 force the general lane-group window kernel (A/B measurements). */
 int ea_cytosine_report_device(ea_handle* h, const ea_report_params* p, int mode, ea_timing* t);
 const char* ea_stage_name(int i);
+/* Name of the window kernel the last report on this handle ran (diagnostics / bench provenance). */
+const char* ea_report_kernel(const ea_handle* h);
 /* Write `bytes` bytes of scratch on the handle's device (L2 flush between timed iterations). */
 int ea_flush_l2(ea_handle* h, int64_t bytes);
 
