@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "window_tpr.cuh"
 #include "window_cpl.cuh"
+#include "window_row.cuh"
 #include "synth.h"
 
 namespace {
@@ -711,6 +712,76 @@ int launch_cpl(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int want, in
   }
 }
 
+// ---- row-per-lane kernel (one requested context, 32-byte-multiple rows of at most 256 bytes): window_row.cuh ----
+struct RowPlan { bool ok = false; int maxu = 0; size_t smem = 0; };
+
+#ifndef EA_ROW_S
+#define EA_ROW_S 2048
+#endif
+RowPlan plan_row(const ea_handle* h, const WinIndex& ix, int nc) {
+  RowPlan t;
+  if (h->n == 0 || ix.n == 0 || ix.S != EA_ROW_S || nc != 1 || !h->rows32 || ix.max_rows > 32767) return t;
+  const int max_nu = (h->max_len + 31) >> 5;
+  if (max_nu < 1 || max_nu > 8) return t;
+  t.maxu = max_nu <= 5 ? 5 : 8;
+  t.smem = sizeof(uint32_t) * (size_t)(nc + 1) * 2 * (kGuardLo + EA_ROW_S + kGuardHi);
+  t.ok = true;
+  return t;
+}
+
+template <int TCTX, int WANT, bool FUSED, int MAXU>
+int launch_row_u(ea_handle* h, const WinIndex& ix, const RowPlan& rp, const ThrParams& thr, const uint8_t* pass_in,
+                 uint8_t* pass_out, const ReportOut& out) {
+  constexpr int S = EA_ROW_S;
+  if (ix.S != S) return fail(EA_ERR_STATE, "window size mismatch");
+  auto kern = k_window_row<TCTX, WANT, FUSED, S, MAXU>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem));
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  ThrTables tb{nullptr, nullptr};
+  int rc;
+  if (FUSED && (rc = thr_tables(h, thr, &tb))) return rc;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
+  kern<<<grid, kRowThreads, rp.smem, h->stream>>>(csr_of(h), wt, thr, tb, pass_in, pass_out, out);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+template <int TCTX, int WANT, bool FUSED>
+int launch_row_t(ea_handle* h, const WinIndex& ix, const RowPlan& rp, const ThrParams& thr, const uint8_t* pass_in,
+                 uint8_t* pass_out, const ReportOut& out) {
+#ifndef EA_FAST_BUILD
+  if (rp.maxu == 8) return launch_row_u<TCTX, WANT, FUSED, 8>(h, ix, rp, thr, pass_in, pass_out, out);
+#endif
+  return launch_row_u<TCTX, WANT, FUSED, 5>(h, ix, rp, thr, pass_in, pass_out, out);
+}
+
+template <int WANT>
+int launch_row_w(ea_handle* h, const WinIndex& ix, const RowPlan& rp, int tctx_fused, const ThrParams& thr,
+                 const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (tctx_fused) {
+    case TC_CG: return launch_row_t<TC_CG, WANT, true>(h, ix, rp, thr, pass_in, pass_out, out);
+#ifndef EA_FAST_BUILD
+    case TC_CHG: return launch_row_t<TC_CHG, WANT, true>(h, ix, rp, thr, pass_in, pass_out, out);
+    case TC_CHH: return launch_row_t<TC_CHH, WANT, true>(h, ix, rp, thr, pass_in, pass_out, out);
+    case TC_CXG: return launch_row_t<TC_CXG, WANT, true>(h, ix, rp, thr, pass_in, pass_out, out);
+    case TC_CX: return launch_row_t<TC_CX, WANT, true>(h, ix, rp, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_row_t<TC_NONE, WANT, false>(h, ix, rp, thr, pass_in, pass_out, out);
+  }
+}
+
+int launch_row(ea_handle* h, const WinIndex& ix, const RowPlan& rp, int want, int tctx_fused, const ThrParams& thr,
+               const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (want) {
+#ifndef EA_FAST_BUILD
+    case 1: return launch_row_w<1>(h, ix, rp, tctx_fused, thr, pass_in, pass_out, out);
+    case 2: return launch_row_w<2>(h, ix, rp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_row_w<4>(h, ix, rp, tctx_fused, thr, pass_in, pass_out, out);
+  }
+}
+
 int ensure_pass(ea_handle* h) {
   if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
   return EA_OK;
@@ -749,8 +820,9 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   WinIndex* ix = nullptr;
   TprPlan tpr;
   CplPlan cpl;
-  // kernel policy: 0 automatic (chunk-per-lane kernel when the data allow it, else the lane-group kernel),
-  // 1 force the general lane-group kernel, 2 prefer the thread-per-row TMA kernel (A/B measurements)
+  RowPlan row;
+  // kernel policy: 0 automatic (row-per-lane kernel, else chunk-per-lane kernel, else the lane-group kernel),
+  // 1 force the general lane-group kernel, 2 prefer the thread-per-row TMA kernel, 3 prefer the chunk-per-lane kernel
   const int policy = rp.kernel == 1 ? 1 : g_kernel_policy;
   if (rp.want && (rc = build_index(h, 2048, &ix))) return rc;
   if (rp.threshold && (rc = ensure_pass(h))) return rc;
@@ -758,9 +830,19 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
   const bool fused = can_fuse && rp.mode == 0;
   if (rp.want) {
-    if (policy == 0) cpl = plan_cpl(h, *ix, nc, fused);
+    if (policy == 0) {
+      if (EA_ROW_S != 2048) {
+        WinIndex* ix2 = nullptr;
+        if ((rc = build_index(h, EA_ROW_S, &ix2))) return rc;
+        row = plan_row(h, *ix2, nc);
+        if (row.ok) ix = ix2;
+      } else {
+        row = plan_row(h, *ix, nc);
+      }
+    }
+    if ((policy == 0 && !row.ok) || policy == 3) cpl = plan_cpl(h, *ix, nc, fused);
     if (policy == 2) tpr = plan_tpr(h, *ix);
-    if (!cpl.ok && !tpr.ok && nc <= 1) {
+    if (!row.ok && !cpl.ok && !tpr.ok && nc <= 1) {
       if ((rc = build_index(h, 4096, &ix))) return rc;
       wide = ix->max_rows > 65535;
     }
@@ -789,13 +871,14 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      h->report_kernel = cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
+      h->report_kernel = row.ok ? "k_window_row (row per lane, 256-bit loads)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
                                 : tpr.ok ? "k_window_tpr (thread-per-row over TMA tiles)" : "k_window (lane-group)";
-      if (cpl.ok) rc = launch_cpl(h, *ix, cpl, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      if (row.ok) rc = launch_row(h, *ix, row, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      else if (cpl.ok) rc = launch_cpl(h, *ix, cpl, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
       if (rc) return rc;
-      launches += ((cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
+      launches += ((row.ok || cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
       CU(cudaEventRecord(h->ev[2], h->stream));
       k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
