@@ -56,6 +56,7 @@ SIGNATURES = {
     "ea_pack_blob": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, _U8P, _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
     "ea_attach_device": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.POINTER(_H)]),
     "ea_free": (None, [_H]),
+    "ea_trim": (C.c_int, [C.c_int]),
     "ea_nrow": (C.c_int64, [_H]),
     "ea_nbytes": (C.c_int64, [_H]),
     "ea_device": (C.c_int, [_H]),

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kThreads)
 k_window(Csr csr, WinTable wt, ThrParams thr, const uint8_t* __restrict__ pass_in, uint8_t* __restrict__ pass_out,
          int g, ReportOut out) {
   constexpr int NC = n_ctx<WANT>();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_scan[kWarps + 1];
   __shared__ long long s_base;
   __shared__ int s_npass;
@@ -518,7 +518,8 @@ k_threshold_generic(Csr csr, LetterWeights lw, ThrParams thr, uint8_t* __restric
 // ------------------------------------------------------------------------------------------------
 // Ordered output: windows are already in (rname,pos) order; w_dst = exclusive scan of w_cnt.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_windows(const int32_t* __restrict__ cnt, long long* __restrict__ dst, int n) {
+__global__ void __launch_bounds__(1024) k_scan_windows(const int32_t* __restrict__ cnt, long long* __restrict__ dst, int n,
+                                                       unsigned long long* total_out = nullptr) {
   __shared__ long long s_part[32];
   __shared__ long long s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -549,6 +550,7 @@ __global__ void __launch_bounds__(1024) k_scan_windows(const int32_t* __restrict
     if (threadIdx.x == 1023) s_carry = carry + s_part[warp] + inc;
     __syncthreads();
   }
+  if (total_out && threadIdx.x == 0) *total_out = (unsigned long long)s_carry;
 }
 
 struct ReportCols { int32_t *rname, *strand, *pos, *ctx, *meth, *unmeth; };
@@ -556,7 +558,7 @@ struct ReportCols { int32_t *rname, *strand, *pos, *ctx, *meth, *unmeth; };
 __global__ void __launch_bounds__(128)
 k_gather_rows(const int4* __restrict__ scratch, const long long* __restrict__ w_base, const long long* __restrict__ w_dst,
               const int32_t* __restrict__ w_cnt, const int32_t* __restrict__ w_rname, int n_win, long long cap,
-              ReportCols out) {
+              ReportCols out, int rname_shift = 0 /* entries per w_rname element, log2 (retire blocks of the streaming kernel) */) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int w = warp; w < n_win; w += n_warps) {
@@ -564,7 +566,7 @@ k_gather_rows(const int4* __restrict__ scratch, const long long* __restrict__ w_
     if (!cnt) continue;
     const long long src = w_base[w], dst = w_dst[w];
     if (src + cnt > cap || dst + cnt > cap) continue;  // capacity overflow: the host grows the buffers and reruns
-    const int rn = w_rname[w];
+    const int rn = w_rname[w >> rname_shift];
     for (int i = lane; i < cnt; i += 32) {
       const int4 v = scratch[src + i];
       out.rname[dst + i] = rn;

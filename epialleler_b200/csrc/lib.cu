@@ -58,10 +58,39 @@ struct Trace {
   void mark(const char* stage) { if (on) { cudaDeviceSynchronize(); const double t = now(); fprintf(stderr, "[ea]   %-28s %8.2f ms\n", stage, t - t0); t0 = t; } }
 };
 
+// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync) with an unlimited release threshold:
+// a handle packs and frees tens of GB per call, and plain cudaMalloc/cudaFree of such blocks costs tens to hundreds of
+// milliseconds (measured, EA_TRACE) while the pool hands the cached blocks back in microseconds.  ea_trim() returns the
+// cached memory to the driver.  Allocation and free are made synchronous here (the callers' work runs on other streams).
+cudaError_t pool_malloc(void** p, size_t bytes) {
+  static thread_local int configured_for = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (configured_for != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    configured_for = dev;
+  }
+  e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(cudaStreamPerThread);
+}
+template <class T>
+cudaError_t pool_malloc(T** p, size_t bytes) { return pool_malloc(reinterpret_cast<void**>(p), bytes); }
+void pool_free(void* p) {
+  if (!p) return;
+  cudaDeviceSynchronize();  // like cudaFree: nothing on any stream may still use the block
+  cudaFreeAsync(p, cudaStreamPerThread);
+}
+
 template <class T>
 int dmalloc(T** p, size_t n) {
   *p = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+  CU(pool_malloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
   return EA_OK;
 }
 
@@ -73,7 +102,7 @@ struct WinIndex {
   int32_t* w_cnt = nullptr;
   int32_t max_rows = 0;  // largest hi-lo
   void release() {
-    cudaFree(rname); cudaFree(pos0); cudaFree(lo); cudaFree(hi); cudaFree(w_base); cudaFree(w_dst); cudaFree(w_cnt);
+    pool_free(rname); pool_free(pos0); pool_free(lo); pool_free(hi); pool_free(w_base); pool_free(w_dst); pool_free(w_cnt);
     *this = WinIndex();
   }
 };
@@ -354,16 +383,16 @@ int finish_handle(ea_handle* h) {
     k_row_keys<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, h->d_sp, d_maxlen, d_flags);
     size_t tb = 0;
     CU(cub::DeviceScan::InclusiveScan(nullptr, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
-    void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+    void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
     CU(cub::DeviceScan::InclusiveScan(tmp, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(tmp);
+    pool_free(tmp);
   }
   unsigned f = 0;
   CU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(&h->max_len, d_maxlen, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  cudaFree(d_flags); cudaFree(d_maxlen);
+  pool_free(d_flags); pool_free(d_maxlen);
   CU(cudaGetLastError());
   h->rows32 = !(f & F_ODDCHUNKS);
   return flags_error(f & ~(unsigned)F_ODDCHUNKS);
@@ -384,13 +413,13 @@ int build_index(ea_handle* h, int S, WinIndex** out) {
   k_count_windows<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, S, d_cnt);
   size_t tb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt, d_woff, (int)h->n, h->stream));
-  void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+  void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
   CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_cnt, d_woff, (int)h->n, h->stream));
   int32_t last_off = 0, last_cnt = 0;
   CU(cudaMemcpyAsync(&last_off, d_woff + h->n - 1, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(&last_cnt, d_cnt + h->n - 1, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  cudaFree(tmp);
+  pool_free(tmp);
   ix->n = last_off + last_cnt;
   if ((rc = dmalloc(&ix->rname, (size_t)ix->n))) return rc;
   if ((rc = dmalloc(&ix->pos0, (size_t)ix->n))) return rc;
@@ -406,7 +435,7 @@ int build_index(ea_handle* h, int S, WinIndex** out) {
   }
   CU(cudaMemcpyAsync(&ix->max_rows, d_max, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  cudaFree(d_cnt); cudaFree(d_woff); cudaFree(d_max);
+  pool_free(d_cnt); pool_free(d_woff); pool_free(d_max);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -789,8 +818,8 @@ int ensure_pass(ea_handle* h) {
 
 int ensure_rows(ea_handle* h, int64_t cap) {
   if (cap <= h->cap_rows) return EA_OK;
-  cudaFree(h->d_scratch); h->d_scratch = nullptr;
-  for (auto& c : h->d_cols) { cudaFree(c); c = nullptr; }
+  pool_free(h->d_scratch); h->d_scratch = nullptr;
+  for (auto& c : h->d_cols) { pool_free(c); c = nullptr; }
   h->cap_rows = 0;
   int rc;
   if ((rc = dmalloc(&h->d_scratch, (size_t)cap))) return rc;
@@ -880,8 +909,8 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       if (rc) return rc;
       launches += ((row.ok || cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
       CU(cudaEventRecord(h->ev[2], h->stream));
-      k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
+      k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
       k_gather_rows<<<std::max(1, std::min(ix->n / 4 + 1, h->sm_count * 16)), 128, 0, h->stream>>>(
           h->d_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, h->cap_rows, cols);
       launches += 2;
@@ -890,7 +919,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       CU(cudaEventRecord(h->ev[2], h->stream));
     }
     CU(cudaEventRecord(h->ev[3], h->stream));
-    unsigned long long counters[2] = {0, 0};
+    unsigned long long counters[3] = {0, 0, 0};
     CU(cudaMemcpyAsync(counters, h->d_counters, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->report_n_launches = launches;
@@ -956,13 +985,13 @@ int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_
   }
   size_t tb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_padded, h->d_off, (int)(h->n + 1)));
-  void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+  void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
   CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_padded, h->d_off, (int)(h->n + 1)));
   unsigned f = 0;
   CU(cudaMemcpy(&f, d_flags, 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(&h->npadded, h->d_off + h->n, 8, cudaMemcpyDeviceToHost));
-  cudaFree(tmp);
-  if (f) { cudaFree(d_flags); cudaFree(d_padded); return flags_error(f); }
+  pool_free(tmp);
+  if (f) { pool_free(d_flags); pool_free(d_padded); return flags_error(f); }
   // true byte total
   {
     int64_t* d_l64; int64_t* d_sum;
@@ -971,15 +1000,15 @@ int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_
     if (h->n > 0) k_len_i64<<<grid_for(h->n, 256), 256>>>(h->d_len, h->n, d_l64);
     size_t tb2 = 0;
     CU(cub::DeviceReduce::Sum(nullptr, tb2, d_l64, d_sum, (int)h->n));
-    void* tmp2; CU(cudaMalloc(&tmp2, std::max<size_t>(tb2, 1)));
+    void* tmp2; CU(pool_malloc(&tmp2, std::max<size_t>(tb2, 1)));
     CU(cub::DeviceReduce::Sum(tmp2, tb2, d_l64, d_sum, (int)h->n));
     CU(cudaMemcpy(&h->nbytes, d_sum, 8, cudaMemcpyDeviceToHost));
-    cudaFree(tmp2); cudaFree(d_l64); cudaFree(d_sum);
+    pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
   }
   if ((rc = dmalloc(&h->d_data, (size_t)h->npadded + 16))) return rc;
   if (h->n > 0) k_repack<<<std::max(1, std::min(grid_for(h->n * 32, 256), h->sm_count * 32)), 256>>>(d_blob, d_soff, d_templid, h->n, h->d_off, h->d_len, h->d_data);
   CU(cudaDeviceSynchronize());
-  cudaFree(d_flags); cudaFree(d_padded);
+  pool_free(d_flags); pool_free(d_padded);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -1052,18 +1081,28 @@ void ea_free(ea_handle* h) {
   Trace tr("ea_free");
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->owns) {
-    cudaFree(h->d_rname); cudaFree(h->d_strand); cudaFree(h->d_start); cudaFree(h->d_off); cudaFree(h->d_data);
+    pool_free(h->d_rname); pool_free(h->d_strand); pool_free(h->d_start); pool_free(h->d_off); pool_free(h->d_data);
   }
-  cudaFree(h->d_len);
-  cudaFree(h->d_maxend);
-  cudaFree(h->d_sp);
+  pool_free(h->d_len);
+  pool_free(h->d_maxend);
+  pool_free(h->d_sp);
   h->idx[0].release(); h->idx[1].release();
-  cudaFree(h->d_pass); cudaFree(h->d_beta); cudaFree(h->d_counters); cudaFree(h->d_thr_tables); cudaFree(h->d_scratch); cudaFree(h->d_flush);
-  for (auto& c : h->d_cols) cudaFree(c);
+  pool_free(h->d_pass); pool_free(h->d_beta); pool_free(h->d_counters); pool_free(h->d_thr_tables); pool_free(h->d_scratch); pool_free(h->d_flush);
+  for (auto& c : h->d_cols) pool_free(c);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   tr.mark("cudaFree");
+}
+
+int ea_trim(int device) {
+  int rc;
+  if ((rc = pick_device(device))) return rc;
+  cudaMemPool_t pool;
+  CU(cudaDeviceSynchronize());
+  CU(cudaDeviceGetDefaultMemPool(&pool, device));
+  CU(cudaMemPoolTrimTo(pool, 0));
+  return EA_OK;
 }
 
 int64_t ea_nrow(const ea_handle* h) { return h ? h->n : -1; }
@@ -1086,7 +1125,7 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
   h->device = device; h->n = nrow;
   int32_t *d_strand32 = nullptr, *d_templid = nullptr; int64_t* d_soff = nullptr; uint8_t* d_blob = nullptr;
   unsigned* d_flags = nullptr;
-  auto cleanup = [&]() { cudaFree(d_strand32); cudaFree(d_templid); cudaFree(d_soff); cudaFree(d_blob); cudaFree(d_flags); };
+  auto cleanup = [&]() { pool_free(d_strand32); pool_free(d_templid); pool_free(d_soff); pool_free(d_blob); pool_free(d_flags); };
 #define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); ea_free(h); return rc; } } while (0)
 #define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   TRY(dmalloc(&h->d_rname, (size_t)nrow));
@@ -1181,9 +1220,9 @@ int ea_attach_device(int32_t* d_rname, uint8_t* d_strand, int32_t* d_start, uint
   int64_t zero = 0; int64_t* d_soff = d_off;
   if (nrow == 0) { if ((rc = dmalloc(&d_soff, 1))) { ea_free(h); return rc; } cudaMemcpy(d_soff, &zero, 8, cudaMemcpyHostToDevice); }
   rc = pack_from_device_blob(h, d_data, d_soff, nrow, nullptr);
-  if (nrow == 0) cudaFree(d_soff);
+  if (nrow == 0) pool_free(d_soff);
   if (rc != EA_OK) { ea_free(h); return rc; }
-  if (take_ownership) { cudaFree(d_rname); cudaFree(d_strand); cudaFree(d_start); cudaFree(d_data); cudaFree(d_off); }
+  if (take_ownership) { pool_free(d_rname); pool_free(d_strand); pool_free(d_start); pool_free(d_data); pool_free(d_off); }
   return adopt_and_finish(h, out);
 }
 
@@ -1288,8 +1327,8 @@ int ea_flush_l2(ea_handle* h, int64_t bytes) {
   if (!h || bytes <= 0) return fail(EA_ERR_ARG, "bad argument");
   CU(cudaSetDevice(h->device));
   if (h->flush_bytes < bytes) {
-    cudaFree(h->d_flush); h->d_flush = nullptr; h->flush_bytes = 0;
-    CU(cudaMalloc(&h->d_flush, (size_t)bytes));
+    pool_free(h->d_flush); h->d_flush = nullptr; h->flush_bytes = 0;
+    CU(pool_malloc(&h->d_flush, (size_t)bytes));
     h->flush_bytes = bytes;
   }
   CU(cudaMemsetAsync(h->d_flush, 0x5A, (size_t)bytes, h->stream));
@@ -1309,35 +1348,35 @@ int ea_synth_device(const ea_synth_cfg* cfg, int64_t row_begin, int64_t row_end,
   h->device = device; h->n = row_end - row_begin;
   const int64_t n = h->n;
   int64_t* d_padded = nullptr;
-#define TRY(x) do { rc = (x); if (rc != EA_OK) { cudaFree(d_padded); ea_free(h); return rc; } } while (0)
-#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaFree(d_padded); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+#define TRY(x) do { rc = (x); if (rc != EA_OK) { pool_free(d_padded); ea_free(h); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { pool_free(d_padded); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   TRY(dmalloc(&h->d_rname, (size_t)n)); TRY(dmalloc(&h->d_start, (size_t)n)); TRY(dmalloc(&h->d_strand, (size_t)n));
   TRY(dmalloc(&h->d_len, (size_t)n)); TRY(dmalloc(&h->d_off, (size_t)n + 1)); TRY(dmalloc(&d_padded, (size_t)n + 1));
   TRYCU(cudaMemset(d_padded, 0, 8 * (size_t)(n + 1)));
   if (n > 0) k_synth_rows<<<grid_for(n, 256), 256>>>(plan, row_begin, n, h->d_rname, h->d_strand, h->d_start, h->d_len, d_padded);
   size_t tb = 0;
   TRYCU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_padded, h->d_off, (int)(n + 1)));
-  void* tmp; TRYCU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+  void* tmp; TRYCU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
   TRYCU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_padded, h->d_off, (int)(n + 1)));
   TRYCU(cudaMemcpy(&h->npadded, h->d_off + n, 8, cudaMemcpyDeviceToHost));
-  cudaFree(tmp);
+  pool_free(tmp);
   {
     int64_t* d_l64; int64_t* d_sum;
     TRY(dmalloc(&d_l64, (size_t)n)); TRY(dmalloc(&d_sum, 1));
     if (n > 0) k_len_i64<<<grid_for(n, 256), 256>>>(h->d_len, n, d_l64);
     size_t tb2 = 0;
     TRYCU(cub::DeviceReduce::Sum(nullptr, tb2, d_l64, d_sum, (int)n));
-    void* tmp2; TRYCU(cudaMalloc(&tmp2, std::max<size_t>(tb2, 1)));
+    void* tmp2; TRYCU(pool_malloc(&tmp2, std::max<size_t>(tb2, 1)));
     TRYCU(cub::DeviceReduce::Sum(tmp2, tb2, d_l64, d_sum, (int)n));
     TRYCU(cudaMemcpy(&h->nbytes, d_sum, 8, cudaMemcpyDeviceToHost));
-    cudaFree(tmp2); cudaFree(d_l64); cudaFree(d_sum);
+    pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
   }
   TRY(dmalloc(&h->d_data, (size_t)h->npadded + 16));
   const int64_t n_chunks = h->npadded / 16;
   const int uniform = plan.len_min == plan.len_max ? (plan.len_min + 15) / 16 : 0;
   if (n_chunks > 0) k_synth_bytes<<<grid_for(n_chunks, 256), 256>>>(plan, row_begin, n, h->d_off, h->d_data, uniform);
   TRYCU(cudaDeviceSynchronize());
-  cudaFree(d_padded); d_padded = nullptr;
+  pool_free(d_padded); d_padded = nullptr;
 #undef TRY
 #undef TRYCU
   return adopt_and_finish(h, out);
@@ -1393,7 +1432,7 @@ int ea_export_host(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* start
     k_len_i64<<<grid_for(n, 256), 256>>>(h->d_len, n, d_l64);
     size_t tb = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_l64, d_toff, (int)(n + 1)));
-    void* tmp; CU(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+    void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
     CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_l64, d_toff, (int)(n + 1)));
     if (off) CU(cudaMemcpy(off, d_toff, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost));
     if (blob && h->nbytes > 0) {
@@ -1401,9 +1440,9 @@ int ea_export_host(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* start
       if ((rc = dmalloc(&d_tight, (size_t)h->nbytes))) return rc;
       k_unpad<<<std::max(1, std::min(grid_for(n * 32, 256), h->sm_count * 32)), 256>>>(h->d_data, h->d_off, h->d_len, d_toff, n, d_tight);
       CU(cudaMemcpy(blob, d_tight, (size_t)h->nbytes, cudaMemcpyDeviceToHost));
-      cudaFree(d_tight);
+      pool_free(d_tight);
     }
-    cudaFree(tmp); cudaFree(d_l64); cudaFree(d_toff);
+    pool_free(tmp); pool_free(d_l64); pool_free(d_toff);
   }
   CU(cudaGetLastError());
   return EA_OK;

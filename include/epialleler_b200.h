@@ -61,9 +61,10 @@ int ea_version(void);
 const char* ea_last_error(void);
 int ea_device_count(void);
 void ea_set_poll(ea_poll_fn fn);
-/* Kernel choice for the report: 0 automatic (default: the chunk-per-lane kernel for reads up to 1 KB, else the
- * general lane-group kernel), 1 always the lane-group kernel, 2 prefer the thread-per-row TMA kernel (reads up to
- * 512 bytes).  Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
+/* Kernel choice for the report: 0 automatic (default: the row-per-lane kernel for one-context reports over rows of at
+ * most 256 bytes that are multiples of 32 bytes, else the chunk-per-lane kernel for reads up to 1 KB, else the general
+ * lane-group kernel), 1 always the lane-group kernel, 2 prefer the thread-per-row TMA kernel (reads up to 512 bytes),
+ * 3 prefer the chunk-per-lane kernel.  Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
 int ea_set_kernel_policy(int policy);
 
 /* ---- packer: host bam.data -> device-resident CSR (row order) ------------------------------ */
@@ -85,6 +86,9 @@ int ea_attach_device(int32_t* d_rname, uint8_t* d_strand, int32_t* d_start, uint
                      int64_t nrow, int device, int take_ownership, ea_handle** out);
 
 void ea_free(ea_handle* h);
+/* Device memory of freed handles stays cached in the device's stream-ordered pool (re-packing tens of GB per call
+ * would otherwise pay cudaMalloc/cudaFree each time); ea_trim returns the cached blocks to the driver. */
+int ea_trim(int device);
 
 int64_t ea_nrow(const ea_handle* h);
 int64_t ea_nbytes(const ea_handle* h); /* sum of string lengths */
