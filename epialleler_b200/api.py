@@ -244,6 +244,124 @@ def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshol
     return rep
 
 
+# ---- BED-assisted reports ------------------------------------------------
+NA_INT = -2147483648  # R's NA_integer_
+
+
+def _bed_cols(bed):
+    """bed: (seqnames, start, end[, ...]) - seqnames = factor codes on the BAM's rname levels (NA_INT = NA), as
+    R/internal.R:467-468 hands them to the matchers; start/end 1-based closed."""
+    c, s, e = (np.ascontiguousarray(a, dtype=np.int32) for a in bed[:3])
+    if not (c.shape[0] == s.shape[0] == e.shape[0]):
+        raise ValueError("BED columns must have the same length")
+    return c, s, e
+
+
+def _bedp(a):
+    return _p(a if a.shape[0] else np.zeros(1, np.int32), C.c_int32)
+
+
+def _match_target(df, mode, bed, param):
+    c, s, e = _bed_cols(bed)
+    out = np.empty(max(df.nrow, 1), np.int32)
+    N.check(N.lib().ea_match_target(df.handle(), mode, _bedp(c), _bedp(s), _bedp(e), c.shape[0], int(param), _p(out, C.c_int32)))
+    return out[:df.nrow]
+
+
+def rcpp_match_amplicon(df, bed, tolerance):
+    """src/rcpp_match_target.cpp:16-45 -> per read the 1-based BED row (first in file order) whose start is within
+    `tolerance` of the read's start or whose end is within `tolerance` of the read's end; NA_INT if none."""
+    return _match_target(df, 0, bed, tolerance)
+
+
+def rcpp_match_capture(df, bed, min_overlap):
+    """src/rcpp_match_target.cpp:51-81 -> first BED row overlapping the read by at least `min_overlap` bases."""
+    return _match_target(df, 1, bed, min_overlap)
+
+
+def _bed_table(counts, nbed):
+    """R/internal.R:537-556: nreads+ / nreads- / VEF per BED row (+ one NA row when reads are unmatched); rows no read
+    matched are NaN (NA after the all=TRUE merge).  counts[row] = {FALSE+, FALSE-, TRUE+, TRUE-}."""
+    cnt = counts.reshape(nbed + 1, 2, 2)
+    n_rows = nbed + (1 if cnt[nbed].sum() > 0 else 0)
+    cnt = cnt[:n_rows]
+    tot = cnt.sum(axis=(1, 2))
+    plus = (cnt[:, 0, 0] + cnt[:, 1, 0]).astype(np.float64)
+    minus = (cnt[:, 0, 1] + cnt[:, 1, 1]).astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        vef = (cnt[:, 1, 0] + cnt[:, 1, 1]) / tot.astype(np.float64)
+    empty = tot == 0
+    plus[empty] = np.nan
+    minus[empty] = np.nan
+    vef[empty] = np.nan
+    rows = np.concatenate([np.arange(1, nbed + 1), [NA_INT] if n_rows > nbed else []]).astype(np.int64)
+    return {"bedrow": rows, "nreads+": plus, "nreads-": minus, "VEF": vef, "counts": cnt}
+
+
+def generateBedReport(bam, bed, report_file=None, bed_type="amplicon", match_tolerance=1, match_min_overlap=1, threshold_reads=True,
+                      threshold_context="CG", min_context_sites=2, min_context_beta=0.5, max_outofcontext_beta=0.1,
+                      return_match=False, **kwargs):
+    """R/generateBedReport.R:219-273: match reads to BED targets, threshold them, count reads per (target, strand) and
+    the fraction of passing reads (VEF) - one device call (ea_bed_report)."""
+    bed_type = _match_arg(bed_type, ("amplicon", "capture"), "bed.type")
+    threshold_context = _match_arg(threshold_context, tuple(CONTEXT_TO_BASES), "threshold.context")
+    bam = preprocessBam(bam, **kwargs)
+    c, s, e = _bed_cols(bed)
+    nbed = int(c.shape[0])
+    p = _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, threshold_context)
+    counts = np.zeros((nbed + 1) * 4, np.int64)
+    match = np.empty(max(bam.nrow, 1), np.int32) if return_match else None
+    N.check(N.lib().ea_bed_report(bam.handle(), 0 if bed_type == "amplicon" else 1, _bedp(c), _bedp(s), _bedp(e), nbed,
+                                  int(match_tolerance if bed_type == "amplicon" else match_min_overlap), C.byref(p), None,
+                                  _p(match, C.c_int32) if return_match else None, None, _p(counts, C.c_int64)))
+    rep = _bed_table(counts, nbed)
+    if not threshold_reads:
+        rep["VEF"] = np.full(rep["VEF"].shape, np.nan)  # R/generateBedReport.R:264
+    if report_file is not None:
+        with open(report_file, "w") as fh:
+            fh.write("bedrow\tnreads+\tnreads-\tVEF\n")
+            for i in range(rep["VEF"].shape[0]):
+                fh.write("%s\t%s\t%s\t%s\n" % tuple("NA" if (isinstance(v, float) and np.isnan(v)) or v == NA_INT else ("%d" % v if k < 3 else repr(float(v)))
+                                                   for k, v in enumerate((int(rep["bedrow"][i]), rep["nreads+"][i], rep["nreads-"][i], rep["VEF"][i]))))
+        return None
+    return (match[:bam.nrow], rep) if return_match else rep
+
+
+def generateAmpliconReport(bam, bed, report_file=None, match_tolerance=1, **kw):
+    """R/generateBedReport.R:187-199."""
+    return generateBedReport(bam, bed, report_file, bed_type="amplicon", match_tolerance=match_tolerance, **kw)
+
+
+def generateCaptureReport(bam, bed, report_file=None, match_min_overlap=1, **kw):
+    """R/generateBedReport.R:203-215."""
+    return generateBedReport(bam, bed, report_file, bed_type="capture", match_min_overlap=match_min_overlap, **kw)
+
+
+def generateBedEcdf(bam, bed, bed_type="amplicon", bed_rows=(1,), match_tolerance=1, match_min_overlap=1, ecdf_context="CG", **kwargs):
+    """R/generateBedEcdf.R + R/internal.R:568-604: per requested BED row the empirical CDFs of the per-read in-context
+    and out-of-context betas (rcpp_get_xm_beta on the device).  bed_rows = None: every matched row (NA row last).
+    Returns {row: {"context": sorted betas, "out.of.context": sorted betas}}; ecdf(x) = searchsorted(v, x, 'right') / len(v)."""
+    bed_type = _match_arg(bed_type, ("amplicon", "capture"), "bed.type")
+    ecdf_context = _match_arg(ecdf_context, tuple(CONTEXT_TO_BASES), "ecdf.context")
+    bam = preprocessBam(bam, **kwargs)
+    match = rcpp_match_amplicon(bam, bed, match_tolerance) if bed_type == "amplicon" else rcpp_match_capture(bam, bed, match_min_overlap)
+    b = CONTEXT_TO_BASES[ecdf_context]
+    ctx_beta = rcpp_get_xm_beta(bam, b[0], b[1])
+    oo_beta = rcpp_get_xm_beta(bam, b[2], b[3])
+    present = sorted(set(int(m) for m in np.unique(match) if m != NA_INT)) + ([NA_INT] if (match == NA_INT).any() else [])
+    rows = present if bed_rows is None else [r for r in bed_rows if r in present]
+    out = {}
+    for r in rows:
+        sel = match == r
+        out[r] = {"context": np.sort(ctx_beta[sel]), "out.of.context": np.sort(oo_beta[sel])}
+    return out
+
+
+def ecdf_at(sorted_values, x):
+    """stats::ecdf(v)(x)."""
+    return float(np.searchsorted(sorted_values, x, side="right")) / float(sorted_values.shape[0])
+
+
 def _write_report(rep, path, gz):
     lv = rep["levels"]
     opener = (lambda p: _gzip.open(p, "wt")) if gz else (lambda p: open(p, "w"))

@@ -21,6 +21,7 @@
 #include "window_tpr.cuh"
 #include "window_cpl.cuh"
 #include "window_row.cuh"
+#include "bed.cuh"
 #include "synth.h"
 
 namespace {
@@ -132,6 +133,7 @@ struct ea_handle {
   uint8_t* d_pass = nullptr;
   double* d_beta = nullptr;
   unsigned long long* d_counters = nullptr;  // [0] row cursor, [1] n_pass
+  int32_t* d_match = nullptr;                // per read: 1-based BED row or NA (ea_match_target)
   uint16_t* d_thr_tables = nullptr;          // 2 x kThrTable integer thresholds of the pass/fail chain (window_cpl.cuh)
   int4* d_scratch = nullptr;
   int32_t* d_cols[6] = {};
@@ -1087,7 +1089,7 @@ void ea_free(ea_handle* h) {
   pool_free(h->d_maxend);
   pool_free(h->d_sp);
   h->idx[0].release(); h->idx[1].release();
-  pool_free(h->d_pass); pool_free(h->d_beta); pool_free(h->d_counters); pool_free(h->d_thr_tables); pool_free(h->d_scratch); pool_free(h->d_flush);
+  pool_free(h->d_pass); pool_free(h->d_beta); pool_free(h->d_counters); pool_free(h->d_thr_tables); pool_free(h->d_match); pool_free(h->d_scratch); pool_free(h->d_flush);
   for (auto& c : h->d_cols) pool_free(c);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1254,6 +1256,123 @@ int ea_get_xm_beta(ea_handle* h, const char* ctx_meth, const char* ctx_unmeth, d
   if ((rc = launch_threshold(h, spec, tp, nullptr, h->d_beta, nullptr))) return rc;
   if (h->n > 0) CU(cudaMemcpyAsync(beta_out, h->d_beta, 8 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return EA_OK;
+}
+
+// ---- BED-assisted report ------------------------------------------------
+namespace {
+struct BedDev {
+  int64_t *s_key = nullptr, *e_key = nullptr;
+  int32_t *s_start = nullptr, *s_end = nullptr, *s_pmax = nullptr, *s_idx = nullptr, *e_idx = nullptr;
+  int32_t n = 0;
+  void release() { pool_free(s_key); pool_free(e_key); pool_free(s_start); pool_free(s_end); pool_free(s_pmax); pool_free(s_idx); pool_free(e_idx); }
+};
+
+// Sort the BED rows whose chromosome the BAM knows by (chr, start) and by (chr, end); file order index kept.
+int upload_bed(ea_handle* h, const int32_t* chr, const int32_t* start, const int32_t* end, int64_t nbed, BedDev* d) {
+  std::vector<int32_t> ord;
+  for (int64_t i = 0; i < nbed; i++)
+    if (chr[i] != kNaInt) ord.push_back((int32_t)i);
+  const size_t n = ord.size();
+  d->n = (int32_t)n;
+  std::vector<int32_t> oe(ord);
+  std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return chr[a] != chr[b] ? chr[a] < chr[b] : start[a] < start[b]; });
+  std::stable_sort(oe.begin(), oe.end(), [&](int32_t a, int32_t b) { return chr[a] != chr[b] ? chr[a] < chr[b] : end[a] < end[b]; });
+  std::vector<int64_t> sk(n), ek(n);
+  std::vector<int32_t> ss(n), se(n), sp(n);
+  for (size_t k = 0; k < n; k++) {
+    const int32_t i = ord[k];
+    sk[k] = bed_key(chr[i], start[i]); ss[k] = start[i]; se[k] = end[i];
+    sp[k] = (k > 0 && chr[ord[k - 1]] == chr[i]) ? std::max(sp[k - 1], end[i]) : end[i];
+    ek[k] = bed_key(chr[oe[k]], end[oe[k]]);
+  }
+  int rc;
+  if ((rc = dmalloc(&d->s_key, n)) || (rc = dmalloc(&d->e_key, n)) || (rc = dmalloc(&d->s_start, n)) || (rc = dmalloc(&d->s_end, n)) ||
+      (rc = dmalloc(&d->s_pmax, n)) || (rc = dmalloc(&d->s_idx, n)) || (rc = dmalloc(&d->e_idx, n)))
+    return rc;
+  if (n) {
+    CU(cudaMemcpyAsync(d->s_key, sk.data(), 8 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d->e_key, ek.data(), 8 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d->s_start, ss.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d->s_end, se.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d->s_pmax, sp.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d->s_idx, ord.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d->e_idx, oe.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));  // the host vectors die with this frame
+  }
+  return EA_OK;
+}
+
+int match_on_device(ea_handle* h, int mode, const int32_t* chr, const int32_t* start, const int32_t* end, int64_t nbed, int32_t param) {
+  if (mode != 0 && mode != 1) return fail(EA_ERR_ARG, "mode must be 0 (amplicon) or 1 (capture)");
+  if (nbed < 0 || nbed > 0x7FFFFFF0ll || (nbed > 0 && (!chr || !start || !end))) return fail(EA_ERR_ARG, "bad BED table");
+  int rc;
+  if (!h->d_match && (rc = dmalloc(&h->d_match, (size_t)h->n))) return rc;
+  BedDev bd;
+  if ((rc = upload_bed(h, chr, start, end, nbed, &bd))) { bd.release(); return rc; }
+  BedIndex bi{bd.s_key, bd.s_start, bd.s_end, bd.s_pmax, bd.s_idx, bd.e_key, bd.e_idx, bd.n};
+  if (h->n > 0) k_match_target<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), bi, mode, param, h->d_match);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  bd.release();
+  return EA_OK;
+}
+}  // namespace
+
+int ea_match_target(ea_handle* h, int mode, const int32_t* bed_chr, const int32_t* bed_start, const int32_t* bed_end, int64_t nbed,
+                    int32_t param, int32_t* match_out) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  if ((rc = match_on_device(h, mode, bed_chr, bed_start, bed_end, nbed, param))) return rc;
+  if (match_out && h->n > 0) {
+    CU(cudaMemcpyAsync(match_out, h->d_match, 4 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return EA_OK;
+}
+
+int ea_bed_report(ea_handle* h, int mode, const int32_t* bed_chr, const int32_t* bed_start, const int32_t* bed_end, int64_t nbed,
+                  int32_t param, const ea_report_params* thr, const uint8_t* pass, int32_t* match_out, uint8_t* pass_out,
+                  int64_t* counts_out) {
+  if (!h || !counts_out) return fail(EA_ERR_ARG, "null argument");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  if ((rc = match_on_device(h, mode, bed_chr, bed_start, bed_end, nbed, param))) return rc;
+  // pass flags: thresholds evaluated on the device, or the caller's flags, or all TRUE
+  const uint8_t* d_pass = nullptr;
+  if (thr && thr->threshold_reads) {
+    if (!thr->ctx_meth || !thr->ctx_unmeth) return fail(EA_ERR_ARG, "ctx_meth/ctx_unmeth must be non-null");
+    if ((rc = ensure_pass(h))) return rc;
+    ThresholdSpec spec;
+    parse_threshold_letters(thr->ctx_meth, thr->ctx_unmeth, thr->ooctx_meth, thr->ooctx_unmeth, &spec);
+    ThrParams tp{thr->min_n_ctx, thr->min_ctx_meth_frac, thr->max_ooctx_meth_frac};
+    CU(cudaMemsetAsync(h->d_pass, 0, (size_t)std::max<int64_t>(h->n, 1), h->stream));
+    if ((rc = launch_threshold(h, spec, tp, h->d_pass, nullptr, nullptr))) return rc;
+    d_pass = h->d_pass;
+  } else if (pass && h->n > 0) {
+    if ((rc = ensure_pass(h))) return rc;
+    CU(cudaMemcpyAsync(h->d_pass, pass, (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    d_pass = h->d_pass;
+  }
+  const size_t n_entries = (size_t)(nbed + 1) * 4;
+  unsigned long long* d_counts;
+  if ((rc = dmalloc(&d_counts, n_entries))) return rc;
+  CU(cudaMemsetAsync(d_counts, 0, 8 * n_entries, h->stream));
+  if (h->n > 0) {
+    const int smem_entries = n_entries <= 8192 ? (int)n_entries : 0;
+    const int grid = std::max(1, std::min(grid_for(h->n, 256), h->sm_count * 8));
+    k_bed_counts<<<grid, 256, (size_t)smem_entries * 4, h->stream>>>(csr_of(h), h->d_match, d_pass, (int)nbed, d_counts, smem_entries);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(counts_out, d_counts, 8 * n_entries, cudaMemcpyDeviceToHost, h->stream));
+  if (match_out && h->n > 0) CU(cudaMemcpyAsync(match_out, h->d_match, 4 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (pass_out && h->n > 0) {
+    if (d_pass) CU(cudaMemcpyAsync(pass_out, d_pass, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    else memset(pass_out, 1, (size_t)h->n);
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  pool_free(d_counts);
   return EA_OK;
 }
 

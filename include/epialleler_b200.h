@@ -129,6 +129,22 @@ typedef struct ea_report_params {
  * Rows are fetched with ea_cx_report_fetch. */
 int ea_cytosine_report(ea_handle* h, const ea_report_params* p, uint8_t* pass_out, int64_t* nrow_out);
 
+/* ---- BED-assisted report ------------------------------------------------ *
+ * ea_match_target replaces rcpp_match_amplicon (mode 0, param = tolerance) and rcpp_match_capture (mode 1, param =
+ * min overlap): src/rcpp_match_target.cpp:16-45,51-81; R/RcppExports.R (rcpp_match_amplicon / rcpp_match_capture).
+ * bed_chr: factor code of the BED row's chromosome on the BAM's rname levels (INT32_MIN = NA, as R/internal.R:467-468
+ * produces), bed_start / bed_end 1-based closed.  match_out: nrow int32, 1-based BED row in FILE order (first match) or
+ * INT32_MIN (NA); may be NULL (the result stays on the device for ea_bed_report). */
+int ea_match_target(ea_handle* h, int mode, const int32_t* bed_chr, const int32_t* bed_start, const int32_t* bed_end, int64_t nbed,
+                    int32_t param, int32_t* match_out);
+/* Body of generateBedReport after preprocessBam (R/generateBedReport.R:243-262, R/internal.R:529-561) in one call: match,
+ * per-read thresholds (thr->threshold_reads != 0; else the caller's `pass` flags, NULL = all TRUE) and the per-target
+ * counts.  counts_out: (nbed + 1) * 4 int64, row i (row nbed = unmatched reads) holds reads by
+ * {FALSE+, FALSE-, TRUE+, TRUE-} (pass, strand).  match_out / pass_out may be NULL. */
+int ea_bed_report(ea_handle* h, int mode, const int32_t* bed_chr, const int32_t* bed_start, const int32_t* bed_end, int64_t nbed,
+                  int32_t param, const ea_report_params* thr, const uint8_t* pass, int32_t* match_out, uint8_t* pass_out,
+                  int64_t* counts_out);
+
 /* ---- measurement hooks (device-resident, no host copies; used by bench.py) ------------------- */
 
 typedef struct ea_timing {

@@ -237,3 +237,23 @@ def from_xm_text(rows, high_nibble: int = 0x10) -> BamData:
     tid = np.arange(len(rows), dtype=np.int32)
     order = np.lexsort((sa, rn))
     return BamData(rn[order], st[order], sa[order], tid[order], seqxm, [])
+
+
+def read_bed(path: str, rname_levels, zero_based: bool = False):
+    """The reference's .readBed + .matchTarget factor step (R/internal.R:206-223,467-468): tab-separated file with a header
+    line, first three columns chr / start / end (1-based closed unless zero_based); seqnames become factor codes on the
+    BAM's rname levels (1-based; INT_MIN = NA when the chromosome is not among them).  Returns (seqnames, start, end, names)."""
+    levels = {str(n): i + 1 for i, n in enumerate(rname_levels)}
+    chr_, st, en, nm = [], [], [], []
+    with open(path) as fh:
+        header = fh.readline()
+        assert header, "empty BED file"
+        for ln in fh:
+            f = ln.rstrip("\n").split("\t")
+            if len(f) < 3 or not f[0]:
+                continue
+            chr_.append(levels.get(f[0], -2147483648))
+            st.append(int(f[1]) + (1 if zero_based else 0))
+            en.append(int(f[2]))
+            nm.append(f[3] if len(f) > 3 else "")
+    return np.asarray(chr_, np.int32), np.asarray(st, np.int32), np.asarray(en, np.int32), nm

@@ -230,3 +230,33 @@ void port_cx_fetch(void* h, int* rname, int* strand, int* pos, int* context, int
   int* dst[6] = {rname, strand, pos, context, meth, unmeth};
   for (int c = 0; c < 6; c++) if (b->nrow) memcpy(dst[c], b->col[c], sizeof(int) * (size_t)b->nrow);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * BED target matching, restating /root/reference/src/rcpp_match_target.cpp:
+ *   mode 0, rcpp_match_amplicon (:16-45): first BED row i (file order) on the read's chromosome whose start is within
+ *           `param` of the read's start OR whose end is within `param` of the read's end;
+ *   mode 1, rcpp_match_capture (:51-81): first BED row on the read's chromosome with
+ *           min(read_end, end_i) - max(read_start, start_i) + 1 >= param.
+ * read_end = start + length(string) - 1 (:33,:68).  Result: 1-based BED row, or INT_MIN (R's NA_integer_).
+ * ------------------------------------------------------------------------------------------------ */
+double port_match_target(void* h, int mode, long nbed, const int* chr, const int* start, const int* end, int param, int* out) {
+  PortBam* b = (PortBam*)h;
+  double t0 = now_s();
+  for (long x = 0; x < b->n; x++) {
+    const int t = b->templid[x];
+    const int rs = b->start[x];
+    const int re = rs + (int)(b->off[t + 1] - b->off[t]) - 1;
+    int res = INT32_MIN;
+    for (long i = 0; i < nbed; i++) {
+      if (b->rname[x] != chr[i]) continue;
+      if (mode == 0) {
+        if (abs(rs - start[i]) <= param || abs(re - end[i]) <= param) { res = (int)i + 1; break; }
+      } else {
+        const int lo = rs > start[i] ? rs : start[i], hi = re < end[i] ? re : end[i];
+        if (hi - lo + 1 >= param) { res = (int)i + 1; break; }
+      }
+    }
+    out[x] = res;
+  }
+  return now_s() - t0;
+}

@@ -46,6 +46,31 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+NA_INT = -2147483648  # R's NA_integer_
+
+
+def bed_report_table(strand, pass_, match, nbed):
+    """The table R/internal.R:529-561 builds with data.table: rows = BED rows 1..nbed in file order, then one NA row
+    if any read is unmatched; columns nreads+ / nreads- (reads of strand 1 / 2 matched to the row, passing or not) and
+    VEF = passing / all.  BED rows that no read matched hold NaN (NA after the all=TRUE merge)."""
+    strand = np.asarray(strand); pass_ = np.asarray(pass_).astype(bool); match = np.asarray(match)
+    na = match == NA_INT
+    idx = np.where(na, nbed, match - 1).astype(np.int64)          # NA bucket last
+    n_rows = nbed + (1 if na.any() else 0)
+    cnt = np.zeros((nbed + 1, 2, 2), np.int64)                      # [row][pass][strand-1]
+    np.add.at(cnt, (idx, pass_.astype(np.int64), strand.astype(np.int64) - 1), 1)
+    cnt = cnt[:n_rows]
+    tot = cnt.sum(axis=(1, 2))
+    plus = (cnt[:, 0, 0] + cnt[:, 1, 0]).astype(np.float64)
+    minus = (cnt[:, 0, 1] + cnt[:, 1, 1]).astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        vef = (cnt[:, 1, 0] + cnt[:, 1, 1]) / tot.astype(np.float64)
+    empty = tot == 0
+    plus[empty] = np.nan; minus[empty] = np.nan; vef[empty] = np.nan
+    return {"bedrow": np.concatenate([np.arange(1, nbed + 1), [NA_INT] if n_rows > nbed else []]).astype(np.int64),
+            "nreads+": plus, "nreads-": minus, "VEF": vef, "counts": cnt}
+
+
 class _Cpu:
     PREFIX = ""
     SO = ""
@@ -66,6 +91,9 @@ class _Cpu:
         getattr(L, px + "cx_report").restype = C.c_long
         getattr(L, px + "cx_report").argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.POINTER(C.c_double)]
         getattr(L, px + "cx_fetch").argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 6
+        getattr(L, px + "match_target").restype = C.c_double
+        getattr(L, px + "match_target").argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.POINTER(C.c_int)] * 3 + [C.c_int, C.POINTER(C.c_int)]
+        self.strand = np.ascontiguousarray(bam.strand, dtype=np.int32)
         self.n = int(bam.rname.shape[0])
         data, off = bam.blob()
         self.nstr = int(off.shape[0] - 1)
@@ -119,6 +147,44 @@ class _Cpu:
         getattr(self.lib, self.PREFIX + "cx_fetch")(self.h, *[_p(c, C.c_int) for c in cols])
         names = ("rname", "strand", "pos", "context", "meth", "unmeth")
         return {k: c[:nrow] for k, c in zip(names, cols)}
+
+    # ---- BED-assisted report ----
+    def _match(self, mode, bed, param):
+        """bed: (seqnames, start, end) int arrays, seqnames = factor code on the BAM's rname levels (NA = INT_MIN)."""
+        chr_, st, en = (np.ascontiguousarray(a, dtype=np.int32) for a in bed)
+        nbed = int(chr_.shape[0])
+        pad = lambda a: a if a.shape[0] else np.zeros(1, np.int32)
+        out = np.zeros(max(self.n, 1), np.int32)
+        self.last_seconds = getattr(self.lib, self.PREFIX + "match_target")(self.h, mode, nbed, _p(pad(chr_), C.c_int), _p(pad(st), C.c_int),
+                                                                            _p(pad(en), C.c_int), int(param), _p(out, C.c_int))
+        return out[:self.n]
+
+    def rcpp_match_amplicon(self, bed, tolerance):
+        """src/rcpp_match_target.cpp:16 -> 1-based BED row per read, INT_MIN = NA."""
+        return self._match(0, bed, tolerance)
+
+    def rcpp_match_capture(self, bed, min_overlap):
+        """src/rcpp_match_target.cpp:51."""
+        return self._match(1, bed, min_overlap)
+
+    def getBedReport(self, pass_, match, nbed):
+        """R/internal.R:529-561 restated with numpy: per BED row (file order) and, when any read is unmatched, one NA row
+        at the end: nreads+, nreads-, VEF = (TRUE+ + TRUE-) / all.  BED rows without reads are NaN (the merge's NA)."""
+        return bed_report_table(self.strand, pass_, match, nbed)
+
+    def generateBedReport(self, bed, bed_type="amplicon", match_tolerance=1, match_min_overlap=1, threshold_reads=True,
+                          threshold_context="CG", min_context_sites=2, min_context_beta=0.5, max_outofcontext_beta=0.1):
+        """R/generateBedReport.R:219-273."""
+        if threshold_reads:
+            b = CONTEXT_TO_BASES[threshold_context]
+            pass_ = self.rcpp_threshold_reads(b[0], b[1], b[2], b[3], min_context_sites, min_context_beta, max_outofcontext_beta)
+        else:
+            pass_ = np.ones(self.n, bool)
+        match = self.rcpp_match_amplicon(bed, match_tolerance) if bed_type == "amplicon" else self.rcpp_match_capture(bed, match_min_overlap)
+        rep = self.getBedReport(pass_, match, int(np.asarray(bed[0]).shape[0]))
+        if not threshold_reads:
+            rep["VEF"] = np.full(rep["VEF"].shape, np.nan)
+        return match, rep
 
     # reference-level glue (R/generateCytosineReport.R:164-208, R/internal.R:439-456,486-500)
     def generateCytosineReport(self, threshold_reads=True, threshold_context="CG", min_context_sites=2,

@@ -2,13 +2,16 @@
 //
 // Minimal stand-in for <Rcpp.h>, just large enough for the reference's three
 // hot-path translation units (src/rcpp_threshold_reads.cpp,
-// src/rcpp_get_xm_beta.cpp, src/rcpp_cx_report.cpp) to compile UNMODIFIED from
+// src/rcpp_get_xm_beta.cpp, src/rcpp_cx_report.cpp) and the BED matcher
+// (src/rcpp_match_target.cpp) to compile UNMODIFIED from
 // /root/reference/src (see oracle/Makefile).  The surface mirrored here is the
 // one listed in SURVEY.md Appendix A.  Nothing from the reference is copied:
 // this is an independent shim of the Rcpp API those files touch.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -16,6 +19,9 @@
 #include <vector>
 
 typedef void* SEXP;
+#ifndef NA_INTEGER
+#define NA_INTEGER INT_MIN  /* R's integer NA (R_ext/Arith.h: R_NaInt = INT_MIN) */
+#endif
 
 namespace Rcpp {
 

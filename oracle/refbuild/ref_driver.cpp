@@ -22,6 +22,9 @@ std::vector<bool> rcpp_threshold_reads(Rcpp::DataFrame& df, const std::string ct
 std::vector<double> rcpp_get_xm_beta(Rcpp::DataFrame& df, const std::string ctx_meth,
                                      const std::string ctx_unmeth);
 Rcpp::DataFrame rcpp_cx_report(Rcpp::DataFrame& df, Rcpp::LogicalVector& pass, const std::string ctx);
+// /root/reference/src/rcpp_match_target.cpp:16,51
+std::vector<int> rcpp_match_amplicon(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, const int tolerance);
+std::vector<int> rcpp_match_capture(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, const signed int min_overlap);
 
 namespace {
 struct RefBam {
@@ -105,6 +108,22 @@ void ref_cx_fetch(void* h, int* rname, int* strand, int* pos, int* context, int*
   for (int c = 0; c < 6; c++)
     if (b->cols[c] && !b->cols[c]->empty())
       std::memcpy(dst[c], b->cols[c]->data(), b->cols[c]->size() * sizeof(int));
+}
+
+// mode 0: rcpp_match_amplicon(df, bed, tolerance = param); mode 1: rcpp_match_capture(df, bed, min_overlap = param).
+// bed columns: seqnames (factor code on the BAM's rname levels, NA_INTEGER if absent), start, end.  out: n ints
+// (1-based BED row or NA_INTEGER).
+double ref_match_target(void* h, int mode, long nbed, const int* chr, const int* start, const int* end, int param, int* out) {
+  RefBam* b = static_cast<RefBam*>(h);
+  Rcpp::DataFrame bed;
+  bed.set_column("seqnames", std::make_shared<std::vector<int>>(chr, chr + nbed));
+  bed.set_column("start", std::make_shared<std::vector<int>>(start, start + nbed));
+  bed.set_column("end", std::make_shared<std::vector<int>>(end, end + nbed));
+  double t0 = now_s();
+  std::vector<int> r = mode == 0 ? rcpp_match_amplicon(b->df, bed, param) : rcpp_match_capture(b->df, bed, param);
+  double t1 = now_s();
+  std::memcpy(out, r.data(), r.size() * sizeof(int));
+  return t1 - t0;
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle.bamdata import read_bam  # noqa: E402
+from oracle.bamdata import read_bam, read_bed  # noqa: E402
 from oracle.oracle import CONTEXT_TO_BASES, RefCpu, build  # noqa: E402
 
 EXT = "/root/reference/inst/extdata/"
@@ -44,7 +44,16 @@ CASES = [
     ("cx_thr_cg_rep", True, "CX", 5, 0.05, 0.1, "CG"),
     ("cg_zero_thresholds", True, "CG", 0, 0.0, 1.0, "CG"),
 ]
-BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh")]
+BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh"), ("beta_oo_cg", "XH", "xh")]
+# BED-assisted report: fixture -> (bed file, [(case, bed.type, match.tolerance / match.min.overlap)])
+BEDS = {
+    "amplicon010meth": (EXT + "amplicon.bed", [("ampl_tol1", "amplicon", 1), ("ampl_tol0", "amplicon", 0), ("ampl_tol25", "amplicon", 25),
+                                               ("ampl_as_capture", "capture", 1)]),
+    "amplicon100meth": (EXT + "amplicon.bed", [("ampl_tol1", "amplicon", 1)]),
+    "capture": (EXT + "capture.bed", [("capt_ov1", "capture", 1), ("capt_ov100", "capture", 100), ("capt_ov_neg", "capture", -200),
+                                      ("capt_as_amplicon", "amplicon", 300)]),
+    "capture_q30_bq20": (EXT + "capture.bed", [("capt_ov1", "capture", 1)]),
+}
 
 
 def main():
@@ -62,6 +71,16 @@ def main():
                 out[cname + "." + k] = v
         for bname, m, u in BETAS:
             out[bname] = ref.rcpp_get_xm_beta(m, u)
+        if name in BEDS:
+            bed_path, cases = BEDS[name]
+            chr_, st, en, _ = read_bed(bed_path, bam.rname_levels)
+            out["bed.chr"], out["bed.start"], out["bed.end"] = chr_, st, en
+            for cname, typ, par in cases:
+                match, rep = ref.generateBedReport((chr_, st, en), typ, match_tolerance=par, match_min_overlap=par)
+                out["bed." + cname + ".match"] = match
+                out["bed." + cname + ".counts"] = rep["counts"]
+                out["bed." + cname + ".vef"] = rep["VEF"]
+                print("  bed", cname, "matched", int((match != -2147483648).sum()), "rows", rep["VEF"].shape[0])
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
         print(name, bam.nrow, int(off[-1]), {c[0]: int(out[c[0] + ".pos"].shape[0]) for c in CASES})
 

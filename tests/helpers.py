@@ -20,7 +20,14 @@ CASES = [
     ("cx_thr_cg_rep", True, "CX", 5, 0.05, 0.1, "CG"),
     ("cg_zero_thresholds", True, "CG", 0, 0.0, 1.0, "CG"),
 ]
-BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh")]
+BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh"), ("beta_oo_cg", "XH", "xh")]
+# fixture -> [(case, bed.type, match.tolerance / match.min.overlap)]; must match tests/golden/make_golden.py
+BED_CASES = {
+    "amplicon010meth": [("ampl_tol1", "amplicon", 1), ("ampl_tol0", "amplicon", 0), ("ampl_tol25", "amplicon", 25), ("ampl_as_capture", "capture", 1)],
+    "amplicon100meth": [("ampl_tol1", "amplicon", 1)],
+    "capture": [("capt_ov1", "capture", 1), ("capt_ov100", "capture", 100), ("capt_ov_neg", "capture", -200), ("capt_as_amplicon", "amplicon", 300)],
+    "capture_q30_bq20": [("capt_ov1", "capture", 1)],
+}
 
 
 def golden_names():

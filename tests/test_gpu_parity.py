@@ -211,3 +211,58 @@ def test_range_sharded_gpu_equals_whole():
                 parts.append(rep); passes.append(own_pass)
             assert np.array_equal(np.concatenate(passes), want_pass), (world, kw)
             assert_report_equal(merge_reports(parts), want, "world=%d" % world)
+
+
+# ---- BED-assisted report: ea_match_target / ea_bed_report ------------------
+from helpers import BED_CASES  # noqa: E402
+from test_oracle import golden_bed, random_bed  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(BED_CASES))
+def test_bed_report_golden_vectors(name):
+    bam, z = load_golden(name)
+    bed = golden_bed(z)
+    for cname, typ, par in BED_CASES[name]:
+        match, rep = ea.generateBedReport(bam, bed, bed_type=typ, match_tolerance=par, match_min_overlap=par, return_match=True)
+        assert np.array_equal(match, z["bed." + cname + ".match"]), (name, cname)
+        assert np.array_equal(rep["counts"], z["bed." + cname + ".counts"]), (name, cname)
+        assert np.array_equal(rep["VEF"], z["bed." + cname + ".vef"], equal_nan=True), (name, cname)
+        m2 = (ea.rcpp_match_amplicon if typ == "amplicon" else ea.rcpp_match_capture)(bam, bed, par)
+        assert np.array_equal(m2, z["bed." + cname + ".match"])
+    bam.close()
+
+
+def test_bed_report_runit_constants_and_ecdf():
+    # inst/unitTests/test_generateBedReport.R:12-54, test_generateBedEcdf.R:8-12, through the public mirror
+    bam, z = load_golden("amplicon010meth")
+    rep = ea.generateAmpliconReport(bam, golden_bed(z))
+    assert rep["VEF"].shape[0] == 5 and np.nansum(rep["nreads-"]) == 440 and np.nansum(rep["nreads+"]) + np.nansum(rep["nreads-"]) == 500
+    assert np.allclose(rep["VEF"], [0.08333333333, 0.11475409836, 0.05376344086, 0.10714285714, 0.13207547170], rtol=0, atol=1e-10)
+    assert np.isnan(ea.generateAmpliconReport(bam, golden_bed(z), threshold_reads=False)["VEF"]).all()
+    ecdfs = ea.generateBedEcdf(bam, golden_bed(z), bed_rows=(1, 2))
+    got = [ea.ecdf_at(ecdfs[r][k], 0.5) for r in (1, 2) for k in ("context", "out.of.context")]
+    assert np.allclose(got, [0.916666666667, 1, 0.885245901639, 1], rtol=0, atol=1e-8)
+    cap, zc = load_golden("capture")
+    rep = ea.generateCaptureReport(cap, golden_bed(zc))
+    assert rep["VEF"].shape[0] == 565 and np.nansum(rep["nreads-"]) == 1472 and np.nansum(rep["nreads+"]) + np.nansum(rep["nreads-"]) == 2968
+    bam.close(); cap.close()
+
+
+def test_bed_matching_random_targets_against_oracle():
+    rng = np.random.default_rng(11)
+    cases = [load_golden("capture")[0], ea.synth_host(ea.synth_config(3, 20000, [60000, 50000], 80, 420)),
+             ea.synth_host(ea.synth_config(4, 30000, [80000], 100, 300, n_islands=3, island_len=1500))]
+    for bam in cases:
+        port = PortCpu(bam)
+        for nbed in (0, 1, 50, 3000):
+            bed = random_bed(rng, bam, nbed)
+            for par in (-3, 0, 1, 60):
+                assert np.array_equal(ea.rcpp_match_amplicon(bam, bed, par), port.rcpp_match_amplicon(bed, par)), (nbed, par, "amplicon")
+                assert np.array_equal(ea.rcpp_match_capture(bam, bed, par), port.rcpp_match_capture(bed, par)), (nbed, par, "capture")
+            want_m, want = port.generateBedReport(bed, "capture", match_min_overlap=20, threshold_context="CxG", min_context_sites=1,
+                                                  min_context_beta=0.2, max_outofcontext_beta=0.6)
+            got_m, got = ea.generateBedReport(bam, bed, bed_type="capture", match_min_overlap=20, threshold_context="CxG", min_context_sites=1,
+                                              min_context_beta=0.2, max_outofcontext_beta=0.6, return_match=True)
+            assert np.array_equal(got_m, want_m) and np.array_equal(got["counts"], want["counts"])
+            assert np.array_equal(got["VEF"], want["VEF"], equal_nan=True)
+        bam.close()

@@ -110,3 +110,79 @@ def test_port_matches_reference_on_synthetic_reads():
             assert np.array_equal(pa, pb)
             assert_report_equal(ra, rb)
             assert ra["pos"].shape[0] > 0
+
+
+# ---- BED-assisted report -------------------------------------------------
+from helpers import BED_CASES  # noqa: E402
+
+
+def golden_bed(z):
+    return z["bed.chr"], z["bed.start"], z["bed.end"]
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_reference_runit_constants_bed_report(oracle):
+    # inst/unitTests/test_generateBedReport.R:12-45 (dims, nreads sums, per-amplicon VEF)
+    bam, z = load_golden("amplicon010meth")
+    o = oracle(bam)
+    _, rep = o.generateBedReport(golden_bed(z), "amplicon")
+    assert rep["VEF"].shape[0] == 5  # four amplicons + the NA row
+    assert np.nansum(rep["nreads-"]) == 440 and np.nansum(rep["nreads+"]) + np.nansum(rep["nreads-"]) == 500
+    assert np.allclose(rep["VEF"], [0.08333333333, 0.11475409836, 0.05376344086, 0.10714285714, 0.13207547170], rtol=0, atol=1e-10)
+    _, nothr = o.generateBedReport(golden_bed(z), "amplicon", threshold_reads=False)
+    assert nothr["VEF"].shape[0] == 5 and np.isnan(nothr["VEF"]).all()  # :47-54
+    bam, z = load_golden("capture")
+    _, rep = oracle(bam).generateBedReport(golden_bed(z), "capture")
+    assert rep["VEF"].shape[0] == 565
+    assert np.nansum(rep["nreads-"]) == 1472 and np.nansum(rep["nreads+"]) + np.nansum(rep["nreads-"]) == 2968
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_reference_runit_constants_bed_ecdf(oracle):
+    # inst/unitTests/test_generateBedEcdf.R:8-12: eCDF(0.5) of the in-context / out-of-context betas of amplicons 1 and 2
+    bam, z = load_golden("amplicon010meth")
+    o = oracle(bam)
+    match = o.rcpp_match_amplicon(golden_bed(z), 1)
+    ctx, oo = o.rcpp_get_xm_beta("Z", "z"), o.rcpp_get_xm_beta("XH", "xh")
+    got = []
+    for row in (1, 2):
+        sel = match == row
+        got += [float((ctx[sel] <= 0.5).mean()), float((oo[sel] <= 0.5).mean())]
+    assert np.allclose(got, [0.916666666667, 1, 0.885245901639, 1], rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+@pytest.mark.parametrize("name", sorted(BED_CASES))
+def test_oracle_reproduces_golden_bed_vectors(oracle, name):
+    bam, z = load_golden(name)
+    o = oracle(bam)
+    for cname, typ, par in BED_CASES[name]:
+        match, rep = o.generateBedReport(golden_bed(z), typ, match_tolerance=par, match_min_overlap=par)
+        assert np.array_equal(match, z["bed." + cname + ".match"]), (name, cname)
+        assert np.array_equal(rep["counts"], z["bed." + cname + ".counts"]), (name, cname)
+        assert np.array_equal(rep["VEF"], z["bed." + cname + ".vef"], equal_nan=True), (name, cname)
+
+
+def random_bed(rng, bam, nbed, overlapping=True):
+    """Unsorted random targets around the reads' own coordinates, with overlaps, duplicates and chromosomes the BAM lacks."""
+    i = rng.integers(0, bam.nrow, nbed)
+    _, off = bam.blob()
+    ln = np.diff(off)[bam.templid[i]]
+    st = bam.start[i] + rng.integers(-30, 30, nbed)
+    en = st + np.maximum(1, (ln * rng.uniform(0.2, 1.5, nbed)).astype(np.int64) + (rng.integers(0, 400, nbed) if overlapping else 0))
+    chr_ = bam.rname[i].astype(np.int32).copy()
+    chr_[rng.random(nbed) < 0.1] = -2147483648
+    return chr_, st.astype(np.int32), en.astype(np.int32)
+
+
+def test_port_matches_reference_on_random_beds():
+    if RefCpu not in ORACLES:
+        pytest.skip("compiled reference not available")
+    rng = np.random.default_rng(7)
+    bam, _ = load_golden("capture")
+    ref, port = RefCpu(bam), PortCpu(bam)
+    for nbed in (0, 1, 37, 400):
+        bed = random_bed(rng, bam, nbed)
+        for par in (-5, 0, 1, 40):
+            assert np.array_equal(ref.rcpp_match_amplicon(bed, par), port.rcpp_match_amplicon(bed, par))
+            assert np.array_equal(ref.rcpp_match_capture(bed, par), port.rcpp_match_capture(bed, par))
