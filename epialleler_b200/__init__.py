@@ -8,5 +8,5 @@ runs in hand-written sm_100a kernels behind the C ABI of include/epialleler_b200
 from .api import (BamData, CONTEXT_TO_BASES, generateCytosineReport, preprocessBam, rcpp_cx_report,  # noqa: F401
                   rcpp_get_xm_beta, rcpp_threshold_reads, synth_config, synth_device, synth_host)
 from .api import (generateBedReport, generateAmpliconReport, generateCaptureReport, generateBedEcdf, ecdf_at,  # noqa: F401
-                  rcpp_match_amplicon, rcpp_match_capture)
+                  rcpp_match_amplicon, rcpp_match_capture, rcpp_mhl_report, generateMhlReport)
 from ._native import EaError  # noqa: F401

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ea_set_poll": (None, [C.c_void_p]),
     "ea_set_kernel_policy": (C.c_int, [C.c_int]),
     "ea_report_kernel": (C.c_char_p, [_H]),
+    "ea_mhl_report": (C.c_int, [_H, C.c_char_p, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_int64)]),
+    "ea_mhl_report_fetch": (C.c_int, [_H, _I32P, _I32P, _I32P, _I32P, _I32P, _F64P, _F64P]),
     "ea_match_target": (C.c_int, [_H, C.c_int, _I32P, _I32P, _I32P, C.c_int64, C.c_int32, _I32P]),
     "ea_bed_report": (C.c_int, [_H, C.c_int, _I32P, _I32P, _I32P, C.c_int64, C.c_int32, C.POINTER(ReportParams), _U8P, _I32P, _U8P, _I64P]),
     "ea_pack": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_void_p), _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),

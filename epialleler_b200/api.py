@@ -244,6 +244,42 @@ def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshol
     return rep
 
 
+
+# ---- lMHL report ---------------------------------------------------------------
+def rcpp_mhl_report(df, ctx, hmax, hmin, max_ooctx_meth_frac):
+    """src/rcpp_mhl_report.cpp:46-228 -> rname, strand, pos, context, coverage (int32), length, lmhl (float64)."""
+    L = N.lib()
+    nrow = C.c_int64(0)
+    N.check(L.ea_mhl_report(df.handle(), ctx.encode(), int(hmax), int(hmin), float(max_ooctx_meth_frac), C.byref(nrow)))
+    n = nrow.value
+    ic = [_host_out(n, np.int32) for _ in range(5)]
+    dc = [_host_out(n, np.float64) for _ in range(2)]
+    N.check(L.ea_mhl_report_fetch(df.handle(), *[_p(c, C.c_int32) for c in ic], *[_p(c, C.c_double) for c in dc]))
+    rep = {k: c[:n] for k, c in zip(("rname", "strand", "pos", "context", "coverage", "length", "lmhl"), ic + dc)}
+    rep["levels"] = {"rname": list(df.rname_levels), "strand": list(STRAND_LEVELS), "context": list(CONTEXT_LEVELS)}
+    return rep
+
+
+def generateMhlReport(bam, report_file=None, haplotype_context="CG", max_haplotype_window=0, min_haplotype_length=0,
+                      max_outofcontext_beta=0.1, **kwargs):
+    """R/generateMhlReport.R:170-197."""
+    haplotype_context = _match_arg(haplotype_context, tuple(CONTEXT_TO_BASES), "haplotype.context")
+    bam = preprocessBam(bam, **kwargs)
+    b = CONTEXT_TO_BASES[haplotype_context]
+    rep = rcpp_mhl_report(bam, b[0] + b[1], max_haplotype_window, min_haplotype_length, max_outofcontext_beta)
+    if report_file is not None:
+        lv = rep["levels"]
+        with open(report_file, "w") as fh:
+            fh.write("rname\tstrand\tpos\tcontext\tcoverage\tlength\tlmhl\n")
+            for i in range(rep["pos"].shape[0]):
+                rn = rep["rname"][i]
+                name = lv["rname"][rn - 1] if 0 < rn <= len(lv["rname"]) else str(rn)
+                fh.write("%s\t%s\t%d\t%s\t%d\t%r\t%r\n" % (name, STRAND_LEVELS[rep["strand"][i] - 1], rep["pos"][i], CONTEXT_LEVELS[rep["context"][i] - 1],
+                                                              rep["coverage"][i], float(rep["length"][i]), float(rep["lmhl"][i])))
+        return None
+    return rep
+
+
 # ---- BED-assisted reports (SURVEY.md 8f ranks 2-3) ------------------------------------------------
 NA_INT = -2147483648  # R's NA_integer_
 

@@ -22,6 +22,7 @@
 #include "window_cpl.cuh"
 #include "window_row.cuh"
 #include "bed.cuh"
+#include "window_mhl.cuh"
 #include "synth.h"
 
 namespace {
@@ -126,7 +127,7 @@ struct ea_handle {
   int64_t* d_off = nullptr;
   uint8_t* d_data = nullptr;
   uint64_t* d_maxend = nullptr;  // per row: rname<<32 | prefix max of row ends
-  WinIndex idx[2];               // S = 4096 and S = 2048
+  WinIndex idx[4];               // small cache of window indexes keyed by S
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[10] = {};
   // per-call state
@@ -134,6 +135,11 @@ struct ea_handle {
   double* d_beta = nullptr;
   unsigned long long* d_counters = nullptr;  // [0] row cursor, [1] n_pass
   int32_t* d_match = nullptr;                // per read: 1-based BED row or NA (ea_match_target)
+  // last lMHL report (ea_mhl_report): scratch rows + ordered columns
+  ea::MhlRow* d_mhl_scratch = nullptr;
+  int32_t* d_mhl_i[5] = {};
+  double* d_mhl_d[2] = {};
+  int64_t mhl_cap = 0, mhl_rows = -1;
   uint16_t* d_thr_tables = nullptr;          // 2 x kThrTable integer thresholds of the pass/fail chain (window_cpl.cuh)
   int4* d_scratch = nullptr;
   int32_t* d_cols[6] = {};
@@ -401,9 +407,11 @@ int finish_handle(ea_handle* h) {
 }
 
 int build_index(ea_handle* h, int S, WinIndex** out) {
-  WinIndex* ix = &h->idx[S == 4096 ? 0 : 1];
+  WinIndex* ix = nullptr;
+  for (auto& c : h->idx) if (c.S == S) { *out = &c; return EA_OK; }
+  for (auto& c : h->idx) if (c.S == 0) { ix = &c; break; }
+  if (!ix) ix = &h->idx[3];
   *out = ix;
-  if (ix->S == S) return EA_OK;
   ix->release();
   ix->S = S;
   if (h->n == 0) return EA_OK;
@@ -1088,8 +1096,10 @@ void ea_free(ea_handle* h) {
   pool_free(h->d_len);
   pool_free(h->d_maxend);
   pool_free(h->d_sp);
-  h->idx[0].release(); h->idx[1].release();
-  pool_free(h->d_pass); pool_free(h->d_beta); pool_free(h->d_counters); pool_free(h->d_thr_tables); pool_free(h->d_match); pool_free(h->d_scratch); pool_free(h->d_flush);
+  for (auto& c : h->idx) c.release();
+  pool_free(h->d_pass); pool_free(h->d_beta); pool_free(h->d_counters); pool_free(h->d_thr_tables); pool_free(h->d_match); pool_free(h->d_mhl_scratch);
+  for (auto& c : h->d_mhl_i) pool_free(c);
+  for (auto& c : h->d_mhl_d) pool_free(c); pool_free(h->d_scratch); pool_free(h->d_flush);
   for (auto& c : h->d_cols) pool_free(c);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1373,6 +1383,82 @@ int ea_bed_report(ea_handle* h, int mode, const int32_t* bed_chr, const int32_t*
   }
   CU(cudaStreamSynchronize(h->stream));
   pool_free(d_counts);
+  return EA_OK;
+}
+
+// ---- lMHL report -----------------------------------------------------------
+int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, double max_ooctx_meth_frac, int64_t* nrow_out) {
+  if (!h || !ctx || !nrow_out) return fail(EA_ERR_ARG, "null argument");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  h->mhl_rows = -1;
+  if (h->max_len > 65535) return fail(EA_ERR_ARG, "lMHL report: rows longer than 65535 bytes are not supported (the reference's lookup table ends there)");
+  MhlParams prm;
+  prm.ctx_mask = 0;
+  for (const unsigned char* p = (const unsigned char*)ctx; *p; p++) prm.ctx_mask |= 1u << code_of(*p);
+  prm.cap = hmax > 0 ? (uint32_t)std::min(hmax, 65536) : 65536u;
+  prm.hmin = hmin;
+  prm.max_ooctx = max_ooctx_meth_frac;
+  WinIndex* ix = nullptr;
+  if ((rc = build_index(h, kMhlS, &ix))) return rc;
+  if (h->n == 0 || ix->n == 0) { h->mhl_rows = 0; *nrow_out = 0; return EA_OK; }
+  if (h->mhl_cap == 0) {
+    const int64_t cap = h->nbytes / 8 + 4096;
+    if ((rc = dmalloc(&h->d_mhl_scratch, (size_t)cap))) return rc;
+    for (auto& c : h->d_mhl_i) if ((rc = dmalloc(&c, (size_t)cap))) return rc;
+    for (auto& c : h->d_mhl_d) if ((rc = dmalloc(&c, (size_t)cap))) return rc;
+    h->mhl_cap = cap;
+  }
+  for (int attempt = 0; attempt < 2; attempt++) {
+    CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
+    MhlOut out{h->d_mhl_scratch, h->mhl_cap, h->d_counters, ix->w_base, ix->w_cnt};
+    WinTable wt;
+    wt.rname = ix->rname; wt.pos0 = ix->pos0; wt.lo = ix->lo; wt.hi = ix->hi; wt.n = ix->n; wt.S = ix->S;
+    const size_t smem = (size_t)2 * 3 * kMhlS * 8 + (size_t)2 * kMhlS * 4 + (size_t)2 * 3 * kMhlS * 4;
+    CU(cudaFuncSetAttribute(k_window_mhl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::max(1, std::min<int>(ix->n, h->sm_count * 32));
+    k_window_mhl<<<grid, kMhlThreads, smem, h->stream>>>(csr_of(h), wt, prm, out);
+    k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
+    MhlCols cols{h->d_mhl_i[0], h->d_mhl_i[1], h->d_mhl_i[2], h->d_mhl_i[3], h->d_mhl_i[4], h->d_mhl_d[0], h->d_mhl_d[1]};
+    k_gather_mhl<<<std::max(1, std::min(ix->n / 4 + 1, h->sm_count * 16)), 128, 0, h->stream>>>(
+        h->d_mhl_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, h->mhl_cap, cols);
+    CU(cudaGetLastError());
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, h->d_counters, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if ((int64_t)total > h->mhl_cap) {  // scratch too small: grow to the exact size and redo
+      if (attempt == 1) return fail(EA_ERR_STATE, "lMHL row capacity exceeded twice");
+      pool_free(h->d_mhl_scratch); h->d_mhl_scratch = nullptr;
+      for (auto& c : h->d_mhl_i) { pool_free(c); c = nullptr; }
+      for (auto& c : h->d_mhl_d) { pool_free(c); c = nullptr; }
+      const int64_t cap = (int64_t)total + 1024;
+      if ((rc = dmalloc(&h->d_mhl_scratch, (size_t)cap))) return rc;
+      for (auto& c : h->d_mhl_i) if ((rc = dmalloc(&c, (size_t)cap))) return rc;
+      for (auto& c : h->d_mhl_d) if ((rc = dmalloc(&c, (size_t)cap))) return rc;
+      h->mhl_cap = cap;
+      continue;
+    }
+    h->mhl_rows = (int64_t)total;
+    break;
+  }
+  *nrow_out = h->mhl_rows;
+  return EA_OK;
+}
+
+int ea_mhl_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* pos, int32_t* context, int32_t* coverage,
+                        double* length, double* lmhl) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  if (h->mhl_rows < 0) return fail(EA_ERR_STATE, "no lMHL report has been computed on this handle");
+  CU(cudaSetDevice(h->device));
+  int32_t* di[5] = {rname, strand, pos, context, coverage};
+  double* dd[2] = {length, lmhl};
+  if (h->mhl_rows > 0) {
+    for (int c = 0; c < 5; c++)
+      if (di[c]) CU(cudaMemcpyAsync(di[c], h->d_mhl_i[c], 4 * (size_t)h->mhl_rows, cudaMemcpyDeviceToHost, h->stream));
+    for (int c = 0; c < 2; c++)
+      if (dd[c]) CU(cudaMemcpyAsync(dd[c], h->d_mhl_d[c], 8 * (size_t)h->mhl_rows, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
   return EA_OK;
 }
 

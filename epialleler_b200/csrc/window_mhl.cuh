@@ -1,0 +1,275 @@
+// Linearised MHL report: replaces rcpp_mhl_report (/root/reference/src/rcpp_mhl_report.cpp:46-228).
+//
+// Same windowing as the cytosine report (one CTA per genomic window, the window's sorted candidate rows, ordered
+// compaction, scan + gather), one THREAD PER READ.  What the reference accumulates per (position, strand) with a map
+// update per byte - coverage, sum of haplotype sizes, lMHL numerator and denominator - is piecewise constant along a
+// read, so it is accumulated here as DIFFERENCE ARRAYS in shared memory (a few events per read: where its non-'-'
+// coverage starts and stops, and around every methylated stretch) and prefix-summed once per window; only the
+// cytosine calls themselves are per-position counts.  Per read:
+//   1. nibble-plane counts over the whole row (like the threshold kernels): h = bytes whose code is in `ctx`,
+//      out-of-context methylated / unmethylated bytes -> the read is dropped if h < hmin or the out-of-context beta
+//      exceeds the limit (IEEE double division, NaN compares false; rcpp_mhl_report.cpp:179-182);
+//   2. one byte-serial sweep: coverage transitions push (+-1, +-h, +-S(min(h,hmax))) into dW / dH / dDe, cytosine calls
+//      count into T, methylated stretches of `ctx` bytes are tracked (:163-176); when a stretch closes, its span is
+//      walked once more to push +-S(min(size,hmax)) into dNu around the span's non-'-' pieces.
+// Row rule and outputs as the reference's spit_results (:72-101): a row for (pos, strand) iff one context c of `ctx`
+// has C + c > floor(cov/2); coverage = C + c, length = sum(h) / coverage, lmhl = numerator / denominator (doubles).
+// Preconditions (dispatcher): rows of at most 65535 bytes, at most 2^31 rows per window.
+#pragma once
+#include "kernels.cuh"
+#include "win_common.cuh"
+
+namespace ea {
+
+constexpr int kMhlThreads = 256;
+constexpr int kMhlWarps = kMhlThreads / 32;
+constexpr int kMhlS = 1024;
+
+struct MhlRow {  // one report row in window-local order
+  int32_t pos, strand_ctx, coverage, pad;
+  double length, lmhl;
+};
+struct MhlOut {
+  MhlRow* scratch;
+  long long cap;
+  unsigned long long* cursor;
+  long long* w_base;
+  int32_t* w_cnt;
+};
+struct MhlParams {
+  uint32_t ctx_mask;     // bit k: code k is in `ctx` (ctx_map of the reference)
+  uint32_t cap;          // min(hmax, 65536), or 65536 when hmax <= 0 (:115)
+  int32_t hmin;
+  double max_ooctx;
+};
+
+__device__ __forceinline__ unsigned long long mhl_S(unsigned long long n) { return n < 2 ? n : (n * (n + 1) * (n + 2)) / 6; }  // nrS, :39-43
+
+template <int NW>
+__device__ __forceinline__ long long block_exscan_i64(long long v, long long* s_warp /* NW+1 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const long long x = lane < NW ? s_warp[lane] : 0;
+    long long xi = x;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+      const long long o = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+      if (lane >= d) xi += o;
+    }
+    if (lane < NW) s_warp[lane] = xi - x;
+  }
+  __syncthreads();
+  return s_warp[warp] + inc - v;
+}
+
+// difference-array event: value v becomes active at window-relative position q (clamped to the window start),
+// nothing to do at or beyond the window end
+__device__ __forceinline__ void diff_event(int q, int S, int* dW, long long* dH, long long* dDe, int w, long long hv, long long dv) {
+  if (q >= S) return;
+  q = max(q, 0);
+  atomicAdd(&dW[q], w);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&dH[q]), (unsigned long long)hv);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&dDe[q]), (unsigned long long)dv);
+}
+
+__global__ void __launch_bounds__(kMhlThreads, 2)
+k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
+  constexpr int S = kMhlS;
+  constexpr int PER = S / kMhlThreads;  // 4
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ long long s_scan[kMhlWarps + 1];
+  __shared__ uint32_t s_scan32[kMhlWarps + 1];
+  __shared__ long long s_base;
+  // per strand: dH, dDe, dNu (int64) then dW (int32) and T[3] (uint32)
+  long long* const L64 = reinterpret_cast<long long*>(smem_raw);               // [2][3][S]
+  int* const dWb = reinterpret_cast<int*>(L64 + 2 * 3 * S);                    // [2][S]
+  uint32_t* const Tb = reinterpret_cast<uint32_t*>(dWb + 2 * S);               // [2][3][S]
+  constexpr int kZero4 = (2 * 3 * S * 8 + 2 * S * 4 + 2 * 3 * S * 4) / 16;
+
+  for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kZero4; i += kMhlThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int w0 = wt.pos0[win];
+    const int lo = wt.lo[win], hi = wt.hi[win];
+
+    for (int r = lo + (int)threadIdx.x; r < hi; r += kMhlThreads) {
+      const long long o0 = csr.off[r], o1 = csr.off[r + 1];
+      const int len = csr.len[r];
+      const int rel0 = csr.start[r] - w0;
+      if (len <= 0 || rel0 + len <= 0) continue;  // rel0 < S by construction of hi
+      const int s = csr.strand[r] - 1;
+      const uint8_t* row = csr.data + o0;
+      const int nch = (int)((o1 - o0) >> 4);
+      // ---- 1. whole-row counts: h, out-of-context methylated / unmethylated ----
+      uint32_t h = 0, om = 0, ou = 0;
+      for (int c = 0; c < nch; c++) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const uint32_t code = (w[k >> 2] >> (8 * (k & 3))) & 15u;  // pad bytes are code 3: in no set below unless ctx holds it (it cannot: 3 is no call letter)
+          const uint32_t in = (prm.ctx_mask >> code) & 1u;
+          h += in;
+          om += (~in) & (0x00E4u >> code) & 1u;   // H U X Z: 2 5 6 7
+          ou += (~in) & (0xE400u >> code) & 1u;   // h u x z: 10 13 14 15
+        }
+      }
+      if ((int)h < prm.hmin || (double)om / (double)(om + ou) > prm.max_ooctx) continue;
+      const long long hv = (long long)h;
+      const long long dv = (long long)mhl_S(h < prm.cap ? h : prm.cap);
+      int* const dW = dWb + s * S;
+      long long* const dH = L64 + (s * 3 + 0) * S;
+      long long* const dDe = L64 + (s * 3 + 1) * S;
+      long long* const dNu = L64 + (s * 3 + 2) * S;
+      uint32_t* const T = Tb + s * 3 * S;
+      // ---- 2. byte-serial sweep ----
+      bool cov = false;
+      uint32_t msz = 0;
+      int ms = 0, me = 0;
+      auto close_stretch = [&]() {  // push +-S(min(size, hmax)) around the non-'-' pieces of [ms, me]
+        const long long nv = (long long)mhl_S(msz < prm.cap ? msz : prm.cap);
+        bool on = false;
+        for (int i = ms; i <= me; i++) {
+          const bool c2 = (__ldg(row + i) & 15u) != 11u;
+          if (c2 != on) {
+            const int q = rel0 + i;
+            if (q < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(q, 0)]), (unsigned long long)(c2 ? nv : -nv));
+            on = c2;
+          }
+        }
+        if (on && rel0 + me + 1 < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + me + 1, 0)]), (unsigned long long)(-nv));
+        msz = 0;
+      };
+      for (int c = 0; c < nch; c++) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
+        const int kmax = min(16, len - 16 * c);
+        for (int k = 0; k < kmax; k++) {
+          const uint32_t word = k < 8 ? (k < 4 ? v.x : v.y) : (k < 12 ? v.z : v.w);
+          const uint32_t code = (word >> (8 * (k & 3))) & 15u;
+          const int i = 16 * c + k;
+          const bool c2 = code != 11u;
+          if (c2 != cov) {
+            diff_event(rel0 + i, S, dW, dH, dDe, c2 ? 1 : -1, c2 ? hv : -hv, c2 ? dv : -dv);
+            cov = c2;
+          }
+          const uint32_t c7 = code & 7u;
+          if (c7 == 2u || c7 == 6u || c7 == 7u) {  // a cytosine call: count it at its position
+            const int q = rel0 + i;
+            if ((unsigned)q < (unsigned)S) atomicAdd(&T[(c7 == 2u ? 0 : (c7 == 6u ? 1 : 2)) * S + q], 1u);
+          }
+          if ((prm.ctx_mask >> code) & 1u) {
+            if (code < 8u) { if (!msz) ms = i; me = i; msz++; }
+            else if (msz) close_stretch();
+          }
+        }
+      }
+      if (cov) diff_event(rel0 + len, S, dW, dH, dDe, -1, -hv, -dv);
+      if (msz) close_stretch();
+    }
+    __syncthreads();
+
+    // ---- finalize: prefix sums of the four difference arrays per strand, row test, ordered compaction ----
+    const int q0 = threadIdx.x * PER;
+    int covv[2][PER];
+    long long Hs[2][PER], De[2][PER], Nu[2][PER];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      int rw = 0; long long rh = 0, rd = 0, rn = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        rw += dWb[s * S + q0 + k]; covv[s][k] = rw;
+        rh += L64[(s * 3 + 0) * S + q0 + k]; Hs[s][k] = rh;
+        rd += L64[(s * 3 + 1) * S + q0 + k]; De[s][k] = rd;
+        rn += L64[(s * 3 + 2) * S + q0 + k]; Nu[s][k] = rn;
+      }
+      const long long ew = block_exscan_i64<kMhlWarps>((long long)rw, s_scan);
+      const long long eh = block_exscan_i64<kMhlWarps>(rh, s_scan);
+      const long long ed = block_exscan_i64<kMhlWarps>(rd, s_scan);
+      const long long en = block_exscan_i64<kMhlWarps>(rn, s_scan);
+#pragma unroll
+      for (int k = 0; k < PER; k++) { covv[s][k] += (int)ew; Hs[s][k] += eh; De[s][k] += ed; Nu[s][k] += en; }
+    }
+    uint32_t flags = 0;   // bit 2k+s
+    uint32_t which = 0;   // 2 bits per (k,s): class slot of the row
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const int cv = covv[s][k];
+        if (cv <= 0) continue;
+        const uint32_t half = (uint32_t)cv >> 1;
+#pragma unroll
+        for (int cls = 0; cls < 3; cls++) {
+          const uint32_t code = cls == 0 ? 2u : (cls == 1 ? 6u : 7u);
+          if (!((prm.ctx_mask >> code) & 1u)) continue;
+          if (Tb[(s * 3 + cls) * S + q0 + k] > half) { flags |= 1u << (2 * k + s); which |= (uint32_t)cls << (2 * (2 * k + s)); }
+        }
+      }
+    uint32_t nrows_u;
+    const int my_off = (int)block_exscan_u32<kMhlWarps>((uint32_t)__popc(flags), &nrows_u, s_scan32);
+    const int nrows_total = (int)nrows_u;
+    if (threadIdx.x == 0) {
+      const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
+      s_base = (long long)bb;
+      out.w_base[win] = (long long)bb;
+      out.w_cnt[win] = nrows_total;
+    }
+    __syncthreads();
+    const long long wbase = s_base;
+    if (flags && wbase + nrows_total <= out.cap) {
+      MhlRow* dst = out.scratch + wbase + my_off;
+#pragma unroll
+      for (int k = 0; k < PER; k++)
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          if (!((flags >> (2 * k + s)) & 1u)) continue;
+          const int cls = (which >> (2 * (2 * k + s))) & 3;
+          const int code = cls == 0 ? 2 : (cls == 1 ? 6 : 7);
+          const int c = (int)Tb[(s * 3 + cls) * S + q0 + k];
+          MhlRow rrow;
+          rrow.pos = w0 + q0 + k; rrow.strand_ctx = (s + 1) | (code << 8); rrow.coverage = c; rrow.pad = 0;
+          rrow.length = (double)(unsigned long long)Hs[s][k] / (double)c;                                  // (double)uint64 / int, :97
+          rrow.lmhl = (double)(unsigned long long)Nu[s][k] / (double)(unsigned long long)De[s][k];       // :98
+          *dst++ = rrow;
+        }
+    }
+  }
+}
+
+struct MhlCols { int32_t *rname, *strand, *pos, *ctx, *coverage; double *length, *lmhl; };
+
+__global__ void __launch_bounds__(128)
+k_gather_mhl(const MhlRow* __restrict__ scratch, const long long* __restrict__ w_base, const long long* __restrict__ w_dst,
+             const int32_t* __restrict__ w_cnt, const int32_t* __restrict__ w_rname, int n_win, long long cap, MhlCols out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = warp; w < n_win; w += n_warps) {
+    const int cnt = w_cnt[w];
+    if (!cnt) continue;
+    const long long src = w_base[w], dst = w_dst[w];
+    if (src + cnt > cap || dst + cnt > cap) continue;
+    const int rn = w_rname[w];
+    for (int i = lane; i < cnt; i += 32) {
+      const MhlRow v = scratch[src + i];
+      out.rname[dst + i] = rn;
+      out.strand[dst + i] = v.strand_ctx & 0xFF;
+      out.pos[dst + i] = v.pos;
+      out.ctx[dst + i] = v.strand_ctx >> 8;
+      out.coverage[dst + i] = v.coverage;
+      out.length[dst + i] = v.length;
+      out.lmhl[dst + i] = v.lmhl;
+    }
+  }
+}
+
+}  // namespace ea

@@ -145,6 +145,16 @@ int ea_bed_report(ea_handle* h, int mode, const int32_t* bed_chr, const int32_t*
                   int32_t param, const ea_report_params* thr, const uint8_t* pass, int32_t* match_out, uint8_t* pass_out,
                   int64_t* counts_out);
 
+/* ---- lMHL report ------------------------------------------------------- *
+ * ea_mhl_report replaces rcpp_mhl_report (src/rcpp_mhl_report.cpp:46-228; R/RcppExports.R rcpp_mhl_report;
+ * R/generateMhlReport.R:170-197): ctx = the haplotype context's methylated + unmethylated letters (e.g. "Zz"),
+ * hmax = max.haplotype.window (<= 0: unlimited), hmin = min.haplotype.length, max_ooctx_meth_frac =
+ * max.outofcontext.beta.  Two-phase like ea_cx_report: the call returns the row count, the caller allocates five int32
+ * and two double columns of that length and fetches (any column may be NULL). */
+int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, double max_ooctx_meth_frac, int64_t* nrow_out);
+int ea_mhl_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* pos, int32_t* context, int32_t* coverage,
+                        double* length, double* lmhl);
+
 /* ---- measurement hooks (device-resident, no host copies; used by bench.py) ------------------- */
 
 typedef struct ea_timing {

@@ -260,3 +260,115 @@ double port_match_target(void* h, int mode, long nbed, const int* chr, const int
   }
   return now_s() - t0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Linearised MHL report, restating /root/reference/src/rcpp_mhl_report.cpp:46-228.
+ * Independent formulation: since flush boundaries are unobservable, positions are accumulated in a dense
+ * per-chromosome-run array (rows are sorted by start) instead of a map.  Per read (:150-182): h = number of bytes
+ * whose code is in `ctx`; methylated stretches (codes < 8 of `ctx`, uninterrupted by an unmethylated `ctx` byte) give
+ * every byte between the first and the last methylated byte of the stretch the numerator S(min(size, hmax));
+ * out-of-context methylated / unmethylated bytes decide the read's fate (skip if h < hmin or the fraction >
+ * max_ooctx; NaN compares false).  Per kept read and non-'-' byte (:184-195): counters of the code, coverage, sum of h,
+ * numerator, denominator S(min(h, hmax)).  Row rule as in the cytosine report (:72-101):
+ * coverage = C + c, length = sum(h) / coverage, lmhl = numerator / denominator (doubles).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t cnt[16]; uint64_t hsum, num, den; } MhlPos;  /* per (position, strand) */
+typedef struct { int* icol[5]; double* dcol[2]; long nrow, cap; } MhlOut;
+static MhlOut g_mhl;  /* last report (single-threaded test helper) */
+
+static uint64_t S_of(uint64_t n) { return n < 2 ? n : (n * (n + 1) * (n + 2)) / 6; }
+
+static void mhl_emit(int rname, int strand, int pos, int ctx, int cov, double len, double lmhl) {
+  MhlOut* o = &g_mhl;
+  if (o->nrow == o->cap) {
+    o->cap = o->cap ? o->cap * 2 : 1024;
+    for (int c = 0; c < 5; c++) o->icol[c] = (int*)realloc(o->icol[c], sizeof(int) * (size_t)o->cap);
+    for (int c = 0; c < 2; c++) o->dcol[c] = (double*)realloc(o->dcol[c], sizeof(double) * (size_t)o->cap);
+  }
+  int v[5] = {rname, strand, pos, ctx, cov};
+  for (int c = 0; c < 5; c++) o->icol[c][o->nrow] = v[c];
+  o->dcol[0][o->nrow] = len; o->dcol[1][o->nrow] = lmhl;
+  o->nrow++;
+}
+
+static void mhl_flush(MhlPos* a, int base, int span, int rname, const unsigned inctx[16]) {
+  for (int p = 0; p < span; p++)
+    for (int st = 0; st < 2; st++) {
+      const MhlPos* v = &a[2 * (size_t)p + st];
+      uint64_t cov = 0;
+      for (int k = 0; k < 16; k++) if (k != 11) cov += v->cnt[k];
+      if (!cov) continue;
+      const uint64_t half = cov / 2;
+      int ctx;
+      if (v->cnt[12] > half) continue;
+      else if (v->cnt[2] + v->cnt[10] > half) ctx = 2;
+      else if (v->cnt[6] + v->cnt[14] > half) ctx = 6;
+      else if (v->cnt[7] + v->cnt[15] > half) ctx = 7;
+      else continue;
+      if (!inctx[ctx]) continue;
+      const int c = (int)(v->cnt[ctx] + v->cnt[ctx | 8]);
+      mhl_emit(rname, st + 1, base + p, ctx, c, (double)v->hsum / c, (double)v->num / (double)v->den);
+    }
+}
+
+long port_mhl_report(void* h, const char* ctx, int hmax, int hmin, double max_ooctx, double* seconds) {
+  PortBam* b = (PortBam*)h;
+  double t0 = now_s();
+  unsigned inctx[16] = {0};
+  for (const unsigned char* p = (const unsigned char*)ctx; *p; p++) inctx[code_of(*p)] = 1;
+  const uint64_t cap = hmax > 0 ? (uint64_t)(hmax < 65536 ? hmax : 65536) : 65536;
+  g_mhl.nrow = 0;
+  MhlPos* a = NULL; size_t acap = 0;
+  uint64_t* nb = NULL; size_t nbcap = 0;
+  int cur_rname = 0, base = 0, span = 0;  /* dense array covers positions [base, base + span) */
+  for (long x = 0; x < b->n; x++) {
+    const int st = b->start[x];
+    if (b->rname[x] != cur_rname || st >= base + span) {  /* new chromosome or coverage gap: everything before is final */
+      if (span) mhl_flush(a, base, span, cur_rname, inctx);
+      cur_rname = b->rname[x]; base = st; span = 0;
+    }
+    const long t = b->templid[x];
+    const uint8_t* s = b->blob + b->off[t];
+    const int64_t len = b->off[t + 1] - b->off[t];
+    if ((size_t)len > nbcap) { nbcap = (size_t)len * 2; nb = (uint64_t*)realloc(nb, sizeof(uint64_t) * nbcap); }
+    memset(nb, 0, sizeof(uint64_t) * (size_t)len);
+    uint64_t hsz = 0, msz = 0, oo[16] = {0};
+    int64_t ms = 0, me = 0;
+    for (int64_t i = 0; i < len; i++) {
+      const unsigned code = s[i] & 15u;
+      if (inctx[code]) {
+        hsz++;
+        if (code < 8) { if (!msz) ms = i; me = i; msz++; }
+        else if (msz) { for (int64_t k = ms; k <= me; k++) nb[k] = S_of(msz < cap ? msz : cap); msz = 0; }
+      } else oo[code]++;
+    }
+    const uint64_t om = oo[2] + oo[5] + oo[6] + oo[7], ou = oo[10] + oo[13] + oo[14] + oo[15];
+    const double frac = (double)om / (double)(om + ou);
+    if ((int)hsz < hmin || frac > max_ooctx) continue;
+    if (msz) for (int64_t k = ms; k <= me; k++) nb[k] = S_of(msz < cap ? msz : cap);
+    const int need = (int)(st - base + len);
+    if (need > span) {
+      if ((size_t)need * 2 > acap) { acap = (size_t)need * 4; a = (MhlPos*)realloc(a, sizeof(MhlPos) * acap); }
+      memset(a + 2 * (size_t)span, 0, sizeof(MhlPos) * 2 * (size_t)(need - span));
+      span = need;
+    }
+    const uint64_t den = S_of(hsz < cap ? hsz : cap);
+    for (int64_t i = 0; i < len; i++) {
+      const unsigned code = s[i] & 15u;
+      if (code == 11) continue;
+      MhlPos* v = &a[2 * (size_t)(st - base + i) + (b->strand[x] - 1)];
+      v->cnt[code]++; v->hsum += hsz; v->num += nb[i]; v->den += den;
+    }
+  }
+  if (span) mhl_flush(a, base, span, cur_rname, inctx);
+  free(a); free(nb);
+  if (seconds) *seconds = now_s() - t0;
+  return g_mhl.nrow;
+}
+
+void port_mhl_fetch(void* h, int* rname, int* strand, int* pos, int* context, int* coverage, double* length, double* lmhl) {
+  (void)h;
+  int* dst[5] = {rname, strand, pos, context, coverage};
+  for (int c = 0; c < 5; c++) if (g_mhl.nrow) memcpy(dst[c], g_mhl.icol[c], sizeof(int) * (size_t)g_mhl.nrow);
+  if (g_mhl.nrow) { memcpy(length, g_mhl.dcol[0], sizeof(double) * (size_t)g_mhl.nrow); memcpy(lmhl, g_mhl.dcol[1], sizeof(double) * (size_t)g_mhl.nrow); }
+}

@@ -94,6 +94,9 @@ class _Cpu:
         getattr(L, px + "match_target").restype = C.c_double
         getattr(L, px + "match_target").argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.POINTER(C.c_int)] * 3 + [C.c_int, C.POINTER(C.c_int)]
         self.strand = np.ascontiguousarray(bam.strand, dtype=np.int32)
+        getattr(L, px + "mhl_report").restype = C.c_long
+        getattr(L, px + "mhl_report").argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
+        getattr(L, px + "mhl_fetch").argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_double)] * 2
         self.n = int(bam.rname.shape[0])
         data, off = bam.blob()
         self.nstr = int(off.shape[0] - 1)
@@ -147,6 +150,23 @@ class _Cpu:
         getattr(self.lib, self.PREFIX + "cx_fetch")(self.h, *[_p(c, C.c_int) for c in cols])
         names = ("rname", "strand", "pos", "context", "meth", "unmeth")
         return {k: c[:nrow] for k, c in zip(names, cols)}
+
+    # ---- lMHL report ----
+    def rcpp_mhl_report(self, ctx, hmax, hmin, max_ooctx_meth_frac):
+        """src/rcpp_mhl_report.cpp:46 -> dict rname, strand, pos, context, coverage (int32), length, lmhl (float64)."""
+        sec = C.c_double(0)
+        nrow = getattr(self.lib, self.PREFIX + "mhl_report")(self.h, ctx.encode(), int(hmax), int(hmin), float(max_ooctx_meth_frac), C.byref(sec))
+        self.last_seconds = sec.value
+        ic = [np.zeros(max(nrow, 1), np.int32) for _ in range(5)]
+        dc = [np.zeros(max(nrow, 1), np.float64) for _ in range(2)]
+        getattr(self.lib, self.PREFIX + "mhl_fetch")(self.h, *[_p(c, C.c_int) for c in ic], *[_p(c, C.c_double) for c in dc])
+        names = ("rname", "strand", "pos", "context", "coverage", "length", "lmhl")
+        return {k: c[:nrow] for k, c in zip(names, ic + dc)}
+
+    def generateMhlReport(self, haplotype_context="CG", max_haplotype_window=0, min_haplotype_length=0, max_outofcontext_beta=0.1):
+        """R/generateMhlReport.R:170-197: ctx = ctx.meth + ctx.unmeth letters of the haplotype context."""
+        b = CONTEXT_TO_BASES[haplotype_context]
+        return self.rcpp_mhl_report(b[0] + b[1], max_haplotype_window, min_haplotype_length, max_outofcontext_beta)
 
     # ---- BED-assisted report (SURVEY.md 8f rank 2) ----
     def _match(self, mode, bed, param):

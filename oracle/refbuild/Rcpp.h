@@ -3,7 +3,8 @@
 // Minimal stand-in for <Rcpp.h>, just large enough for the reference's three
 // hot-path translation units (src/rcpp_threshold_reads.cpp,
 // src/rcpp_get_xm_beta.cpp, src/rcpp_cx_report.cpp) and the BED matcher
-// (src/rcpp_match_target.cpp) to compile UNMODIFIED from
+// (src/rcpp_match_target.cpp) and the lMHL report
+// (src/rcpp_mhl_report.cpp, 8f rank 1) to compile UNMODIFIED from
 // /root/reference/src (see oracle/Makefile).  The surface mirrored here is the
 // one listed in SURVEY.md Appendix A.  Nothing from the reference is copied:
 // this is an independent shim of the Rcpp API those files touch.
@@ -12,6 +13,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -70,11 +72,14 @@ class CharacterVector {
 };
 
 struct NamedColumn { std::string name; std::vector<int> values; };
+struct NamedDoubleColumn { std::string name; std::vector<double> values; };
 struct Named {
   std::string name;
   explicit Named(const char* n) : name(n) {}
   NamedColumn operator=(const std::vector<int>& v) const { return NamedColumn{name, v}; }
+  NamedDoubleColumn operator=(const std::vector<double>& v) const { return NamedDoubleColumn{name, v}; }
 };
+inline void stop(const char*) { std::abort(); }
 
 class DataFrame {
  public:
@@ -97,6 +102,11 @@ class DataFrame {
   void add(NamedColumn&& c) {
     cols_[c.name] = IntegerVector(std::make_shared<std::vector<int>>(std::move(c.values)));
   }
+  void add(NamedDoubleColumn&& c) { dcols_[c.name] = std::make_shared<std::vector<double>>(std::move(c.values)); }
+ public:
+  std::shared_ptr<std::vector<double>> double_column(const char* name) { return dcols_[name]; }
+ private:
+  std::map<std::string, std::shared_ptr<std::vector<double>>> dcols_;
   std::map<std::string, IntegerVector> cols_;
   std::map<std::string, SEXP> attrs_;
 };

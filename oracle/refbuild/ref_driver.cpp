@@ -25,6 +25,8 @@ Rcpp::DataFrame rcpp_cx_report(Rcpp::DataFrame& df, Rcpp::LogicalVector& pass, c
 // /root/reference/src/rcpp_match_target.cpp:16,51
 std::vector<int> rcpp_match_amplicon(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, const int tolerance);
 std::vector<int> rcpp_match_capture(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, const signed int min_overlap);
+// /root/reference/src/rcpp_mhl_report.cpp:46
+Rcpp::DataFrame rcpp_mhl_report(Rcpp::DataFrame& df, const std::string ctx, int hmax, const int hmin, const double max_ooctx_meth_frac);
 
 namespace {
 struct RefBam {
@@ -33,6 +35,9 @@ struct RefBam {
   long n = 0;
   // last report
   std::shared_ptr<std::vector<int>> cols[6];
+  // last lMHL report: rname, strand, pos, context, coverage + length, lmhl
+  std::shared_ptr<std::vector<int>> mcols[5];
+  std::shared_ptr<std::vector<double>> mdcols[2];
 };
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -124,6 +129,30 @@ double ref_match_target(void* h, int mode, long nbed, const int* chr, const int*
   double t1 = now_s();
   std::memcpy(out, r.data(), r.size() * sizeof(int));
   return t1 - t0;
+}
+
+// rcpp_mhl_report(df, ctx, hmax, hmin, max_ooctx_meth_frac); returns the row count, rows fetched with ref_mhl_fetch.
+long ref_mhl_report(void* h, const char* ctx, int hmax, int hmin, double max_ooctx, double* seconds) {
+  RefBam* b = static_cast<RefBam*>(h);
+  double t0 = now_s();
+  Rcpp::DataFrame res = rcpp_mhl_report(b->df, ctx, hmax, hmin, max_ooctx);
+  double t1 = now_s();
+  if (seconds) *seconds = t1 - t0;
+  static const char* names[5] = {"rname", "strand", "pos", "context", "coverage"};
+  for (int c = 0; c < 5; c++) b->mcols[c] = res[names[c]].shared();
+  b->mdcols[0] = res.double_column("length");
+  b->mdcols[1] = res.double_column("lmhl");
+  return static_cast<long>(b->mcols[0]->size());
+}
+
+void ref_mhl_fetch(void* h, int* rname, int* strand, int* pos, int* context, int* coverage, double* length, double* lmhl) {
+  RefBam* b = static_cast<RefBam*>(h);
+  int* dst[5] = {rname, strand, pos, context, coverage};
+  for (int c = 0; c < 5; c++)
+    if (b->mcols[c] && !b->mcols[c]->empty()) std::memcpy(dst[c], b->mcols[c]->data(), b->mcols[c]->size() * sizeof(int));
+  double* dd[2] = {length, lmhl};
+  for (int c = 0; c < 2; c++)
+    if (b->mdcols[c] && !b->mdcols[c]->empty()) std::memcpy(dd[c], b->mdcols[c]->data(), b->mdcols[c]->size() * sizeof(double));
 }
 
 }  // extern "C"

@@ -45,6 +45,9 @@ CASES = [
     ("cg_zero_thresholds", True, "CG", 0, 0.0, 1.0, "CG"),
 ]
 BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh"), ("beta_oo_cg", "XH", "xh")]
+# lMHL report: (case, haplotype.context, max.haplotype.window, min.haplotype.length, max.outofcontext.beta)
+MHL_CASES = [("mhl_default", "CG", 0, 0, 0.1), ("mhl_win1", "CG", 1, 0, 0.1), ("mhl_nofilter", "CG", 0, 0, 1.0), ("mhl_cx_win3_len2", "CX", 3, 2, 0.5),
+             ("mhl_chh_len5", "CHH", 0, 5, 0.2), ("mhl_cxg_win2", "CxG", 2, 1, 0.05)]
 # BED-assisted report: fixture -> (bed file, [(case, bed.type, match.tolerance / match.min.overlap)])
 BEDS = {
     "amplicon010meth": (EXT + "amplicon.bed", [("ampl_tol1", "amplicon", 1), ("ampl_tol0", "amplicon", 0), ("ampl_tol25", "amplicon", 25),
@@ -71,6 +74,10 @@ def main():
                 out[cname + "." + k] = v
         for bname, m, u in BETAS:
             out[bname] = ref.rcpp_get_xm_beta(m, u)
+        for cname, hctx, hmax, hmin, moo in MHL_CASES:
+            rep = ref.generateMhlReport(hctx, hmax, hmin, moo)
+            for k, v in rep.items():
+                out[cname + "." + k] = v
         if name in BEDS:
             bed_path, cases = BEDS[name]
             chr_, st, en, _ = read_bed(bed_path, bam.rname_levels)

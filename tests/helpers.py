@@ -21,6 +21,9 @@ CASES = [
     ("cg_zero_thresholds", True, "CG", 0, 0.0, 1.0, "CG"),
 ]
 BETAS = [("beta_cg", "Z", "z"), ("beta_cxg", "ZX", "zx"), ("beta_cx", "ZXH", "zxh"), ("beta_oo_cg", "XH", "xh")]
+MHL_CASES = [("mhl_default", "CG", 0, 0, 0.1), ("mhl_win1", "CG", 1, 0, 0.1), ("mhl_nofilter", "CG", 0, 0, 1.0), ("mhl_cx_win3_len2", "CX", 3, 2, 0.5),
+             ("mhl_chh_len5", "CHH", 0, 5, 0.2), ("mhl_cxg_win2", "CxG", 2, 1, 0.05)]
+MHL_COLS = ("rname", "strand", "pos", "context", "coverage", "length", "lmhl")
 # fixture -> [(case, bed.type, match.tolerance / match.min.overlap)]; must match tests/golden/make_golden.py
 BED_CASES = {
     "amplicon010meth": [("ampl_tol1", "amplicon", 1), ("ampl_tol0", "amplicon", 0), ("ampl_tol25", "amplicon", 25), ("ampl_as_capture", "capture", 1)],
@@ -98,3 +101,13 @@ def kat_c4_rows():
         s[i % 10] = "Z"
         rows.append((1, 1, 1, "".join(s)))
     return rows
+
+
+def assert_mhl_equal(got, want, what=""):
+    """Bit-exact: integer columns equal, double columns equal including NaN payload positions."""
+    for k in MHL_COLS:
+        g, w = np.asarray(got[k]), np.asarray(want[k])
+        assert g.shape == w.shape, "%s: %s has %d rows, expected %d" % (what, k, g.shape[0], w.shape[0])
+        if not np.array_equal(g, w, equal_nan=(g.dtype.kind == "f")):
+            i = int(np.nonzero(~((g == w) | ((g != g) & (w != w))))[0][0])
+            raise AssertionError("%s: column %s differs first at row %d: got %r want %r (pos %s)" % (what, k, i, g[i], w[i], want["pos"][i]))

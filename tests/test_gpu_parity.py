@@ -266,3 +266,38 @@ def test_bed_matching_random_targets_against_oracle():
             assert np.array_equal(got_m, want_m) and np.array_equal(got["counts"], want["counts"])
             assert np.array_equal(got["VEF"], want["VEF"], equal_nan=True)
         bam.close()
+
+
+# ---- lMHL report: ea_mhl_report ------------------------------------------------
+from helpers import MHL_CASES, assert_mhl_equal  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_mhl_report_golden_vectors(name, kernel_policy):
+    if kernel_policy != "auto":
+        pytest.skip("the lMHL report has one kernel")
+    bam, z = load_golden(name)
+    for cname, hctx, hmax, hmin, moo in MHL_CASES:
+        rep = ea.generateMhlReport(bam, haplotype_context=hctx, max_haplotype_window=hmax, min_haplotype_length=hmin, max_outofcontext_beta=moo)
+        assert_mhl_equal(rep, {k: z[cname + "." + k] for k in ("rname", "strand", "pos", "context", "coverage", "length", "lmhl")}, "%s/%s" % (name, cname))
+    bam.close()
+
+
+def test_mhl_report_identity_and_synthetic(kernel_policy):
+    if kernel_policy != "auto":
+        pytest.skip("the lMHL report has one kernel")
+    # inst/unitTests/test_generateMhlReport.R:7-12: window 1 == meth/(meth+unmeth) of the unthresholded CG report, identical()
+    bam, _ = load_golden("capture")
+    m1 = ea.generateMhlReport(bam, max_haplotype_window=1)
+    cg = ea.generateCytosineReport(bam, threshold_reads=False)
+    assert np.array_equal(m1["pos"], cg["pos"]) and np.array_equal(m1["lmhl"], cg["meth"] / (cg["meth"] + cg["unmeth"]))
+    bam.close()
+    for shape in ("wgbs150", "pe_merged", "capture_islands", "tiny_reads", "long_reads"):
+        host = ea.synth_host(ea.synth_config(**SYNTH[shape]))
+        oracle = PortCpu(host)
+        for hctx, hmax, hmin, moo in (("CG", 0, 0, 0.1), ("CX", 2, 3, 0.6), ("CHG", 0, 1, 1.0)):
+            want = oracle.generateMhlReport(hctx, hmax, hmin, moo)
+            got = ea.generateMhlReport(host, haplotype_context=hctx, max_haplotype_window=hmax, min_haplotype_length=hmin, max_outofcontext_beta=moo)
+            assert want["pos"].shape[0] > 0
+            assert_mhl_equal(got, want, "%s %s" % (shape, hctx))
+        host.close()

@@ -186,3 +186,42 @@ def test_port_matches_reference_on_random_beds():
         for par in (-5, 0, 1, 40):
             assert np.array_equal(ref.rcpp_match_amplicon(bed, par), port.rcpp_match_amplicon(bed, par))
             assert np.array_equal(ref.rcpp_match_capture(bed, par), port.rcpp_match_capture(bed, par))
+
+
+# ---- lMHL report -------------------------------------------------------------
+from helpers import MHL_CASES, assert_mhl_equal  # noqa: E402
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_reference_runit_constants_mhl(oracle):
+    # inst/unitTests/test_generateMhlReport.R:7-30,48-83
+    bam, _ = load_golden("capture")
+    o = oracle(bam)
+    m1 = o.generateMhlReport(max_haplotype_window=1)
+    _, cg = o.generateCytosineReport(threshold_reads=False)
+    assert np.array_equal(m1["lmhl"], cg["meth"] / (cg["meth"] + cg["unmeth"]))  # :7-12, identical()
+    m = o.generateMhlReport()
+    sp, sm = m["strand"] == 1, m["strand"] == 2
+    assert (int(m["coverage"].sum()), int(m["coverage"][sp].sum()), int(m["coverage"][sm].sum())) == (20219, 10188, 10031)
+    assert np.allclose([m["length"].sum(), m["lmhl"].sum()], [229119.960, 2666.456], rtol=1e-6, atol=0)  # RUnit::checkEquals tolerance
+    assert np.allclose([m["length"][sp].sum(), m["lmhl"][sp].sum(), m["length"][sm].sum(), m["lmhl"][sm].sum()],
+                       [119605.010, 1281.342, 109514.950, 1385.114], rtol=1e-6, atol=0)
+    bam, _ = load_golden("amplicon010meth")
+    o = oracle(bam)
+    for kw, want in ((dict(max_outofcontext_beta=1), (7081, 342, 6739, 6060.46765, 45.78637, 2380.83333, 34.03206, 3679.63432, 11.75431)),
+                     ({}, (7070, 339, 6731, 6051.54262, 43.53694, 2375.83333, 33.78206, 3675.709286, 9.754883))):
+        m = o.generateMhlReport(**kw)
+        sp, sm = m["strand"] == 1, m["strand"] == 2
+        assert (int(m["coverage"].sum()), int(m["coverage"][sp].sum()), int(m["coverage"][sm].sum())) == want[:3]
+        assert np.allclose([m["length"].sum(), m["lmhl"].sum(), m["length"][sp].sum(), m["lmhl"][sp].sum(), m["length"][sm].sum(), m["lmhl"][sm].sum()],
+                           want[3:], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_golden_mhl_vectors(oracle, name):
+    bam, z = load_golden(name)
+    o = oracle(bam)
+    for cname, hctx, hmax, hmin, moo in MHL_CASES:
+        rep = o.generateMhlReport(hctx, hmax, hmin, moo)
+        assert_mhl_equal(rep, {k: z[cname + "." + k] for k in rep}, "%s/%s" % (name, cname))
