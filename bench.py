@@ -167,6 +167,29 @@ def run_ours(args):
     two_pass = dict(total_ms=round(tm.total_ms, 4), threshold_ms=round(tm.kernel_ms[0], 4), window_ms=round(tm.kernel_ms[1], 4),
                     rows=int(tm.n_rows), n_pass=int(tm.n_pass))
 
+    # ---- the widened paths on the same resident reads, for the record: device call + row-count read-back ----
+    widened = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        widened = {}
+        nrow = C.c_int64(0)
+        for _ in range(2):
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            N.check(L.ea_mhl_report(dev.handle(), b"Zz", 0, 0, 0.1, C.byref(nrow)))
+            torch.cuda.synchronize(); dt = time.perf_counter() - t1
+        widened["mhl_report"] = {"seconds": dt, "reads_per_s": own_reads / dt, "rows": int(nrow.value), "what": "ea_mhl_report (rcpp_mhl_report), CG haplotypes, defaults"}
+        rng = np.random.default_rng(1)
+        nb = 20000
+        bst = np.sort(rng.integers(1, CHR1 - 3000, nb)).astype(np.int32)
+        bed = (np.ones(nb, np.int32), bst, (bst + 2000).astype(np.int32))
+        counts = np.zeros((nb + 1) * 4, np.int64)
+        i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        for _ in range(2):
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            N.check(L.ea_bed_report(dev.handle(), 1, i32(bed[0]), i32(bed[1]), i32(bed[2]), nb, 1, C.byref(p), None, None, None, counts.ctypes.data_as(C.POINTER(C.c_int64))))
+            torch.cuda.synchronize(); dt = time.perf_counter() - t1
+        widened["bed_report"] = {"seconds": dt, "reads_per_s": own_reads / dt, "targets": nb, "reads_matched": int(counts[:-4].sum()),
+                                 "what": "ea_bed_report (rcpp_match_capture + thresholds + per-target counts), 20000 targets of 2 kb"}
+
     # ---- end to end through the public API with HOST buffers (pack + H2D + kernels + D2H) ----
     e2e = None
     if not args.no_e2e:
@@ -252,6 +275,8 @@ def run_ours(args):
                            "what": "ea_pack_blob (H2D + device repack + validation + window index) + fused report + D2H of pass flags and rows + free"}
         if cpu:
             line["cpu_baseline"] = cpu
+        if widened:
+            line["widened_paths"] = widened
         emit(line)
     dev.close()
     if world > 1:
