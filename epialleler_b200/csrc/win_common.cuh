@@ -63,6 +63,8 @@ __device__ __forceinline__ bool eval_pass_tables(uint32_t m, uint32_t all, uint3
 __device__ __forceinline__ void red_shared(uint32_t addr, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// 4 * position (within a 32-byte unit) of merged-indicator bit i: the shared table (one LDS) or pure ALU (EA_POS_ALU)
+__device__ __forceinline__ uint32_t pos4_of(uint32_t bp_tbl, int i);
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -121,6 +123,15 @@ __device__ __forceinline__ void want_masks(const Planes& p, uint32_t (&m)[3], ui
   if (WANT & W_CG) { const uint32_t a = cls_cg(p.A0, p.B0, p.C0), b = cls_cg(p.A1, p.B1, p.C1); m[slot] = a | b; meth[slot] = (a & ~p.D0) | (b & ~p.D1); slot++; }
 }
 
+__device__ __forceinline__ uint32_t pos4_of(uint32_t bp_tbl, int i) {
+#ifdef EA_POS_ALU
+  const uint32_t u = (uint32_t)i;
+  return ((u & 3u) << 5) | ((u & 4u) << 2) | ((u >> 1) & 0xCu);
+#else
+  return lds_u8(bp_tbl + i);
+#endif
+}
+
 // '-' bytes (code 11) of one 16-byte chunk.  Isolated ones (at most two per chunk) are returned as a merged-layout mask
 // and counted in D by the caller; longer runs (mate gaps) become coverage deltas in W right here: -1 where a run starts,
 // +1 right after it ends, clamped to the window start.  w_addr = shared BYTE address of the chunk's byte 0 in W,
@@ -135,7 +146,7 @@ __device__ __forceinline__ uint32_t dash_events(const Planes& p, uint32_t w_addr
       const int i = 31 - __clz(mm);
       const uint32_t bit = 1u << i;
       mm ^= bit;
-      red_shared(max(w_addr + lds_u8(bp_tbl + i), w_floor), (starts & bit) ? 0u - sinc : sinc);
+      red_shared(max(w_addr + pos4_of(bp_tbl, i), w_floor), (starts & bit) ? 0u - sinc : sinc);
     }
     if ((E >> 29) & 1u) red_shared(max(w_addr + 64u, w_floor), sinc);  // the run reaches the chunk end
     E = 0u;
@@ -154,7 +165,7 @@ __device__ __forceinline__ void unit_events(const uint32_t (&m)[3], uint32_t E, 
     const int i = 31 - __clz(ev);
     const uint32_t bit = 1u << i;
     ev ^= bit;
-    const uint32_t bp4 = lds_u8(bp_tbl + i);
+    const uint32_t bp4 = pos4_of(bp_tbl, i);
     uint32_t a = t_addr;
     uint32_t v = (methpass & bit) ? 0x10001u : 1u;
     if (NC > 1 && (m[1] & bit)) a = t_addr + 2 * SG * 4;
@@ -176,7 +187,7 @@ __device__ __forceinline__ void push_meth(uint32_t mm, uint32_t t_addr, uint32_t
   while (mm) {
     const int i = 31 - __clz(mm);
     mm ^= 1u << i;
-    red_shared(t_addr + lds_u8(bp_tbl + i), 0x10000u);
+    red_shared(t_addr + pos4_of(bp_tbl, i), 0x10000u);
   }
 }
 

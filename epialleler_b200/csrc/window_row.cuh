@@ -61,16 +61,11 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
     const int w0 = wt.pos0[win];
     const int lo = wt.lo[win], hi = wt.hi[win];
     int npass_w = 0;
-    // Tiles: full rounds of kRowWarps tiles of 32 rows, then the remaining rows split evenly over the warps.
-    const int n_full = (hi - lo) / (kRowWarps * 32);
-    const int rem_lo = lo + n_full * kRowWarps * 32;
-    const int rem_tile = (hi - rem_lo + kRowWarps - 1) / kRowWarps;  // <= 32
-
-    for (int t = 0; t <= n_full; t++) {
-      int base, tend;
-      if (t < n_full) { base = lo + (t * kRowWarps + warp) * 32; tend = base + 32; }
-      else { base = rem_lo + warp * rem_tile; tend = min(base + rem_tile, hi); }
-      if (base >= tend) break;
+    // Tiles of 32 consecutive rows, dealt round robin to the warps.  The kernel is bound by instruction issue, so a full
+    // tile on some warps (the others wait at the barrier and leave their issue slots to the co-resident CTAs) beats
+    // spreading the window's last rows over all warps as partly filled tiles (measured).
+    for (int base = lo + warp * 32; base < hi; base += kRowWarps * 32) {
+      const int tend = min(base + 32, hi);
       const int r = base + lane;
       const bool valid = r < tend;
       const long long o0 = csr.off[valid ? r : tend];
