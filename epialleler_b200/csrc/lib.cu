@@ -752,18 +752,41 @@ int launch_cpl(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int want, in
 }
 
 // ---- row-per-lane kernel (one requested context, 32-byte-multiple rows of at most 256 bytes): window_row.cuh ----
-struct RowPlan { bool ok = false; int maxu = 0; size_t smem = 0; };
 
-#ifndef EA_ROW_S
-#define EA_ROW_S 2048
+struct RowPlan { bool ok = false; int maxu = 0; int S = 0; size_t smem = 0; };
+
+// Window size of the row kernel.  A window's rows are dealt to 8 warps in tiles of 32, so the sweep takes
+// ceil(rows / 256) rounds and the last one is only partly filled; S is chosen per data set so that a window holds
+// close to a whole number of rounds (k * 256 rows including the halo rows that start before the window).
+int pick_row_window(const ea_handle* h, const WinIndex& ix2048) {
+#ifdef EA_ROW_S
+  return EA_ROW_S;
+#else
+  if (ix2048.n <= 0 || h->n <= 0) return 2048;
+  const double dens = (double)h->n / ((double)ix2048.n * 2048.0);        // rows per covered position
+  const double halo = ((double)h->nbytes / (double)h->n) * dens;          // rows that start before a window and reach into it
+  if (!(dens > 0)) return 2048;
+  int best = 2048; double best_eff = 0;
+  for (int k = 1; k <= 8; k++) {
+    const double s_exact = (256.0 * k - halo) / dens;
+    int S = (int)(s_exact / 32.0) * 32;                                   // a little under k full rounds
+    if (S < 1024 || S > 2560) continue;                                   // 5 CTAs/SM: (S + 80) * 16 B <= 42 KB
+    const double rows = S * dens + halo;
+    const double eff = rows / (256.0 * k) * (1.0 - halo / rows * 0.5);    // round filling, mild preference for less halo
+    if (eff > best_eff) { best_eff = eff; best = S; }
+  }
+  return best;
 #endif
+}
+
 RowPlan plan_row(const ea_handle* h, const WinIndex& ix, int nc) {
   RowPlan t;
-  if (h->n == 0 || ix.n == 0 || ix.S != EA_ROW_S || nc != 1 || !h->rows32 || ix.max_rows > 32767) return t;
+  if (h->n == 0 || ix.n == 0 || nc != 1 || !h->rows32 || ix.max_rows > 32767 || ix.S > kRowMaxS || (ix.S & 31)) return t;
   const int max_nu = (h->max_len + 31) >> 5;
   if (max_nu < 1 || max_nu > 8) return t;
   t.maxu = max_nu <= 5 ? 5 : 8;
-  t.smem = sizeof(uint32_t) * (size_t)(nc + 1) * 2 * (kGuardLo + EA_ROW_S + kGuardHi);
+  t.S = ix.S;
+  t.smem = sizeof(uint32_t) * (size_t)(nc + 1) * 2 * (kGuardLo + ix.S + kGuardHi);
   t.ok = true;
   return t;
 }
@@ -771,9 +794,8 @@ RowPlan plan_row(const ea_handle* h, const WinIndex& ix, int nc) {
 template <int TCTX, int WANT, bool FUSED, int MAXU>
 int launch_row_u(ea_handle* h, const WinIndex& ix, const RowPlan& rp, const ThrParams& thr, const uint8_t* pass_in,
                  uint8_t* pass_out, const ReportOut& out) {
-  constexpr int S = EA_ROW_S;
-  if (ix.S != S) return fail(EA_ERR_STATE, "window size mismatch");
-  auto kern = k_window_row<TCTX, WANT, FUSED, S, MAXU>;
+  if (ix.S != rp.S) return fail(EA_ERR_STATE, "window size mismatch");
+  auto kern = k_window_row<TCTX, WANT, FUSED, MAXU>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem));
   WinTable wt;
   wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
@@ -869,15 +891,12 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
   const bool fused = can_fuse && rp.mode == 0;
   if (rp.want) {
-    if (policy == 0) {
-      if (EA_ROW_S != 2048) {
-        WinIndex* ix2 = nullptr;
-        if ((rc = build_index(h, EA_ROW_S, &ix2))) return rc;
-        row = plan_row(h, *ix2, nc);
-        if (row.ok) ix = ix2;
-      } else {
-        row = plan_row(h, *ix, nc);
-      }
+    if (policy == 0 && nc == 1 && h->rows32 && ((h->max_len + 31) >> 5) <= 8) {
+      const int S = pick_row_window(h, *ix);
+      WinIndex* ixr = ix;
+      if (S != 2048 && (rc = build_index(h, S, &ixr))) return rc;
+      row = plan_row(h, *ixr, nc);
+      if (row.ok) ix = ixr;
     }
     if ((policy == 0 && !row.ok) || policy == 3) cpl = plan_cpl(h, *ix, nc, fused);
     if (policy == 2) tpr = plan_tpr(h, *ix);

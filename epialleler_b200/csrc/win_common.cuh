@@ -194,21 +194,24 @@ __device__ __forceinline__ void push_meth(uint32_t mm, uint32_t t_addr, uint32_t
 
 // Finalize one window: coverage prefix sum, row test total_ctx > floor(cov/2) (src/rcpp_cx_report.cpp:58-85), ordered
 // compaction into the scratch rows.  All NT threads of the CTA call it after a __syncthreads().
-template <int WANT, int S, int NT, bool FUSED>
-__device__ __forceinline__ void window_finalize(const uint32_t* __restrict__ W, const uint32_t* __restrict__ D, const uint32_t* __restrict__ T,
-                                                int w0, int win, const ReportOut& out, uint32_t* s_scan, long long* s_base, const int* s_npass) {
+template <int WANT, int PER, int NT, bool FUSED>
+__device__ __forceinline__ void window_finalize_rt(const uint32_t* __restrict__ W, const uint32_t* __restrict__ D, const uint32_t* __restrict__ T,
+                                                   int S /* positions, multiple of 4, <= PER * NT */, int w0, int win, const ReportOut& out,
+                                                   uint32_t* s_scan, long long* s_base, const int* s_npass) {
   constexpr int NC = n_ctx<WANT>();
-  constexpr int SG = kGuardLo + S + kGuardHi;
-  constexpr int PER = S / NT;
   constexpr int NW = NT / 32;
+  const int SG = kGuardLo + S + kGuardHi;
   const int q0 = threadIdx.x * PER;
   uint32_t cov[PER];  // coverage of both strands: '+' | '-' << 16
   {
     uint32_t run = 0;
 #pragma unroll
     for (int v4 = 0; v4 < PER / 4; v4++) {
-      const uint4 w = *reinterpret_cast<const uint4*>(&W[kGuardLo + q0 + v4 * 4]);
-      const uint4 d = *reinterpret_cast<const uint4*>(&D[kGuardLo + q0 + v4 * 4]);
+      uint4 w = make_uint4(0, 0, 0, 0), d = make_uint4(0, 0, 0, 0);
+      if (q0 + v4 * 4 < S) {
+        w = *reinterpret_cast<const uint4*>(&W[kGuardLo + q0 + v4 * 4]);
+        d = *reinterpret_cast<const uint4*>(&D[kGuardLo + q0 + v4 * 4]);
+      }
       run += w.x; cov[v4 * 4 + 0] = run - d.x;
       run += w.y; cov[v4 * 4 + 1] = run - d.y;
       run += w.z; cov[v4 * 4 + 2] = run - d.z;
@@ -226,7 +229,8 @@ __device__ __forceinline__ void window_finalize(const uint32_t* __restrict__ W, 
     for (int c = 0; c < NC; c++)
 #pragma unroll
       for (int v4 = 0; v4 < PER / 4; v4++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&T[(c * 2 + s) * SG + kGuardLo + q0 + v4 * 4]);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 + v4 * 4 < S) v = *reinterpret_cast<const uint4*>(&T[(c * 2 + s) * SG + kGuardLo + q0 + v4 * 4]);
         if (v.x | v.y | v.z | v.w) {
           const uint32_t t[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -274,6 +278,13 @@ __device__ __forceinline__ void window_finalize(const uint32_t* __restrict__ W, 
       *dst++ = make_int4(w0 + q0 + k, (s + 1) | (code << 8), (int)(val >> 16), (int)((val & 0xFFFFu) - (val >> 16)));
     }
   }
+}
+
+// compile-time window size: PER = S / NT positions per thread
+template <int WANT, int S, int NT, bool FUSED>
+__device__ __forceinline__ void window_finalize(const uint32_t* __restrict__ W, const uint32_t* __restrict__ D, const uint32_t* __restrict__ T,
+                                                int w0, int win, const ReportOut& out, uint32_t* s_scan, long long* s_base, const int* s_npass) {
+  window_finalize_rt<WANT, S / NT, NT, FUSED>(W, D, T, S, w0, win, out, s_scan, s_base, s_npass);
 }
 
 }  // namespace ea

@@ -28,13 +28,17 @@ constexpr int kRowWarps = kRowThreads / 32;
 #define EA_ROW_MINB 5   // measured on B200: 5 CTAs/SM (48 registers) beats 4 and 6
 #endif
 
-template <int TCTX, int WANT, bool FUSED, int S, int MAXU>
+constexpr int kRowPer = 12;                        // positions per thread in the finalize: windows of up to 3072 positions
+constexpr int kRowMaxS = kRowPer * kRowThreads;
+
+template <int TCTX, int WANT, bool FUSED, int MAXU>
 __global__ void __launch_bounds__(kRowThreads, EA_ROW_MINB)
 k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* __restrict__ pass_in, uint8_t* __restrict__ pass_out,
              ReportOut out) {
   constexpr int NC = n_ctx<WANT>();
   static_assert(NC == 1, "k_window_row handles one requested context");
-  constexpr int SG = kGuardLo + S + kGuardHi;
+  const int S = wt.S;                                 // window size: runtime, chosen by the dispatcher (multiple of 32)
+  const int SG = kGuardLo + S + kGuardHi;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t s_scan[kRowWarps + 1];
@@ -45,7 +49,7 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   uint32_t* const W = reinterpret_cast<uint32_t*>(smem_raw);  // [SG]
   uint32_t* const D = W + SG;                                 // [SG]
   uint32_t* const T = D + SG;                                 // [2][SG]
-  constexpr int kZero4 = (NC + 1) * 2 * SG / 4;
+  const int kZero4 = (NC + 1) * 2 * SG / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t w_base = smem_u32(W), d_base = smem_u32(D), t_base = smem_u32(T), bp_tbl = smem_u32(s_bp4);
   const uint32_t w_floor = w_base + 4u * kGuardLo;
@@ -119,7 +123,7 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
             }
             m[1] = m[2] = 0u;
             if (inwin) {
-              unit_events<NC, SG>(m, E, (!FUSED && pass_known) ? meth[0] : 0u, dq + 128u * u, tq + 128u * u, sinc, bp_tbl);
+              unit_events<NC, 0>(m, E, (!FUSED && pass_known) ? meth[0] : 0u, dq + 128u * u, tq + 128u * u, sinc, bp_tbl);  // NC == 1: the SG stride is unused
               methm[u] = meth[0];
             }
             if (FUSED && (u & 3) == 3) {  // byte-wide fields hold the counts of four units
@@ -152,7 +156,7 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
     }
     __syncthreads();
 
-    window_finalize<WANT, S, kRowThreads, FUSED>(W, D, T, w0, win, out, s_scan, &s_base, &s_npass);
+    window_finalize_rt<WANT, kRowPer, kRowThreads, FUSED>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
   }
 }
 
