@@ -197,15 +197,17 @@ def run_ours(args):
         blob, off = host.blob()
         pinned = True
         try:
-            pin = [torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True) for a in (blob, off, host.rname, host.strand, host.start)]
-            for t, a in zip(pin, (blob, off, host.rname, host.strand, host.start)):
+            src = (blob, off, host.rname, host.strand, host.start, np.arange(host.nrow, dtype=np.int32))
+            pin = [torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True) for a in src]
+            for t, a in zip(pin, src):
                 t.numpy()[...] = a
-            blob, off, rn, st, sa = [t.numpy() for t in pin]
+            blob, off, rn, st, sa, tid = [t.numpy() for t in pin]
+            del src
         except Exception:
             pinned = False
             rn, st, sa = host.rname, host.strand, host.start
+            tid = np.arange(host.nrow, dtype=np.int32)
         n_loc = host.nrow
-        tid = np.arange(n_loc, dtype=np.int32)
         del host
         e2e_steps = max(1, min(args.steps, 5))
         times = []
@@ -222,7 +224,7 @@ def run_ours(args):
                 times.append(dt)
             rows_e2e = rep["pos"].shape[0]
         e2e_s = float(np.median(times))  # a pack allocates and frees ~20 GB: single outliers of the allocator are not the path's speed
-        h2d = int(blob.nbytes + off.nbytes + rn.nbytes + st.nbytes + sa.nbytes)
+        h2d = int(blob.nbytes + off.nbytes + rn.nbytes + st.nbytes + sa.nbytes + tid.nbytes)
         d2h = int(n_loc + 24 * rows_e2e)
         e2e = dict(seconds=e2e_s, h2d=h2d, d2h=d2h, pinned=pinned, steps=e2e_steps, rows=rows_e2e, n_pass=int(pass_flags.sum()))
 

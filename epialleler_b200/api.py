@@ -6,6 +6,7 @@ function); the bodies only marshal numpy arrays across the C ABI (epialleler_b20
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import gzip as _gzip
 from typing import Optional, Sequence
 
@@ -171,10 +172,25 @@ def rcpp_get_xm_beta(df, ctx_meth, ctx_unmeth):
     return out[:df.nrow]
 
 
+_PINNED_MIN_BYTES = 1 << 20
+
+
 def _host_out(n, dtype):
-    """Result buffer for a device->host copy (plain pageable memory: page-locked result buffers were measured and
-    rejected - cudaHostAlloc of a few hundred MB costs more than the pageable copy it would speed up)."""
-    return np.empty(max(int(n), 1), dtype)
+    """Result buffer for a device->host copy.  Large results live in page-locked blocks from the library's cache
+    (ea_host_alloc): the copy runs at PCIe speed instead of through the driver's pageable staging, and the block goes
+    back to the cache when the last numpy view of it is garbage collected.  Small results are plain numpy arrays."""
+    n = max(int(n), 1)
+    dt = np.dtype(dtype)
+    nbytes = n * dt.itemsize
+    if nbytes < _PINNED_MIN_BYTES:
+        return np.empty(n, dt)
+    L = N.lib()
+    p = L.ea_host_alloc(nbytes)
+    if not p:
+        return np.empty(n, dt)
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    weakref.finalize(buf, L.ea_host_free, p)
+    return np.frombuffer(buf, dtype=dt, count=n)
 
 
 def _fetch_report(df, nrow):

@@ -9,8 +9,10 @@
 #include <cstring>
 #include <cstdlib>
 #include <ctime>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include <cub/device/device_reduce.cuh>
@@ -87,6 +89,11 @@ void pool_free(void* p) {
   if (!p) return;
   cudaDeviceSynchronize();  // like cudaFree: nothing on any stream may still use the block
   cudaFreeAsync(p, cudaStreamPerThread);
+}
+
+// stream-ordered free: for blocks whose every use was on stream s (no device-wide synchronisation)
+void pool_free_on(void* p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
 }
 
 template <class T>
@@ -178,7 +185,8 @@ int pick_device(int device) {
 // pack-time kernels
 // ---------------------------------------------------------------------------------------------
 enum { F_UNSORTED = 1, F_DOMAIN = 2, F_TEMPLID = 4, F_NEGSTART = 8, F_STRAND = 16, F_TOOLONG = 32,
-       F_ODDCHUNKS = 64 /* informational: some padded row is not a multiple of 32 bytes */ };
+       F_ODDCHUNKS = 64 /* informational: some padded row is not a multiple of 32 bytes */,
+       F_NONIDENT = 128 /* informational: templid is not the identity (rows are not the strings in file order) */ };
 
 __global__ void k_lens_from_templid(const int64_t* __restrict__ soff, const int32_t* __restrict__ templid, int64_t n,
                                     int64_t nstr, int32_t* __restrict__ len, int64_t* __restrict__ padded,
@@ -187,6 +195,7 @@ __global__ void k_lens_from_templid(const int64_t* __restrict__ soff, const int3
   if (r >= n) return;
   const int64_t t = templid ? templid[r] : r;
   int64_t l = 0;
+  if (t != r) atomicOr(flags, F_NONIDENT);
   if (t < 0 || t >= nstr) atomicOr(flags, F_TEMPLID);
   else l = soff[t + 1] - soff[t];
   if (l < 0 || l > 0x7FFFFFF0ll) { atomicOr(flags, F_TOOLONG); l = 0; }
@@ -194,33 +203,73 @@ __global__ void k_lens_from_templid(const int64_t* __restrict__ soff, const int3
   padded[r] = (l + 15) & ~15ll;
 }
 
-// one warp per row: tight source string -> 16-byte aligned destination row padded with code 3 (kernels.cuh)
+// Tight source strings -> 16-byte aligned destination rows padded with code 3 (kernels.cuh); the last pad byte carries the
+// pad count in its high nibble.  One warp per batch of 32 consecutive rows [row0, row1): the lanes read the rows' metadata
+// coalesced, then every lane moves 16-byte chunks of the batch (a warp scan of the chunk counts maps chunk -> row); the
+// unaligned source is read as aligned 32-bit words and assembled with funnel shifts.
 __global__ void k_repack(const uint8_t* __restrict__ blob, const int64_t* __restrict__ soff,
-                         const int32_t* __restrict__ templid, int64_t n, const int64_t* __restrict__ doff,
+                         const int32_t* __restrict__ templid, int64_t row0, int64_t row1, const int64_t* __restrict__ doff,
                          const int32_t* __restrict__ len, uint8_t* __restrict__ dst) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp; r < n; r += n_warps) {
-    const int64_t t = templid ? templid[r] : r;
-    const uint8_t* src = blob + soff[t];
-    const int l = len[r];
-    uint8_t* d = dst + doff[r];
+  const int64_t n_batches = (row1 - row0 + 31) >> 5;
+  for (int64_t b = warp; b < n_batches; b += n_warps) {
+    const int64_t r = row0 + b * 32 + lane;
+    long long s = 0, d = 0;
+    int l = 0;
+    if (r < row1) {
+      const int64_t t = templid ? templid[r] : r;
+      s = soff[t]; l = len[r]; d = doff[r];
+    }
     const int nch = (l + 15) >> 4;
-    for (int c = lane; c < nch; c += 32) {
-      uint32_t w[4] = {0x03030303u, 0x03030303u, 0x03030303u, 0x03030303u};
-      const int b0 = c * 16;
-      const int m = min(16, l - b0);
-      if (m < 16) w[3] |= (uint32_t)(16 - m) << 28;  // last pad byte carries the pad count
-      for (int i = 0; i < m; i++) {
-        const uint32_t v = src[b0 + i];
-        w[i >> 2] = (w[i >> 2] & ~(0xFFu << ((i & 3) * 8))) | (v << ((i & 3) * 8));
+    int inc = nch;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+      const int o = __shfl_up_sync(FULL, inc, k);
+      if (lane >= k) inc += o;
+    }
+    const int ex = inc - nch;
+    const int total = __shfl_sync(FULL, inc, 31);
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      int j = 0;  // the row of chunk c: the last lane whose exclusive chunk count is <= c
+#pragma unroll
+      for (int step = 16; step; step >>= 1) {
+        const int e = __shfl_sync(FULL, ex, j + step);
+        if (e <= c) j += step;
       }
-      *reinterpret_cast<uint4*>(d + b0) = make_uint4(w[0], w[1], w[2], w[3]);
+      const long long sj = __shfl_sync(FULL, s, j), dj = __shfl_sync(FULL, d, j);
+      const int lj = __shfl_sync(FULL, l, j), ej = __shfl_sync(FULL, ex, j);
+      if (c < total) {
+        const int b0 = (c - ej) * 16;
+        const int m = min(16, lj - b0);
+        const uintptr_t p = reinterpret_cast<uintptr_t>(blob + sj + b0);
+        const uint32_t sh = (uint32_t)(p & 3) * 8u;
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(p & ~(uintptr_t)3);
+        const int need = (int)(p & 3) + m;  // bytes of the aligned words that belong to this chunk
+        const uint32_t w0 = a[0], w1 = need > 4 ? a[1] : 0u, w2 = need > 8 ? a[2] : 0u, w3 = need > 12 ? a[3] : 0u,
+                       w4 = need > 16 ? a[4] : 0u;
+        uint32_t o[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+        if (m < 16) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int v = m - 4 * k;
+            if (v < 4) {
+              const uint32_t keep = v <= 0 ? 0u : (1u << (8 * v)) - 1u;
+              o[k] = (o[k] & keep) | (0x03030303u & ~keep);
+            }
+          }
+          o[3] |= (uint32_t)(16 - m) << 28;
+        }
+        *reinterpret_cast<uint4*>(dst + dj + b0) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
 
+// padded rows -> tight strings (ea_to_host; not on the hot path)
 __global__ void k_unpad(const uint8_t* __restrict__ data, const int64_t* __restrict__ doff, const int32_t* __restrict__ len,
                         const int64_t* __restrict__ toff, int64_t n, uint8_t* __restrict__ out) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -373,9 +422,7 @@ int flags_error(unsigned f) {
 
 // Common tail of every constructor: validation, row-end keys, stream/events.
 int finish_handle(ea_handle* h) {
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, h->device));
-  h->sm_count = prop.multiProcessorCount;
+  CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
   int rc;
@@ -393,14 +440,13 @@ int finish_handle(ea_handle* h) {
     CU(cub::DeviceScan::InclusiveScan(nullptr, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
     void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
     CU(cub::DeviceScan::InclusiveScan(tmp, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    pool_free(tmp);
+    pool_free_on(tmp, h->stream);
   }
   unsigned f = 0;
   CU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(&h->max_len, d_maxlen, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  pool_free(d_flags); pool_free(d_maxlen);
+  pool_free_on(d_flags, h->stream); pool_free_on(d_maxlen, h->stream);
   CU(cudaGetLastError());
   h->rows32 = !(f & F_ODDCHUNKS);
   return flags_error(f & ~(unsigned)F_ODDCHUNKS);
@@ -906,7 +952,13 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
     }
   }
   tr.mark("window index");
-  if (h->cap_rows == 0 && (rc = ensure_rows(h, h->nbytes / 24 + 4096))) return rc;
+  // First guess of the row capacity (40 bytes per row): one report row per ~512 bytes of calls for a CpG report, more for the
+  // denser contexts.  The window kernel counts the rows it would have written, so an overflow costs one exact-size retry
+  // (a second pass over the data) - far cheaper than reserving the worst case of one row per call up front.
+  if (h->cap_rows == 0) {
+    const int64_t per = (rp.want & W_CHH) ? 64 : (rp.want & W_CHG) ? 192 : 512;
+    if ((rc = ensure_rows(h, h->nbytes / per + 4096))) return rc;
+  }
   tr.mark("row buffers");
 
   for (int attempt = 0; attempt < 2; attempt++) {
@@ -1035,7 +1087,7 @@ int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_
     pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
   }
   if ((rc = dmalloc(&h->d_data, (size_t)h->npadded + 16))) return rc;
-  if (h->n > 0) k_repack<<<std::max(1, std::min(grid_for(h->n * 32, 256), h->sm_count * 32)), 256>>>(d_blob, d_soff, d_templid, h->n, h->d_off, h->d_len, h->d_data);
+  if (h->n > 0) k_repack<<<std::max(1, std::min(grid_for(h->n, 256), h->sm_count * 8)), 256>>>(d_blob, d_soff, d_templid, 0, h->n, h->d_off, h->d_len, h->d_data);
   CU(cudaDeviceSynchronize());
   pool_free(d_flags); pool_free(d_padded);
   CU(cudaGetLastError());
@@ -1126,6 +1178,51 @@ void ea_free(ea_handle* h) {
   tr.mark("cudaFree");
 }
 
+// Page-locked host blocks for results (ea_host_alloc / ea_host_free): cudaHostAlloc of a few hundred MB costs more than the
+// pageable copy it would speed up, so freed blocks are kept in a small cache and handed out again (first fit within 2x).
+namespace {
+struct HostBlock { void* p; size_t bytes; };
+std::mutex g_host_mu;
+std::vector<HostBlock> g_host_free;                 // cached, not in use
+std::unordered_map<void*, size_t> g_host_live;      // handed out
+}  // namespace
+
+void* ea_host_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_host_free.size(); i++)
+      if (g_host_free[i].bytes >= bytes && g_host_free[i].bytes <= 2 * bytes + (1u << 20) &&
+          (best < 0 || g_host_free[i].bytes < g_host_free[best].bytes)) best = i;
+    if (best >= 0) {
+      const HostBlock b = g_host_free[best];
+      g_host_free.erase(g_host_free.begin() + best);
+      g_host_live[b.p] = b.bytes;
+      return b.p;
+    }
+  }
+  void* p = nullptr;
+  const size_t rounded = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+  if (cudaHostAlloc(&p, rounded, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    fail(EA_ERR_CUDA, "cudaHostAlloc(%zu) failed", rounded);
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  g_host_live[p] = rounded;
+  return p;
+}
+
+void ea_host_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  auto it = g_host_live.find(p);
+  if (it == g_host_live.end()) return;
+  g_host_free.push_back(HostBlock{p, it->second});
+  g_host_live.erase(it);
+}
+
 int ea_trim(int device) {
   int rc;
   if ((rc = pick_device(device))) return rc;
@@ -1133,6 +1230,12 @@ int ea_trim(int device) {
   CU(cudaDeviceSynchronize());
   CU(cudaDeviceGetDefaultMemPool(&pool, device));
   CU(cudaMemPoolTrimTo(pool, 0));
+  std::vector<HostBlock> blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    blocks.swap(g_host_free);
+  }
+  for (auto& b : blocks) cudaFreeHost(b.p);
   return EA_OK;
 }
 
@@ -1140,6 +1243,14 @@ int64_t ea_nrow(const ea_handle* h) { return h ? h->n : -1; }
 int64_t ea_nbytes(const ea_handle* h) { return h ? h->nbytes : -1; }
 int ea_device(const ea_handle* h) { return h ? h->device : -1; }
 
+// Host columns + one tight string blob -> packed handle, as a two-stream pipeline:
+//   copy stream    : row metadata, then the blob in chunks of whole strings (one event per chunk);
+//   kernel stream  : strand/length/offset kernels as soon as the metadata landed, then per chunk the domain check and -
+//                    when templid is the identity (rows are the strings in file order, what preprocessBam produces) - the
+//                    repack of that chunk's rows, so only the last chunk's repack is not hidden behind the PCIe transfer;
+//   handle stream  : sortedness validation, row-end keys and pad counts (finish_handle) while the blob is still in flight.
+// With page-locked caller memory the copies are asynchronous and everything overlaps; with pageable memory the same code
+// runs with the copies serialised by the driver.
 int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                  int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out) {
   if (!out) return fail(EA_ERR_ARG, "null out");
@@ -1154,49 +1265,119 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
   Trace tr("ea_pack_blob");
   ea_handle* h = new ea_handle;
   h->device = device; h->n = nrow;
-  int32_t *d_strand32 = nullptr, *d_templid = nullptr; int64_t* d_soff = nullptr; uint8_t* d_blob = nullptr;
-  unsigned* d_flags = nullptr;
-  auto cleanup = [&]() { pool_free(d_strand32); pool_free(d_templid); pool_free(d_soff); pool_free(d_blob); pool_free(d_flags); };
+  constexpr int kMaxChunks = 32;
+  int64_t chunk_bytes = 256ll << 20;  // ~5 ms of PCIe 5 x16 per chunk; EA_PACK_CHUNK_MB overrides (tests)
+  if (const char* e = getenv("EA_PACK_CHUNK_MB")) chunk_bytes = std::max<int64_t>(1, atoll(e)) << 20;
+  const int n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)kMaxChunks, total / chunk_bytes + 1, std::max<int64_t>(nstr, 1)}));
+  int32_t *d_strand32 = nullptr, *d_templid = nullptr; int64_t *d_soff = nullptr, *d_padded = nullptr; uint8_t* d_blob = nullptr;
+  unsigned* d_flags = nullptr; void* d_tmp = nullptr;
+  cudaStream_t sc = nullptr, sk = nullptr;
+  cudaEvent_t ev_meta = nullptr, ev_chunk[kMaxChunks] = {};
+  auto cleanup = [&]() {
+    cudaDeviceSynchronize();
+    pool_free(d_strand32); pool_free(d_templid); pool_free(d_soff); pool_free(d_blob); pool_free(d_flags); pool_free(d_padded); pool_free(d_tmp);
+    if (sc) cudaStreamDestroy(sc);
+    if (sk) cudaStreamDestroy(sk);
+    if (ev_meta) cudaEventDestroy(ev_meta);
+    for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
+  };
 #define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); ea_free(h); return rc; } } while (0)
 #define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  TRYCU(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+  TRYCU(cudaStreamCreateWithFlags(&sk, cudaStreamNonBlocking));
+  TRYCU(cudaEventCreateWithFlags(&ev_meta, cudaEventDisableTiming));
+  for (int k = 0; k < n_chunks; k++) TRYCU(cudaEventCreateWithFlags(&ev_chunk[k], cudaEventDisableTiming));
   TRY(dmalloc(&h->d_rname, (size_t)nrow));
   TRY(dmalloc(&h->d_start, (size_t)nrow));
   TRY(dmalloc(&h->d_strand, (size_t)nrow));
+  TRY(dmalloc(&h->d_len, (size_t)nrow));
+  TRY(dmalloc(&h->d_off, (size_t)nrow + 1));
   TRY(dmalloc(&d_strand32, (size_t)nrow));
+  TRY(dmalloc(&d_padded, (size_t)nrow + 1));
   TRY(dmalloc(&d_soff, (size_t)nstr + 1));
   TRY(dmalloc(&d_blob, (size_t)total + 16));
   TRY(dmalloc(&d_flags, 1));
-  TRYCU(cudaMemset(d_flags, 0, 4));
+  if (templid && nrow > 0) TRY(dmalloc(&d_templid, (size_t)nrow));
+  size_t tb = 0;
+  TRYCU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_padded, h->d_off, (int)(nrow + 1), sk));
+  TRYCU(pool_malloc(&d_tmp, std::max<size_t>(tb, 1)));
   tr.mark("cudaMalloc staging");
-  // templid is resolved on the device (k_lens_from_templid / k_repack); no host pass over it
-  const bool identity = templid == nullptr;
+
+  // copy stream: metadata, then the blob in chunks of whole strings
   if (nrow > 0) {
-    TRYCU(cudaMemcpy(h->d_rname, rname, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
-    TRYCU(cudaMemcpy(h->d_start, start, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
-    TRYCU(cudaMemcpy(d_strand32, strand, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
-    k_strand_u8<<<grid_for(nrow, 256), 256>>>(d_strand32, nrow, h->d_strand, d_flags);
-    if (!identity) {
-      TRY(dmalloc(&d_templid, (size_t)nrow));
-      TRYCU(cudaMemcpy(d_templid, templid, 4 * (size_t)nrow, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpyAsync(h->d_rname, rname, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
+    TRYCU(cudaMemcpyAsync(h->d_start, start, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
+    TRYCU(cudaMemcpyAsync(d_strand32, strand, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
+    if (d_templid) TRYCU(cudaMemcpyAsync(d_templid, templid, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
+  }
+  if (nstr > 0) TRYCU(cudaMemcpyAsync(d_soff, off, 8 * (size_t)(nstr + 1), cudaMemcpyHostToDevice, sc));
+  else TRYCU(cudaMemsetAsync(d_soff, 0, 8, sc));
+  TRYCU(cudaEventRecord(ev_meta, sc));
+  // kernel stream: everything that only needs the metadata
+  TRYCU(cudaMemsetAsync(d_flags, 0, 4, sk));
+  TRYCU(cudaMemsetAsync(d_padded + nrow, 0, 8, sk));
+  TRYCU(cudaStreamWaitEvent(sk, ev_meta, 0));
+  if (nrow > 0) {
+    k_strand_u8<<<grid_for(nrow, 256), 256, 0, sk>>>(d_strand32, nrow, h->d_strand, d_flags);
+    k_lens_from_templid<<<grid_for(nrow, 256), 256, 0, sk>>>(d_soff, d_templid, nrow, nstr, h->d_len, d_padded, d_flags);
+  }
+  TRYCU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_padded, h->d_off, (int)(nrow + 1), sk));
+  int64_t s_begin[kMaxChunks + 1];  // string index range of every chunk
+  for (int k = 0; k <= n_chunks; k++) s_begin[k] = nstr * k / n_chunks;
+  for (int k = 0; k < n_chunks; k++) {
+    const int64_t b0 = nstr > 0 ? off[s_begin[k]] : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] : 0;
+    if (b1 < b0 || b1 > total) { cleanup(); ea_free(h); return fail(EA_ERR_ARG, "string offsets are not ascending"); }
+    if (b1 > b0) TRYCU(cudaMemcpyAsync(d_blob + b0, blob + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sc));
+    TRYCU(cudaEventRecord(ev_chunk[k], sc));
+  }
+  unsigned f = 0;
+  TRYCU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, sk));
+  TRYCU(cudaMemcpyAsync(&h->npadded, h->d_off + nrow, 8, cudaMemcpyDeviceToHost, sk));
+  TRYCU(cudaStreamSynchronize(sk));
+  tr.mark("H2D metadata + row kernels");
+  if (f & ~(unsigned)F_NONIDENT) { cleanup(); ea_free(h); return flags_error(f); }
+  const bool by_chunk = !(f & F_NONIDENT) && nstr >= nrow;  // rows == strings in file order: repack chunk by chunk
+  TRY(dmalloc(&h->d_data, (size_t)h->npadded + 16));
+  rc = finish_handle(h);  // validation + row keys on the handle's own stream, while the blob is in flight
+  if (rc != EA_OK) { cleanup(); ea_free(h); return rc; }
+  const int rp_grid = std::max(1, h->sm_count * 8);
+  for (int k = 0; k < n_chunks; k++) {
+    const int64_t b0 = nstr > 0 ? off[s_begin[k]] : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] : 0;
+    TRYCU(cudaStreamWaitEvent(sk, ev_chunk[k], 0));
+    if (b1 > b0) k_validate_domain<<<(int)std::min<int64_t>(((b1 - b0) / 16 + 256) / 256, h->sm_count * 16), 256, 0, sk>>>(d_blob + b0, b1 - b0, d_flags);
+    if (by_chunk) {
+      const int64_t r0 = std::min(s_begin[k], nrow), r1 = std::min(s_begin[k + 1], nrow);
+      if (r1 > r0) k_repack<<<std::min(grid_for(r1 - r0, 256), rp_grid), 256, 0, sk>>>(d_blob, d_soff, nullptr, r0, r1, h->d_off, h->d_len, h->d_data);
     }
   }
-  if (nstr > 0) TRYCU(cudaMemcpy(d_soff, off, 8 * (size_t)(nstr + 1), cudaMemcpyHostToDevice));
-  else TRYCU(cudaMemset(d_soff, 0, 8));
-  tr.mark("H2D metadata");
-  if (total > 0) TRYCU(cudaMemcpy(d_blob, blob, (size_t)total, cudaMemcpyHostToDevice));
-  tr.mark("H2D blob");
-  unsigned f = 0;
-  TRYCU(cudaMemcpy(&f, d_flags, 4, cudaMemcpyDeviceToHost));
-  if (f) { cleanup(); ea_free(h); return flags_error(f); }
-  TRY(pack_from_device_blob(h, d_blob, d_soff, nstr, identity ? nullptr : d_templid));
-  tr.mark("device repack");
+  if (!by_chunk && nrow > 0)
+    k_repack<<<std::min(grid_for(nrow, 256), rp_grid), 256, 0, sk>>>(d_blob, d_soff, d_templid, 0, nrow, h->d_off, h->d_len, h->d_data);
+  TRYCU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, sk));
+  TRYCU(cudaStreamSynchronize(sk));
+  TRYCU(cudaGetLastError());
+  tr.mark("H2D blob + repack");
+  if (f & ~(unsigned)F_NONIDENT) { cleanup(); ea_free(h); return flags_error(f); }
+  if (by_chunk && nstr == nrow) {
+    h->nbytes = total;
+  } else {  // sum of the referenced strings' lengths
+    int64_t* d_l64; int64_t* d_sum;
+    TRY(dmalloc(&d_l64, (size_t)nrow));
+    TRY(dmalloc(&d_sum, 1));
+    if (nrow > 0) k_len_i64<<<grid_for(nrow, 256), 256, 0, sk>>>(h->d_len, nrow, d_l64);
+    size_t tb2 = 0;
+    TRYCU(cub::DeviceReduce::Sum(nullptr, tb2, d_l64, d_sum, (int)nrow, sk));
+    void* tmp2; TRYCU(pool_malloc(&tmp2, std::max<size_t>(tb2, 1)));
+    TRYCU(cub::DeviceReduce::Sum(tmp2, tb2, d_l64, d_sum, (int)nrow, sk));
+    TRYCU(cudaMemcpyAsync(&h->nbytes, d_sum, 8, cudaMemcpyDeviceToHost, sk));
+    TRYCU(cudaStreamSynchronize(sk));
+    pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
+  }
   cleanup();
   tr.mark("free staging");
 #undef TRY
 #undef TRYCU
-  rc = adopt_and_finish(h, out);
-  tr.mark("validate + row keys");
-  return rc;
+  *out = h;
+  return EA_OK;
 }
 
 int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,

@@ -195,33 +195,48 @@ __device__ __forceinline__ void push_meth(uint32_t mm, uint32_t t_addr, uint32_t
 // Finalize one window: coverage prefix sum, row test total_ctx > floor(cov/2) (src/rcpp_cx_report.cpp:58-85), ordered
 // compaction into the scratch rows.  All NT threads of the CTA call it after a __syncthreads().
 template <int WANT, int PER, int NT, bool FUSED>
-__device__ __forceinline__ void window_finalize_rt(const uint32_t* __restrict__ W, const uint32_t* __restrict__ D, const uint32_t* __restrict__ T,
+__device__ __forceinline__ void window_finalize_rt(uint32_t* __restrict__ W, uint32_t* __restrict__ D, uint32_t* __restrict__ T,
                                                    int S /* positions, multiple of 4, <= PER * NT */, int w0, int win, const ReportOut& out,
-                                                   uint32_t* s_scan, long long* s_base, const int* s_npass) {
+                                                   uint32_t* s_scan /* 2 * NT/32 words */, long long* s_base, int* s_npass) {
+  // Finalizes the window AND leaves its state zeroed for the next one (the kernels zero only once, before their window
+  // loop).  Three CTA barriers: per-warp coverage totals, per-warp row counts, the window's base in the scratch rows.
   constexpr int NC = n_ctx<WANT>();
   constexpr int NW = NT / 32;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   const int SG = kGuardLo + S + kGuardHi;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = threadIdx.x * PER;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   uint32_t cov[PER];  // coverage of both strands: '+' | '-' << 16
-  {
-    uint32_t run = 0;
+  uint32_t run = 0;
 #pragma unroll
-    for (int v4 = 0; v4 < PER / 4; v4++) {
-      uint4 w = make_uint4(0, 0, 0, 0), d = make_uint4(0, 0, 0, 0);
-      if (q0 + v4 * 4 < S) {
-        w = *reinterpret_cast<const uint4*>(&W[kGuardLo + q0 + v4 * 4]);
-        d = *reinterpret_cast<const uint4*>(&D[kGuardLo + q0 + v4 * 4]);
-      }
-      run += w.x; cov[v4 * 4 + 0] = run - d.x;
-      run += w.y; cov[v4 * 4 + 1] = run - d.y;
-      run += w.z; cov[v4 * 4 + 2] = run - d.z;
-      run += w.w; cov[v4 * 4 + 3] = run - d.w;
+  for (int v4 = 0; v4 < PER / 4; v4++) {
+    uint4 w = zero4, d = zero4;
+    if (q0 + v4 * 4 < S) {
+      uint4* pw = reinterpret_cast<uint4*>(&W[kGuardLo + q0 + v4 * 4]);
+      uint4* pd = reinterpret_cast<uint4*>(&D[kGuardLo + q0 + v4 * 4]);
+      w = *pw; d = *pd;
+      *pw = zero4; *pd = zero4;
     }
-    uint32_t tot;
-    const uint32_t ex = block_exscan_u32<NW>(run, &tot, s_scan);
-#pragma unroll
-    for (int k = 0; k < PER; k++) cov[k] += ex;
+    run += w.x; cov[v4 * 4 + 0] = run - d.x;
+    run += w.y; cov[v4 * 4 + 1] = run - d.y;
+    run += w.z; cov[v4 * 4 + 2] = run - d.z;
+    run += w.w; cov[v4 * 4 + 3] = run - d.w;
   }
+  uint32_t inc = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(FULL, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_scan[warp] = inc;
+  __syncthreads();
+  uint32_t ex = inc - run;
+#pragma unroll
+  for (int w = 0; w < NW; w++) ex += (w < warp) ? s_scan[w] : 0u;
+#pragma unroll
+  for (int k = 0; k < PER; k++) cov[k] += ex;
+
   uint32_t flags = 0;  // bit 2k+s: (q0+k, strand s) is a report row
 #pragma unroll
   for (int s = 0; s < 2; s++)
@@ -229,7 +244,7 @@ __device__ __forceinline__ void window_finalize_rt(const uint32_t* __restrict__ 
     for (int c = 0; c < NC; c++)
 #pragma unroll
       for (int v4 = 0; v4 < PER / 4; v4++) {
-        uint4 v = make_uint4(0, 0, 0, 0);
+        uint4 v = zero4;
         if (q0 + v4 * 4 < S) v = *reinterpret_cast<const uint4*>(&T[(c * 2 + s) * SG + kGuardLo + q0 + v4 * 4]);
         if (v.x | v.y | v.z | v.w) {
           const uint32_t t[4] = {v.x, v.y, v.z, v.w};
@@ -241,15 +256,31 @@ __device__ __forceinline__ void window_finalize_rt(const uint32_t* __restrict__ 
           }
         }
       }
-  uint32_t nrows_u;
-  const int my_off = (int)block_exscan_u32<NW>((uint32_t)__popc(flags), &nrows_u, s_scan);
-  const int nrows_total = (int)nrows_u;
+  const int mine = __popc(flags);
+  int rinc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(FULL, rinc, d);
+    if (lane >= d) rinc += o;
+  }
+  if (lane == 31) s_scan[NW + warp] = (uint32_t)rinc;
+  __syncthreads();
+  int my_off = rinc - mine, nrows_total = 0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    const int c = (int)s_scan[NW + w];
+    nrows_total += c;
+    my_off += (w < warp) ? c : 0;
+  }
   if (threadIdx.x == 0) {
     const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
     *s_base = (long long)bb;
     out.w_base[win] = (long long)bb;
     out.w_cnt[win] = nrows_total;
-    if (FUSED && *s_npass) atomicAdd(out.n_pass, (unsigned long long)*s_npass);
+    if (FUSED) {
+      if (*s_npass) atomicAdd(out.n_pass, (unsigned long long)*s_npass);
+      *s_npass = 0;
+    }
   }
   __syncthreads();
   const long long wbase = *s_base;
@@ -278,12 +309,20 @@ __device__ __forceinline__ void window_finalize_rt(const uint32_t* __restrict__ 
       *dst++ = make_int4(w0 + q0 + k, (s + 1) | (code << 8), (int)(val >> 16), (int)((val & 0xFFFFu) - (val >> 16)));
     }
   }
+  // leave T zeroed (the caller's barrier at the top of its window loop orders this before the next sweep)
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int v4 = 0; v4 < PER / 4; v4++)
+        if (q0 + v4 * 4 < S) *reinterpret_cast<uint4*>(&T[(c * 2 + s) * SG + kGuardLo + q0 + v4 * 4]) = zero4;
 }
 
 // compile-time window size: PER = S / NT positions per thread
 template <int WANT, int S, int NT, bool FUSED>
-__device__ __forceinline__ void window_finalize(const uint32_t* __restrict__ W, const uint32_t* __restrict__ D, const uint32_t* __restrict__ T,
-                                                int w0, int win, const ReportOut& out, uint32_t* s_scan, long long* s_base, const int* s_npass) {
+__device__ __forceinline__ void window_finalize(uint32_t* __restrict__ W, uint32_t* __restrict__ D, uint32_t* __restrict__ T,
+                                                int w0, int win, const ReportOut& out, uint32_t* s_scan, long long* s_base, int* s_npass) {
   window_finalize_rt<WANT, S / NT, NT, FUSED>(W, D, T, S, w0, win, out, s_scan, s_base, s_npass);
 }
 

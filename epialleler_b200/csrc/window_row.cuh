@@ -41,7 +41,7 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   const int SG = kGuardLo + S + kGuardHi;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint32_t s_scan[kRowWarps + 1];
+  __shared__ uint32_t s_scan[2 * kRowWarps];
   __shared__ long long s_base;
   __shared__ int s_npass;
   __shared__ __align__(4) uint8_t s_bp4[32];
@@ -56,10 +56,11 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
 
   if (threadIdx.x < 32) s_bp4[threadIdx.x] = (uint8_t)(4 * bit_pos32(threadIdx.x));
 
+  // the window state is zeroed once; every finalize leaves it zeroed again (guard bands are never read)
+  for (int i = threadIdx.x; i < kZero4; i += kRowThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) s_npass = 0;
+
   for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kZero4; i += kRowThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) s_npass = 0;
     __syncthreads();
 
     const int w0 = wt.pos0[win];

@@ -60,7 +60,7 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[kTprWarps];
-  __shared__ uint32_t s_scan[kTprWarps + 1];
+  __shared__ uint32_t s_scan[2 * kTprWarps];
   __shared__ long long s_base;
   __shared__ int s_npass;
   __shared__ __align__(4) uint8_t s_bp4[32];
@@ -81,10 +81,11 @@ k_window_tpr(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   if (lane == 0) mbar_init(my_bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
+  // the window state is zeroed once; every finalize leaves it zeroed again (guard bands are never read)
+  for (int i = threadIdx.x; i < kZero4; i += kTprThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) s_npass = 0;
+
   for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kZero4; i += kTprThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) s_npass = 0;
     __syncthreads();
 
     const int w0 = wt.pos0[win];

@@ -36,6 +36,7 @@
 #ifndef EPIALLELER_B200_H
 #define EPIALLELER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -89,6 +90,11 @@ void ea_free(ea_handle* h);
 /* Device memory of freed handles stays cached in the device's stream-ordered pool (re-packing tens of GB per call
  * would otherwise pay cudaMalloc/cudaFree each time); ea_trim returns the cached blocks to the driver. */
 int ea_trim(int device);
+
+/* Page-locked host memory for result buffers (device->host copies into it run at full PCIe speed).  Freed blocks are
+ * cached and reused by later ea_host_alloc calls; ea_trim releases the cache.  NULL on failure (see ea_last_error). */
+void* ea_host_alloc(size_t bytes);
+void ea_host_free(void* p);
 
 int64_t ea_nrow(const ea_handle* h);
 int64_t ea_nbytes(const ea_handle* h); /* sum of string lengths */

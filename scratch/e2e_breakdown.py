@@ -8,17 +8,17 @@ cfg = bench.synth_cfg(ea, 1, reads)
 dev = ea.synth_device(cfg, 0, reads, device=0)
 host = dev.to_host(); dev.close()
 blob, off = host.blob()
-pin = [torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True) for a in (blob, off, host.rname, host.strand, host.start)]
-for t, a in zip(pin, (blob, off, host.rname, host.strand, host.start)): t.numpy()[...] = a
-blob, off, rn, st, sa = [t.numpy() for t in pin]
-tid = np.arange(host.nrow, dtype=np.int32)
+src = (blob, off, host.rname, host.strand, host.start, np.arange(host.nrow, dtype=np.int32))
+pin = [torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True) for a in src]
+for t, a in zip(pin, src): t.numpy()[...] = a
+blob, off, rn, st, sa, tid = [t.numpy() for t in pin]
 # raw H2D bandwidth
 d = torch.empty(blob.shape[0], dtype=torch.uint8, device="cuda")
 for _ in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter(); d.copy_(pin[0], non_blocking=True); torch.cuda.synchronize(); dt = time.perf_counter() - t0
 print("raw H2D %.1f GB in %.1f ms = %.1f GB/s" % (blob.nbytes / 1e9, dt * 1e3, blob.nbytes / 1e9 / dt))
 del d; torch.cuda.empty_cache()
-for it in range(3):
+for it in range(4):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     b = ea.BamData(rn, st, sa, tid, blob, off, device=0); b.handle(); torch.cuda.synchronize(); t1 = time.perf_counter()
     p, rep = ea.generateCytosineReport(b, return_pass=True, **bench.THRESH); torch.cuda.synchronize(); t2 = time.perf_counter()

@@ -193,6 +193,64 @@ def test_string_pointer_packer_matches_blob_packer():
     L.ea_free(h)
 
 
+def test_pack_pipeline_chunks_and_shuffled_strings(monkeypatch):
+    """ea_pack_blob: (a) the blob travels in several chunks, each repacked behind the next one's transfer (identity
+    templid); (b) templid is a permutation and there are more strings than rows - the one-shot repack after the last
+    chunk.  Both must give the same bytes as the device generator / the oracle.  Odd lengths exercise every source
+    alignment and tail length of the funnel-shift repack."""
+    monkeypatch.setenv("EA_PACK_CHUNK_MB", "1")
+    cfg = ea.synth_config(77, 60000, [250000, 100000], 1, 333)
+    host = ea.synth_host(cfg)
+    blob, off = host.blob()
+    assert blob.nbytes > 8 << 20  # at least 8 chunks of 1 MB
+    oracle = PortCpu(host)
+    want_p, want = oracle.generateCytosineReport(True, "CG", 2, 0.5, 0.1, "CX")
+    # (a) chunked, identity
+    a = ea.BamData(host.rname, host.strand, host.start, np.arange(host.nrow, dtype=np.int32), blob, off)
+    view = ea.api.DeviceBam(a.handle(), 0)  # export the packed rows again: the repack must be lossless
+    back = view.to_host()
+    view._h = None                           # the handle stays owned by `a`
+    assert np.array_equal(back.blob()[0], blob) and np.array_equal(back.blob()[1], off)
+    p, rep = ea.generateCytosineReport(a, report_context="CX", return_pass=True)
+    assert np.array_equal(p, want_p)
+    assert_report_equal(rep, want, "chunked pack")
+    # (b) strings stored in a shuffled order, with unreferenced decoys in between
+    rng = np.random.default_rng(5)
+    n = host.nrow
+    nstr = n + 1000
+    slot = rng.permutation(nstr)[:n].astype(np.int32)          # row r's string lives in slot[r]
+    lens = np.zeros(nstr, np.int64)
+    lens[slot] = np.diff(off)
+    decoy = np.setdiff1d(np.arange(nstr), slot)
+    lens[decoy] = rng.integers(0, 50, decoy.shape[0])
+    off2 = np.zeros(nstr + 1, np.int64)
+    np.cumsum(lens, out=off2[1:])
+    blob2 = np.full(int(off2[-1]), 0x1C, np.uint8)              # decoys: valid '.' bytes
+    for r in range(n):
+        blob2[off2[slot[r]]:off2[slot[r]] + lens[slot[r]]] = blob[off[r]:off[r + 1]]
+    b = ea.BamData(host.rname, host.strand, host.start, slot, blob2, off2)
+    p, rep = ea.generateCytosineReport(b, report_context="CX", return_pass=True)
+    assert np.array_equal(p, want_p)
+    assert_report_equal(rep, want, "shuffled strings")
+    assert N.lib().ea_nbytes(b.handle()) == int(np.diff(off).sum())
+    a.close(); b.close(); host.close()
+
+
+def test_row_capacity_retry_on_sparse_coverage():
+    """A CX report over ~1x coverage has about one row per five bytes of calls, far above the first capacity guess:
+    the window kernel only counts, the pipeline re-runs with the exact capacity, and the rows are still bit-exact."""
+    cfg = ea.synth_config(78, 60000, [9000000], 150)
+    host = ea.synth_host(cfg)
+    want_p, want = PortCpu(host).generateCytosineReport(False, "CG", 2, 0.5, 0.1, "CX")
+    assert want["pos"].shape[0] > host.blob()[0].nbytes // 64 + 4096
+    for bam in (host, ea.synth_device(cfg)):
+        rep = ea.generateCytosineReport(bam, threshold_reads=False, report_context="CX")
+        assert_report_equal(rep, want, "capacity retry")
+        rep = ea.generateCytosineReport(bam, threshold_reads=False, report_context="CG")  # smaller report, same buffers
+        assert_report_equal(rep, PortCpu(host).generateCytosineReport(False, "CG", 2, 0.5, 0.1, "CG")[1], "after retry")
+        bam.close()
+
+
 def test_range_sharded_gpu_equals_whole():
     """The N>1 data path on one GPU: every rank's shard (halo included) through the CUDA kernels, ownership
     filter, concatenation == the unsharded oracle report."""
