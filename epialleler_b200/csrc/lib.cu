@@ -23,6 +23,7 @@
 #include "window_tpr.cuh"
 #include "window_cpl.cuh"
 #include "window_row.cuh"
+#include "window_long.cuh"
 #include "bed.cuh"
 #include "window_mhl.cuh"
 #include "synth.h"
@@ -634,7 +635,11 @@ int launch_window(ea_handle* h, const WinIndex& ix, int want, int tctx_fused, bo
     case 3: return launch_window_w<3>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
     case 5: return launch_window_w<5>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
     case 6: return launch_window_w<6>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+#endif
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
     case 7: return launch_window_w<7>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
+#endif
+#ifndef EA_FAST_BUILD
 #endif
     default: return launch_window_w<4>(h, ix, tctx_fused, wide, tp, pass_in, pass_out, out);
   }
@@ -731,7 +736,10 @@ CplPlan plan_cpl(const ea_handle* h, const WinIndex& ix, int nc, bool fused) {
   const int cpu = t.ub / 16;
   const int max_nu = (max_nch + cpu - 1) / cpu;
   const int avg_nu = (int)((h->npadded / t.ub + h->n - 1) / h->n);
-  int tc = std::min(640 / cpu, std::max(320 / cpu, 32 * std::max(avg_nu, 1)));  // units per tile
+#ifndef EA_CPL_TCMAX
+#define EA_CPL_TCMAX 320   // measured: 320 keeps two CTAs per SM for three-context (CX) reports (cfg 3: 7.2 -> 4.7 ms), 160 starves the unit phase
+#endif
+  int tc = std::min(EA_CPL_TCMAX / cpu, std::max(320 / cpu, 32 * std::max(avg_nu, 1)));  // units per tile
   tc = std::max(tc, max_nu);
   tc = (tc + 31) & ~31;
   t.rpt = std::min(32, tc / max_nu);
@@ -791,7 +799,11 @@ int launch_cpl(ea_handle* h, const WinIndex& ix, const CplPlan& cp, int want, in
     case 3: return launch_cpl_w<3>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
     case 5: return launch_cpl_w<5>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
     case 6: return launch_cpl_w<6>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
     case 7: return launch_cpl_w<7>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+#ifndef EA_FAST_BUILD
 #endif
     default: return launch_cpl_w<4>(h, ix, cp, tctx_fused, thr, pass_in, pass_out, out);
   }
@@ -889,6 +901,53 @@ int launch_row(ea_handle* h, const WinIndex& ix, const RowPlan& rp, int want, in
   }
 }
 
+// ---- long-read kernel (window_long.cuh): pass flags are an input ----
+struct LongPlan { bool ok = false; int S = 0; size_t smem = 0; };
+
+LongPlan plan_long(const ea_handle* h, const WinIndex& ix, int nc) {
+  LongPlan t;
+  if (h->n == 0 || ix.n == 0 || nc < 1 || nc > 3 || ix.max_rows > 32767 || ix.S > kLongMaxS || (ix.S & 31)) return t;
+  t.S = ix.S;
+  t.smem = sizeof(uint32_t) * (size_t)(nc + 1) * 2 * (kGuardLo + ix.S + kGuardHi);
+  t.ok = true;
+  return t;
+}
+
+template <int WANT>
+int launch_long_w(ea_handle* h, const WinIndex& ix, const LongPlan& lp, const uint8_t* pass_in, const ReportOut& out) {
+  if (ix.S != lp.S) return fail(EA_ERR_STATE, "window size mismatch");
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
+  if (h->rows32) {
+    auto kern = k_window_long<WANT, true>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+    kern<<<grid, kRowThreads, lp.smem, h->stream>>>(csr_of(h), wt, pass_in, out);
+  } else {
+    auto kern = k_window_long<WANT, false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+    kern<<<grid, kRowThreads, lp.smem, h->stream>>>(csr_of(h), wt, pass_in, out);
+  }
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+int launch_long(ea_handle* h, const WinIndex& ix, const LongPlan& lp, int want, const uint8_t* pass_in, const ReportOut& out) {
+  switch (want) {
+#ifndef EA_FAST_BUILD
+    case 1: return launch_long_w<1>(h, ix, lp, pass_in, out);
+    case 2: return launch_long_w<2>(h, ix, lp, pass_in, out);
+    case 3: return launch_long_w<3>(h, ix, lp, pass_in, out);
+    case 5: return launch_long_w<5>(h, ix, lp, pass_in, out);
+    case 6: return launch_long_w<6>(h, ix, lp, pass_in, out);
+#endif
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
+    case 7: return launch_long_w<7>(h, ix, lp, pass_in, out);
+#endif
+    default: return launch_long_w<4>(h, ix, lp, pass_in, out);
+  }
+}
+
 int ensure_pass(ea_handle* h) {
   if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
   return EA_OK;
@@ -928,6 +987,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   TprPlan tpr;
   CplPlan cpl;
   RowPlan row;
+  LongPlan lng;
   // kernel policy: 0 automatic (row-per-lane kernel, else chunk-per-lane kernel, else the lane-group kernel),
   // 1 force the general lane-group kernel, 2 prefer the thread-per-row TMA kernel, 3 prefer the chunk-per-lane kernel
   const int policy = rp.kernel == 1 ? 1 : g_kernel_policy;
@@ -935,7 +995,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   if (rp.threshold && (rc = ensure_pass(h))) return rc;
   bool wide = ix && ix->max_rows > 65535;
   const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
-  const bool fused = can_fuse && rp.mode == 0;
+  const bool fused = can_fuse && rp.mode == 0 && policy != 4;  // the long-read kernel takes the flags as an input
   if (rp.want) {
     if (policy == 0 && nc == 1 && h->rows32 && ((h->max_len + 31) >> 5) <= 8) {
       const int S = pick_row_window(h, *ix);
@@ -946,7 +1006,13 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
     }
     if ((policy == 0 && !row.ok) || policy == 3) cpl = plan_cpl(h, *ix, nc, fused);
     if (policy == 2) tpr = plan_tpr(h, *ix);
-    if (!row.ok && !cpl.ok && !tpr.ok && nc <= 1) {
+    if ((policy == 0 && !row.ok && !cpl.ok && !fused) || policy == 4) {  // long reads: (row, unit block) items
+      WinIndex* ixl = nullptr;
+      if ((rc = build_index(h, nc == 1 ? EA_LONG_S : 2048, &ixl))) return rc;
+      lng = plan_long(h, *ixl, nc);
+      if (lng.ok) ix = ixl;
+    }
+    if (!row.ok && !cpl.ok && !tpr.ok && !lng.ok && nc <= 1) {
       if ((rc = build_index(h, 4096, &ix))) return rc;
       wide = ix->max_rows > 65535;
     }
@@ -981,9 +1047,10 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      h->report_kernel = row.ok ? "k_window_row (row per lane, 256-bit loads)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
+      h->report_kernel = row.ok ? "k_window_row (row per lane, 256-bit loads)" : lng.ok ? "k_window_long (warp per row, lane per 32-byte unit)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
                                 : tpr.ok ? "k_window_tpr (thread-per-row over TMA tiles)" : "k_window (lane-group)";
       if (row.ok) rc = launch_row(h, *ix, row, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      else if (lng.ok) rc = launch_long(h, *ix, lng, rp.want, pass_for_window, out);
       else if (cpl.ok) rc = launch_cpl(h, *ix, cpl, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);

@@ -63,9 +63,11 @@ const char* ea_last_error(void);
 int ea_device_count(void);
 void ea_set_poll(ea_poll_fn fn);
 /* Kernel choice for the report: 0 automatic (default: the row-per-lane kernel for one-context reports over rows of at
- * most 256 bytes that are multiples of 32 bytes, else the chunk-per-lane kernel for reads up to 1 KB, else the general
+ * most 256 bytes that are multiples of 32 bytes, else the chunk-per-lane kernel for reads up to 1 KB, else the long-read
+ * kernel (flags from the stand-alone threshold pass), else - more than 32767 rows over one window - the general
  * lane-group kernel), 1 always the lane-group kernel, 2 prefer the thread-per-row TMA kernel (reads up to 512 bytes),
- * 3 prefer the chunk-per-lane kernel.  Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
+ * 3 prefer the chunk-per-lane kernel, 4 prefer the long-read kernel (any read length; thresholding runs as its own pass).
+ * Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
 int ea_set_kernel_policy(int policy);
 
 /* ---- packer: host bam.data -> device-resident CSR (row order) ------------------------------ */
