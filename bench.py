@@ -230,12 +230,12 @@ def run_ours(args):
 
     ms_step = tot / args.steps
     stats = torch.tensor([ms_step, wall_ms / args.steps, win / args.steps, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device="cuda")
-    sums = torch.tensor([float(own_reads), float(alg_bytes), float(dev.nbytes), float(n_rows)], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(own_reads), float(alg_bytes), float(dev.nbytes), float(n_rows), float(n_pass)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     ms_step, wall_step, win_step, e2e_s = [float(x) for x in stats.tolist()]
-    tot_reads, tot_alg, tot_xm, tot_rows = [float(x) for x in sums.tolist()]
+    tot_reads, tot_alg, tot_xm, tot_rows, tot_pass = [float(x) for x in sums.tolist()]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -260,7 +260,7 @@ def run_ours(args):
                        % (args.reads, READ_LEN, CHR1, world), "reads_per_gpu": args.reads, "read_len": READ_LEN, "report_context": "CG",
                        "threshold_context": "CG", "sharding": "contiguous genomic ranges with halo rows, no collective" if world > 1 else "single GPU",
                        "l2": "inputs (%.1f GB per GPU) are larger than L2 (126 MB); no flush needed" % (dev.nbytes / 1e9), "seed": SEED,
-                       "report_rows": int(tot_rows), "reads_passing": n_pass},
+                       "report_rows": int(tot_rows), "reads_passing": int(tot_pass)},
             "xm_gbs": tot_xm / 1e9 / (ms_step / 1e3),
             "wall_ms_per_step": wall_step,
             "gpu_launches": launches * args.steps,
