@@ -414,6 +414,166 @@ def ecdf_at(sorted_values, x):
     return float(np.searchsorted(sorted_values, x, side="right")) / float(sorted_values.shape[0])
 
 
+# ---- VCF-assisted report -------------------------------------------------------------
+def rcpp_get_base_freqs(df, pass_, vcf):
+    """src/rcpp_get_base_freqs.cpp:15-61 -> float64 matrix (n_vcf, 20) with the reference's column order
+    U+A U+C U+G U+T U+N, U-..., M+..., M-...  vcf: (seqnames, start) or a dict with those keys; seqnames = factor codes
+    on the BAM's rname levels (NA_INT = NA), entries sorted by (seqnames, start).  pass_: logical vector of nrow
+    (None = all TRUE)."""
+    chr_, pos = (vcf["seqnames"], vcf["start"]) if isinstance(vcf, dict) else vcf
+    chr_ = np.ascontiguousarray(chr_, dtype=np.int32)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    nv = int(chr_.shape[0])
+    if pos.shape[0] != nv:
+        raise ValueError("seqnames/start must have the same length")
+    pp = None
+    if pass_ is not None:
+        pp = np.ascontiguousarray(np.asarray(pass_) != 0, dtype=np.uint8)
+        if pp.shape[0] != df.nrow:
+            raise ValueError("pass must have nrow(bam) entries")
+    out = np.zeros((20, max(nv, 1)), np.float64)  # column-major n_vcf x 20
+    if nv:
+        N.check(N.lib().ea_base_freqs(df.handle(), _p(pp, C.c_uint8) if pp is not None and pp.shape[0] else None,
+                                      _p(chr_, C.c_int32), _p(pos, C.c_int32), nv, _p(out, C.c_double)))
+    return np.ascontiguousarray(out[:, :nv].T)
+
+
+def rcpp_fep(a, b, c, d):
+    """src/rcpp_fep.cpp:9-36: two-sided Fisher's exact p per row; NA_INT in any cell -> NaN."""
+    cols = [np.ascontiguousarray(x, dtype=np.int32) for x in (a, b, c, d)]
+    n = int(cols[0].shape[0])
+    out = np.zeros(max(n, 1), np.float64)
+    if n:
+        N.check(N.lib().ea_fisher_exact(*[_p(x, C.c_int32) for x in cols], n, _p(out, C.c_double)))
+    return out[:n]
+
+
+# R/internal.R:642-665 as data: (REF, ALT) -> base columns summed into Ref / Alt on the '+' strand and on the '-' strand;
+# None = NA (bisulfite conversion makes the alleles indistinguishable on that strand: C>T on '+', G>A on '-')
+BASE_FREQ_RULES = {
+    ("A", "C"): ("A", "CT", "A", "C"), ("A", "T"): ("A", "T", "A", "T"), ("A", "G"): ("A", "G", None, None),
+    ("C", "A"): ("CT", "A", "C", "A"), ("C", "T"): (None, None, "C", "T"), ("C", "G"): ("CT", "G", "C", "AG"),
+    ("T", "A"): ("T", "A", "T", "A"), ("T", "C"): (None, None, "T", "C"), ("T", "G"): ("T", "G", "T", "AG"),
+    ("G", "A"): ("G", "A", None, None), ("G", "C"): ("G", "CT", "AG", "C"), ("G", "T"): ("G", "T", "AG", "T"),
+}
+_FREQ_BLOCK = {"U+": 0, "U-": 5, "M+": 10, "M-": 15}
+_FREQ_BASE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def _base_freq_report(freqs, ref, alt):
+    """.getBaseFreqReport (R/internal.R:636-672) after rcpp_get_base_freqs: Ref/Alt counts per strand and methylation
+    status (NaN = NA), SumRef / SumAlt (rowSums, na.rm=TRUE), FEp+ / FEp- (Fisher's exact test on {M Ref, U Ref; M Alt, U Alt})."""
+    n = freqs.shape[0]
+    names = ("M+Ref", "U+Ref", "M-Ref", "U-Ref", "M+Alt", "U+Alt", "M-Alt", "U-Alt")
+    rep = {k: np.full(n, np.nan) for k in names}
+    ref = np.asarray(ref, dtype=object); alt = np.asarray(alt, dtype=object)
+    for (r, a), rule in BASE_FREQ_RULES.items():
+        rows = np.nonzero((ref == r) & (alt == a))[0]
+        if rows.shape[0] == 0:
+            continue
+        for strand, (rb, ab) in (("+", rule[0:2]), ("-", rule[2:4])):
+            if rb is None:
+                continue
+            for m in "MU":
+                blk = _FREQ_BLOCK[m + strand]
+                rep[m + strand + "Ref"][rows] = sum(freqs[rows, blk + _FREQ_BASE[x]] for x in rb)
+                rep[m + strand + "Alt"][rows] = sum(freqs[rows, blk + _FREQ_BASE[x]] for x in ab)
+    rep["SumRef"] = np.nansum([rep[k] for k in ("M+Ref", "U+Ref", "M-Ref", "U-Ref")], axis=0)
+    rep["SumAlt"] = np.nansum([rep[k] for k in ("M+Alt", "U+Alt", "M-Alt", "U-Alt")], axis=0)
+    as_int = lambda x: np.where(np.isnan(x), NA_INT, np.nan_to_num(x)).astype(np.int32)
+    rep["FEp+"] = rcpp_fep(*[as_int(rep[k]) for k in ("M+Ref", "U+Ref", "M+Alt", "U+Alt")])
+    rep["FEp-"] = rcpp_fep(*[as_int(rep[k]) for k in ("M-Ref", "U-Ref", "M-Alt", "U-Alt")])
+    return rep
+
+
+def _ucsc_name(name):
+    if name.startswith("chr"):
+        return name
+    return "chrM" if name in ("MT", "M") else "chr" + name
+
+
+def read_vcf(vcf_file, rname_levels, bed=None, vcf_style=None, zero_based_bed=False):
+    """.readVcf + the filters of .getBaseFreqReport (R/internal.R:230-267,617-625) without VariantAnnotation: records of a
+    (gzipped) VCF - only those overlapping the reduced BED ranges when `bed` (a BED file) is given - expanded to one row
+    per ALT allele, sorted by (chromosome, start, end), then REF of width 1 and single-letter ALT only.  vcf_style="NCBI":
+    the VCF names chromosomes 1..22,X,Y,MT and they are renamed to the BED/BAM style (chr1..).  seqnames are factor codes on
+    `rname_levels` (NA_INT when absent).  Host-side parsing, like the reference."""
+    levels = {str(nm): i + 1 for i, nm in enumerate(rname_levels)}
+    conv = _ucsc_name if (vcf_style or "").upper() == "NCBI" else (lambda x: x)
+    ranges = None
+    if bed is not None:
+        ranges = {}
+        with open(bed) as fh:
+            fh.readline()
+            for ln in fh:
+                f = ln.rstrip("\n").split("\t")
+                if len(f) >= 3 and f[0]:
+                    ranges.setdefault(f[0], []).append([int(f[1]) + (1 if zero_based_bed else 0), int(f[2])])
+        for k, v in ranges.items():  # GenomicRanges::reduce
+            v.sort()
+            merged = [v[0]]
+            for a, b in v[1:]:
+                if a <= merged[-1][1] + 1:
+                    merged[-1][1] = max(merged[-1][1], b)
+                else:
+                    merged.append([a, b])
+            ranges[k] = merged
+    rows, order = [], {}
+    opener = _gzip.open if str(vcf_file).endswith(".gz") else open
+    with opener(vcf_file, "rt") as fh:
+        for ln in fh:
+            if ln.startswith("#"):
+                continue
+            f = ln.rstrip("\n").split("\t")
+            if len(f) < 5:
+                continue
+            chrom, pos, vid, ref = conv(f[0]), int(f[1]), f[2], f[3]
+            end = pos + len(ref) - 1
+            if ranges is not None and not any(a <= end and pos <= b for a, b in ranges.get(chrom, ())):
+                continue
+            order.setdefault(chrom, len(order))
+            for alt in f[4].split(","):
+                rows.append((order[chrom], pos, end, chrom, ref, alt, vid if vid != "." else "%s:%d_%s/%s" % (chrom, pos, ref, alt)))
+    rows.sort(key=lambda r: (r[0], r[1], r[2]))
+    rows = [r for r in rows if len(r[4]) == 1 and len(r[5]) == 1]
+    return {"seqnames": np.asarray([levels.get(r[3], NA_INT) for r in rows], np.int32), "start": np.asarray([r[1] for r in rows], np.int32),
+            "REF": [r[4] for r in rows], "ALT": [r[5] for r in rows], "name": [r[6] for r in rows], "chrom": [r[3] for r in rows]}
+
+
+def generateVcfReport(bam, vcf, vcf_style=None, bed=None, report_file=None, zero_based_bed=False, threshold_reads=True,
+                      threshold_context="CG", min_context_sites=2, min_context_beta=0.5, max_outofcontext_beta=0.1,
+                      gzip=False, **kwargs):
+    """R/generateVcfReport.R:169-231: per SNV of the VCF the reads carrying the reference / alternative base among the
+    passing ("M") and failing ("U") reads of each strand, and Fisher's exact p per strand.  vcf: a VCF file (read_vcf) or
+    the dict read_vcf returns.  Returns a dict of columns: name, seqnames, range, REF, ALT, the eight Ref/Alt counts,
+    SumRef, SumAlt, FEp+, FEp- (NaN = NA)."""
+    threshold_context = _match_arg(threshold_context, tuple(CONTEXT_TO_BASES), "threshold.context")
+    bam = preprocessBam(bam, **kwargs)
+    if not isinstance(vcf, dict):
+        vcf = read_vcf(vcf, bam.rname_levels, bed=bed, vcf_style=vcf_style, zero_based_bed=zero_based_bed)
+    if len(vcf["REF"]) and np.all(np.asarray(vcf["seqnames"]) == NA_INT):
+        raise ValueError("Looks like seqlevels styles of BAM and VCF don't match. Please provide VCF as an object with correct seqlevels.")
+    if threshold_reads:
+        b = CONTEXT_TO_BASES[threshold_context]
+        pass_ = rcpp_threshold_reads(bam, b[0], b[1], b[2], b[3], min_context_sites, min_context_beta, max_outofcontext_beta)
+    else:
+        pass_ = None
+    freqs = rcpp_get_base_freqs(bam, pass_, vcf)
+    rep = {"name": list(vcf["name"]), "seqnames": np.asarray(vcf["seqnames"], np.int32), "range": np.asarray(vcf["start"], np.int32),
+           "REF": list(vcf["REF"]), "ALT": list(vcf["ALT"])}
+    rep.update(_base_freq_report(freqs, vcf["REF"], vcf["ALT"]))
+    if report_file is None:
+        return rep
+    cols = ("name", "seqnames", "range", "REF", "ALT", "M+Ref", "U+Ref", "M-Ref", "U-Ref", "M+Alt", "U+Alt", "M-Alt", "U-Alt", "SumRef", "SumAlt", "FEp+", "FEp-")
+    fmt = lambda v: "NA" if (isinstance(v, float) and np.isnan(v)) else (repr(float(v)) if isinstance(v, float) and v != int(v) else str(int(v)) if isinstance(v, (float, np.floating, np.integer, int)) else str(v))
+    chrom = vcf.get("chrom") or [str(x) for x in rep["seqnames"]]
+    with (_gzip.open(report_file, "wt") if gzip else open(report_file, "w")) as fh:
+        fh.write("\t".join(cols) + "\n")
+        for i in range(len(rep["name"])):
+            fh.write("\t".join(fmt(chrom[i] if k == "seqnames" else (rep[k][i] if not isinstance(rep[k][i], np.floating) else float(rep[k][i]))) for k in cols) + "\n")
+    return None
+
+
 def _write_report(rep, path, gz):
     lv = rep["levels"]
     opener = (lambda p: _gzip.open(p, "wt")) if gz else (lambda p: open(p, "w"))

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -25,6 +27,7 @@
 #include "window_row.cuh"
 #include "window_long.cuh"
 #include "bed.cuh"
+#include "vcf.cuh"
 #include "window_mhl.cuh"
 #include "synth.h"
 
@@ -1605,6 +1608,126 @@ int ea_match_target(ea_handle* h, int mode, const int32_t* bed_chr, const int32_
   if (match_out && h->n > 0) {
     CU(cudaMemcpyAsync(match_out, h->d_match, 4 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+  }
+  return EA_OK;
+}
+
+// rcpp_get_base_freqs (src/rcpp_get_base_freqs.cpp:15-61): see vcf.cuh.  The VCF entries must be sorted by
+// (chromosome code, position), as the reference's cursor walk assumes; entries with an NA chromosome never match.
+int ea_base_freqs(ea_handle* h, const uint8_t* pass, const int32_t* vcf_chr, const int32_t* vcf_pos, int64_t n_vcf, double* freqs_out) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  if (n_vcf < 0 || n_vcf > 0x7FFFFFFFll || (n_vcf > 0 && (!vcf_chr || !vcf_pos || !freqs_out))) return fail(EA_ERR_ARG, "bad VCF table");
+  if (n_vcf == 0) return EA_OK;
+  int rc;
+  CU(cudaSetDevice(h->device));
+  std::vector<uint64_t> keys, na_key;     // valid entries; per NA entry the key of the last valid entry in front of it
+  std::vector<int32_t> idx, na_after;     // row in the caller's table; per NA entry the number of valid entries in front of it
+  keys.reserve((size_t)n_vcf); idx.reserve((size_t)n_vcf);
+  for (int64_t i = 0; i < n_vcf; i++) {
+    if (vcf_chr[i] == INT32_MIN) {
+      if (!keys.empty()) { na_key.push_back(keys.back()); na_after.push_back((int32_t)keys.size()); }
+      continue;
+    }
+    if (vcf_chr[i] < 0 || vcf_pos[i] < 0) return fail(EA_ERR_ARG, "negative VCF chromosome code or position");
+    const uint64_t k = ((uint64_t)(uint32_t)vcf_chr[i] << 32) | (uint32_t)vcf_pos[i];
+    if (!keys.empty() && k < keys.back())
+      return fail(EA_ERR_UNSORTED, "VCF entries are not sorted by (seqnames, start): rcpp_get_base_freqs assumes sorted reads and VCF entries (rcpp_get_base_freqs.cpp:6)");
+    keys.push_back(k); idx.push_back((int32_t)i);
+  }
+  const size_t cells = (size_t)n_vcf * 20;
+  unsigned int* d_counts = nullptr; double* d_out = nullptr; uint64_t* d_keys = nullptr; int32_t* d_idx = nullptr; uint8_t* d_p = nullptr;
+  uint64_t* d_na_key = nullptr; int32_t* d_na_limit = nullptr; int32_t* d_limit = nullptr;
+  auto cleanup = [&]() { pool_free(d_counts); pool_free(d_out); pool_free(d_keys); pool_free(d_idx); pool_free(d_p); pool_free(d_na_key); pool_free(d_na_limit); pool_free(d_limit); };
+#define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  TRY(dmalloc(&d_counts, cells));
+  TRY(dmalloc(&d_out, cells));
+  TRY(dmalloc(&d_keys, keys.size()));
+  TRY(dmalloc(&d_idx, idx.size()));
+  TRY(dmalloc(&d_limit, keys.size()));
+  TRYCU(cudaMemsetAsync(d_counts, 0, 4 * cells, h->stream));
+  if (!keys.empty() && h->n > 0) {
+    // visibility limits (see vcf.cuh): one binary search per NA entry on the prefix maximum of row ends, spread on the host
+    std::vector<int32_t> limit(keys.size(), 0x7FFFFFFF);
+    if (!na_key.empty()) {
+      std::vector<int32_t> na_limit(na_key.size());
+      TRY(dmalloc(&d_na_key, na_key.size()));
+      TRY(dmalloc(&d_na_limit, na_key.size()));
+      TRYCU(cudaMemcpyAsync(d_na_key, na_key.data(), 8 * na_key.size(), cudaMemcpyHostToDevice, h->stream));
+      k_vcf_na_limits<<<grid_for((int64_t)na_key.size(), 128), 128, 0, h->stream>>>(h->d_maxend, h->n, d_na_key, (int32_t)na_key.size(), d_na_limit);
+      TRYCU(cudaMemcpyAsync(na_limit.data(), d_na_limit, 4 * na_key.size(), cudaMemcpyDeviceToHost, h->stream));
+      TRYCU(cudaStreamSynchronize(h->stream));
+      // entry v (0-based among the valid ones) is governed by the first NA entry with na_after > v
+      size_t j = 0;
+      for (size_t v = 0; v < keys.size(); v++) {
+        while (j < na_after.size() && (size_t)na_after[j] <= v) j++;
+        if (j < na_after.size()) limit[v] = na_limit[j];
+      }
+    }
+    TRYCU(cudaMemcpyAsync(d_keys, keys.data(), 8 * keys.size(), cudaMemcpyHostToDevice, h->stream));
+    TRYCU(cudaMemcpyAsync(d_idx, idx.data(), 4 * idx.size(), cudaMemcpyHostToDevice, h->stream));
+    TRYCU(cudaMemcpyAsync(d_limit, limit.data(), 4 * limit.size(), cudaMemcpyHostToDevice, h->stream));
+    if (pass) {
+      TRY(dmalloc(&d_p, (size_t)h->n));
+      TRYCU(cudaMemcpyAsync(d_p, pass, (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    }
+    k_base_freqs<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), d_p, d_keys, d_idx, d_limit, (int32_t)keys.size(), n_vcf, d_counts);
+    TRYCU(cudaStreamSynchronize(h->stream));  // the host vectors above must outlive their copies
+  }
+  k_counts_to_double<<<grid_for((int64_t)cells, 256), 256, 0, h->stream>>>(d_counts, (int64_t)cells, d_out);
+  TRYCU(cudaGetLastError());
+  TRYCU(cudaMemcpyAsync(freqs_out, d_out, 8 * cells, cudaMemcpyDeviceToHost, h->stream));
+  TRYCU(cudaStreamSynchronize(h->stream));
+#undef TRY
+#undef TRYCU
+  cleanup();
+  return EA_OK;
+}
+
+// rcpp_fep (src/rcpp_fep.cpp:9-36): two-sided Fisher's exact test per row of a small table, HOST arithmetic like the
+// reference's call into HTSlib's kt_fisher_exact, whose published algorithm is restated here (HTSlib is not a
+// dependency): hypergeometric probabilities of the tables with the observed margins, summed from the smallest and from
+// the largest n11 while they stay below the observed table's (relative guards 0.99999999 / 1.00000001), each step
+// derived from the previous one and recomputed from log-gamma every 11th table.  INT32_MIN (NA) in any cell -> NaN.
+namespace {
+double fe_lbinom(int n, int k) { return (n == 0 || k == 0 || n == k) ? 0.0 : std::lgamma(n + 1.0) - std::lgamma(k + 1.0) - std::lgamma(n - k + 1.0); }
+struct FeState {
+  int n11, n1_, n_1, n; double p;
+  double at(int k11) {  // probability of the table with n11 = k11, stepping from the current one when adjacent
+    if (k11 % 11 && k11 + n - n1_ - n_1) {
+      if (k11 == n11 + 1) { p *= (double)(n1_ - n11) / k11 * (n_1 - n11) / (k11 + n - n1_ - n_1); n11 = k11; return p; }
+      if (k11 == n11 - 1) { p *= (double)n11 / (n1_ - k11) * (n11 + n - n1_ - n_1) / (n_1 - k11); n11 = k11; return p; }
+    }
+    n11 = k11;
+    p = std::exp(fe_lbinom(n1_, n11) + fe_lbinom(n - n1_, n_1 - n11) - fe_lbinom(n, n_1));
+    return p;
+  }
+};
+double fisher_two_sided(int a, int b, int c, int d) {
+  FeState s{a, a + b, a + c, a + b + c + d, 0.0};
+  const int mx = s.n_1 < s.n1_ ? s.n_1 : s.n1_;
+  const int mn = std::max(0, s.n1_ + s.n_1 - s.n);
+  if (mn == mx) return 1.0;
+  s.p = std::exp(fe_lbinom(s.n1_, a) + fe_lbinom(s.n - s.n1_, s.n_1 - a) - fe_lbinom(s.n, s.n_1));
+  const double q = s.p;
+  if (q == 0.0) return 0.0;
+  double p = s.at(mn), left = 0.0, right = 0.0;
+  int i, j;
+  for (i = mn + 1; p < 0.99999999 * q && i <= mx; ++i) { left += p; p = s.at(i); }
+  if (p < 1.00000001 * q) left += p;
+  p = s.at(mx);
+  for (j = mx - 1; p < 0.99999999 * q && j >= 0; --j) { right += p; p = s.at(j); }
+  if (p < 1.00000001 * q) right += p;
+  return std::min(1.0, left + right);
+}
+}  // namespace
+
+int ea_fisher_exact(const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d, int64_t n, double* p_out) {
+  if (n < 0 || (n > 0 && (!a || !b || !c || !d || !p_out))) return fail(EA_ERR_ARG, "bad table");
+  for (int64_t i = 0; i < n; i++) {
+    if (a[i] == INT32_MIN || b[i] == INT32_MIN || c[i] == INT32_MIN || d[i] == INT32_MIN) { p_out[i] = std::nan(""); continue; }
+    if (a[i] < 0 || b[i] < 0 || c[i] < 0 || d[i] < 0) return fail(EA_ERR_ARG, "negative count in row %lld", (long long)i);
+    p_out[i] = fisher_two_sided(a[i], b[i], c[i], d[i]);
   }
   return EA_OK;
 }

@@ -153,6 +153,19 @@ int ea_bed_report(ea_handle* h, int mode, const int32_t* bed_chr, const int32_t*
                   int32_t param, const ea_report_params* thr, const uint8_t* pass, int32_t* match_out, uint8_t* pass_out,
                   int64_t* counts_out);
 
+/* ---- VCF-assisted report ------------------------------------------------- *
+ * ea_base_freqs replaces rcpp_get_base_freqs (src/rcpp_get_base_freqs.cpp:15-61; R/RcppExports.R rcpp_get_base_freqs):
+ * for every VCF entry the number of reads covering it, by base (high nibble of the packed byte through HTSlib's
+ * seq_nt16_int: A,C,G,T,other), strand and pass flag.  pass: nrow bytes (NULL = all TRUE).  vcf_chr: factor code of the
+ * entry's chromosome on the BAM's rname levels (INT32_MIN = NA: never matches), vcf_pos 1-based; the entries must be
+ * sorted by (vcf_chr, vcf_pos) like the reference assumes (EA_ERR_UNSORTED otherwise).  freqs_out: n_vcf x 20 doubles,
+ * COLUMN-major like R's NumericMatrix: U+A U+C U+G U+T U+N, U-..., M+..., M-... */
+int ea_base_freqs(ea_handle* h, const uint8_t* pass, const int32_t* vcf_chr, const int32_t* vcf_pos, int64_t n_vcf, double* freqs_out);
+/* rcpp_fep (src/rcpp_fep.cpp:9-36): two-sided Fisher's exact p of the 2x2 tables {a b; c d}, INT32_MIN in any cell ->
+ * NaN (R's NA).  Host arithmetic on the report's few rows (the reference calls HTSlib's kt_fisher_exact here). */
+int ea_fisher_exact(const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d, int64_t n, double* p_out);
+
+
 /* ---- lMHL report ------------------------------------------------------- *
  * ea_mhl_report replaces rcpp_mhl_report (src/rcpp_mhl_report.cpp:46-228; R/RcppExports.R rcpp_mhl_report;
  * R/generateMhlReport.R:170-197): ctx = the haplotype context's methylated + unmethylated letters (e.g. "Zz"),

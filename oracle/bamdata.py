@@ -257,3 +257,62 @@ def read_bed(path: str, rname_levels, zero_based: bool = False):
             en.append(int(f[2]))
             nm.append(f[3] if len(f) > 3 else "")
     return np.asarray(chr_, np.int32), np.asarray(st, np.int32), np.asarray(en, np.int32), nm
+
+
+def _ucsc_name(name: str) -> str:
+    """NCBI -> UCSC sequence name, the part of GenomeInfoDb::seqlevelsStyle<- the fixtures need."""
+    if name.startswith("chr"):
+        return name
+    return "chrM" if name in ("MT", "M") else "chr" + name
+
+
+def read_vcf(path: str, rname_levels, bed_path: str = None, vcf_style: str = None, zero_based_bed: bool = False):
+    """The reference's .readVcf + the filtering of .getBaseFreqReport (R/internal.R:230-267,617-625), restated without
+    VariantAnnotation: records of a (gzipped) VCF, restricted to those overlapping the reduced BED ranges when a BED file is
+    given, expanded to one row per ALT allele, sorted by (seqnames, start, end), then only REF of width 1 and single-letter
+    ALT kept.  seqnames become factor codes on the BAM's rname levels (INT_MIN = NA).  vcf_style "NCBI" means the VCF
+    names chromosomes 1..22,X,Y,MT while the BED/BAM use chr1..: the names are converted like seqlevelsStyle<- does.
+    Returns dict(seqnames, start, REF, ALT, name)."""
+    import gzip
+    levels = {str(n): i + 1 for i, n in enumerate(rname_levels)}
+    conv = _ucsc_name if (vcf_style or "").upper() == "NCBI" else (lambda x: x)
+    ranges = None
+    if bed_path is not None:
+        ranges = {}
+        with open(bed_path) as fh:
+            fh.readline()
+            for ln in fh:
+                f = ln.rstrip("\n").split("\t")
+                if len(f) >= 3 and f[0]:
+                    ranges.setdefault(f[0], []).append((int(f[1]) + (1 if zero_based_bed else 0), int(f[2])))
+        for k, v in ranges.items():  # GenomicRanges::reduce
+            v.sort()
+            merged = [list(v[0])]
+            for a, b in v[1:]:
+                if a <= merged[-1][1] + 1:
+                    merged[-1][1] = max(merged[-1][1], b)
+                else:
+                    merged.append([a, b])
+            ranges[k] = merged
+    rows = []
+    order = {}
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rt") as fh:
+        for ln in fh:
+            if ln.startswith("#"):
+                continue
+            f = ln.rstrip("\n").split("\t")
+            if len(f) < 5:
+                continue
+            chrom, pos, vid, ref, alts = conv(f[0]), int(f[1]), f[2], f[3], f[4]
+            end = pos + len(ref) - 1
+            if ranges is not None and not any(a <= end and pos <= b for a, b in ranges.get(chrom, ())):
+                continue
+            order.setdefault(chrom, len(order))
+            for alt in alts.split(","):
+                rows.append((order[chrom], pos, end, chrom, ref, alt, vid if vid != "." else "%s:%d_%s/%s" % (chrom, pos, ref, alt)))
+    rows.sort(key=lambda r: (r[0], r[1], r[2]))  # stable, like BiocGenerics::sort on GRanges
+    rows = [r for r in rows if len(r[4]) == 1 and len(r[5]) == 1]
+    return {"seqnames": np.asarray([levels.get(r[3], -2147483648) for r in rows], np.int32),
+            "start": np.asarray([r[1] for r in rows], np.int32),
+            "REF": [r[4] for r in rows], "ALT": [r[5] for r in rows], "name": [r[6] for r in rows]}

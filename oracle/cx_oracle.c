@@ -13,12 +13,16 @@
  *   port_threshold_reads()  pass/fail chain       /root/reference/src/rcpp_threshold_reads.cpp:27-71
  *   port_get_xm_beta()      per-read beta         /root/reference/src/rcpp_get_xm_beta.cpp:18-40
  *   port_cx_report()        aggregation + flush   /root/reference/src/rcpp_cx_report.cpp:58-131
+ *   port_base_freqs()       base counts at SNVs   /root/reference/src/rcpp_get_base_freqs.cpp:15-61
+ *   port_fep()              Fisher's exact test   /root/reference/src/rcpp_fep.cpp:9-36 (HTSlib kt_fisher_exact, by definition)
  *
  * The data structure is deliberately NOT the reference's (sorted flat_map of 32-int arrays):
  * an open-addressing hash keyed by position plus a key sort at flush time.  Semantics kept:
  * flush when start > max_pos or rname changes, stale last-position carry-over after an
  * all-'-' read, NA pass == TRUE, rows emitted in ascending position, '+' before '-'.
  */
+#include <limits.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -371,4 +375,97 @@ void port_mhl_fetch(void* h, int* rname, int* strand, int* pos, int* context, in
   int* dst[5] = {rname, strand, pos, context, coverage};
   for (int c = 0; c < 5; c++) if (g_mhl.nrow) memcpy(dst[c], g_mhl.icol[c], sizeof(int) * (size_t)g_mhl.nrow);
   if (g_mhl.nrow) { memcpy(length, g_mhl.dcol[0], sizeof(double) * (size_t)g_mhl.nrow); memcpy(lmhl, g_mhl.dcol[1], sizeof(double) * (size_t)g_mhl.nrow); }
+}
+
+
+/* ---- base frequencies at VCF positions ---------------------------------------------------
+ * /root/reference/src/rcpp_get_base_freqs.cpp:15-61 walks reads and VCF entries with a shared cursor and ASSUMES both
+ * are sorted.  Restated from the other side, without a cursor: per read, binary-search the sorted valid entries for the
+ * ones inside [start, start+len-1] on the read's chromosome.  Entries whose chromosome is NA (INT_MIN) never match, but
+ * they are not inert in the reference: its cursor treats them as "before the read" and moves onto them as soon as a
+ * read's scan reaches them (rcpp_get_base_freqs.cpp:44-47), which hides every earlier entry from all LATER reads.  A
+ * scan reaches an NA entry exactly when the read's end is not before the last valid entry in front of it, so:
+ *   limit(i) = the first read (in row order) whose (rname, end) >= the key of the last valid entry before the first NA
+ *              entry that follows entry i;   entry i is visible to reads 0..limit(i) only.
+ * out: nvcf x 20 doubles, column-major; column = base (A,C,G,T = 0..3, anything else 4; HTSlib's seq_nt16_int of the
+ * high nibble) + 5*(strand-1) + 10*pass. */
+static const int kNt16Int[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
+
+double port_base_freqs(void* h, const uint8_t* pass, long nvcf, const int* chr, const int* pos, double* out) {
+  PortBam* b = (PortBam*)h;
+  double t0 = now_s();
+  for (long i = 0; i < nvcf * 20; i++) out[i] = 0.0;
+  const size_t cap = (size_t)(nvcf > 0 ? nvcf : 1);
+  long nv = 0;
+  long* idx = (long*)malloc(sizeof(long) * cap);
+  long* limit = (long*)malloc(sizeof(long) * cap);
+  int64_t* key = (int64_t*)malloc(sizeof(int64_t) * cap);
+  /* running maximum of the reads' (rname, end) keys: reads are sorted by (rname, start), ends are not */
+  int64_t* endmax = (int64_t*)malloc(sizeof(int64_t) * (size_t)(b->n > 0 ? b->n : 1));
+  int64_t run = INT64_MIN;
+  for (long x = 0; x < b->n; x++) {
+    const long t = b->templid[x];
+    const int64_t len = b->off[t + 1] - b->off[t];
+    const int64_t e = (((int64_t)b->rname[x] << 32) | (uint32_t)b->start[x]) + len - 1;
+    if (e > run) run = e;
+    endmax[x] = run;
+  }
+  for (long i = 0; i < nvcf; i++)
+    if (chr[i] != INT32_MIN) { idx[nv] = i; key[nv] = ((int64_t)chr[i] << 32) | (uint32_t)pos[i]; nv++; }
+  {  /* visibility limits, from the back: the nearest following NA entry decides */
+    long cur_limit = LONG_MAX;   /* no NA entry behind: visible to every read */
+    long v = nv;                 /* valid entries in front of position i */
+    for (long i = nvcf - 1; i >= 0; i--) {
+      if (chr[i] == INT32_MIN) {
+        if (v == 0) { cur_limit = -1; continue; }  /* nothing valid in front of it: irrelevant for the entries behind */
+        const int64_t K = key[v - 1];
+        long a = 0, z = b->n;      /* first read whose running end reaches K */
+        while (a < z) { const long m = (a + z) >> 1; if (endmax[m] < K) a = m + 1; else z = m; }
+        cur_limit = a;             /* == n: no read reaches it */
+      } else {
+        v--;
+        limit[v] = cur_limit;
+      }
+    }
+  }
+  for (long x = 0; x < b->n; x++) {
+    const long t = b->templid[x];
+    const int64_t len = b->off[t + 1] - b->off[t];
+    if (len <= 0) continue;
+    const int64_t lo_key = ((int64_t)b->rname[x] << 32) | (uint32_t)b->start[x];
+    const int64_t hi_key = lo_key + (len - 1);
+    long a = 0, z = nv;
+    while (a < z) { const long m = (a + z) >> 1; if (key[m] < lo_key) a = m + 1; else z = m; }
+    for (long k = a; k < nv && key[k] <= hi_key; k++) {
+      if (x > limit[k]) continue;
+      const uint8_t c = b->blob[b->off[t] + (key[k] - lo_key)];
+      const int col = kNt16Int[c >> 4] + (b->strand[x] - 1) * 5 + (pass[x] ? 10 : 0);
+      out[(long)col * nvcf + idx[k]] += 1.0;
+    }
+  }
+  free(idx); free(key); free(limit); free(endmax);
+  return now_s() - t0;
+}
+
+/* Two-sided Fisher's exact test by definition: the sum of the probabilities of all 2x2 tables with the observed margins
+ * that are not more probable than the observed one (relative guard 1e-8, as HTSlib's kt_fisher_exact uses), every
+ * probability computed directly from log-gamma.  NA (INT_MIN) in any cell -> NaN. */
+static double lchoose_(int n, int k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
+void port_fep(long n, const int* a, const int* b_, const int* c, const int* d, double* out) {
+  for (long x = 0; x < n; x++) {
+    if (a[x] == INT32_MIN || b_[x] == INT32_MIN || c[x] == INT32_MIN || d[x] == INT32_MIN) { out[x] = NAN; continue; }
+    const int n11 = a[x], n1_ = a[x] + b_[x], n_1 = a[x] + c[x], nn = a[x] + b_[x] + c[x] + d[x];
+    const int mx = n_1 < n1_ ? n_1 : n1_;
+    int mn = n1_ + n_1 - nn;
+    if (mn < 0) mn = 0;
+    if (mn == mx) { out[x] = 1.0; continue; }
+    const double lden = lchoose_(nn, n_1);
+    const double q = exp(lchoose_(n1_, n11) + lchoose_(nn - n1_, n_1 - n11) - lden);
+    double two = 0.0;
+    for (int i = mn; i <= mx; i++) {
+      const double pi = exp(lchoose_(n1_, i) + lchoose_(nn - n1_, n_1 - i) - lden);
+      if (pi < 1.00000001 * q) two += pi;
+    }
+    out[x] = two > 1.0 ? 1.0 : two;
+  }
 }

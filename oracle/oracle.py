@@ -71,6 +71,46 @@ def bed_report_table(strand, pass_, match, nbed):
             "nreads+": plus, "nreads-": minus, "VEF": vef, "counts": cnt}
 
 
+# .getBaseFreqReport's REF/ALT table (R/internal.R:642-665), restated as data: for every (REF, ALT) the base columns that
+# are summed into the Ref and the Alt count on the '+' and on the '-' strand; None = NA (that strand cannot tell the two
+# alleles apart after bisulfite conversion: C>T on '+', G>A on '-').
+BASE_FREQ_RULES = {
+    ("A", "C"): (("A",), ("C", "T"), ("A",), ("C",)),
+    ("A", "T"): (("A",), ("T",), ("A",), ("T",)),
+    ("A", "G"): (("A",), ("G",), None, None),
+    ("C", "A"): (("C", "T"), ("A",), ("C",), ("A",)),
+    ("C", "T"): (None, None, ("C",), ("T",)),
+    ("C", "G"): (("C", "T"), ("G",), ("C",), ("A", "G")),
+    ("T", "A"): (("T",), ("A",), ("T",), ("A",)),
+    ("T", "C"): (None, None, ("T",), ("C",)),
+    ("T", "G"): (("T",), ("G",), ("T",), ("A", "G")),
+    ("G", "A"): (("G",), ("A",), None, None),
+    ("G", "C"): (("G",), ("C", "T"), ("A", "G"), ("C",)),
+    ("G", "T"): (("G",), ("T",), ("A", "G"), ("T",)),
+}
+_BASE_COL = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def base_freq_table(freqs, ref, alt):
+    """freqs: (n, 20) from rcpp_get_base_freqs; ref/alt: sequences of single letters.  Returns the eight Ref/Alt columns
+    (NaN = NA), SumRef and SumAlt (rowSums with na.rm=TRUE).  Rows whose (REF, ALT) is not in the table stay NA."""
+    n = freqs.shape[0]
+    cols = {k: np.full(n, np.nan) for k in ("M+Ref", "U+Ref", "M-Ref", "U-Ref", "M+Alt", "U+Alt", "M-Alt", "U-Alt")}
+    block = {"U+": 0, "U-": 5, "M+": 10, "M-": 15}
+    for i in range(n):
+        rule = BASE_FREQ_RULES.get((ref[i], alt[i]))
+        if rule is None:
+            continue
+        for strand, (r, a) in (("+", rule[0:2]), ("-", rule[2:4])):
+            for m in ("M", "U"):
+                if r is not None:
+                    cols[m + strand + "Ref"][i] = sum(freqs[i, block[m + strand] + _BASE_COL[x]] for x in r)
+                    cols[m + strand + "Alt"][i] = sum(freqs[i, block[m + strand] + _BASE_COL[x]] for x in a)
+    cols["SumRef"] = np.nansum([cols["M+Ref"], cols["U+Ref"], cols["M-Ref"], cols["U-Ref"]], axis=0)
+    cols["SumAlt"] = np.nansum([cols["M+Alt"], cols["U+Alt"], cols["M-Alt"], cols["U-Alt"]], axis=0)
+    return cols
+
+
 class _Cpu:
     PREFIX = ""
     SO = ""
@@ -97,6 +137,9 @@ class _Cpu:
         getattr(L, px + "mhl_report").restype = C.c_long
         getattr(L, px + "mhl_report").argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
         getattr(L, px + "mhl_fetch").argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_double)] * 2
+        getattr(L, px + "base_freqs").restype = C.c_double
+        getattr(L, px + "base_freqs").argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        getattr(L, px + "fep").argtypes = [C.c_long] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_double)]
         self.n = int(bam.rname.shape[0])
         data, off = bam.blob()
         self.nstr = int(off.shape[0] - 1)
@@ -205,6 +248,47 @@ class _Cpu:
         if not threshold_reads:
             rep["VEF"] = np.full(rep["VEF"].shape, np.nan)
         return match, rep
+
+    # ---- VCF-assisted report ----
+    def rcpp_get_base_freqs(self, pass_, vcf):
+        """src/rcpp_get_base_freqs.cpp:15 -> float64 matrix (n_vcf, 20): U+ACGTN, U-ACGTN, M+ACGTN, M-ACGTN.
+        vcf: (seqnames, start) int arrays sorted by (seqnames, start), seqnames = factor code on the BAM's rname
+        levels (NA = INT_MIN)."""
+        chr_, pos = (np.ascontiguousarray(a, dtype=np.int32) for a in vcf)
+        nv = int(chr_.shape[0])
+        pv = np.ascontiguousarray(np.asarray(pass_).astype(bool).astype(np.uint8))
+        if pv.shape[0] != self.n:
+            raise ValueError("pass must have one entry per read")
+        pad = lambda a, t: a if a.shape[0] else np.zeros(1, t)
+        out = np.zeros((20, max(nv, 1)), np.float64)  # column-major nv x 20
+        self.last_seconds = getattr(self.lib, self.PREFIX + "base_freqs")(self.h, _p(pad(pv, np.uint8), C.c_uint8), nv, _p(pad(chr_, np.int32), C.c_int),
+                                                                          _p(pad(pos, np.int32), C.c_int), _p(out, C.c_double))
+        return np.ascontiguousarray(out[:, :nv].T)
+
+    def rcpp_fep(self, a, b, c, d):
+        """src/rcpp_fep.cpp:9: two-sided Fisher exact p per row of four int columns (INT_MIN = NA -> NaN)."""
+        cols = [np.ascontiguousarray(x, dtype=np.int32) for x in (a, b, c, d)]
+        n = int(cols[0].shape[0])
+        out = np.zeros(max(n, 1), np.float64)
+        if n:
+            getattr(self.lib, self.PREFIX + "fep")(n, *[_p(x, C.c_int) for x in cols], _p(out, C.c_double))
+        return out[:n]
+
+    def generateVcfReport(self, vcf, threshold_reads=True, threshold_context="CG", min_context_sites=2, min_context_beta=0.5,
+                          max_outofcontext_beta=0.1):
+        """R/generateVcfReport.R:196-231 + .getBaseFreqReport (R/internal.R:611-675).  vcf: dict with seqnames (factor
+        codes), start, REF, ALT (single letters), already expanded / sorted / filtered (oracle.bamdata.read_vcf)."""
+        if threshold_reads:
+            b = CONTEXT_TO_BASES[threshold_context]
+            pass_ = self.rcpp_threshold_reads(b[0], b[1], b[2], b[3], min_context_sites, min_context_beta, max_outofcontext_beta)
+        else:
+            pass_ = np.ones(self.n, bool)
+        freqs = self.rcpp_get_base_freqs(pass_, (vcf["seqnames"], vcf["start"]))
+        rep = base_freq_table(freqs, vcf["REF"], vcf["ALT"])
+        na = lambda x: np.where(np.isnan(x), NA_INT, np.nan_to_num(x)).astype(np.int32)
+        rep["FEp+"] = self.rcpp_fep(na(rep["M+Ref"]), na(rep["U+Ref"]), na(rep["M+Alt"]), na(rep["U+Alt"]))
+        rep["FEp-"] = self.rcpp_fep(na(rep["M-Ref"]), na(rep["U-Ref"]), na(rep["M-Alt"]), na(rep["U-Alt"]))
+        return freqs, rep
 
     # reference-level glue (R/generateCytosineReport.R:164-208, R/internal.R:439-456,486-500)
     def generateCytosineReport(self, threshold_reads=True, threshold_context="CG", min_context_sites=2,

@@ -24,6 +24,9 @@ typedef void* SEXP;
 #ifndef NA_INTEGER
 #define NA_INTEGER INT_MIN  /* R's integer NA (R_ext/Arith.h: R_NaInt = INT_MIN) */
 #endif
+#ifndef NA_REAL
+#define NA_REAL (std::nan("1954"))  /* a NaN stands in for R's NA_real_; the driver reports NA as NaN */
+#endif
 
 namespace Rcpp {
 
@@ -60,11 +63,26 @@ class IntegerVector {
   int& operator[](long i) { return (*v_)[static_cast<size_t>(i)]; }
   const int& operator[](long i) const { return (*v_)[static_cast<size_t>(i)]; }
   AttrProxy attr(const char*) { return AttrProxy(); }
+  static bool is_na(int x) { return x == NA_INTEGER; }
   std::shared_ptr<std::vector<int>> shared() const { return v_; }
  private:
   std::shared_ptr<std::vector<int>> v_;
 };
 typedef IntegerVector LogicalVector;
+
+// column-major double matrix, zero-initialised (R's NumericMatrix(nrow, ncol))
+class NumericMatrix {
+ public:
+  NumericMatrix() : r_(0), c_(0), v_(std::make_shared<std::vector<double>>()) {}
+  NumericMatrix(long nrow, long ncol) : r_(nrow), c_(ncol), v_(std::make_shared<std::vector<double>>(static_cast<size_t>(nrow * ncol), 0.0)) {}
+  double& operator()(long i, long j) { return (*v_)[static_cast<size_t>(j * r_ + i)]; }
+  long nrow() const { return r_; }
+  long ncol() const { return c_; }
+  std::shared_ptr<std::vector<double>> shared() const { return v_; }
+ private:
+  long r_, c_;
+  std::shared_ptr<std::vector<double>> v_;
+};
 
 class CharacterVector {
  public:
@@ -89,6 +107,7 @@ class DataFrame {
     if (it == cols_.end()) it = cols_.emplace(name, IntegerVector()).first;
     return it->second;
   }
+  IntegerVector operator[](const std::string& name) { return (*this)[name.c_str()]; }
   AttrProxy attr(const char* name) { return AttrProxy(&attrs_[name]); }
   void set_column(const char* name, std::shared_ptr<std::vector<int>> v) {
     cols_[name] = IntegerVector(std::move(v));

@@ -28,6 +28,72 @@ std::vector<int> rcpp_match_capture(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, c
 // /root/reference/src/rcpp_mhl_report.cpp:46
 Rcpp::DataFrame rcpp_mhl_report(Rcpp::DataFrame& df, const std::string ctx, int hmax, const int hmin, const double max_ooctx_meth_frac);
 
+// /root/reference/src/rcpp_get_base_freqs.cpp:15, /root/reference/src/rcpp_fep.cpp:9
+Rcpp::NumericMatrix rcpp_get_base_freqs(Rcpp::DataFrame& df, std::vector<bool> pass, Rcpp::DataFrame& vcf);
+std::vector<double> rcpp_fep(Rcpp::DataFrame& df, std::vector<std::string> colnames);
+
+// HTSlib's base-code table (hts.c: seq_nt16_int): 4-bit BAM base code "=ACMGRSVTWYHKDBN" -> A,C,G,T = 0..3, else 4
+extern "C" const int seq_nt16_int[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
+
+// Fisher's exact test as HTSlib's kfunc.c publishes it (restated, HTSlib is absent here): probabilities of the 2x2
+// tables with the observed margins, accumulated from the smallest and from the largest n11 while they stay below the
+// observed table's probability (relative guards 0.99999999 / 1.00000001); two-sided p = left tail + right tail.
+namespace {
+double lbinom(int n, int k) { return (n == 0 || k == 0 || n == k) ? 0.0 : std::lgamma(n + 1.0) - std::lgamma(k + 1.0) - std::lgamma(n - k + 1.0); }
+double hypergeo(int n11, int n1_, int n_1, int n) { return std::exp(lbinom(n1_, n11) + lbinom(n - n1_, n_1 - n11) - lbinom(n, n_1)); }
+struct HgAcc { int n11, n1_, n_1, n; double p; };
+double hypergeo_acc(int n11, int n1_, int n_1, int n, HgAcc* a) {
+  if (n1_ || n_1 || n) {
+    a->n11 = n11; a->n1_ = n1_; a->n_1 = n_1; a->n = n;
+  } else {  // step from the previous table
+    if (n11 % 11 && n11 + a->n - a->n1_ - a->n_1) {
+      if (n11 == a->n11 + 1) {
+        a->p *= (double)(a->n1_ - a->n11) / n11 * (a->n_1 - a->n11) / (n11 + a->n - a->n1_ - a->n_1);
+        a->n11 = n11;
+        return a->p;
+      }
+      if (n11 == a->n11 - 1) {
+        a->p *= (double)a->n11 / (a->n1_ - n11) * (a->n11 + a->n - a->n1_ - a->n_1) / (a->n_1 - n11);
+        a->n11 = n11;
+        return a->p;
+      }
+    }
+    a->n11 = n11;
+  }
+  a->p = hypergeo(a->n11, a->n1_, a->n_1, a->n);
+  return a->p;
+}
+}  // namespace
+extern "C" double kt_fisher_exact(int n11, int n12, int n21, int n22, double* _left, double* _right, double* two) {
+  const int n1_ = n11 + n12, n_1 = n11 + n21, n = n11 + n12 + n21 + n22;
+  const int max = n_1 < n1_ ? n_1 : n1_;
+  int min = n1_ + n_1 - n;
+  if (min < 0) min = 0;
+  *two = *_left = *_right = 1.0;
+  if (min == max) return 1.0;
+  HgAcc aux;
+  const double q = hypergeo_acc(n11, n1_, n_1, n, &aux);
+  if (q == 0.0) {  // the observed table is (numerically) impossible: the tails cannot be compared with it
+    if (n11 * (n + 2) < (n_1 + 1) * (n1_ + 1)) { *_left = 0.0; *_right = 1.0; *two = 0.0; }
+    else { *_left = 1.0; *_right = 0.0; *two = 0.0; }
+    return 0.0;
+  }
+  double p = hypergeo_acc(min, 0, 0, 0, &aux), left, right;
+  int i, j;
+  for (left = 0.0, i = min + 1; p < 0.99999999 * q && i <= max; ++i) { left += p; p = hypergeo_acc(i, 0, 0, 0, &aux); }
+  --i;
+  if (p < 1.00000001 * q) left += p; else --i;
+  p = hypergeo_acc(max, 0, 0, 0, &aux);
+  for (right = 0.0, j = max - 1; p < 0.99999999 * q && j >= 0; --j) { right += p; p = hypergeo_acc(j, 0, 0, 0, &aux); }
+  ++j;
+  if (p < 1.00000001 * q) right += p; else ++j;
+  *two = left + right;
+  if (*two > 1.0) *two = 1.0;
+  if (std::abs(i - n11) < std::abs(j - n11)) right = 1.0 - left + q; else left = 1.0 - right + q;
+  *_left = left; *_right = right;
+  return q;
+}
+
 namespace {
 struct RefBam {
   Rcpp::DataFrame df;
@@ -153,6 +219,33 @@ void ref_mhl_fetch(void* h, int* rname, int* strand, int* pos, int* context, int
   double* dd[2] = {length, lmhl};
   for (int c = 0; c < 2; c++)
     if (b->mdcols[c] && !b->mdcols[c]->empty()) std::memcpy(dd[c], b->mdcols[c]->data(), b->mdcols[c]->size() * sizeof(double));
+}
+
+// rcpp_get_base_freqs(df, pass, vcf): pass = n bytes (0/1); vcf columns seqnames (factor code on the BAM's rname levels,
+// NA_INTEGER if absent) and start; out = nvcf x 20 doubles, column-major (R's NumericMatrix).
+double ref_base_freqs(void* h, const uint8_t* pass, long nvcf, const int* chr, const int* pos, double* out) {
+  RefBam* b = static_cast<RefBam*>(h);
+  Rcpp::DataFrame vcf;
+  vcf.set_column("seqnames", std::make_shared<std::vector<int>>(chr, chr + nvcf));
+  vcf.set_column("start", std::make_shared<std::vector<int>>(pos, pos + nvcf));
+  std::vector<bool> pv(static_cast<size_t>(b->n));
+  for (long i = 0; i < b->n; i++) pv[static_cast<size_t>(i)] = pass[i] != 0;
+  double t0 = now_s();
+  Rcpp::NumericMatrix res = rcpp_get_base_freqs(b->df, pv, vcf);
+  double t1 = now_s();
+  if (nvcf > 0) std::memcpy(out, res.shared()->data(), static_cast<size_t>(nvcf) * 20 * sizeof(double));
+  return t1 - t0;
+}
+
+// rcpp_fep(df, colnames) over four int columns (NA_INTEGER = NA); out = n doubles, NaN where the reference returns NA.
+void ref_fep(long n, const int* a, const int* b_, const int* c, const int* d, double* out) {
+  Rcpp::DataFrame df;
+  df.set_column("A", std::make_shared<std::vector<int>>(a, a + n));
+  df.set_column("B", std::make_shared<std::vector<int>>(b_, b_ + n));
+  df.set_column("C", std::make_shared<std::vector<int>>(c, c + n));
+  df.set_column("D", std::make_shared<std::vector<int>>(d, d + n));
+  std::vector<double> r = rcpp_fep(df, {"A", "B", "C", "D"});
+  if (n > 0) std::memcpy(out, r.data(), static_cast<size_t>(n) * sizeof(double));
 }
 
 }  // extern "C"

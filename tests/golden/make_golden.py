@@ -16,7 +16,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle.bamdata import read_bam, read_bed  # noqa: E402
+from oracle.bamdata import read_bam, read_bed, read_vcf  # noqa: E402
 from oracle.oracle import CONTEXT_TO_BASES, RefCpu, build  # noqa: E402
 
 EXT = "/root/reference/inst/extdata/"
@@ -59,6 +59,13 @@ BEDS = {
 }
 
 
+# VCF-assisted report: fixture -> (vcf file, bed file or None, vcf.style, [(case, threshold.reads)])
+VCFS = {
+    "amplicon010meth": (EXT + "amplicon.vcf.gz", EXT + "amplicon.bed", "NCBI", [("vcf_thr", True), ("vcf_nothr", False)]),
+    "capture": (EXT + "capture.vcf.gz", None, None, [("vcf_thr", True)]),  # test_generateVcfReport.R:9-17: a pre-read VCF, BED has no effect -> 26292 rows
+}
+
+
 def main():
     build(("ref",))
     for name, (path, kw) in FIXTURES.items():
@@ -88,6 +95,17 @@ def main():
                 out["bed." + cname + ".counts"] = rep["counts"]
                 out["bed." + cname + ".vef"] = rep["VEF"]
                 print("  bed", cname, "matched", int((match != -2147483648).sum()), "rows", rep["VEF"].shape[0])
+        if name in VCFS:
+            vcf_path, bed_path, style, cases = VCFS[name]
+            vcf = read_vcf(vcf_path, bam.rname_levels, bed_path, style)
+            out["vcf.chr"], out["vcf.start"] = vcf["seqnames"], vcf["start"]
+            out["vcf.ref"], out["vcf.alt"] = np.array(vcf["REF"]), np.array(vcf["ALT"])
+            for cname, thr in cases:
+                freqs, rep = ref.generateVcfReport(vcf, threshold_reads=thr)
+                out["vcf." + cname + ".freqs"] = freqs
+                for k in ("M+Ref", "U+Ref", "M-Ref", "U-Ref", "M+Alt", "U+Alt", "M-Alt", "U-Alt", "SumRef", "SumAlt", "FEp+", "FEp-"):
+                    out["vcf." + cname + "." + k] = rep[k]
+                print("  vcf", cname, "entries", freqs.shape[0], "covered", int((freqs.sum(axis=1) > 0).sum()), "SumRef", rep["SumRef"].sum(), "SumAlt", rep["SumAlt"].sum())
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
         print(name, bam.nrow, int(off[-1]), {c[0]: int(out[c[0] + ".pos"].shape[0]) for c in CASES})
 

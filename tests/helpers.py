@@ -111,3 +111,26 @@ def assert_mhl_equal(got, want, what=""):
         if not np.array_equal(g, w, equal_nan=(g.dtype.kind == "f")):
             i = int(np.nonzero(~((g == w) | ((g != g) & (w != w))))[0][0])
             raise AssertionError("%s: column %s differs first at row %d: got %r want %r (pos %s)" % (what, k, i, g[i], w[i], want["pos"][i]))
+
+# VCF-assisted report: fixture -> [(case, threshold.reads)]
+VCF_CASES = {"amplicon010meth": [("vcf_thr", True), ("vcf_nothr", False)], "capture": [("vcf_thr", True)]}
+VCF_COLS = ("M+Ref", "U+Ref", "M-Ref", "U-Ref", "M+Alt", "U+Alt", "M-Alt", "U-Alt", "SumRef", "SumAlt")
+
+
+def golden_vcf(z):
+    return {"seqnames": z["vcf.chr"], "start": z["vcf.start"], "REF": [str(x) for x in z["vcf.ref"]], "ALT": [str(x) for x in z["vcf.alt"]],
+            "name": ["v%d" % i for i in range(z["vcf.chr"].shape[0])]}
+
+
+def random_vcf(rng, bam, n, na_frac=0.05):
+    """Sorted random SNV positions around the reads' own coordinates (duplicates included), a few NA chromosomes sprinkled in."""
+    i = rng.integers(0, bam.nrow, n)
+    pos = bam.start[i].astype(np.int64) + rng.integers(-20, 400, n)
+    chr_ = bam.rname[i].astype(np.int64)
+    order = np.lexsort((pos, chr_))
+    chr_, pos = chr_[order].astype(np.int32), np.maximum(pos[order], 0).astype(np.int32)
+    chr_[rng.random(n) < na_frac] = -2147483648
+    letters = np.array(list("ACGT"))
+    ref = letters[rng.integers(0, 4, n)]
+    alt = letters[(np.searchsorted(letters, ref) + rng.integers(1, 4, n)) % 4]
+    return {"seqnames": chr_, "start": pos, "REF": list(ref), "ALT": list(alt), "name": ["r%d" % k for k in range(n)]}

@@ -359,3 +359,48 @@ def test_mhl_report_identity_and_synthetic(kernel_policy):
             assert want["pos"].shape[0] > 0
             assert_mhl_equal(got, want, "%s %s" % (shape, hctx))
         host.close()
+
+
+# ---- VCF-assisted report: ea_base_freqs / ea_fisher_exact --------------------------
+from helpers import VCF_CASES, VCF_COLS, golden_vcf, random_vcf  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(VCF_CASES))
+def test_vcf_report_golden_vectors(name):
+    bam, z = load_golden(name)
+    vcf = golden_vcf(z)
+    for cname, thr in VCF_CASES[name]:
+        rep = ea.generateVcfReport(bam, vcf, threshold_reads=thr)
+        for k in VCF_COLS:
+            assert np.array_equal(rep[k], z["vcf." + cname + "." + k], equal_nan=True), (name, cname, k)
+        for k in ("FEp+", "FEp-"):  # same walk as the reference build's kt_fisher_exact stand-in
+            assert np.array_equal(rep[k], z["vcf." + cname + "." + k], equal_nan=True), (name, cname, k)
+        pass_ = z["cg_default.pass"] if thr else None
+        assert np.array_equal(ea.rcpp_get_base_freqs(bam, pass_, vcf), z["vcf." + cname + ".freqs"]), (name, cname)
+    if name == "amplicon010meth":  # inst/unitTests/test_generateVcfReport.R:56-74
+        rep = ea.generateVcfReport(bam, vcf)
+        assert np.nansum(rep["FEp+"]) == 40 and abs(np.nansum(rep["FEp-"]) - 40.15024191) < 1e-8
+        assert np.nansum(rep["SumRef"]) == 5282 and np.nansum(rep["SumAlt"]) == 14
+
+
+def test_base_freqs_random_vcfs_against_oracle():
+    """Sorted random SNV tables with duplicates and NA chromosomes (which hide earlier entries from later reads in the
+    reference's cursor walk, rcpp_get_base_freqs.cpp:44-47) on fixtures and synthetic reads, random pass flags."""
+    rng = np.random.default_rng(23)
+    cases = [load_golden("capture")[0], load_golden("amplicon010meth")[0],
+             ea.synth_host(ea.synth_config(5, 20000, [150000, 90000, 40000], 150, 450)),
+             ea.synth_host(ea.synth_config(9, 30000, [30000], 1, 40)),
+             ea.synth_host(ea.synth_config(11, 70000, [20000], 120, 260, n_islands=1, island_len=600))]
+    for bam in cases:
+        o = PortCpu(bam)
+        for n, na in ((0, 0.0), (1, 0.0), (300, 0.0), (5000, 0.05), (2000, 0.5)):
+            vcf = random_vcf(rng, bam, n, na_frac=na)
+            pass_ = rng.random(bam.nrow) < 0.4
+            want = o.rcpp_get_base_freqs(pass_, (vcf["seqnames"], vcf["start"]))
+            got = ea.rcpp_get_base_freqs(bam, pass_, vcf)
+            assert got.shape == (n, 20) and np.array_equal(got, want), (bam.nrow, n, na)
+        want = o.rcpp_get_base_freqs(np.ones(bam.nrow, bool), (vcf["seqnames"], vcf["start"]))
+        assert np.array_equal(ea.rcpp_get_base_freqs(bam, None, vcf), want)  # pass = NULL: every read passes
+    with pytest.raises(ea.EaError) as e:  # unsorted entries: the reference's stated precondition
+        ea.rcpp_get_base_freqs(cases[0], None, ([1, 1], [500, 400]))
+    assert e.value.code == -3

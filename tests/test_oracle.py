@@ -225,3 +225,81 @@ def test_oracle_reproduces_golden_mhl_vectors(oracle, name):
     for cname, hctx, hmax, hmin, moo in MHL_CASES:
         rep = o.generateMhlReport(hctx, hmax, hmin, moo)
         assert_mhl_equal(rep, {k: z[cname + "." + k] for k in rep}, "%s/%s" % (name, cname))
+
+
+# ---- VCF-assisted report -------------------------------------------------------
+from helpers import VCF_CASES, VCF_COLS, golden_vcf, random_vcf  # noqa: E402
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_reference_runit_constants_vcf_report(oracle):
+    # inst/unitTests/test_generateVcfReport.R:33-125 (amplicon010meth + amplicon.bed + amplicon.vcf.gz, vcf.style NCBI)
+    bam, z = load_golden("amplicon010meth")
+    vcf = golden_vcf(z)
+    assert len(vcf["REF"]) == 56                                                           # dim(amplicon.report)[1]
+    _, rep = oracle(bam).generateVcfReport(vcf)
+    assert np.nansum(rep["FEp+"]) == 40                                                    # :56-59
+    assert abs(np.nansum(rep["FEp-"]) - 40.15024191) < 1e-8                                # :60-64
+    assert np.nansum(rep["SumRef"]) == 5282 and np.nansum(rep["SumAlt"]) == 14            # :66-74
+    groups = sorted(set(zip(vcf["REF"], vcf["ALT"])))
+    by = lambda col: [int(np.nansum([rep[col][i] for i in range(56) if (vcf["REF"][i], vcf["ALT"][i]) == g])) for g in groups]
+    assert [sum(1 for i in range(56) if (vcf["REF"][i], vcf["ALT"][i]) == g) for g in groups] == [3, 4, 1, 7, 2, 13, 11, 5, 4, 2, 3, 1]
+    assert by("M+Ref") == [0] * 12 and by("U+Ref") == [0] * 12 and by("M+Alt") == [0] * 12 and by("U+Alt") == [0] * 12
+    assert by("M-Ref") == [25, 0, 13, 72, 20, 149, 0, 54, 53, 26, 39, 12]
+    assert by("U-Ref") == [201, 0, 142, 722, 196, 1617, 0, 555, 534, 285, 427, 140]
+    assert by("M-Alt") == [0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0]
+    assert by("U-Alt") == [0, 0, 0, 3, 1, 4, 0, 1, 1, 0, 1, 2]
+    assert by("SumRef") == [226, 0, 155, 794, 216, 1766, 0, 609, 587, 311, 466, 152]
+    assert by("SumAlt") == [0, 0, 0, 4, 1, 4, 0, 1, 1, 0, 1, 2]
+    bam, z = load_golden("capture")
+    assert z["vcf.chr"].shape[0] == 26292                                                  # dim(capture.report)[1], :42-45
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+@pytest.mark.parametrize("name", sorted(VCF_CASES))
+def test_oracle_reproduces_golden_vcf_vectors(oracle, name):
+    bam, z = load_golden(name)
+    o = oracle(bam)
+    for cname, thr in VCF_CASES[name]:
+        freqs, rep = o.generateVcfReport(golden_vcf(z), threshold_reads=thr)
+        assert np.array_equal(freqs, z["vcf." + cname + ".freqs"]), (name, cname)
+        for k in VCF_COLS:
+            assert np.array_equal(rep[k], z["vcf." + cname + "." + k], equal_nan=True), (name, cname, k)
+        for k in ("FEp+", "FEp-"):  # the port sums the tables by definition, HTSlib's walk steps from table to table
+            assert np.allclose(rep[k], z["vcf." + cname + "." + k], rtol=0, atol=1e-9, equal_nan=True), (name, cname, k)
+
+
+def test_port_matches_reference_on_random_vcfs():
+    if RefCpu not in ORACLES:
+        pytest.skip("compiled reference not available")
+    rng = np.random.default_rng(11)
+    for name in ("capture", "amplicon010meth"):
+        bam, _ = load_golden(name)
+        ref, port = RefCpu(bam), PortCpu(bam)
+        for n in (0, 1, 50, 3000):
+            vcf = random_vcf(rng, bam, n)
+            pass_ = rng.random(bam.nrow) < 0.4
+            a = ref.rcpp_get_base_freqs(pass_, (vcf["seqnames"], vcf["start"]))
+            b = port.rcpp_get_base_freqs(pass_, (vcf["seqnames"], vcf["start"]))
+            assert a.shape == (n, 20) and np.array_equal(a, b), (name, n)
+
+
+def test_fisher_exact_host_function_matches_the_oracles():
+    """ea_fisher_exact is host arithmetic inside the product library (no GPU needed): same walk as the reference build's
+    kt_fisher_exact stand-in -> bit-identical; the port sums every table by definition -> 1e-9."""
+    import epialleler_b200 as ea
+    rng = np.random.default_rng(3)
+    n = 5000
+    cols = [rng.integers(0, m, n).astype(np.int32) for m in (300, 3000, 20, 200)]
+    cols[1][::97] = -2147483648
+    cols.append(None)
+    bam = bam_from_xm([(1, 1, 1, "Z")])
+    got = ea.rcpp_fep(*cols[:4])
+    want = PortCpu(bam).rcpp_fep(*cols[:4])
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(got).sum() == len(range(0, n, 97))
+    assert np.allclose(got, want, rtol=0, atol=1e-9, equal_nan=True)
+    if RefCpu in ORACLES:
+        assert np.array_equal(got, RefCpu(bam).rcpp_fep(*cols[:4]), equal_nan=True)
+    # textbook values: Fisher's tea-tasting table and a balanced table
+    p = ea.rcpp_fep([3, 5, 0], [1, 5, 0], [1, 5, 0], [3, 5, 0])
+    assert abs(p[0] - 34.0 / 70.0) < 1e-12 and p[1] == 1.0 and p[2] == 1.0
