@@ -190,6 +190,17 @@ def run_ours(args):
         widened["bed_report"] = {"seconds": dt, "reads_per_s": own_reads / dt, "targets": nb, "reads_matched": int(counts[:-4].sum()),
                                  "what": "ea_bed_report (rcpp_match_capture + thresholds + per-target counts), 20000 targets of 2 kb"}
 
+        nv = 1_000_000
+        vpos = np.sort(rng.integers(1, CHR1, nv)).astype(np.int32)
+        vchr = np.ones(nv, np.int32)
+        freqs = np.zeros(nv * 20, np.float64)
+        for _ in range(2):
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            N.check(L.ea_base_freqs(dev.handle(), None, i32(vchr), i32(vpos), nv, freqs.ctypes.data_as(C.POINTER(C.c_double))))
+            torch.cuda.synchronize(); dt = time.perf_counter() - t1
+        widened["base_freqs"] = {"seconds": dt, "reads_per_s": own_reads / dt, "snvs": nv, "bases_counted": int(freqs.sum()),
+                                 "what": "ea_base_freqs (rcpp_get_base_freqs), 1 M sorted SNV positions, all reads passing"}
+
     # ---- end to end through the public API with HOST buffers (pack + H2D + kernels + D2H) ----
     e2e = None
     if not args.no_e2e:

@@ -1805,9 +1805,14 @@ int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, dou
     WinTable wt;
     wt.rname = ix->rname; wt.pos0 = ix->pos0; wt.lo = ix->lo; wt.hi = ix->hi; wt.n = ix->n; wt.S = ix->S;
     const size_t smem = (size_t)2 * 3 * kMhlS * 8 + (size_t)2 * kMhlS * 4 + (size_t)2 * 3 * kMhlS * 4;
-    CU(cudaFuncSetAttribute(k_window_mhl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // `ctx` made of whole letter pairs Hh / Xx / Zz (and nothing else): the mask sweep; otherwise the byte-serial one
+    const uint32_t pair_bits = (1u << 2) | (1u << 10) | (1u << 6) | (1u << 14) | (1u << 7) | (1u << 15);
+    const bool pairs = (prm.ctx_mask & ~pair_bits) == 0 && ((prm.ctx_mask >> 2) & 1u) == ((prm.ctx_mask >> 10) & 1u) &&
+                       ((prm.ctx_mask >> 6) & 1u) == ((prm.ctx_mask >> 14) & 1u) && ((prm.ctx_mask >> 7) & 1u) == ((prm.ctx_mask >> 15) & 1u);
+    auto kern = pairs ? k_window_mhl<true> : k_window_mhl<false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::max(1, std::min<int>(ix->n, h->sm_count * 32));
-    k_window_mhl<<<grid, kMhlThreads, smem, h->stream>>>(csr_of(h), wt, prm, out);
+    kern<<<grid, kMhlThreads, smem, h->stream>>>(csr_of(h), wt, prm, out);
     k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
     MhlCols cols{h->d_mhl_i[0], h->d_mhl_i[1], h->d_mhl_i[2], h->d_mhl_i[3], h->d_mhl_i[4], h->d_mhl_d[0], h->d_mhl_d[1]};
     k_gather_mhl<<<std::max(1, std::min(ix->n / 4 + 1, h->sm_count * 16)), 128, 0, h->stream>>>(

@@ -71,6 +71,38 @@ __device__ __forceinline__ long long block_exscan_i64(long long v, long long* s_
   return s_warp[warp] + inc - v;
 }
 
+// exclusive block scan of four int64 values at once (three barriers instead of twelve); s_warp: [4][NW]
+template <int NW>
+__device__ __forceinline__ void block_exscan4_i64(long long (&v)[4], long long* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long inc[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) inc[j] = v[j];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const long long o = __shfl_up_sync(0xFFFFFFFFu, inc[j], d);
+      if (lane >= d) inc[j] += o;
+    }
+  __syncthreads();  // protects s_warp against the previous call's readers
+  if (lane == 31) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) s_warp[j * NW + warp] = inc[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    long long ex = inc[j] - v[j];
+#pragma unroll
+    for (int w = 0; w < NW; w++) ex += (w < warp) ? s_warp[j * NW + w] : 0ll;
+    v[j] = ex;
+  }
+}
+
+// bit 0 of every byte of t (t & 0x01010101 == t) gathered into a nibble: bit k = byte k
+__device__ __forceinline__ uint32_t gather4(uint32_t t) { return (t * 0x01020408u) >> 24; }
+
 // difference-array event: value v becomes active at window-relative position q (clamped to the window start),
 // nothing to do at or beyond the window end
 __device__ __forceinline__ void diff_event(int q, int S, int* dW, long long* dH, long long* dDe, int w, long long hv, long long dv) {
@@ -81,12 +113,17 @@ __device__ __forceinline__ void diff_event(int q, int S, int* dW, long long* dH,
   atomicAdd(reinterpret_cast<unsigned long long*>(&dDe[q]), (unsigned long long)dv);
 }
 
+// PAIRS: `ctx` is a union of the letter pairs Hh / Xx / Zz (what generateMhlReport passes, R/generateMhlReport.R:178-180):
+// the row is swept 16 bytes at a time with per-word indicator planes gathered into byte-order masks, and only the set bits
+// (coverage transitions, calls of the haplotype context, stretch events) are visited.  Any other letter set takes the
+// byte-serial sweep.
+template <bool PAIRS>
 __global__ void __launch_bounds__(kMhlThreads, 2)
 k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
   constexpr int S = kMhlS;
   constexpr int PER = S / kMhlThreads;  // 4
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ long long s_scan[kMhlWarps + 1];
+  __shared__ long long s_scan[4 * kMhlWarps];
   __shared__ uint32_t s_scan32[kMhlWarps + 1];
   __shared__ long long s_base;
   // per strand: dH, dDe, dNu (int64) then dW (int32) and T[3] (uint32)
@@ -112,6 +149,23 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
       const int nch = (int)((o1 - o0) >> 4);
       // ---- 1. whole-row counts: h, out-of-context methylated / unmethylated ----
       uint32_t h = 0, om = 0, ou = 0;
+      const uint32_t sel2 = (prm.ctx_mask >> 2) & 1u ? 0xFFFFFFFFu : 0u, sel6 = (prm.ctx_mask >> 6) & 1u ? 0xFFFFFFFFu : 0u,
+                     sel7 = (prm.ctx_mask >> 7) & 1u ? 0xFFFFFFFFu : 0u;
+      if (PAIRS) {
+        for (int c = 0; c < nch; c++) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {  // bit 0 of every byte; pad bytes (code 3) are in none of the classes
+            const uint32_t b0 = w[k], b1 = w[k] >> 1, b2 = w[k] >> 2, b3 = w[k] >> 3;
+            const uint32_t in = (((~b0 & b1 & ~b2) & sel2) | ((~b0 & b1 & b2) & sel6) | ((b0 & b1 & b2) & sel7)) & 0x01010101u;
+            const uint32_t ooc = ((b1 & ~b0) | (b0 & b2)) & 0x01010101u & ~in;  // low three bits 2, 6 | 5, 7: a call letter
+            h += __popc(in);
+            om += __popc(ooc & ~b3);
+            ou += __popc(ooc & b3);
+          }
+        }
+      } else {
       for (int c = 0; c < nch; c++) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -123,6 +177,7 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
           om += (~in) & (0x00E4u >> code) & 1u;   // H U X Z: 2 5 6 7
           ou += (~in) & (0xE400u >> code) & 1u;   // h u x z: 10 13 14 15
         }
+      }
       }
       if ((int)h < prm.hmin || (double)om / (double)(om + ou) > prm.max_ooctx) continue;
       const long long hv = (long long)h;
@@ -150,6 +205,47 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
         if (on && rel0 + me + 1 < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + me + 1, 0)]), (unsigned long long)(-nv));
         msz = 0;
       };
+      if (PAIRS) {
+        uint32_t covb = 0;  // coverage state as a bit
+        for (int c = 0; c < nch; c++) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          const int kmax = min(16, len - 16 * c);
+          const uint32_t valid = kmax >= 16 ? 0xFFFFu : ((1u << kmax) - 1u);
+          uint32_t dash16 = 0, meth16 = 0, t16[3] = {0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t b0 = w[k], b1 = w[k] >> 1, b2 = w[k] >> 2, b3 = w[k] >> 3;
+            const uint32_t c2 = ~b0 & b1 & ~b2 & sel2 & 0x01010101u, c6 = ~b0 & b1 & b2 & sel6 & 0x01010101u, c7 = b0 & b1 & b2 & sel7 & 0x01010101u;
+            dash16 |= gather4(b0 & b1 & ~b2 & b3 & 0x01010101u) << (4 * k);
+            meth16 |= gather4((c2 | c6 | c7) & ~b3) << (4 * k);
+            t16[0] |= gather4(c2) << (4 * k);
+            t16[1] |= gather4(c6) << (4 * k);
+            t16[2] |= gather4(c7) << (4 * k);
+          }
+          const uint32_t nd16 = ~dash16 & valid;
+          const int base = rel0 + 16 * c;
+          for (uint32_t tr = (nd16 ^ ((nd16 << 1) | covb)) & valid; tr; tr &= tr - 1u) {  // coverage transitions
+            const int k = __ffs(tr) - 1;
+            const bool on = (nd16 >> k) & 1u;
+            diff_event(base + k, S, dW, dH, dDe, on ? 1 : -1, on ? hv : -hv, on ? dv : -dv);
+          }
+          covb = (nd16 >> (kmax - 1)) & 1u;
+#pragma unroll
+          for (int cls = 0; cls < 3; cls++)  // calls of the haplotype context (the other classes' counters are never read)
+            for (uint32_t m = t16[cls] & valid; m; m &= m - 1u) {
+              const int q = base + __ffs(m) - 1;
+              if ((unsigned)q < (unsigned)S) atomicAdd(&T[cls * S + q], 1u);
+            }
+          for (uint32_t m = (t16[0] | t16[1] | t16[2]) & valid; m; m &= m - 1u) {  // methylated stretches, in position order
+            const int k = __ffs(m) - 1;
+            const int i = 16 * c + k;
+            if ((meth16 >> k) & 1u) { if (!msz) ms = i; me = i; msz++; }
+            else if (msz) close_stretch();
+          }
+        }
+        cov = covb != 0u;
+      } else {
       for (int c = 0; c < nch; c++) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
         const int kmax = min(16, len - 16 * c);
@@ -173,6 +269,7 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
           }
         }
       }
+      }
       if (cov) diff_event(rel0 + len, S, dW, dH, dDe, -1, -hv, -dv);
       if (msz) close_stretch();
     }
@@ -192,12 +289,10 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
         rd += L64[(s * 3 + 1) * S + q0 + k]; De[s][k] = rd;
         rn += L64[(s * 3 + 2) * S + q0 + k]; Nu[s][k] = rn;
       }
-      const long long ew = block_exscan_i64<kMhlWarps>((long long)rw, s_scan);
-      const long long eh = block_exscan_i64<kMhlWarps>(rh, s_scan);
-      const long long ed = block_exscan_i64<kMhlWarps>(rd, s_scan);
-      const long long en = block_exscan_i64<kMhlWarps>(rn, s_scan);
+      long long ex[4] = {(long long)rw, rh, rd, rn};
+      block_exscan4_i64<kMhlWarps>(ex, s_scan);
 #pragma unroll
-      for (int k = 0; k < PER; k++) { covv[s][k] += (int)ew; Hs[s][k] += eh; De[s][k] += ed; Nu[s][k] += en; }
+      for (int k = 0; k < PER; k++) { covv[s][k] += (int)ex[0]; Hs[s][k] += ex[1]; De[s][k] += ex[2]; Nu[s][k] += ex[3]; }
     }
     uint32_t flags = 0;   // bit 2k+s
     uint32_t which = 0;   // 2 bits per (k,s): class slot of the row

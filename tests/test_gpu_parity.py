@@ -358,6 +358,11 @@ def test_mhl_report_identity_and_synthetic(kernel_policy):
             got = ea.generateMhlReport(host, haplotype_context=hctx, max_haplotype_window=hmax, min_haplotype_length=hmin, max_outofcontext_beta=moo)
             assert want["pos"].shape[0] > 0
             assert_mhl_equal(got, want, "%s %s" % (shape, hctx))
+        # letter sets that are not whole Hh/Xx/Zz pairs take the byte-serial sweep (rcpp_mhl_report is called directly)
+        for ctx, hmax, hmin, moo in (("Z", 0, 0, 0.5), ("zX", 3, 0, 1.0), ("ZzU", 0, 2, 0.3)):
+            want = oracle.rcpp_mhl_report(ctx, hmax, hmin, moo)
+            got = ea.rcpp_mhl_report(host, ctx, hmax, hmin, moo)
+            assert_mhl_equal(got, want, "%s ctx=%s" % (shape, ctx))
         host.close()
 
 
