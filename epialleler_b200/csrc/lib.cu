@@ -1786,6 +1786,12 @@ int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, dou
   MhlParams prm;
   prm.ctx_mask = 0;
   for (const unsigned char* p = (const unsigned char*)ctx; *p; p++) prm.ctx_mask |= 1u << code_of(*p);
+  prm.n_cls = 0;
+  for (int cls = 0; cls < 3; cls++) {  // CHH (H h: 2 10), CHG (X x: 6 14), CG (Z z: 7 15): a counter plane if any of its letters is in ctx
+    const int code = cls == 0 ? 2 : (cls == 1 ? 6 : 7);
+    prm.slot[cls] = ((prm.ctx_mask >> code) & 1u) ? prm.n_cls++ : -1;   // rows need the METHYLATED letter in ctx (rcpp_mhl_report.cpp:72-101)
+  }
+  if (prm.n_cls == 0) { prm.n_cls = 1; }
   prm.cap = hmax > 0 ? (uint32_t)std::min(hmax, 65536) : 65536u;
   prm.hmin = hmin;
   prm.max_ooctx = max_ooctx_meth_frac;
@@ -1804,12 +1810,23 @@ int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, dou
     MhlOut out{h->d_mhl_scratch, h->mhl_cap, h->d_counters, ix->w_base, ix->w_cnt};
     WinTable wt;
     wt.rname = ix->rname; wt.pos0 = ix->pos0; wt.lo = ix->lo; wt.hi = ix->hi; wt.n = ix->n; wt.S = ix->S;
-    const size_t smem = (size_t)2 * 3 * kMhlS * 8 + (size_t)2 * kMhlS * 4 + (size_t)2 * 3 * kMhlS * 4;
+    const size_t smem = (size_t)2 * 3 * kMhlS * 8 + (size_t)2 * kMhlS * 4 + (size_t)2 * prm.n_cls * kMhlS * 4;
     // `ctx` made of whole letter pairs Hh / Xx / Zz (and nothing else): the mask sweep; otherwise the byte-serial one
     const uint32_t pair_bits = (1u << 2) | (1u << 10) | (1u << 6) | (1u << 14) | (1u << 7) | (1u << 15);
     const bool pairs = (prm.ctx_mask & ~pair_bits) == 0 && ((prm.ctx_mask >> 2) & 1u) == ((prm.ctx_mask >> 10) & 1u) &&
                        ((prm.ctx_mask >> 6) & 1u) == ((prm.ctx_mask >> 14) & 1u) && ((prm.ctx_mask >> 7) & 1u) == ((prm.ctx_mask >> 15) & 1u);
-    auto kern = pairs ? k_window_mhl<true> : k_window_mhl<false>;
+    const int cls = pairs ? (int)(((prm.ctx_mask >> 2) & 1u) | (((prm.ctx_mask >> 6) & 1u) << 1) | (((prm.ctx_mask >> 7) & 1u) << 2)) : 0;
+    void (*kern)(Csr, WinTable, MhlParams, MhlOut) = k_window_mhl<0>;
+    switch (cls) {
+      case 1: kern = k_window_mhl<1>; break;
+      case 2: kern = k_window_mhl<2>; break;
+      case 3: kern = k_window_mhl<3>; break;
+      case 4: kern = k_window_mhl<4>; break;
+      case 5: kern = k_window_mhl<5>; break;
+      case 6: kern = k_window_mhl<6>; break;
+      case 7: kern = k_window_mhl<7>; break;
+      default: break;
+    }
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::max(1, std::min<int>(ix->n, h->sm_count * 32));
     kern<<<grid, kMhlThreads, smem, h->stream>>>(csr_of(h), wt, prm, out);

@@ -38,6 +38,8 @@ struct MhlOut {
 };
 struct MhlParams {
   uint32_t ctx_mask;     // bit k: code k is in `ctx` (ctx_map of the reference)
+  int32_t n_cls;         // cytosine classes (CHH, CHG, CG) that get a counter plane in shared memory: those with a letter in `ctx`
+  int32_t slot[3];       // class -> plane (or -1: the class cannot produce a row, its calls are not counted)
   uint32_t cap;          // min(hmax, 65536), or 65536 when hmax <= 0 (:115)
   int32_t hmin;
   double max_ooctx;
@@ -117,20 +119,22 @@ __device__ __forceinline__ void diff_event(int q, int S, int* dW, long long* dH,
 // the row is swept 16 bytes at a time with per-word indicator planes gathered into byte-order masks, and only the set bits
 // (coverage transitions, calls of the haplotype context, stretch events) are visited.  Any other letter set takes the
 // byte-serial sweep.
-template <bool PAIRS>
-__global__ void __launch_bounds__(kMhlThreads, 2)
+template <int CLS /* 0: any letter set (byte-serial sweep); else bit 0 Hh, bit 1 Xx, bit 2 Zz */>
+__global__ void __launch_bounds__(kMhlThreads, 3)
 k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
+  constexpr bool PAIRS = CLS != 0;
   constexpr int S = kMhlS;
   constexpr int PER = S / kMhlThreads;  // 4
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ long long s_scan[4 * kMhlWarps];
   __shared__ uint32_t s_scan32[kMhlWarps + 1];
   __shared__ long long s_base;
-  // per strand: dH, dDe, dNu (int64) then dW (int32) and T[3] (uint32)
+  // per strand: dH, dDe, dNu (int64) then dW (int32) and T[n_cls] (uint32)
+  const int NCLS = prm.n_cls;
   long long* const L64 = reinterpret_cast<long long*>(smem_raw);               // [2][3][S]
   int* const dWb = reinterpret_cast<int*>(L64 + 2 * 3 * S);                    // [2][S]
-  uint32_t* const Tb = reinterpret_cast<uint32_t*>(dWb + 2 * S);               // [2][3][S]
-  constexpr int kZero4 = (2 * 3 * S * 8 + 2 * S * 4 + 2 * 3 * S * 4) / 16;
+  uint32_t* const Tb = reinterpret_cast<uint32_t*>(dWb + 2 * S);               // [2][NCLS][S]
+  const int kZero4 = (2 * 3 * S * 8 + 2 * S * 4 + 2 * NCLS * S * 4) / 16;
 
   for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
     __syncthreads();
@@ -149,8 +153,7 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
       const int nch = (int)((o1 - o0) >> 4);
       // ---- 1. whole-row counts: h, out-of-context methylated / unmethylated ----
       uint32_t h = 0, om = 0, ou = 0;
-      const uint32_t sel2 = (prm.ctx_mask >> 2) & 1u ? 0xFFFFFFFFu : 0u, sel6 = (prm.ctx_mask >> 6) & 1u ? 0xFFFFFFFFu : 0u,
-                     sel7 = (prm.ctx_mask >> 7) & 1u ? 0xFFFFFFFFu : 0u;
+      constexpr uint32_t sel2 = (CLS & 1) ? 0xFFFFFFFFu : 0u, sel6 = (CLS & 2) ? 0xFFFFFFFFu : 0u, sel7 = (CLS & 4) ? 0xFFFFFFFFu : 0u;
       if (PAIRS) {
         for (int c = 0; c < nch; c++) {
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
@@ -186,23 +189,40 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
       long long* const dH = L64 + (s * 3 + 0) * S;
       long long* const dDe = L64 + (s * 3 + 1) * S;
       long long* const dNu = L64 + (s * 3 + 2) * S;
-      uint32_t* const T = Tb + s * 3 * S;
+      uint32_t* const T = Tb + s * NCLS * S;
       // ---- 2. byte-serial sweep ----
       bool cov = false;
       uint32_t msz = 0;
       int ms = 0, me = 0;
+      // '-' bytes seen since the open stretch began: up to four 16-bit row positions packed into 64 bits (rows are at most
+      // 65535 bytes); more than four, or the byte-serial sweep (which does not track them): walk the span byte by byte
+      unsigned long long dlist = 0;
+      int dcnt = PAIRS ? 0 : 5;
       auto close_stretch = [&]() {  // push +-S(min(size, hmax)) around the non-'-' pieces of [ms, me]
         const long long nv = (long long)mhl_S(msz < prm.cap ? msz : prm.cap);
-        bool on = false;
-        for (int i = ms; i <= me; i++) {
-          const bool c2 = (__ldg(row + i) & 15u) != 11u;
-          if (c2 != on) {
-            const int q = rel0 + i;
-            if (q < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(q, 0)]), (unsigned long long)(c2 ? nv : -nv));
-            on = c2;
+        if (dcnt <= 4) {
+          // the whole span, then every '-' byte strictly inside it switched off for one position (adjacent ones compose)
+          if (rel0 + ms < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + ms, 0)]), (unsigned long long)nv);
+          if (rel0 + me + 1 < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + me + 1, 0)]), (unsigned long long)(-nv));
+          for (int j = 0; j < dcnt; j++) {
+            const int p = (int)((dlist >> (16 * j)) & 0xFFFFull);
+            if (p < me) {
+              if (rel0 + p < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + p, 0)]), (unsigned long long)(-nv));
+              if (rel0 + p + 1 < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + p + 1, 0)]), (unsigned long long)nv);
+            }
           }
+        } else {
+          bool on = false;
+          for (int i = ms; i <= me; i++) {
+            const bool c2 = (__ldg(row + i) & 15u) != 11u;
+            if (c2 != on) {
+              const int q = rel0 + i;
+              if (q < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(q, 0)]), (unsigned long long)(c2 ? nv : -nv));
+              on = c2;
+            }
+          }
+          if (on && rel0 + me + 1 < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + me + 1, 0)]), (unsigned long long)(-nv));
         }
-        if (on && rel0 + me + 1 < S) atomicAdd(reinterpret_cast<unsigned long long*>(&dNu[max(rel0 + me + 1, 0)]), (unsigned long long)(-nv));
         msz = 0;
       };
       if (PAIRS) {
@@ -216,14 +236,15 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const uint32_t b0 = w[k], b1 = w[k] >> 1, b2 = w[k] >> 2, b3 = w[k] >> 3;
-            const uint32_t c2 = ~b0 & b1 & ~b2 & sel2 & 0x01010101u, c6 = ~b0 & b1 & b2 & sel6 & 0x01010101u, c7 = b0 & b1 & b2 & sel7 & 0x01010101u;
             dash16 |= gather4(b0 & b1 & ~b2 & b3 & 0x01010101u) << (4 * k);
-            meth16 |= gather4((c2 | c6 | c7) & ~b3) << (4 * k);
-            t16[0] |= gather4(c2) << (4 * k);
-            t16[1] |= gather4(c6) << (4 * k);
-            t16[2] |= gather4(c7) << (4 * k);
+            uint32_t in = 0;
+            if (sel2) { const uint32_t c2 = ~b0 & b1 & ~b2 & 0x01010101u; t16[0] |= gather4(c2) << (4 * k); in |= c2; }
+            if (sel6) { const uint32_t c6 = ~b0 & b1 & b2 & 0x01010101u; t16[1] |= gather4(c6) << (4 * k); in |= c6; }
+            if (sel7) { const uint32_t c7 = b0 & b1 & b2 & 0x01010101u; t16[2] |= gather4(c7) << (4 * k); in |= c7; }
+            meth16 |= gather4(in & ~b3) << (4 * k);
           }
           const uint32_t nd16 = ~dash16 & valid;
+          const uint32_t call16 = (t16[0] | t16[1] | t16[2]) & valid;
           const int base = rel0 + 16 * c;
           for (uint32_t tr = (nd16 ^ ((nd16 << 1) | covb)) & valid; tr; tr &= tr - 1u) {  // coverage transitions
             const int k = __ffs(tr) - 1;
@@ -232,16 +253,23 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
           }
           covb = (nd16 >> (kmax - 1)) & 1u;
 #pragma unroll
-          for (int cls = 0; cls < 3; cls++)  // calls of the haplotype context (the other classes' counters are never read)
+          for (int cls = 0; cls < 3; cls++)  // calls of the haplotype context (the other classes cannot produce rows)
             for (uint32_t m = t16[cls] & valid; m; m &= m - 1u) {
               const int q = base + __ffs(m) - 1;
-              if ((unsigned)q < (unsigned)S) atomicAdd(&T[cls * S + q], 1u);
+              if ((unsigned)q < (unsigned)S) atomicAdd(&T[prm.slot[cls] * S + q], 1u);
             }
-          for (uint32_t m = (t16[0] | t16[1] | t16[2]) & valid; m; m &= m - 1u) {  // methylated stretches, in position order
+          // methylated stretches: context calls and '-' bytes in position order
+          for (uint32_t m = call16 | (msz || (call16 & meth16) ? dash16 & valid : 0u); m; m &= m - 1u) {
             const int k = __ffs(m) - 1;
             const int i = 16 * c + k;
-            if ((meth16 >> k) & 1u) { if (!msz) ms = i; me = i; msz++; }
-            else if (msz) close_stretch();
+            if (!((call16 >> k) & 1u)) {  // a '-' byte
+              if (msz) { dlist = (dlist << 16) | (unsigned long long)i; dcnt++; }
+              continue;
+            }
+            if ((meth16 >> k) & 1u) {
+              if (!msz) { ms = i; dcnt = 0; }
+              me = i; msz++;
+            } else if (msz) close_stretch();
           }
         }
         cov = covb != 0u;
@@ -261,7 +289,8 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
           const uint32_t c7 = code & 7u;
           if (c7 == 2u || c7 == 6u || c7 == 7u) {  // a cytosine call: count it at its position
             const int q = rel0 + i;
-            if ((unsigned)q < (unsigned)S) atomicAdd(&T[(c7 == 2u ? 0 : (c7 == 6u ? 1 : 2)) * S + q], 1u);
+            const int sl = prm.slot[c7 == 2u ? 0 : (c7 == 6u ? 1 : 2)];
+            if (sl >= 0 && (unsigned)q < (unsigned)S) atomicAdd(&T[sl * S + q], 1u);
           }
           if ((prm.ctx_mask >> code) & 1u) {
             if (code < 8u) { if (!msz) ms = i; me = i; msz++; }
@@ -275,39 +304,43 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
     }
     __syncthreads();
 
-    // ---- finalize: prefix sums of the four difference arrays per strand, row test, ordered compaction ----
+    // ---- finalize: the four difference arrays of each strand become their prefix sums IN PLACE (every thread owns
+    //      PER consecutive positions), then the row test and the ordered compaction read them back ----
     const int q0 = threadIdx.x * PER;
-    int covv[2][PER];
-    long long Hs[2][PER], De[2][PER], Nu[2][PER];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
+      int* const pw = dWb + s * S + q0;
+      long long* const ph = L64 + (s * 3 + 0) * S + q0;
+      long long* const pd = L64 + (s * 3 + 1) * S + q0;
+      long long* const pn = L64 + (s * 3 + 2) * S + q0;
       int rw = 0; long long rh = 0, rd = 0, rn = 0;
 #pragma unroll
-      for (int k = 0; k < PER; k++) {
-        rw += dWb[s * S + q0 + k]; covv[s][k] = rw;
-        rh += L64[(s * 3 + 0) * S + q0 + k]; Hs[s][k] = rh;
-        rd += L64[(s * 3 + 1) * S + q0 + k]; De[s][k] = rd;
-        rn += L64[(s * 3 + 2) * S + q0 + k]; Nu[s][k] = rn;
-      }
+      for (int k = 0; k < PER; k++) { rw += pw[k]; rh += ph[k]; rd += pd[k]; rn += pn[k]; }
       long long ex[4] = {(long long)rw, rh, rd, rn};
       block_exscan4_i64<kMhlWarps>(ex, s_scan);
+      rw = (int)ex[0]; rh = ex[1]; rd = ex[2]; rn = ex[3];
 #pragma unroll
-      for (int k = 0; k < PER; k++) { covv[s][k] += (int)ex[0]; Hs[s][k] += ex[1]; De[s][k] += ex[2]; Nu[s][k] += ex[3]; }
+      for (int k = 0; k < PER; k++) {
+        rw += pw[k]; pw[k] = rw;
+        rh += ph[k]; ph[k] = rh;
+        rd += pd[k]; pd[k] = rd;
+        rn += pn[k]; pn[k] = rn;
+      }
     }
     uint32_t flags = 0;   // bit 2k+s
-    uint32_t which = 0;   // 2 bits per (k,s): class slot of the row
+    uint32_t which = 0;   // 2 bits per (k,s): class of the row
 #pragma unroll
     for (int k = 0; k < PER; k++)
 #pragma unroll
       for (int s = 0; s < 2; s++) {
-        const int cv = covv[s][k];
+        const int cv = dWb[s * S + q0 + k];
         if (cv <= 0) continue;
         const uint32_t half = (uint32_t)cv >> 1;
 #pragma unroll
         for (int cls = 0; cls < 3; cls++) {
           const uint32_t code = cls == 0 ? 2u : (cls == 1 ? 6u : 7u);
           if (!((prm.ctx_mask >> code) & 1u)) continue;
-          if (Tb[(s * 3 + cls) * S + q0 + k] > half) { flags |= 1u << (2 * k + s); which |= (uint32_t)cls << (2 * (2 * k + s)); }
+          if (Tb[(s * NCLS + prm.slot[cls]) * S + q0 + k] > half) { flags |= 1u << (2 * k + s); which |= (uint32_t)cls << (2 * (2 * k + s)); }
         }
       }
     uint32_t nrows_u;
@@ -330,11 +363,11 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
           if (!((flags >> (2 * k + s)) & 1u)) continue;
           const int cls = (which >> (2 * (2 * k + s))) & 3;
           const int code = cls == 0 ? 2 : (cls == 1 ? 6 : 7);
-          const int c = (int)Tb[(s * 3 + cls) * S + q0 + k];
+          const int c = (int)Tb[(s * NCLS + prm.slot[cls]) * S + q0 + k];
           MhlRow rrow;
           rrow.pos = w0 + q0 + k; rrow.strand_ctx = (s + 1) | (code << 8); rrow.coverage = c; rrow.pad = 0;
-          rrow.length = (double)(unsigned long long)Hs[s][k] / (double)c;                                  // (double)uint64 / int, :97
-          rrow.lmhl = (double)(unsigned long long)Nu[s][k] / (double)(unsigned long long)De[s][k];       // :98
+          rrow.length = (double)(unsigned long long)L64[(s * 3 + 0) * S + q0 + k] / (double)c;                                            // (double)uint64 / int, :97
+          rrow.lmhl = (double)(unsigned long long)L64[(s * 3 + 2) * S + q0 + k] / (double)(unsigned long long)L64[(s * 3 + 1) * S + q0 + k];  // :98
           *dst++ = rrow;
         }
     }
