@@ -113,6 +113,27 @@ def shard_rows(ea, cfg, rank, world):
     return own_lo - back + halo, own_lo - back + own, own_hi
 
 
+def bind_host_to_gpu(local):
+    """Pin this rank's host threads (and with them the first-touch placement of its page-locked buffers) to the CPUs that
+    share a NUMA node with its GPU: with 8 ranks each pushing 8.7 GB per step over PCIe, host buffers on the far socket
+    halve the end-to-end rate.  Uses NVML's ideal CPU affinity; silently does nothing where that is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d CPUs local to GPU %d (NVML affinity)" % (len(cpus), local)
+    except Exception:
+        pass
+    return "not set"
+
+
 def run_ours(args):
     import torch
 
@@ -125,6 +146,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         raise SystemExit("launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
+    host_affinity = bind_host_to_gpu(local) if world > 1 else "not set (single GPU)"
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -284,7 +306,7 @@ def run_ours(args):
         }
         if e2e:
             line["e2e"] = {"value": tot_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "seconds_per_step": e2e_s, "pinned_host_memory": e2e["pinned"], "steps": e2e["steps"],
+                           "seconds_per_step": e2e_s, "pinned_host_memory": e2e["pinned"], "host_affinity": host_affinity, "steps": e2e["steps"],
                            "what": "ea_pack_blob (H2D + device repack + validation + window index) + fused report + D2H of pass flags and rows + free"}
         if cpu:
             line["cpu_baseline"] = cpu
