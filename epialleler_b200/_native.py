@@ -61,6 +61,8 @@ SIGNATURES = {
     "ea_attach_device": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.POINTER(_H)]),
     "ea_free": (None, [_H]),
     "ea_trim": (C.c_int, [C.c_int]),
+    "ea_cx_report_text": (C.c_int, [_H, C.POINTER(C.c_char_p), C.c_int32, C.c_int, C.POINTER(C.c_int64)]),
+    "ea_cx_report_text_fetch": (C.c_int, [_H, C.c_void_p]),
     "ea_base_freqs": (C.c_int, [_H, _U8P, _I32P, _I32P, C.c_int64, _F64P]),
     "ea_fisher_exact": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, _F64P]),
     "ea_host_alloc": (C.c_void_p, [C.c_size_t]),

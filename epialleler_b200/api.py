@@ -251,10 +251,10 @@ def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshol
     nrow = C.c_int64(0)
     pass_out = _host_out(bam.nrow, np.uint8) if return_pass else None
     N.check(L.ea_cytosine_report(bam.handle(), C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow)))
-    rep = _fetch_report(bam, nrow.value)
-    if report_file is not None:
-        _write_report(rep, report_file, gzip)
+    if report_file is not None:  # formatted on the device, the rows never become Python objects
+        _write_report_text(report_text(bam), report_file, gzip)
         return None
+    rep = _fetch_report(bam, nrow.value)
     if return_pass:
         return pass_out[:bam.nrow].view(np.bool_), rep  # the library writes 0/1 bytes
     return rep
@@ -574,16 +574,23 @@ def generateVcfReport(bam, vcf, vcf_style=None, bed=None, report_file=None, zero
     return None
 
 
-def _write_report(rep, path, gz):
-    lv = rep["levels"]
-    opener = (lambda p: _gzip.open(p, "wt")) if gz else (lambda p: open(p, "w"))
-    with opener(path) as fh:
-        fh.write("rname\tstrand\tpos\tcontext\tmeth\tunmeth\n")
-        for i in range(rep["pos"].shape[0]):
-            rn = rep["rname"][i]
-            name = lv["rname"][rn - 1] if 0 < rn <= len(lv["rname"]) else str(rn)
-            fh.write("%s\t%s\t%d\t%s\t%d\t%d\n" % (name, STRAND_LEVELS[rep["strand"][i] - 1], rep["pos"][i],
-                                                  CONTEXT_LEVELS[rep["context"][i] - 1], rep["meth"][i], rep["unmeth"][i]))
+def report_text(df, header=True):
+    """The last cytosine report computed on `df` as the bytes .writeReport / data.table::fwrite would put into the file
+    (R/internal.R:273-287), formatted on the device (ea_cx_report_text).  Returns a uint8 numpy array."""
+    L = N.lib()
+    names = [str(x).encode() for x in df.rname_levels]
+    arr = (C.c_char_p * max(len(names), 1))(*names)
+    nbytes = C.c_int64(0)
+    N.check(L.ea_cx_report_text(df.handle(), arr, len(names), 1 if header else 0, C.byref(nbytes)))
+    out = _host_out(nbytes.value, np.uint8)
+    if nbytes.value:
+        N.check(L.ea_cx_report_text_fetch(df.handle(), out.ctypes.data_as(C.c_void_p)))
+    return out[:nbytes.value]
+
+
+def _write_report_text(text, path, gz):
+    with (_gzip.open(path, "wb") if gz else open(path, "wb")) as fh:
+        fh.write(memoryview(np.ascontiguousarray(text)))
 
 
 # ---- deterministic synthetic reads (bench / parity at BASELINE.json sizes) -----------------------

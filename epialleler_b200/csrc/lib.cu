@@ -28,6 +28,7 @@
 #include "window_long.cuh"
 #include "bed.cuh"
 #include "vcf.cuh"
+#include "writer.cuh"
 #include "window_mhl.cuh"
 #include "synth.h"
 
@@ -158,6 +159,8 @@ struct ea_handle {
   int64_t n_rows = -1;
   int32_t report_n_launches = 0;
   const char* report_kernel = "";  // which window kernel the last report ran
+  char* d_text = nullptr;      // last formatted report (ea_cx_report_text)
+  int64_t text_bytes = -1;
   void* d_flush = nullptr;
   int64_t flush_bytes = 0;
   int sm_count = 148;
@@ -1240,7 +1243,7 @@ void ea_free(ea_handle* h) {
   for (auto& c : h->idx) c.release();
   pool_free(h->d_pass); pool_free(h->d_beta); pool_free(h->d_counters); pool_free(h->d_thr_tables); pool_free(h->d_match); pool_free(h->d_mhl_scratch);
   for (auto& c : h->d_mhl_i) pool_free(c);
-  for (auto& c : h->d_mhl_d) pool_free(c); pool_free(h->d_scratch); pool_free(h->d_flush);
+  for (auto& c : h->d_mhl_d) pool_free(c); pool_free(h->d_scratch); pool_free(h->d_flush); pool_free(h->d_text);
   for (auto& c : h->d_cols) pool_free(c);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1905,6 +1908,71 @@ int ea_cx_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* p
       if (dst[c]) CU(cudaMemcpyAsync(dst[c], h->d_cols[c], 4 * (size_t)h->n_rows, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   tr.mark("D2H rows");
+  return EA_OK;
+}
+
+// The last report as text (writer.cuh).  rname_levels: n_levels NUL-terminated chromosome names (the factor levels of
+// bam$rname); header != 0 prepends the column-name line.  Returns the byte count; ea_cx_report_text_fetch copies the text.
+int ea_cx_report_text(ea_handle* h, const char* const* rname_levels, int32_t n_levels, int header, int64_t* nbytes_out) {
+  if (!h || !nbytes_out) return fail(EA_ERR_ARG, "null argument");
+  if (h->n_rows < 0) return fail(EA_ERR_STATE, "no report has been computed on this handle");
+  if (n_levels < 0 || (n_levels > 0 && !rname_levels)) return fail(EA_ERR_ARG, "bad rname levels");
+  int rc;
+  CU(cudaSetDevice(h->device));
+  static const char kHeader[] = "rname\tstrand\tpos\tcontext\tmeth\tunmeth\n";
+  const int64_t hdr = header ? (int64_t)(sizeof(kHeader) - 1) : 0;
+  std::string chars;
+  std::vector<int32_t> off((size_t)n_levels + 1, 0);
+  for (int32_t i = 0; i < n_levels; i++) {
+    if (!rname_levels[i]) return fail(EA_ERR_ARG, "null rname level %d", i);
+    chars += rname_levels[i];
+    off[(size_t)i + 1] = (int32_t)chars.size();
+  }
+  pool_free(h->d_text); h->d_text = nullptr; h->text_bytes = -1;
+  const int64_t n = h->n_rows;
+  char* d_chars = nullptr; int32_t* d_off = nullptr; int64_t* d_len = nullptr; int64_t* d_pos = nullptr; void* d_tmp = nullptr;
+  auto cleanup = [&]() { pool_free(d_chars); pool_free(d_off); pool_free(d_len); pool_free(d_pos); pool_free(d_tmp); };
+#define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  TRY(dmalloc(&d_chars, chars.size()));
+  TRY(dmalloc(&d_off, off.size()));
+  TRY(dmalloc(&d_len, (size_t)n + 1));
+  TRY(dmalloc(&d_pos, (size_t)n + 1));
+  if (!chars.empty()) TRYCU(cudaMemcpyAsync(d_chars, chars.data(), chars.size(), cudaMemcpyHostToDevice, h->stream));
+  TRYCU(cudaMemcpyAsync(d_off, off.data(), 4 * off.size(), cudaMemcpyHostToDevice, h->stream));
+  TRYCU(cudaMemsetAsync(d_len + n, 0, 8, h->stream));
+  const TextLevels lv{d_chars, d_off, n_levels};
+  const ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
+  if (n > 0) k_text_len<<<grid_for(n, 256), 256, 0, h->stream>>>(cols, n, lv, d_len);
+  size_t tb = 0;
+  TRYCU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_len, d_pos, (int)(n + 1), h->stream));
+  TRYCU(pool_malloc(&d_tmp, std::max<size_t>(tb, 1)));
+  TRYCU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_len, d_pos, (int)(n + 1), h->stream));
+  int64_t body = 0;
+  TRYCU(cudaMemcpyAsync(&body, d_pos + n, 8, cudaMemcpyDeviceToHost, h->stream));
+  TRYCU(cudaStreamSynchronize(h->stream));  // also: chars / off must outlive their copies
+  TRY(dmalloc(&h->d_text, (size_t)(hdr + body)));
+  if (hdr) TRYCU(cudaMemcpyAsync(h->d_text, kHeader, (size_t)hdr, cudaMemcpyHostToDevice, h->stream));
+  if (n > 0) k_text_write<<<grid_for(n, 256), 256, 0, h->stream>>>(cols, n, lv, d_pos, hdr, h->d_text);
+  TRYCU(cudaGetLastError());
+  TRYCU(cudaStreamSynchronize(h->stream));
+#undef TRY
+#undef TRYCU
+  cleanup();
+  h->text_bytes = hdr + body;
+  *nbytes_out = h->text_bytes;
+  return EA_OK;
+}
+
+int ea_cx_report_text_fetch(ea_handle* h, char* out) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  if (h->text_bytes < 0) return fail(EA_ERR_STATE, "no report text has been formatted on this handle");
+  CU(cudaSetDevice(h->device));
+  if (h->text_bytes > 0) {
+    if (!out) return fail(EA_ERR_ARG, "null output buffer");
+    CU(cudaMemcpyAsync(out, h->d_text, (size_t)h->text_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   return EA_OK;
 }
 

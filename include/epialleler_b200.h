@@ -119,6 +119,13 @@ int ea_cx_report(ea_handle* h, const uint8_t* pass, const char* ctx, int64_t* nr
 int ea_cx_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* pos, int32_t* context,
                        int32_t* meth, int32_t* unmeth);
 
+/* Report writer: the last report of this handle as the text .writeReport produces through
+ * data.table::fwrite (R/internal.R:273-287): tab separated, header line if header != 0, factor labels for rname (taken
+ * from rname_levels, the levels of bam$rname), strand (+ -) and context (CHH CHG CG), decimal integers, "\n" line ends.
+ * Formatted on the device; two-phase like the row fetch: byte count first, then the caller's buffer is filled. */
+int ea_cx_report_text(ea_handle* h, const char* const* rname_levels, int32_t n_levels, int header, int64_t* nbytes_out);
+int ea_cx_report_text_fetch(ea_handle* h, char* out);
+
 /* ---- fused generateCytosineReport body ------------------------------------------------------- */
 
 typedef struct ea_report_params {

@@ -134,3 +134,14 @@ def random_vcf(rng, bam, n, na_frac=0.05):
     ref = letters[rng.integers(0, 4, n)]
     alt = letters[(np.searchsorted(letters, ref) + rng.integers(1, 4, n)) % 4]
     return {"seqnames": chr_, "start": pos, "REF": list(ref), "ALT": list(alt), "name": ["r%d" % k for k in range(n)]}
+
+
+def format_report_text(rep, rname_levels, header=True):
+    """What data.table::fwrite(report, quote=FALSE, sep="\\t", col.names=TRUE) writes for a cytosine report
+    (/root/reference/R/internal.R:273-287): factor labels for rname / strand / context, plain integers."""
+    ctx = {2: "CHH", 6: "CHG", 7: "CG"}
+    lines = ["rname\tstrand\tpos\tcontext\tmeth\tunmeth\n"] if header else []
+    for i in range(rep["pos"].shape[0]):
+        lines.append("%s\t%s\t%d\t%s\t%d\t%d\n" % (rname_levels[rep["rname"][i] - 1], "+-"[rep["strand"][i] - 1], rep["pos"][i],
+                                                    ctx[int(rep["context"][i])], rep["meth"][i], rep["unmeth"][i]))
+    return "".join(lines).encode()

@@ -409,3 +409,34 @@ def test_base_freqs_random_vcfs_against_oracle():
     with pytest.raises(ea.EaError) as e:  # unsorted entries: the reference's stated precondition
         ea.rcpp_get_base_freqs(cases[0], None, ([1, 1], [500, 400]))
     assert e.value.code == -3
+
+
+# ---- report writer: ea_cx_report_text ---------------------------------------------
+from helpers import format_report_text  # noqa: E402
+
+
+def test_report_text_matches_fwrite_format(tmp_path):
+    """The device-formatted report is byte for byte what the reference's .writeReport (data.table::fwrite, tab separated,
+    factor labels, header) writes for the oracle's rows; through the file path of generateCytosineReport too (plain and gzip)."""
+    import gzip
+    for name, kw in (("amplicon010meth", dict()), ("capture", dict(threshold_reads=False, report_context="CX")), ("dragen_se", dict(report_context="CHG"))):
+        bam, z = load_golden(name)
+        want_p, want = PortCpu(bam).generateCytosineReport(kw.get("threshold_reads", True), "CG", 2, 0.5, 0.1, kw.get("report_context", "CG"))
+        expect = format_report_text(want, bam.rname_levels)
+        ea.generateCytosineReport(bam, **kw)
+        assert bytes(ea.report_text(bam)) == expect, name
+        assert bytes(ea.report_text(bam, header=False)) == format_report_text(want, bam.rname_levels, header=False), name
+        f1, f2 = tmp_path / (name + ".tsv"), tmp_path / (name + ".tsv.gz")
+        assert ea.generateCytosineReport(bam, report_file=str(f1), **kw) is None
+        assert ea.generateCytosineReport(bam, report_file=str(f2), gzip=True, **kw) is None
+        assert f1.read_bytes() == expect and gzip.open(f2, "rb").read() == expect, name
+        bam.close()
+    # an empty report is the header line; large positions and counts keep all their digits
+    empty = ea.BamData.from_strings([], [], [], [], [], rname_levels=["chr1"])
+    ea.generateCytosineReport(empty)
+    assert bytes(ea.report_text(empty)) == b"rname\tstrand\tpos\tcontext\tmeth\tunmeth\n"
+    rows = [(2, 1, 2000000000, "Z"), (2, 2, 2000000001, "zZ" * 20)]
+    b = bam_from_xm(rows)
+    b.rname_levels = ["chrA", "a-very-long-contig-name|with|pipes"]
+    rep = ea.generateCytosineReport(b, threshold_reads=False)
+    assert bytes(ea.report_text(b)) == format_report_text(rep, b.rname_levels)
