@@ -186,8 +186,12 @@ def run_ours(args):
     # ---- two-pass variant (threshold kernel + report kernel), for the record ----
     N.check(L.ea_cytosine_report_device(dev.handle(), C.byref(p), 1, C.byref(tm)))
     N.check(L.ea_cytosine_report_device(dev.handle(), C.byref(p), 1, C.byref(tm)))
+    thr_alg = int(dev.nbytes) + 9 * int(dev.nrow)  # rcpp_threshold_reads alone: every XM byte once, 8 B offset read + 1 B flag written per row
     two_pass = dict(total_ms=round(tm.total_ms, 4), threshold_ms=round(tm.kernel_ms[0], 4), window_ms=round(tm.kernel_ms[1], 4),
-                    rows=int(tm.n_rows), n_pass=int(tm.n_pass))
+                    rows=int(tm.n_rows), n_pass=int(tm.n_pass),
+                    threshold_kernel={"what": "rcpp_threshold_reads stand-alone (k_threshold_row + thr tables)", "algorithmic_bytes": thr_alg,
+                                      "achieved_gbs": round(thr_alg / max(tm.kernel_ms[0], 1e-9) / 1e6, 1),
+                                      "frac_of_hbm_peak": round(thr_alg / max(tm.kernel_ms[0], 1e-9) / 1e6 / measured_peak()[0], 4)})
 
     # ---- the widened paths on the same resident reads, for the record: device call + row-count read-back ----
     widened = None

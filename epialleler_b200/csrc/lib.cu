@@ -26,6 +26,7 @@
 #include "window_cpl.cuh"
 #include "window_row.cuh"
 #include "window_long.cuh"
+#include "threshold_row.cuh"
 #include "bed.cuh"
 #include "vcf.cuh"
 #include "writer.cuh"
@@ -566,8 +567,19 @@ int group_lanes(const ea_handle* h) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
+int thr_tables(ea_handle* h, const ThrParams& thr, ThrTables* tb);
+
 template <int TCTX>
 void launch_threshold_t(ea_handle* h, const ThrParams& tp, uint8_t* pass, double* beta, unsigned long long* n_pass) {
+  // short reads: row per lane (threshold_row.cuh); the integer tables cover counts up to 1024
+  if (g_kernel_policy != 1 && h->max_len <= 1024 && h->npadded / std::max<int64_t>(h->n, 1) <= 512) {
+    ThrTables tb{nullptr, nullptr};
+    if (pass && thr_tables(h, tp, &tb) != EA_OK) return;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((h->n + 255) / 256, (int64_t)h->sm_count * 48));
+    if (h->rows32) k_threshold_row<TCTX, true><<<blocks, 256, 0, h->stream>>>(csr_of(h), tp, tb, pass, beta, n_pass);
+    else k_threshold_row<TCTX, false><<<blocks, 256, 0, h->stream>>>(csr_of(h), tp, tb, pass, beta, n_pass);
+    return;
+  }
   const int g = group_lanes(h);
   const int rpw = 32 / g;
   const int64_t warps_needed = (h->n + rpw - 1) / rpw;
