@@ -3,11 +3,13 @@
 // from Python/ctypes by the test-suite).
 //
 // Drop this file into the reference's src/ in place of rcpp_threshold_reads.cpp, rcpp_get_xm_beta.cpp
-// and rcpp_cx_report.cpp, add `PKG_LIBS += -L$(EA_B200_LIB) -lepialleler_b200` and
+// and rcpp_cx_report.cpp (and, for the siblings at the end of the file, rcpp_mhl_report.cpp, rcpp_match_target.cpp,
+// rcpp_get_base_freqs.cpp, rcpp_fep.cpp), add `PKG_LIBS += -L$(EA_B200_LIB) -lepialleler_b200` and
 // `PKG_CPPFLAGS += -I$(EA_B200_INCLUDE)` to src/Makevars, and re-run Rcpp::compileAttributes():
 // the three exported R closures (R/RcppExports.R:12-14,28-30,64-66) and the registered native
 // symbols (src/RcppExports.cpp:253-271) keep their names, arity and argument meaning.
 #include <Rcpp.h>
+#include <cstdio>
 #include <epialleler_b200.h>
 
 namespace {
@@ -109,4 +111,86 @@ Rcpp::DataFrame rcpp_cytosine_report_fused(Rcpp::DataFrame& df, const bool thres
   int64_t n = 0;
   ea_check(ea_cytosine_report(h, &p, nullptr, &n));
   return wrap_report(h, n, df);
+}
+
+// ---- the siblings that reuse the packed reads; same exported names and signatures as the reference ----
+
+// R/RcppExports.R:40-42, src/rcpp_mhl_report.cpp:46
+// [[Rcpp::export("rcpp_mhl_report")]]
+Rcpp::DataFrame rcpp_mhl_report(Rcpp::DataFrame& df, const std::string ctx, int hmax, const int hmin, const double max_ooctx_meth_frac) {
+  ea_handle* h = handle_of(df);
+  int64_t n = 0;
+  ea_check(ea_mhl_report(h, ctx.c_str(), hmax, hmin, max_ooctx_meth_frac, &n));
+  Rcpp::IntegerVector rname(n), strand(n), pos(n), context(n), coverage(n);
+  Rcpp::NumericVector length(n), lmhl(n);
+  ea_check(ea_mhl_report_fetch(h, rname.begin(), strand.begin(), pos.begin(), context.begin(), coverage.begin(), length.begin(), lmhl.begin()));
+  Rcpp::IntegerVector in_rname = df["rname"], in_strand = df["strand"];
+  rname.attr("class") = "factor";   rname.attr("levels") = in_rname.attr("levels");
+  strand.attr("class") = "factor";  strand.attr("levels") = in_strand.attr("levels");
+  context.attr("class") = "factor";
+  context.attr("levels") = Rcpp::CharacterVector::create("NA1", "CHH", "NA3", "NA4", "NA5", "CHG", "CG");
+  return Rcpp::DataFrame::create(Rcpp::Named("rname") = rname, Rcpp::Named("strand") = strand, Rcpp::Named("pos") = pos,
+                                 Rcpp::Named("context") = context, Rcpp::Named("coverage") = coverage,
+                                 Rcpp::Named("length") = length, Rcpp::Named("lmhl") = lmhl);
+}
+
+namespace {
+std::vector<int> match_target(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, int mode, int param) {
+  ea_handle* h = handle_of(df);
+  Rcpp::IntegerVector chr = bed["seqnames"], start = bed["start"], end = bed["end"];   // factor codes on levels(bam$rname), NA_INTEGER = INT32_MIN
+  std::vector<int> out(static_cast<size_t>(ea_nrow(h)));
+  ea_check(ea_match_target(h, mode, chr.begin(), start.begin(), end.begin(), chr.size(), param, out.data()));
+  return out;                                                                           // 1-based BED row or NA_INTEGER
+}
+}  // namespace
+
+// R/RcppExports.R:32-38, src/rcpp_match_target.cpp:16,51
+// [[Rcpp::export("rcpp_match_amplicon")]]
+std::vector<int> rcpp_match_amplicon(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, const int tolerance) { return match_target(df, bed, 0, tolerance); }
+// [[Rcpp::export("rcpp_match_capture")]]
+std::vector<int> rcpp_match_capture(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, const signed int min_overlap) { return match_target(df, bed, 1, min_overlap); }
+
+// R/RcppExports.R:24-26, src/rcpp_get_base_freqs.cpp:15
+// [[Rcpp::export("rcpp_get_base_freqs")]]
+Rcpp::NumericMatrix rcpp_get_base_freqs(Rcpp::DataFrame& df, std::vector<bool> pass, Rcpp::DataFrame& vcf) {
+  ea_handle* h = handle_of(df);
+  Rcpp::IntegerVector chr = vcf["seqnames"], pos = vcf["start"];
+  std::vector<uint8_t> flags(pass.begin(), pass.end());
+  Rcpp::NumericMatrix res(pos.size(), 20);                                              // column-major, like the library's output
+  ea_check(ea_base_freqs(h, flags.data(), chr.begin(), pos.begin(), pos.size(), res.begin()));
+  return res;
+}
+
+// R/RcppExports.R:20-22, src/rcpp_fep.cpp:9
+// [[Rcpp::export]]
+std::vector<double> rcpp_fep(Rcpp::DataFrame& df, std::vector<std::string> colnames) {
+  Rcpp::IntegerVector A = df[colnames[0]], B = df[colnames[1]], C = df[colnames[2]], D = df[colnames[3]];
+  std::vector<double> p(A.size(), NA_REAL);
+  ea_check(ea_fisher_exact(A.begin(), B.begin(), C.begin(), D.begin(), A.size(), p.data()));
+  for (auto& x : p) if (x != x) x = NA_REAL;                                            // the library reports NA as NaN
+  return p;
+}
+
+// .writeReport for the cytosine report (R/internal.R:273-287): the file's bytes come formatted from the device.
+// R side: rcpp_write_cx_report(bam, report.file) after rcpp_cx_report / rcpp_cytosine_report_fused on the same bam.
+// [[Rcpp::export("rcpp_write_cx_report")]]
+void rcpp_write_cx_report(Rcpp::DataFrame& df, const std::string path) {
+  ea_handle* h = handle_of(df);
+  Rcpp::IntegerVector in_rname = df["rname"];
+  Rcpp::CharacterVector lv = in_rname.attr("levels");
+  std::vector<std::string> names(lv.size());
+  std::vector<const char*> ptr(lv.size());
+  for (R_xlen_t i = 0; i < lv.size(); i++) { names[i] = Rcpp::as<std::string>(lv[i]); ptr[i] = names[i].c_str(); }
+  int64_t nbytes = 0;
+  ea_check(ea_cx_report_text(h, ptr.data(), static_cast<int32_t>(ptr.size()), /*header=*/1, &nbytes));
+  char* buf = static_cast<char*>(ea_host_alloc(static_cast<size_t>(nbytes)));           // page-locked, cached by the library
+  if (!buf) Rcpp::stop("epialleler_b200: %s", ea_last_error());
+  int rc = ea_cx_report_text_fetch(h, buf);
+  if (rc == EA_OK) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (f) { std::fwrite(buf, 1, static_cast<size_t>(nbytes), f); std::fclose(f); } else rc = -1000;
+  }
+  ea_host_free(buf);
+  if (rc == -1000) Rcpp::stop("cannot open %s", path.c_str());
+  ea_check(rc);
 }
