@@ -112,6 +112,38 @@ __device__ __forceinline__ uint32_t count4(const Planes& p) {
   return c;
 }
 
+// out-of-context calls of a chunk and their methylated subset (merged-indicator layout)
+template <int TCTX>
+__device__ __forceinline__ void out_masks(const Planes& p, uint32_t& o, uint32_t& om) {
+  const uint32_t o0 = cls_out<TCTX>(p.A0, p.B0, p.C0), o1 = cls_out<TCTX>(p.A1, p.B1, p.C1);
+  o = o0 | o1;
+  om = (o0 & ~p.D0) | (o1 & ~p.D1);
+}
+
+// When every class of the threshold context is also reported, the in-context counts of the pass/fail chain are the
+// popcounts of the event masks want_masks() produces anyway (the default: CG thresholds, CG report), and only the
+// out-of-context classification is extra work.
+template <int TCTX, int WANT>
+__host__ __device__ constexpr bool in_from_want() {
+  return (TCTX == TC_CG && (WANT & W_CG)) || (TCTX == TC_CHG && (WANT & W_CHG)) || (TCTX == TC_CHH && (WANT & W_CHH)) ||
+         (TCTX == TC_CXG && (WANT & W_CG) && (WANT & W_CHG)) || (TCTX == TC_CX && WANT == 7);
+}
+// packed byte-wide counts like count4(): in-context total | methylated << 8 | out-of-context total << 16 | methylated << 24;
+// m / meth: want_masks() of the chunk or unit, oc / ocm: out_masks() (merged the same way)
+template <int TCTX, int WANT>
+__device__ __forceinline__ uint32_t count_from_masks(const uint32_t (&m)[3], const uint32_t (&meth)[3], uint32_t oc, uint32_t ocm) {
+  constexpr int s_chg = (WANT & W_CHH) ? 1 : 0, s_cg = ((WANT & W_CHH) ? 1 : 0) + ((WANT & W_CHG) ? 1 : 0);
+  uint32_t in, inm;
+  if (TCTX == TC_CG) { in = m[s_cg]; inm = meth[s_cg]; }
+  else if (TCTX == TC_CHG) { in = m[s_chg]; inm = meth[s_chg]; }
+  else if (TCTX == TC_CHH) { in = m[0]; inm = meth[0]; }
+  else if (TCTX == TC_CXG) { in = m[s_chg] | m[s_cg]; inm = meth[s_chg] | meth[s_cg]; }
+  else { in = m[0] | m[1] | m[2]; inm = meth[0] | meth[1] | meth[2]; }
+  uint32_t c = __popc(in) + (__popc(inm) << 8);
+  if (TCTX != TC_CX) c += (__popc(oc) << 16) + (__popc(ocm) << 24);
+  return c;
+}
+
 // calls of the requested contexts (slot order CHH, CHG, CG among the requested) and their methylated subsets
 template <int WANT>
 __device__ __forceinline__ void want_masks(const Planes& p, uint32_t (&m)[3], uint32_t (&meth)[3]) {

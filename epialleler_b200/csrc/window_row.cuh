@@ -37,6 +37,8 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
              ReportOut out) {
   constexpr int NC = n_ctx<WANT>();
   static_assert(NC == 1, "k_window_row handles one requested context");
+  // thresholds on the reported context (the default: CG / CG): no separate in-context classification for the counts
+  constexpr bool SAME = FUSED && in_from_want<TCTX, WANT>();
   const int S = wt.S;                                 // window size: runtime, chosen by the dispatcher (multiple of 32)
   const int SG = kGuardLo + S + kGuardHi;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -106,11 +108,13 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
             const int rel = rel0 + 32 * u;
             const bool inwin = (unsigned)(rel + 31) < (unsigned)(S + 31);  // -32 < rel < S
             uint32_t m[3], meth[3], E = 0u;
+            uint32_t oc = 0u, ocm = 0u;  // SAME: out-of-context calls of the unit and their methylated subset
             {
               Planes p;
               make_planes(va, p);
               want_masks<WANT>(p, m, meth);
-              if (FUSED) cnt += count4<TCTX>(p);
+              if (FUSED && !SAME) cnt += count4<TCTX>(p);
+              if (FUSED && SAME) out_masks<TCTX>(p, oc, ocm);
               if (inwin) E = dash_events(p, wq + 128u * u, sinc, w_floor, bp_tbl);
             }
             {
@@ -118,10 +122,17 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
               make_planes(vb, p);
               uint32_t m2[3], meth2[3];
               want_masks<WANT>(p, m2, meth2);
-              if (FUSED) cnt += count4<TCTX>(p);
+              if (FUSED && !SAME) cnt += count4<TCTX>(p);
+              if (FUSED && SAME) {
+                uint32_t o2, om2;
+                out_masks<TCTX>(p, o2, om2);
+                oc += o2 << 2; ocm += om2 << 2;  // disjoint bits: the second chunk's indicators sit two bits higher
+              }
               if (inwin) E |= dash_events(p, wq + 128u * u + 64u, sinc, w_floor, bp_tbl) << 2;
               m[0] |= m2[0] << 2; meth[0] |= meth2[0] << 2;
             }
+            // thresholds and report on the same context: the in-context counts are the popcounts of the event masks
+            if (FUSED && SAME) cnt += count_from_masks<TCTX, WANT>(m, meth, oc, ocm);
             m[1] = m[2] = 0u;
             if (inwin) {
               unit_events<NC, 0>(m, E, (!FUSED && pass_known) ? meth[0] : 0u, dq + 128u * u, tq + 128u * u, sinc, bp_tbl);  // NC == 1: the SG stride is unused
