@@ -19,6 +19,11 @@ __global__ void __launch_bounds__(256, EA_THRROW_MINB)
 k_threshold_row(Csr csr, ThrParams thr, ThrTables tbl, uint8_t* __restrict__ pass_out, double* __restrict__ beta_out,
                 unsigned long long* n_pass) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
+  __shared__ uint16_t s_mmin[kThrTable], s_omax[kThrTable];  // pass-chain tables, staged (win_common.cuh)
+  if (pass_out) {
+    stage_thr_tables(tbl, s_mmin, s_omax, kThrTable - 1);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   uint32_t my_pass = 0;
@@ -59,7 +64,7 @@ k_threshold_row(Csr csr, ThrParams thr, ThrTables tbl, uint8_t* __restrict__ pas
     acc_out += ((cnt >> 16) & 0xFFu) | ((cnt >> 24) << 16);
     const uint32_t m = acc_in >> 16, all = acc_in & 0xFFFFu;
     if (pass_out) {
-      const bool pass = eval_pass_tables(m, all, acc_out >> 16, acc_out & 0xFFFFu, thr, tbl);
+      const bool pass = eval_pass_staged(m, all, acc_out >> 16, acc_out & 0xFFFFu, thr, s_mmin, s_omax, kThrTable - 1);
       pass_out[r] = pass ? 1 : 0;
       my_pass += pass;
     }

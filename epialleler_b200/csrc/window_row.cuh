@@ -47,6 +47,8 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   __shared__ long long s_base;
   __shared__ int s_npass;
   __shared__ __align__(4) uint8_t s_bp4[32];
+  // the pass chain's integer tables (win_common.cuh) for counts up to the longest row this instance handles
+  __shared__ uint16_t s_mmin[FUSED ? MAXU * 32 + 1 : 1], s_omax[FUSED ? MAXU * 32 + 1 : 1];
 
   uint32_t* const W = reinterpret_cast<uint32_t*>(smem_raw);  // [SG]
   uint32_t* const D = W + SG;                                 // [SG]
@@ -57,6 +59,7 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
   const uint32_t w_floor = w_base + 4u * kGuardLo;
 
   if (threadIdx.x < 32) s_bp4[threadIdx.x] = (uint8_t)(4 * bit_pos32(threadIdx.x));
+  if (FUSED) stage_thr_tables(tbl, s_mmin, s_omax, MAXU * 32);
 
   // the window state is zeroed once; every finalize leaves it zeroed again (guard bands are never read)
   for (int i = threadIdx.x; i < kZero4; i += kRowThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
@@ -149,7 +152,9 @@ k_window_row(Csr csr, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* 
         if (FUSED) {
           acc_in += (cnt & 0xFFu) | ((cnt & 0xFF00u) << 8);
           acc_out += ((cnt >> 16) & 0xFFu) | ((cnt >> 24) << 16);
-          const bool pass = eval_pass_tables(acc_in >> 16, acc_in & 0xFFFFu, acc_out >> 16, acc_out & 0xFFFFu, thr, tbl);
+          // a row of at most MAXU*32 bytes cannot count more than that: always inside the shared tables
+          const uint32_t pm = acc_in >> 16, pall = acc_in & 0xFFFFu, pom = acc_out >> 16, poall = acc_out & 0xFFFFu;
+          const bool pass = pm != 0u && pall >= thr.min_n && pm >= (uint32_t)s_mmin[pall] && (pom == 0u || pom <= (uint32_t)s_omax[poall]);
           if (rel0 >= 0) {  // the window that holds the row's start owns its flag
             pass_out[r] = pass ? 1 : 0;
             npass_w += pass;
