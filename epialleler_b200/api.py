@@ -431,7 +431,7 @@ def rcpp_get_base_freqs(df, pass_, vcf):
         pp = np.ascontiguousarray(np.asarray(pass_) != 0, dtype=np.uint8)
         if pp.shape[0] != df.nrow:
             raise ValueError("pass must have nrow(bam) entries")
-    out = np.zeros((20, max(nv, 1)), np.float64)  # column-major n_vcf x 20
+    out = _host_out(20 * max(nv, 1), np.float64).reshape(20, max(nv, 1))  # column-major n_vcf x 20 (page-locked when large)
     if nv:
         N.check(N.lib().ea_base_freqs(df.handle(), _p(pp, C.c_uint8) if pp is not None and pp.shape[0] else None,
                                       _p(chr_, C.c_int32), _p(pos, C.c_int32), nv, _p(out, C.c_double)))

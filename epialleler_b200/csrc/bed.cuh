@@ -84,7 +84,13 @@ k_bed_counts(Csr csr, const int32_t* __restrict__ match, const uint8_t* __restri
     const int row = m == kNaInt ? nbed : m - 1;
     const int p = pass ? (pass[r] != 0) : 1;
     const int e = row * 4 + p * 2 + (csr.strand[r] - 1);
-    if (priv) atomicAdd(&s_cnt[e], 1u); else atomicAdd(&counts[e], 1ull);
+    // rows are sorted, so the 32 consecutive reads of a warp fall into a handful of buckets (most of them into the same
+    // target, or into the "unmatched" bucket): one atomic per distinct bucket and warp instead of one per read
+    const unsigned peers = __match_any_sync(__activemask(), e);
+    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+      const unsigned c = (unsigned)__popc(peers);
+      if (priv) atomicAdd(&s_cnt[e], c); else atomicAdd(&counts[e], (unsigned long long)c);
+    }
   }
   if (priv) {
     __syncthreads();
