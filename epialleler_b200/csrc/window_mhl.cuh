@@ -155,8 +155,10 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
       uint32_t h = 0, om = 0, ou = 0;
       constexpr uint32_t sel2 = (CLS & 1) ? 0xFFFFFFFFu : 0u, sel6 = (CLS & 2) ? 0xFFFFFFFFu : 0u, sel7 = (CLS & 4) ? 0xFFFFFFFFu : 0u;
       if (PAIRS) {
+        uint4 vn = nch > 0 ? __ldg(reinterpret_cast<const uint4*>(row)) : make_uint4(0, 0, 0, 0);
         for (int c = 0; c < nch; c++) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
+          const uint4 v = vn;
+          if (c + 1 < nch) vn = __ldg(reinterpret_cast<const uint4*>(row) + c + 1);  // next chunk in flight while this one is counted
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int k = 0; k < 4; k++) {  // bit 0 of every byte; pad bytes (code 3) are in none of the classes
@@ -227,8 +229,10 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
       };
       if (PAIRS) {
         uint32_t covb = 0;  // coverage state as a bit
+        uint4 vn = __ldg(reinterpret_cast<const uint4*>(row));
         for (int c = 0; c < nch; c++) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c);
+          const uint4 v = vn;
+          if (c + 1 < nch) vn = __ldg(reinterpret_cast<const uint4*>(row) + c + 1);  // next chunk in flight while this one is swept
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
           const int kmax = min(16, len - 16 * c);
           const uint32_t valid = kmax >= 16 ? 0xFFFFu : ((1u << kmax) - 1u);
