@@ -1479,11 +1479,10 @@ int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, c
   const int64_t total = off[(size_t)nstr];
   int rc;
   if ((rc = pick_device(device))) return rc;
-  uint8_t* blob = nullptr;
-  if (cudaMallocHost(reinterpret_cast<void**>(&blob), (size_t)std::max<int64_t>(total, 1)) != cudaSuccess) {
-    cudaGetLastError();
-    return fail(EA_ERR_CUDA, "cudaMallocHost(%lld) failed", (long long)total);
-  }
+  // the gather target is a page-locked block from the library's cache (ea_host_alloc): the H2D copy of ea_pack_blob then
+  // overlaps with the repack, and a second pack of similar size does not pay cudaHostAlloc again
+  uint8_t* blob = static_cast<uint8_t*>(ea_host_alloc((size_t)std::max<int64_t>(total, 1)));
+  if (!blob) return EA_ERR_CUDA;
   const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, total / (8 << 20) + 1}));
   std::vector<std::thread> th;
   for (int t = 0; t < nt; t++)
@@ -1493,7 +1492,7 @@ int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, c
     });
   for (auto& x : th) x.join();
   rc = ea_pack_blob(rname, strand, start, templid, nrow, blob, off.data(), nstr, device, out);
-  cudaFreeHost(blob);
+  ea_host_free(blob);
   return rc;
 }
 
