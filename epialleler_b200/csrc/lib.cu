@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <cstdlib>
 #include <ctime>
 #include <mutex>
@@ -1336,8 +1337,21 @@ int ea_device(const ea_handle* h) { return h ? h->device : -1; }
 //   handle stream  : sortedness validation, row-end keys and pad counts (finish_handle) while the blob is still in flight.
 // With page-locked caller memory the copies are asynchronous and everything overlaps; with pageable memory the same code
 // runs with the copies serialised by the driver.
+// fill (optional): called with a range of strings right before their chunk of the blob is sent - ea_pack gathers the
+// scattered strings of chunk k into the page-locked blob while chunk k-1 is on its way to the device.
+namespace {
+int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                   int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out,
+                   const std::function<void(int64_t, int64_t)>* fill);
+}
 int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                  int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out) {
+  return pack_blob_impl(rname, strand, start, templid, nrow, blob, off, nstr, device, out, nullptr);
+}
+namespace {
+int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                   int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out,
+                   const std::function<void(int64_t, int64_t)>* fill) {
   if (!out) return fail(EA_ERR_ARG, "null out");
   *out = nullptr;
   if (nrow < 0 || nstr < 0 || nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row/string count");
@@ -1412,6 +1426,7 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
   for (int k = 0; k < n_chunks; k++) {
     const int64_t b0 = nstr > 0 ? off[s_begin[k]] : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] : 0;
     if (b1 < b0 || b1 > total) { cleanup(); ea_free(h); return fail(EA_ERR_ARG, "string offsets are not ascending"); }
+    if (fill && b1 > b0) (*fill)(s_begin[k], s_begin[k + 1]);
     if (b1 > b0) TRYCU(cudaMemcpyAsync(d_blob + b0, blob + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sc));
     TRYCU(cudaEventRecord(ev_chunk[k], sc));
   }
@@ -1464,6 +1479,7 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
   *out = h;
   return EA_OK;
 }
+}  // namespace
 
 int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
             const uint8_t* const* str, const int64_t* len, int64_t nstr, int device, ea_handle** out) {
@@ -1483,15 +1499,20 @@ int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, c
   // overlaps with the repack, and a second pack of similar size does not pay cudaHostAlloc again
   uint8_t* blob = static_cast<uint8_t*>(ea_host_alloc((size_t)std::max<int64_t>(total, 1)));
   if (!blob) return EA_ERR_CUDA;
-  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, total / (8 << 20) + 1}));
-  std::vector<std::thread> th;
-  for (int t = 0; t < nt; t++)
-    th.emplace_back([&, t]() {
-      for (int64_t i = nstr * t / nt; i < nstr * (t + 1) / nt; i++)
+  const int nt_max = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)std::thread::hardware_concurrency(), 16));
+  const std::function<void(int64_t, int64_t)> gather = [&](int64_t s0, int64_t s1) {  // strings [s0, s1) -> their place in the blob
+    const int64_t bytes = off[(size_t)s1] - off[(size_t)s0];
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt_max, bytes / (4 << 20) + 1));
+    auto work = [&](int t) {
+      for (int64_t i = s0 + (s1 - s0) * t / nt; i < s0 + (s1 - s0) * (t + 1) / nt; i++)
         if (len[i]) memcpy(blob + off[(size_t)i], str[i], (size_t)len[i]);
-    });
-  for (auto& x : th) x.join();
-  rc = ea_pack_blob(rname, strand, start, templid, nrow, blob, off.data(), nstr, device, out);
+    };
+    if (nt == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  };
+  rc = pack_blob_impl(rname, strand, start, templid, nrow, blob, off.data(), nstr, device, out, &gather);
   ea_host_free(blob);
   return rc;
 }
