@@ -32,6 +32,7 @@
 #include "vcf.cuh"
 #include "writer.cuh"
 #include "window_mhl.cuh"
+#include "planar.cuh"
 #include "synth.h"
 
 namespace {
@@ -141,6 +142,12 @@ struct ea_handle {
   int64_t* d_off = nullptr;
   uint8_t* d_data = nullptr;
   uint64_t* d_maxend = nullptr;  // per row: rname<<32 | prefix max of row ends
+  // bit-sliced call planes in tiles of 32 rows (planar.cuh); built for data sets whose rows are at most 1024 positions
+  uint4* d_pl_units = nullptr;
+  int64_t* d_pl_toff = nullptr;
+  uint32_t* d_pl_ls = nullptr;
+  int64_t pl_tiles = 0, pl_unit_rows = 0;
+  bool pl_ok = false;
   WinIndex idx[4];               // small cache of window indexes keyed by S
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[10] = {};
@@ -506,6 +513,62 @@ int build_index(ea_handle* h, int S, WinIndex** out) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// planar call planes (planar.cuh): built once per handle from the padded byte rows
+// ---------------------------------------------------------------------------------------------
+Planar planar_of(const ea_handle* h) {
+  Planar p;
+  p.units = h->d_pl_units; p.toff = h->d_pl_toff; p.ls = h->d_pl_ls; p.start = h->d_start; p.n = h->n;
+  return p;
+}
+
+bool planar_wanted(const ea_handle* h) {
+  static const bool off = getenv("EA_NO_PLANAR") != nullptr;
+  return !off && h->n > 0 && h->max_len >= 1 && h->max_len <= 1024;
+}
+
+// Tile table (unit rows per tile, prefix sum) and ls[] on stream s; needs d_len / d_strand.  Synchronizes s.
+int planar_tiles(ea_handle* h, cudaStream_t s) {
+  int rc;
+  h->pl_tiles = (h->n + 31) >> 5;
+  int64_t* d_nu = nullptr;
+  if ((rc = dmalloc(&d_nu, (size_t)h->pl_tiles + 1))) return rc;
+  if ((rc = dmalloc(&h->d_pl_toff, (size_t)h->pl_tiles + 1))) { pool_free_on(d_nu, s); return rc; }
+  if ((rc = dmalloc(&h->d_pl_ls, (size_t)h->n))) { pool_free_on(d_nu, s); return rc; }
+  CU(cudaMemsetAsync(d_nu, 0, 8 * (size_t)(h->pl_tiles + 1), s));
+  k_pl_tile_units<<<grid_for(h->n, 256), 256, 0, s>>>(h->d_len, h->d_strand, h->n, d_nu, h->d_pl_ls);
+  size_t tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_nu, h->d_pl_toff, (int)(h->pl_tiles + 1), s));
+  void* tmp = nullptr;
+  CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_nu, h->d_pl_toff, (int)(h->pl_tiles + 1), s));
+  CU(cudaMemcpyAsync(&h->pl_unit_rows, h->d_pl_toff + h->pl_tiles, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  pool_free_on(tmp, s); pool_free_on(d_nu, s);
+  return EA_OK;
+}
+
+// transpose the rows of tiles [t0, t1) on stream s (their padded byte rows must be complete in stream order)
+int planar_fill(ea_handle* h, int64_t t0, int64_t t1, cudaStream_t s) {
+  if (t1 <= t0) return EA_OK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t1 - t0 + 7) / 8, (int64_t)h->sm_count * 16));
+  k_planarize<<<grid, 256, 0, s>>>(h->d_data, h->d_off, h->d_len, h->n, h->d_pl_toff, t0, t1, h->d_pl_units);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+// whole handle at once (device-resident constructors)
+int build_planar(ea_handle* h) {
+  if (h->pl_ok || !planar_wanted(h)) return EA_OK;
+  int rc;
+  if ((rc = planar_tiles(h, h->stream))) return rc;
+  if ((rc = dmalloc(&h->d_pl_units, (size_t)h->pl_unit_rows * 32))) return rc;
+  if ((rc = planar_fill(h, 0, h->pl_tiles, h->stream))) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  h->pl_ok = true;
+  return EA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // letter sets
 // ---------------------------------------------------------------------------------------------
 inline unsigned code_of(unsigned char c) { return ((c + 2u) >> 2) & 15u; }  // src/epialleleR.h:28
@@ -571,37 +634,49 @@ int group_lanes(const ea_handle* h) {
 int thr_tables(ea_handle* h, const ThrParams& thr, ThrTables* tb);
 
 template <int TCTX>
-void launch_threshold_t(ea_handle* h, const ThrParams& tp, uint8_t* pass, double* beta, unsigned long long* n_pass) {
+int launch_threshold_t(ea_handle* h, const ThrParams& tp, uint8_t* pass, double* beta, unsigned long long* n_pass) {
+  int rc;
+  // planar call planes (planar.cuh): a warp per tile of 32 rows, 512 contiguous bytes per load
+  if ((g_kernel_policy == 0 || g_kernel_policy == 6) && h->pl_ok) {
+    ThrTables tb{nullptr, nullptr};
+    if (pass && (rc = thr_tables(h, tp, &tb))) return rc;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((h->pl_tiles + 7) / 8, (int64_t)h->sm_count * 32));
+    k_threshold_pl<TCTX><<<blocks, 256, 0, h->stream>>>(planar_of(h), h->pl_tiles, tp, tb, pass, beta, n_pass);
+    return EA_OK;
+  }
   // short reads: row per lane (threshold_row.cuh); the integer tables cover counts up to 1024
   if (g_kernel_policy != 1 && h->max_len <= 1024 && h->npadded / std::max<int64_t>(h->n, 1) <= 512) {
     ThrTables tb{nullptr, nullptr};
-    if (pass && thr_tables(h, tp, &tb) != EA_OK) return;
+    if (pass && (rc = thr_tables(h, tp, &tb))) return rc;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((h->n + 255) / 256, (int64_t)h->sm_count * 48));
     if (h->rows32) k_threshold_row<TCTX, true><<<blocks, 256, 0, h->stream>>>(csr_of(h), tp, tb, pass, beta, n_pass);
     else k_threshold_row<TCTX, false><<<blocks, 256, 0, h->stream>>>(csr_of(h), tp, tb, pass, beta, n_pass);
-    return;
+    return EA_OK;
   }
   const int g = group_lanes(h);
   const int rpw = 32 / g;
   const int64_t warps_needed = (h->n + rpw - 1) / rpw;
   const int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)h->sm_count * 16);
   k_threshold<TCTX><<<std::max(blocks, 1), 256, 0, h->stream>>>(csr_of(h), tp, g, pass, beta, n_pass);
+  return EA_OK;
 }
 
 int launch_threshold(ea_handle* h, const ThresholdSpec& spec, const ThrParams& tp, uint8_t* pass, double* beta,
                      unsigned long long* n_pass) {
   if (h->n == 0) return EA_OK;
+  int rc = EA_OK;
   if (spec.tctx < 0 || h->max_len > 65535) {
     k_threshold_generic<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), spec.lw, tp, pass, beta, n_pass);
   } else {
     switch (spec.tctx) {
-      case TC_CG: launch_threshold_t<TC_CG>(h, tp, pass, beta, n_pass); break;
-      case TC_CHG: launch_threshold_t<TC_CHG>(h, tp, pass, beta, n_pass); break;
-      case TC_CHH: launch_threshold_t<TC_CHH>(h, tp, pass, beta, n_pass); break;
-      case TC_CXG: launch_threshold_t<TC_CXG>(h, tp, pass, beta, n_pass); break;
-      default: launch_threshold_t<TC_CX>(h, tp, pass, beta, n_pass); break;
+      case TC_CG: rc = launch_threshold_t<TC_CG>(h, tp, pass, beta, n_pass); break;
+      case TC_CHG: rc = launch_threshold_t<TC_CHG>(h, tp, pass, beta, n_pass); break;
+      case TC_CHH: rc = launch_threshold_t<TC_CHH>(h, tp, pass, beta, n_pass); break;
+      case TC_CXG: rc = launch_threshold_t<TC_CXG>(h, tp, pass, beta, n_pass); break;
+      default: rc = launch_threshold_t<TC_CX>(h, tp, pass, beta, n_pass); break;
     }
   }
+  if (rc) return rc;
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -967,6 +1042,87 @@ int launch_long(ea_handle* h, const WinIndex& ix, const LongPlan& lp, int want, 
   }
 }
 
+// ---- window kernel on the planar call planes (planar.cuh) ----
+struct PlPlan { bool ok = false; int maxu = 0; int S = 0; size_t smem = 0; };
+
+// Window size: as many positions as keep EA_PL_MINB CTAs (one context) resident; more contexts take more state per position.
+int pick_pl_window(const ea_handle* h, const WinIndex& ix2048, int nc) {
+  if (const char* e = getenv("EA_PL_S")) { const int v = atoi(e) & ~31; if (v >= 256 && v <= kRowMaxS) return v; }
+  if (nc == 1) return pick_row_window(h, ix2048);
+  return 2048;
+}
+
+PlPlan plan_pl(const ea_handle* h, const WinIndex& ix, int nc) {
+  PlPlan t;
+  if (!h->pl_ok || h->n == 0 || ix.n == 0 || nc < 1 || ix.max_rows > 32767 || ix.S > kRowMaxS || (ix.S & 31)) return t;
+  const int max_nu = (h->max_len + 31) >> 5;
+  t.maxu = max_nu <= 5 ? 5 : 0;
+  t.S = ix.S;
+  t.smem = sizeof(uint32_t) * (size_t)(nc + 1) * 2 * (kGuardLo + ix.S + kGuardHi);
+  t.ok = true;
+  return t;
+}
+
+template <int TCTX, int WANT, bool FUSED, int MAXU>
+int launch_pl_u(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const ThrParams& thr, const uint8_t* pass_in,
+                uint8_t* pass_out, const ReportOut& out) {
+  if (ix.S != pp.S) return fail(EA_ERR_STATE, "window size mismatch");
+  auto kern = k_window_pl<TCTX, WANT, FUSED, MAXU>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  ThrTables tb{nullptr, nullptr};
+  int rc;
+  if (FUSED && (rc = thr_tables(h, thr, &tb))) return rc;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
+  kern<<<grid, kRowThreads, pp.smem, h->stream>>>(planar_of(h), wt, thr, tb, pass_in, pass_out, out);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+template <int TCTX, int WANT, bool FUSED>
+int launch_pl_t(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const ThrParams& thr, const uint8_t* pass_in,
+                uint8_t* pass_out, const ReportOut& out) {
+  if (pp.maxu == 5) return launch_pl_u<TCTX, WANT, FUSED, 5>(h, ix, pp, thr, pass_in, pass_out, out);
+#ifndef EA_FAST_BUILD
+  return launch_pl_u<TCTX, WANT, FUSED, 0>(h, ix, pp, thr, pass_in, pass_out, out);
+#else
+  return fail(EA_ERR_STATE, "fast build: rows of more than 160 positions are not compiled in");
+#endif
+}
+
+template <int WANT>
+int launch_pl_w(ea_handle* h, const WinIndex& ix, const PlPlan& pp, int tctx_fused, const ThrParams& thr,
+                const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (tctx_fused) {
+    case TC_CG: return launch_pl_t<TC_CG, WANT, true>(h, ix, pp, thr, pass_in, pass_out, out);
+#ifndef EA_FAST_BUILD
+    case TC_CHG: return launch_pl_t<TC_CHG, WANT, true>(h, ix, pp, thr, pass_in, pass_out, out);
+    case TC_CHH: return launch_pl_t<TC_CHH, WANT, true>(h, ix, pp, thr, pass_in, pass_out, out);
+    case TC_CXG: return launch_pl_t<TC_CXG, WANT, true>(h, ix, pp, thr, pass_in, pass_out, out);
+    case TC_CX: return launch_pl_t<TC_CX, WANT, true>(h, ix, pp, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_pl_t<TC_NONE, WANT, false>(h, ix, pp, thr, pass_in, pass_out, out);
+  }
+}
+
+int launch_pl(ea_handle* h, const WinIndex& ix, const PlPlan& pp, int want, int tctx_fused, const ThrParams& thr,
+              const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (want) {
+#ifndef EA_FAST_BUILD
+    case 1: return launch_pl_w<1>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+    case 2: return launch_pl_w<2>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+    case 3: return launch_pl_w<3>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+    case 5: return launch_pl_w<5>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+    case 6: return launch_pl_w<6>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
+    case 7: return launch_pl_w<7>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_pl_w<4>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+  }
+}
+
 int ensure_pass(ea_handle* h) {
   if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
   return EA_OK;
@@ -1007,25 +1163,35 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   CplPlan cpl;
   RowPlan row;
   LongPlan lng;
-  // kernel policy: 0 automatic (row-per-lane kernel, else chunk-per-lane kernel, else the lane-group kernel),
-  // 1 force the general lane-group kernel, 2 prefer the thread-per-row TMA kernel, 3 prefer the chunk-per-lane kernel
+  // kernel policy: 0 automatic (planar call planes when the handle has them, else as policy 5), 1 force the general
+  // lane-group kernel, 2 prefer the thread-per-row TMA kernel, 3 prefer the chunk-per-lane kernel, 4 prefer the long-read
+  // kernel, 5 automatic over the byte rows only (row-per-lane kernel, else chunk-per-lane kernel, else the lane-group kernel)
   const int policy = rp.kernel == 1 ? 1 : g_kernel_policy;
+  PlPlan pln;
   if (rp.want && (rc = build_index(h, 2048, &ix))) return rc;
   if (rp.threshold && (rc = ensure_pass(h))) return rc;
   bool wide = ix && ix->max_rows > 65535;
   const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
-  const bool fused = can_fuse && rp.mode == 0 && policy != 4;  // the long-read kernel takes the flags as an input
-  if (rp.want) {
-    if (policy == 0 && nc == 1 && h->rows32 && ((h->max_len + 31) >> 5) <= 8) {
+  bool fused = can_fuse && rp.mode == 0 && policy != 4;  // the long-read kernel takes the flags as an input
+  if (rp.want && policy == 0 && h->pl_ok) {
+    const int S = pick_pl_window(h, *ix, nc);
+    WinIndex* ixp = ix;
+    if (S != 2048 && (rc = build_index(h, S, &ixp))) return rc;
+    pln = plan_pl(h, *ixp, nc);
+    if (pln.ok) ix = ixp;
+  }
+  const bool byte_auto = (policy == 0 && !pln.ok) || policy == 5;
+  if (rp.want && !pln.ok) {
+    if (byte_auto && nc == 1 && h->rows32 && ((h->max_len + 31) >> 5) <= 8) {
       const int S = pick_row_window(h, *ix);
       WinIndex* ixr = ix;
       if (S != 2048 && (rc = build_index(h, S, &ixr))) return rc;
       row = plan_row(h, *ixr, nc);
       if (row.ok) ix = ixr;
     }
-    if ((policy == 0 && !row.ok) || policy == 3) cpl = plan_cpl(h, *ix, nc, fused);
+    if ((byte_auto && !row.ok) || policy == 3) cpl = plan_cpl(h, *ix, nc, fused);
     if (policy == 2) tpr = plan_tpr(h, *ix);
-    if ((policy == 0 && !row.ok && !cpl.ok && !fused) || policy == 4) {  // long reads: (row, unit block) items
+    if ((byte_auto && !row.ok && !cpl.ok && !fused) || policy == 4) {  // long reads: (row, unit block) items
       WinIndex* ixl = nullptr;
       if ((rc = build_index(h, nc == 1 ? EA_LONG_S : 2048, &ixl))) return rc;
       lng = plan_long(h, *ixl, nc);
@@ -1034,6 +1200,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
     if (!row.ok && !cpl.ok && !tpr.ok && !lng.ok && nc <= 1) {
       if ((rc = build_index(h, 4096, &ix))) return rc;
       wide = ix->max_rows > 65535;
+      if (wide) fused = false;  // 64-bit counters: thresholds run as their own pass
     }
   }
   tr.mark("window index");
@@ -1066,15 +1233,16 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      h->report_kernel = row.ok ? "k_window_row (row per lane, 256-bit loads)" : lng.ok ? "k_window_long (warp per row, lane per 32-byte unit)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
+      h->report_kernel = pln.ok ? (pln.maxu ? "k_window_pl<MAXU=5> (planar call planes, row per lane, tile-coalesced 128-bit loads)" : "k_window_pl<any> (planar call planes, row per lane)") : row.ok ? "k_window_row (row per lane, 256-bit loads)" : lng.ok ? "k_window_long (warp per row, lane per 32-byte unit)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
                                 : tpr.ok ? "k_window_tpr (thread-per-row over TMA tiles)" : "k_window (lane-group)";
-      if (row.ok) rc = launch_row(h, *ix, row, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      if (pln.ok) rc = launch_pl(h, *ix, pln, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      else if (row.ok) rc = launch_row(h, *ix, row, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (lng.ok) rc = launch_long(h, *ix, lng, rp.want, pass_for_window, out);
       else if (cpl.ok) rc = launch_cpl(h, *ix, cpl, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
       if (rc) return rc;
-      launches += ((row.ok || cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
+      launches += ((pln.ok || row.ok || cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
       CU(cudaEventRecord(h->ev[2], h->stream));
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
       k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
@@ -1127,7 +1295,8 @@ int make_plan_from_params(const ea_report_params* p, int mode, ReportPlan* rp) {
 }
 
 int adopt_and_finish(ea_handle* h, ea_handle** out) {
-  const int rc = finish_handle(h);
+  int rc = finish_handle(h);
+  if (rc == EA_OK) rc = build_planar(h);
   if (rc != EA_OK) { ea_free(h); return rc; }
   *out = h;
   return EA_OK;
@@ -1253,6 +1422,7 @@ void ea_free(ea_handle* h) {
   pool_free(h->d_len);
   pool_free(h->d_maxend);
   pool_free(h->d_sp);
+  pool_free(h->d_pl_units); pool_free(h->d_pl_toff); pool_free(h->d_pl_ls);
   for (auto& c : h->idx) c.release();
   pool_free(h->d_pass); pool_free(h->d_beta); pool_free(h->d_counters); pool_free(h->d_thr_tables); pool_free(h->d_match); pool_free(h->d_mhl_scratch);
   for (auto& c : h->d_mhl_i) pool_free(c);
@@ -1359,6 +1529,7 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   if (nstr > 0 && !off) return fail(EA_ERR_ARG, "null offsets");
   int rc;
   if ((rc = pick_device(device))) return rc;
+  if (nstr > 0 && off[0] != 0) return fail(EA_ERR_ARG, "string offsets must start at 0");
   const int64_t total = nstr > 0 ? off[nstr] : 0;
   if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
   Trace tr("ea_pack_blob");
@@ -1472,6 +1643,8 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
     TRYCU(cudaStreamSynchronize(sk));
     pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
   }
+  TRY(build_planar(h));
+  tr.mark("planar call planes");
   cleanup();
   tr.mark("free staging");
 #undef TRY
