@@ -1063,11 +1063,11 @@ PlPlan plan_pl(const ea_handle* h, const WinIndex& ix, int nc) {
   return t;
 }
 
-template <int TCTX, int WANT, bool FUSED, int MAXU>
+template <int TCTX, int WANT, bool FUSED, int MAXU, int PER>
 int launch_pl_u(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const ThrParams& thr, const uint8_t* pass_in,
                 uint8_t* pass_out, const ReportOut& out) {
-  if (ix.S != pp.S) return fail(EA_ERR_STATE, "window size mismatch");
-  auto kern = k_window_pl<TCTX, WANT, FUSED, MAXU>;
+  if (ix.S != pp.S || ix.S > PER * kRowThreads) return fail(EA_ERR_STATE, "window size mismatch");
+  auto kern = k_window_pl<TCTX, WANT, FUSED, MAXU, PER>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
   WinTable wt;
   wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
@@ -1083,9 +1083,14 @@ int launch_pl_u(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const ThrPar
 template <int TCTX, int WANT, bool FUSED>
 int launch_pl_t(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const ThrParams& thr, const uint8_t* pass_in,
                 uint8_t* pass_out, const ReportOut& out) {
-  if (pp.maxu == 5) return launch_pl_u<TCTX, WANT, FUSED, 5>(h, ix, pp, thr, pass_in, pass_out, out);
+  // positions per thread in the finalize: 8 for windows of up to 2048 positions, 12 up to 3072
+  if (pp.maxu == 5) {
+    if (ix.S <= 8 * kRowThreads) return launch_pl_u<TCTX, WANT, FUSED, 5, 8>(h, ix, pp, thr, pass_in, pass_out, out);
+    return launch_pl_u<TCTX, WANT, FUSED, 5, 12>(h, ix, pp, thr, pass_in, pass_out, out);
+  }
 #ifndef EA_FAST_BUILD
-  return launch_pl_u<TCTX, WANT, FUSED, 0>(h, ix, pp, thr, pass_in, pass_out, out);
+  if (ix.S <= 8 * kRowThreads) return launch_pl_u<TCTX, WANT, FUSED, 0, 8>(h, ix, pp, thr, pass_in, pass_out, out);
+  return launch_pl_u<TCTX, WANT, FUSED, 0, 12>(h, ix, pp, thr, pass_in, pass_out, out);
 #else
   return fail(EA_ERR_STATE, "fast build: rows of more than 160 positions are not compiled in");
 #endif

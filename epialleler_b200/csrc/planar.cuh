@@ -139,6 +139,7 @@ __device__ __forceinline__ uint32_t pl_dash(uint32_t E, uint32_t Eprev, uint32_t
 template <int NC>
 __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, uint32_t methnow, uint32_t d_addr, uint32_t t_addr,
                                           uint32_t ctx_stride, uint32_t sinc) {
+#ifdef EA_PL_MERGED_EVENTS
   uint32_t ev = m[0] | m[1] | m[2] | iso;
   while (ev) {
     const int i = 31 - __clz(ev);
@@ -151,6 +152,24 @@ __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, 
     if (iso & bit) { a = d_addr; v = sinc; }
     red_shared(a + 4u * (uint32_t)i, v);
   }
+#else
+  // two loops without address / value selects: calls, then isolated '-' bytes
+  uint32_t ev = m[0] | m[1] | m[2];
+  while (ev) {
+    const int i = 31 - __clz(ev);
+    const uint32_t bit = 1u << i;
+    ev ^= bit;
+    uint32_t a = t_addr;
+    if (NC > 1 && (m[1] & bit)) a = t_addr + ctx_stride;
+    if (NC > 2 && (m[2] & bit)) a = t_addr + 2u * ctx_stride;
+    red_shared(a + 4u * (uint32_t)i, (methnow & bit) ? 0x10001u : 1u);
+  }
+  while (iso) {
+    const int i = 31 - __clz(iso);
+    iso ^= 1u << i;
+    red_shared(d_addr + 4u * (uint32_t)i, sinc);
+  }
+#endif
 }
 
 // methylated calls of a passing row's unit (fused kernels, after the flag is known)
@@ -163,19 +182,159 @@ __device__ __forceinline__ void pl_push_meth(uint32_t mm, uint32_t t_addr) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Finalize of one window, packed-compare form of window_finalize_rt (win_common.cuh): same state, same three barriers, same
+// ordered compaction, leaves the state zeroed.  The row test `total_ctx > floor(cov/2)` (src/rcpp_cx_report.cpp:58-85) is
+// `2*total > cov` and is evaluated for BOTH strands of a position at once on 16-bit fields: PRMT packs the two strands'
+// totals, VIADDMNMX.U16x2 (max(2*total, coverage)) against the packed coverage differs from the coverage exactly in the fields where the test
+// holds (totals and coverages are at most 32767: the dispatcher's precondition).  No divergent code before the row loop.
+// flags: bit k = (position q0+k, '+'), bit 16+k = (position q0+k, '-');  PER <= 16.
+// ---------------------------------------------------------------------------------------------------------------
+template <int WANT, int PER, int NT, bool FUSED>
+__device__ __forceinline__ void window_finalize_pk(uint32_t* __restrict__ W, uint32_t* __restrict__ D, uint32_t* __restrict__ T,
+                                                   int S /* multiple of 4, <= PER * NT */, int w0, int win, const ReportOut& out,
+                                                   uint32_t* s_scan /* 2 * NT/32 words */, long long* s_base, int* s_npass) {
+  constexpr int NC = n_ctx<WANT>();
+  constexpr int NW = NT / 32;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  static_assert(PER % 4 == 0 && PER <= 16, "PER");
+  const int SG = kGuardLo + S + kGuardHi;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q0 = threadIdx.x * PER;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  uint32_t cov[PER];  // coverage of both strands: '+' | '-' << 16
+  uint32_t run = 0;
+#pragma unroll
+  for (int v4 = 0; v4 < PER / 4; v4++) {
+    uint4 w = zero4, d = zero4;
+    if (q0 + v4 * 4 < S) {
+      uint4* pw = reinterpret_cast<uint4*>(&W[kGuardLo + q0 + v4 * 4]);
+      uint4* pd = reinterpret_cast<uint4*>(&D[kGuardLo + q0 + v4 * 4]);
+      w = *pw; d = *pd;
+      *pw = zero4; *pd = zero4;
+    }
+    run += w.x; cov[v4 * 4 + 0] = run - d.x;
+    run += w.y; cov[v4 * 4 + 1] = run - d.y;
+    run += w.z; cov[v4 * 4 + 2] = run - d.z;
+    run += w.w; cov[v4 * 4 + 3] = run - d.w;
+  }
+  uint32_t inc = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(FULL, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_scan[warp] = inc;
+  __syncthreads();
+  uint32_t ex = inc - run;
+#pragma unroll
+  for (int w = 0; w < NW; w++) ex += (w < warp) ? s_scan[w] : 0u;
+
+  uint32_t flags = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+#pragma unroll
+    for (int v4 = 0; v4 < PER / 4; v4++) {
+      uint4 tp = zero4, tm = zero4;
+      if (q0 + v4 * 4 < S) {
+        uint4* pp = reinterpret_cast<uint4*>(&T[(c * 2 + 0) * SG + kGuardLo + q0 + v4 * 4]);
+        uint4* pm = reinterpret_cast<uint4*>(&T[(c * 2 + 1) * SG + kGuardLo + q0 + v4 * 4]);
+        tp = *pp; tm = *pm;
+      }
+      const uint32_t a[4] = {tp.x, tp.y, tp.z, tp.w}, b[4] = {tm.x, tm.y, tm.z, tm.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int k = v4 * 4 + j;
+        const uint32_t tot = __byte_perm(a[j], b[j], 0x5410);         // total '+' | total '-' << 16
+        const uint32_t cv = cov[k] + ex;
+        const uint32_t df = __viaddmax_u16x2(tot, tot, cv) ^ cv;      // max(2 * total, coverage): non-zero field <=> 2 * total > coverage
+        flags += __vimin3_u16x2(df, 0x00010001u, 0x00010001u) << k;                // fields never collide: at most one context wins a position
+      }
+    }
+  const int mine = __popc(flags);
+  int rinc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(FULL, rinc, d);
+    if (lane >= d) rinc += o;
+  }
+  if (lane == 31) s_scan[NW + warp] = (uint32_t)rinc;
+  __syncthreads();
+  int my_off = rinc - mine, nrows_total = 0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    const int c = (int)s_scan[NW + w];
+    nrows_total += c;
+    my_off += (w < warp) ? c : 0;
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
+    *s_base = (long long)bb;
+    out.w_base[win] = (long long)bb;
+    out.w_cnt[win] = nrows_total;
+    if (FUSED) {
+      if (*s_npass) atomicAdd(out.n_pass, (unsigned long long)*s_npass);
+      *s_npass = 0;
+    }
+  }
+  __syncthreads();
+  const long long wbase = *s_base;
+  if (flags && wbase + nrows_total <= out.cap) {
+    int4* dst = out.scratch + wbase + my_off;
+    uint32_t pos_bits = (flags | (flags >> 16)) & 0xFFFFu;
+    while (pos_bits) {  // ascending position, '+' before '-'
+      const int k = __ffs(pos_bits) - 1;
+      pos_bits &= pos_bits - 1u;
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (!((flags >> (16 * s + k)) & 1u)) continue;
+        int code = (WANT & W_CHH) ? 2 : ((WANT & W_CHG) ? 6 : 7);
+        uint32_t val = T[s * SG + kGuardLo + q0 + k];
+        if (NC > 1) {  // which of the requested contexts holds the majority
+          uint32_t cv = 0;
+#pragma unroll
+          for (int kk = 0; kk < PER; kk++) cv = (kk == k) ? cov[kk] : cv;
+          cv += ex;
+          const uint32_t half = s ? (cv >> 17) : ((cv & 0xFFFFu) >> 1);
+          int slot = 0;
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            if (!((WANT >> cc) & 1)) continue;
+            const uint32_t v = T[(slot * 2 + s) * SG + kGuardLo + q0 + k];
+            if ((v & 0xFFFFu) > half) { code = cc == 0 ? 2 : (cc == 1 ? 6 : 7); val = v; }
+            slot++;
+          }
+        }
+        *dst++ = make_int4(w0 + q0 + k, (s + 1) | (code << 8), (int)(val >> 16), (int)((val & 0xFFFFu) - (val >> 16)));
+      }
+    }
+  }
+  // leave T zeroed (the caller's barrier at the top of its window loop orders this before the next sweep)
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int v4 = 0; v4 < PER / 4; v4++)
+        if (q0 + v4 * 4 < S) *reinterpret_cast<uint4*>(&T[(c * 2 + s) * SG + kGuardLo + q0 + v4 * 4]) = zero4;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Window kernel on planar tiles: one CTA per genomic window, a warp per tile, ONE LANE PER ROW.
-//   MAXU > 0 : rows of at most MAXU units; the methylated-call masks of a row's units stay in registers until its pass
-//              flag is known (SURVEY.md 8a invariant 4), the unit loop is unrolled, all loads of a row are in flight at once;
-//   MAXU == 0: any row length up to 1024 positions; passing rows read their in-window units a second time (L2 hits).
-// The pass/fail chain (src/rcpp_threshold_reads.cpp:39-70) runs for 32 rows per instruction through the exact integer
-// tables of win_common.cuh, staged in shared memory.
-// Preconditions (dispatcher): rows <= 1024 positions, at most 32767 rows overlap a window, S a multiple of 32, <= kRowMaxS.
+//   MAXU > 0 : rows of at most MAXU units.  All units of a row are loaded up front and stay in registers (missing units
+//              as zeros, so the code below is branch-free per unit): first the class counts of the whole row and its
+//              pass flag (src/rcpp_threshold_reads.cpp:39-70), then ONE sweep of events in which a passing row's
+//              methylated calls ride on the same shared-memory reduction as the call itself (total | methylated << 16).
+//   MAXU == 0: any row length up to 1024 positions, single streaming sweep; the pass flag is known only at the row's end,
+//              so passing rows read their in-window units a second time (L2 hits) to add their methylated calls
+//              (SURVEY.md 8a invariant 4: only the methylated count depends on `pass`).
+// The pass/fail chain runs for 32 rows per instruction through the exact integer tables of win_common.cuh (shared memory).
+// Preconditions (dispatcher): rows <= 1024 positions, at most 32767 rows overlap a window, S a multiple of 32, <= PER*256.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef EA_PL_MINB
 #define EA_PL_MINB 5
 #endif
 
-template <int TCTX, int WANT, bool FUSED, int MAXU>
+template <int TCTX, int WANT, bool FUSED, int MAXU, int PER>
 __global__ void __launch_bounds__(kRowThreads, EA_PL_MINB)
 k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t* __restrict__ pass_in, uint8_t* __restrict__ pass_out,
             ReportOut out) {
@@ -226,85 +385,94 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
       const uint32_t sinc = strand0 ? 0x10000u : 1u;
       const uint32_t rel4 = 4u * (uint32_t)(rel0 + kGuardLo);
       const uint32_t wq = w_base + rel4, dq = d_base + rel4, tq = t_base + 4u * strand0 * (uint32_t)SG + rel4;
-      const bool pass_known = FUSED ? false : (valid && (pass_in == nullptr || pass_in[r] != 0));
       if (overlaps) {
         red_shared(w_floor + 4u * (uint32_t)max(rel0, 0), sinc);
         const int e = rel0 + len;
         if (e < S) red_shared(w_floor + 4u * (uint32_t)e, 0u - sinc);
       }
-      uint32_t n_in = 0, n_inm = 0, n_out = 0, n_outm = 0;
-      uint32_t Eprev = 0;
-      bool entered = false;
-      uint32_t methm[KU][NC];
-
-      auto do_unit = [&](const uint4& v, int u, uint32_t (&mk)[NC]) {
-        const int rel = rel0 + 32 * u;
-        const bool inwin = (unsigned)(rel + 31) < (unsigned)(S + 31);  // -32 < rel < S
-        if (FUSED) {
-          const uint32_t ci = cls_in<TCTX>(v.x, v.y, v.z), co = cls_out<TCTX>(v.x, v.y, v.z);
-          n_in += __popc(ci); n_inm += __popc(ci & ~v.w);
-          if (TCTX != TC_CX) { n_out += __popc(co); n_outm += __popc(co & ~v.w); }
-        }
-        const uint32_t E = v.x & v.y & ~v.z & v.w;
-#pragma unroll
-        for (int c = 0; c < NC; c++) mk[c] = 0u;
-        if (inwin) {
-          const uint32_t off4 = 128u * (uint32_t)u;
-          if (!entered && (Eprev >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
-          entered = true;
-          uint32_t m[3];
-          pl_want<WANT>(v, m);
-          const uint32_t iso = pl_dash(E, Eprev, wq + off4, sinc, w_floor);
-          uint32_t methnow = 0u;
-#pragma unroll
-          for (int c = 0; c < NC; c++) { mk[c] = m[c] & ~v.w; methnow |= mk[c]; }
-          pl_events<NC>(m, iso, pass_known ? methnow : 0u, dq + off4, tq + off4, ctx_stride, sinc);
-        }
-        Eprev = E;
-      };
 
       if (KEEP) {
         uint4 v[KU];
 #pragma unroll
-        for (int u = 0; u < KU; u++)
+        for (int u = 0; u < KU; u++) {
+          v[u] = make_uint4(0, 0, 0, 0);
           if (u < nu) v[u] = ldg_plunit(src + u * 32);
+        }
+        bool pass = valid && (pass_in == nullptr || pass_in[r] != 0);
+        if (FUSED) {
+          uint32_t n_in = 0, n_inm = 0, n_out = 0, n_outm = 0;
+#pragma unroll
+          for (int u = 0; u < KU; u++) {
+            const uint32_t ci = cls_in<TCTX>(v[u].x, v[u].y, v[u].z), co = cls_out<TCTX>(v[u].x, v[u].y, v[u].z);
+            n_in += __popc(ci); n_inm += __popc(ci & ~v[u].w);
+            if (TCTX != TC_CX) { n_out += __popc(co); n_outm += __popc(co & ~v[u].w); }
+          }
+          pass = n_inm != 0u && n_in >= thr.min_n && n_inm >= (uint32_t)s_mmin[n_in] && (n_outm == 0u || n_outm <= (uint32_t)s_omax[n_out]);
+          if (overlaps && rel0 >= 0) {  // the window that holds the row's start owns its flag
+            pass_out[r] = pass ? 1 : 0;
+            npass_w += pass;
+          }
+        }
+        const uint32_t passm = pass ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int u = 0; u < KU; u++) {
-#pragma unroll
-          for (int c = 0; c < NC; c++) methm[u][c] = 0u;
-          if (u < nu) do_unit(v[u], u, methm[u]);
+          const int rel = rel0 + 32 * u;
+          if ((unsigned)(rel + 31) < (unsigned)(S + 31)) {  // -32 < rel < S; lanes without a row have rel0 = -w0 <= -32... see below
+            const uint32_t E = v[u].x & v[u].y & ~v[u].z & v[u].w;
+            const uint32_t Eprev = u ? (v[u ? u - 1 : 0].x & v[u ? u - 1 : 0].y & ~v[u ? u - 1 : 0].z & v[u ? u - 1 : 0].w) : 0u;
+            const uint32_t off4 = 128u * (uint32_t)u;
+            if (u > 0 && rel <= 0 && (Eprev >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
+            uint32_t m[3];
+            pl_want<WANT>(v[u], m);
+            const uint32_t iso = pl_dash(E, Eprev, wq + off4, sinc, w_floor);
+            pl_events<NC>(m, iso, (m[0] | m[1] | m[2]) & ~v[u].w & passm, dq + off4, tq + off4, ctx_stride, sinc);
+          }
+        }
+        if (overlaps && nu == KU && (len & 31) == 0) {  // a '-' run that reaches the end of a row filling all KU units
+          const uint32_t El = v[KU - 1].x & v[KU - 1].y & ~v[KU - 1].z & v[KU - 1].w;
+          if ((El >> 31) && rel0 + len < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);
         }
       } else {
+        const bool pass_known = FUSED ? false : (valid && (pass_in == nullptr || pass_in[r] != 0));
+        uint32_t n_in = 0, n_inm = 0, n_out = 0, n_outm = 0;
+        uint32_t Eprev = 0;
+        bool entered = false;
         uint4 cur, nxt;
         if (nu > 0) cur = ldg_plunit(src);
         for (int u = 0; u < nu; u++) {
           if (u + 1 < nu) nxt = ldg_plunit(src + (u + 1) * 32);
-          uint32_t mk[NC];
-          do_unit(cur, u, mk);
+          const uint4 v = cur;
+          const int rel = rel0 + 32 * u;
+          const bool inwin = (unsigned)(rel + 31) < (unsigned)(S + 31);  // -32 < rel < S
+          if (FUSED) {
+            const uint32_t ci = cls_in<TCTX>(v.x, v.y, v.z), co = cls_out<TCTX>(v.x, v.y, v.z);
+            n_in += __popc(ci); n_inm += __popc(ci & ~v.w);
+            if (TCTX != TC_CX) { n_out += __popc(co); n_outm += __popc(co & ~v.w); }
+          }
+          const uint32_t E = v.x & v.y & ~v.z & v.w;
+          if (inwin) {
+            const uint32_t off4 = 128u * (uint32_t)u;
+            if (!entered && (Eprev >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
+            entered = true;
+            uint32_t m[3];
+            pl_want<WANT>(v, m);
+            const uint32_t iso = pl_dash(E, Eprev, wq + off4, sinc, w_floor);
+            pl_events<NC>(m, iso, pass_known ? ((m[0] | m[1] | m[2]) & ~v.w) : 0u, dq + off4, tq + off4, ctx_stride, sinc);
+          }
+          Eprev = E;
           cur = nxt;
         }
-      }
-      if (overlaps) {
-        const int e = rel0 + len;
-        if ((len & 31) == 0 && (Eprev >> 31) && e < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);  // a run that reaches the row end
-      }
-      if (FUSED && overlaps) {
-        const uint32_t all = n_in, oall = n_out;
-        bool pass;
-        if (KEEP) pass = n_inm != 0u && all >= thr.min_n && n_inm >= (uint32_t)s_mmin[all] && (n_outm == 0u || n_outm <= (uint32_t)s_omax[oall]);
-        else pass = eval_pass_staged(n_inm, all, n_outm, oall, thr, s_mmin, s_omax, (uint32_t)TBL);
-        if (rel0 >= 0) {  // the window that holds the row's start owns its flag
-          pass_out[r] = pass ? 1 : 0;
-          npass_w += pass;
+        if (overlaps) {
+          const int e = rel0 + len;
+          if ((len & 31) == 0 && (Eprev >> 31) && e < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);  // a run that reaches the row end
         }
-        if (pass) {
-          if (KEEP) {
-#pragma unroll
-            for (int u = 0; u < KU; u++)
-#pragma unroll
-              for (int c = 0; c < NC; c++)
-                if (methm[u][c]) pl_push_meth(methm[u][c], tq + 128u * u + (uint32_t)c * ctx_stride);
-          } else {
+        if (FUSED && overlaps) {
+          const bool pass = eval_pass_staged(n_inm, n_in, n_outm, n_out, thr, s_mmin, s_omax, (uint32_t)TBL);
+          if (rel0 >= 0) {  // the window that holds the row's start owns its flag
+            pass_out[r] = pass ? 1 : 0;
+            npass_w += pass;
+          }
+          if (pass) {
             const int u_lo = rel0 <= -32 ? (-rel0) >> 5 : 0;
             const int u_hi = min(nu, (S - rel0 + 31) >> 5);
             for (int u = u_lo; u < u_hi; u++) {
@@ -326,7 +494,11 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
       if (lane == 0 && npass_w) atomicAdd(&s_npass, npass_w);
     }
     __syncthreads();
-    window_finalize_rt<WANT, kRowPer, kRowThreads, FUSED>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
+#ifdef EA_PL_OLD_FINALIZE
+    window_finalize_rt<WANT, PER, kRowThreads, FUSED>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
+#else
+    window_finalize_pk<WANT, PER, kRowThreads, FUSED>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
+#endif
   }
 }
 
