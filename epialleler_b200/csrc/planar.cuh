@@ -108,6 +108,19 @@ k_planarize(const uint8_t* __restrict__ data, const int64_t* __restrict__ off, c
 // events of one unit (32 positions) on the shared-memory window state
 // ---------------------------------------------------------------------------------------------------------------
 
+// red.shared.add.u32 executed only where cond != 0 (a predicated instruction: no branch, no reconvergence point)
+__device__ __forceinline__ void red_shared_if(uint32_t cond, uint32_t addr, uint32_t v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.shared.add.u32 [%1], %2;\n\t}" ::"r"(cond), "r"(addr), "r"(v) : "memory");
+}
+// highest set bit of x as a mask (0 for x == 0; PTX shifts clamp at 32)
+__device__ __forceinline__ uint32_t top_bit(uint32_t x, int& idx) {
+  uint32_t lz, b;
+  asm("clz.b32 %0, %1;" : "=r"(lz) : "r"(x));
+  asm("shr.u32 %0, %1, %2;" : "=r"(b) : "r"(0x80000000u), "r"(lz));
+  idx = 31 - (int)lz;
+  return b;
+}
+
 // calls of the requested contexts (slot order CHH, CHG, CG among the requested) of one unit
 template <int WANT>
 __device__ __forceinline__ void pl_want(const uint4& v, uint32_t (&m)[3]) {
@@ -118,24 +131,31 @@ __device__ __forceinline__ void pl_want(const uint4& v, uint32_t (&m)[3]) {
   if (WANT & W_CG) m[slot++] = cls_cg(v.x, v.y, v.z);
 }
 
-// '-' bytes of a unit: E = the unit's '-' positions, Eprev = those of the row's previous unit.  Isolated ones (returned)
-// are counted in D by the caller; the edges of longer runs become coverage deltas in W right here: -1 where a run starts,
-// +1 right after it ends, clamped to the window start.  w_addr = shared BYTE address of the unit's position 0 in W.
-__device__ __forceinline__ uint32_t pl_dash(uint32_t E, uint32_t Eprev, uint32_t w_addr, uint32_t sinc, uint32_t w_floor) {
-  const uint32_t prev = __funnelshift_l(Eprev, E, 1);                    // "the position before me is a '-'"
-  const uint32_t iso = E & ~prev & ~(E >> 1) & 0x7FFFFFFFu;              // bit 31 may continue in the next unit: an edge
-  uint32_t ed = (E ^ prev) & ~(iso | (iso << 1));
+// '-' bytes.  Isolated ones are counted in D (pl_events); the edges of longer runs become coverage deltas in W: -1 where a
+// run starts, +1 right after it ends, clamped to the window start (pl_edges; `ed` = edge positions of the unit, E = its '-'
+// positions, w_addr = shared BYTE address of the unit's position 0 in W).
+__device__ __forceinline__ void pl_edges(uint32_t ed, uint32_t E, uint32_t w_addr, uint32_t sinc, uint32_t w_floor) {
   while (ed) {
     const int i = 31 - __clz(ed);
     const uint32_t bit = 1u << i;
     ed ^= bit;
     red_shared(max(w_addr + 4u * (uint32_t)i, w_floor), (E & bit) ? 0u - sinc : sinc);
   }
+}
+// Streaming form (the next unit is not at hand): a '-' at position 31 is treated as a run edge, it may continue.
+__device__ __forceinline__ uint32_t pl_dash(uint32_t E, uint32_t Eprev, uint32_t w_addr, uint32_t sinc, uint32_t w_floor) {
+  const uint32_t prev = __funnelshift_l(Eprev, E, 1);                    // "the position before me is a '-'"
+  const uint32_t iso = E & ~prev & ~(E >> 1) & 0x7FFFFFFFu;
+  pl_edges((E ^ prev) & ~(iso | (iso << 1)), E, w_addr, sinc, w_floor);
   return iso;
 }
+__device__ __forceinline__ uint32_t pl_dashes(const uint4& v) { return v.x & v.y & ~v.z & v.w; }
 
 // m[k] = calls of requested context k, iso = isolated '-' positions, methnow = methylated calls to be counted right now
 // (0 in the fused kernels).  d_addr / t_addr = shared BYTE addresses of the unit's position 0 in D and in T[0][strand].
+#ifndef EA_PL_STEPS
+#define EA_PL_STEPS 1
+#endif
 template <int NC>
 __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, uint32_t methnow, uint32_t d_addr, uint32_t t_addr,
                                           uint32_t ctx_stride, uint32_t sinc) {
@@ -153,8 +173,19 @@ __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, 
     red_shared(a + 4u * (uint32_t)i, v);
   }
 #else
-  // two loops without address / value selects: calls, then isolated '-' bytes
+  // two loops without address / value selects: calls, then isolated '-' bytes.  A lane rarely holds more than one or two
+  // events of a kind per unit: the first EA_PL_STEPS are straight-line predicated code, the loop takes the rest.
   uint32_t ev = m[0] | m[1] | m[2];
+#pragma unroll
+  for (int k = 0; k < EA_PL_STEPS; k++) {
+    int i;
+    const uint32_t bit = top_bit(ev, i);
+    ev ^= bit;
+    uint32_t a = t_addr;
+    if (NC > 1 && (m[1] & bit)) a = t_addr + ctx_stride;
+    if (NC > 2 && (m[2] & bit)) a = t_addr + 2u * ctx_stride;
+    red_shared_if(bit, a + 4u * (uint32_t)i, (methnow & bit) ? 0x10001u : 1u);
+  }
   while (ev) {
     const int i = 31 - __clz(ev);
     const uint32_t bit = 1u << i;
@@ -163,6 +194,13 @@ __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, 
     if (NC > 1 && (m[1] & bit)) a = t_addr + ctx_stride;
     if (NC > 2 && (m[2] & bit)) a = t_addr + 2u * ctx_stride;
     red_shared(a + 4u * (uint32_t)i, (methnow & bit) ? 0x10001u : 1u);
+  }
+#pragma unroll
+  for (int k = 0; k < EA_PL_STEPS; k++) {
+    int i;
+    const uint32_t bit = top_bit(iso, i);
+    iso ^= bit;
+    red_shared_if(bit, d_addr + 4u * (uint32_t)i, sinc);
   }
   while (iso) {
     const int i = 31 - __clz(iso);
@@ -391,6 +429,17 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
         if (e < S) red_shared(w_floor + 4u * (uint32_t)e, 0u - sinc);
       }
 
+#ifndef EA_PL_NO_PREFETCH
+      if (t + kRowWarps < t_hi && lane < 2) {  // the warp's next tile: its unit rows (one bulk L2 prefetch) and its row metadata
+        const long long nt0 = pl.toff[t + kRowWarps], nt1 = pl.toff[t + kRowWarps + 1];
+        if (lane == 0 && nt1 > nt0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pl.units + nt0 * 32), "r"((uint32_t)(nt1 - nt0) * 512u) : "memory");
+        if (lane == 1) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.start + (t + kRowWarps) * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pl.ls + (t + kRowWarps) * 32));
+        }
+      }
+#endif
       if (KEEP) {
         uint4 v[KU];
 #pragma unroll
@@ -414,23 +463,27 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
           }
         }
         const uint32_t passm = pass ? 0xFFFFFFFFu : 0u;
+        // '-' masks with exact neighbours across unit borders: E of the previous / this / the next unit are all in registers
+        uint32_t Em1 = 0u, isom1 = 0u, E = pl_dashes(v[0]);
 #pragma unroll
         for (int u = 0; u < KU; u++) {
+          const uint32_t Enext = u + 1 < KU ? pl_dashes(v[u + 1 < KU ? u + 1 : u]) : 0u;
+          const uint32_t prev = __funnelshift_l(Em1, E, 1), next = __funnelshift_r(E, Enext, 1);
+          const uint32_t iso = E & ~prev & ~next;
+          const uint32_t ed = (E ^ prev) & ~(iso | __funnelshift_l(isom1, iso, 1));
           const int rel = rel0 + 32 * u;
-          if ((unsigned)(rel + 31) < (unsigned)(S + 31)) {  // -32 < rel < S; lanes without a row have rel0 = -w0 <= -32... see below
-            const uint32_t E = v[u].x & v[u].y & ~v[u].z & v[u].w;
-            const uint32_t Eprev = u ? (v[u ? u - 1 : 0].x & v[u ? u - 1 : 0].y & ~v[u ? u - 1 : 0].z & v[u ? u - 1 : 0].w) : 0u;
+          if ((unsigned)(rel + 31) < (unsigned)(S + 31)) {  // -32 < rel < S (units of lanes without a row are zero: no events)
             const uint32_t off4 = 128u * (uint32_t)u;
-            if (u > 0 && rel <= 0 && (Eprev >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
+            if (u > 0 && rel <= 0 && ((Em1 & ~isom1) >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
             uint32_t m[3];
             pl_want<WANT>(v[u], m);
-            const uint32_t iso = pl_dash(E, Eprev, wq + off4, sinc, w_floor);
+            pl_edges(ed, E, wq + off4, sinc, w_floor);
             pl_events<NC>(m, iso, (m[0] | m[1] | m[2]) & ~v[u].w & passm, dq + off4, tq + off4, ctx_stride, sinc);
           }
+          Em1 = E; isom1 = iso; E = Enext;
         }
         if (overlaps && nu == KU && (len & 31) == 0) {  // a '-' run that reaches the end of a row filling all KU units
-          const uint32_t El = v[KU - 1].x & v[KU - 1].y & ~v[KU - 1].z & v[KU - 1].w;
-          if ((El >> 31) && rel0 + len < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);
+          if (((Em1 & ~isom1) >> 31) && rel0 + len < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);
         }
       } else {
         const bool pass_known = FUSED ? false : (valid && (pass_in == nullptr || pass_in[r] != 0));

@@ -13,15 +13,18 @@ def find(name, needle, after=0):
         if i + 1 > after and needle in l: return i + 1
     raise KeyError(needle)
 P = "planar.cuh"
+kp = find(P, "k_window_pl(Planar pl")
 marks = [(find(P, "__device__ __forceinline__ uint32_t pl_dash"), "dash edges"),
-         (find(P, "__device__ __forceinline__ void pl_events"), "event loop"),
+         (find(P, "__device__ __forceinline__ void pl_events"), "event loops"),
          (find(P, "__device__ __forceinline__ void pl_push_meth"), "meth push loop"),
-         (find(P, "k_window_pl(Planar pl"), "kernel prologue"),
-         (find(P, "for (int win = blockIdx.x"), "window/tile setup + row metadata"),
-         (find(P, "auto do_unit"), "unit: classify/count"),
-         (find(P, "if (KEEP) {", find(P, "auto do_unit")), "unit loads + loop"),
-         (find(P, "if (FUSED && overlaps)"), "pass chain + flag + meth push"),
-         (find(P, "if (FUSED) {", find(P, "if (FUSED && overlaps)")), "npass reduce + barrier"),
+         (find(P, "__device__ __forceinline__ void window_finalize_pk"), "finalize"),
+         (kp, "kernel prologue / hoisted address arithmetic"),
+         (find(P, "for (int win = blockIdx.x", kp), "window/tile setup + row metadata + coverage deltas"),
+         (find(P, "if (KEEP) {", kp), "unit loads"),
+         (find(P, "if (FUSED) {", find(P, "if (KEEP) {", kp)), "class counts + pass chain + flag"),
+         (find(P, "const uint32_t passm"), "event sweep: masks, dash logic, loop control"),
+         (find(P, "} else {", find(P, "const uint32_t passm")), "streaming variant (MAXU=0)"),
+         (find(P, "if (FUSED) {", find(P, "const bool pass_known")), "npass reduce + barrier + finalize call"),
          (find(P, "k_threshold_pl") - 3, "other")]
 fin0 = find("win_common.cuh", "window_finalize_rt(")
 out = {}; fname = None; hdr = None
