@@ -33,6 +33,7 @@
 #include "writer.cuh"
 #include "window_mhl.cuh"
 #include "planar.cuh"
+#include "window_vs.cuh"
 #include "synth.h"
 
 namespace {
@@ -1084,12 +1085,13 @@ template <int TCTX, int WANT, bool FUSED>
 int launch_pl_t(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const ThrParams& thr, const uint8_t* pass_in,
                 uint8_t* pass_out, const ReportOut& out) {
   // positions per thread in the finalize: 8 for windows of up to 2048 positions, 12 up to 3072
+  const bool per8 = ix.S <= 8 * kRowThreads;
   if (pp.maxu == 5) {
-    if (ix.S <= 8 * kRowThreads) return launch_pl_u<TCTX, WANT, FUSED, 5, 8>(h, ix, pp, thr, pass_in, pass_out, out);
+    if (per8) return launch_pl_u<TCTX, WANT, FUSED, 5, 8>(h, ix, pp, thr, pass_in, pass_out, out);
     return launch_pl_u<TCTX, WANT, FUSED, 5, 12>(h, ix, pp, thr, pass_in, pass_out, out);
   }
-#ifndef EA_FAST_BUILD
-  if (ix.S <= 8 * kRowThreads) return launch_pl_u<TCTX, WANT, FUSED, 0, 8>(h, ix, pp, thr, pass_in, pass_out, out);
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
+  if (per8) return launch_pl_u<TCTX, WANT, FUSED, 0, 8>(h, ix, pp, thr, pass_in, pass_out, out);
   return launch_pl_u<TCTX, WANT, FUSED, 0, 12>(h, ix, pp, thr, pass_in, pass_out, out);
 #else
   return fail(EA_ERR_STATE, "fast build: rows of more than 160 positions are not compiled in");
@@ -1125,6 +1127,84 @@ int launch_pl(ea_handle* h, const WinIndex& ix, const PlPlan& pp, int want, int 
     case 7: return launch_pl_w<7>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
 #endif
     default: return launch_pl_w<4>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
+  }
+}
+
+// ---- window kernel with vertical (bit-sliced) counters on the planar call planes (window_vs.cuh) ----
+struct VsPlan { bool ok = false; int k = 0; int lognb = 0; int S = 0; size_t smem = 0; };
+
+int pick_vs_window(const ea_handle* h, const WinIndex& ix2048) {
+  if (const char* e = getenv("EA_VS_S")) { const int v = atoi(e); if (v == 512 || v == 2048) return v; }
+  (void)h;
+  return ix2048.max_rows > 511 ? 512 : 2048;   // deep data: smaller windows, more lanes per block
+}
+
+VsPlan plan_vs(const ea_handle* h, const WinIndex& ix, int nc) {
+  VsPlan t;
+  if (!h->pl_ok || h->n == 0 || ix.n == 0 || nc < 1 || (ix.S != 2048 && ix.S != 512)) return t;
+  t.lognb = ix.S == 2048 ? 6 : 4;
+  t.k = ix.S == 2048 ? 9 : 12;                  // planes per counter: 511 / 4095 rows over one window at most
+  if (ix.max_rows > (1 << t.k) - 1) return t;
+  t.S = ix.S;
+  t.smem = (size_t)kVsCapUnitRows * 512 + sizeof(VsRec) * 2 * kVsRecCap;
+  t.ok = true;
+  return t;
+}
+
+template <int TCTX, int WANT, bool FUSED, int K, int LOGNB>
+int launch_vs_u(ea_handle* h, const WinIndex& ix, const VsPlan& vp, const ThrParams& thr, const uint8_t* pass_in,
+                uint8_t* pass_out, const ReportOut& out) {
+  if (ix.S != vp.S || ix.S != (32 << LOGNB)) return fail(EA_ERR_STATE, "window size mismatch");
+  auto kern = k_window_vs<TCTX, WANT, FUSED, K, LOGNB>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vp.smem));
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  ThrTables tb{nullptr, nullptr};
+  int rc;
+  if (FUSED && (rc = thr_tables(h, thr, &tb))) return rc;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 32));
+  kern<<<grid, kVsThreads, vp.smem, h->stream>>>(planar_of(h), wt, thr, tb, pass_in, pass_out, out, h->max_len);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+template <int TCTX, int WANT, bool FUSED>
+int launch_vs_t(ea_handle* h, const WinIndex& ix, const VsPlan& vp, const ThrParams& thr, const uint8_t* pass_in,
+                uint8_t* pass_out, const ReportOut& out) {
+  if (vp.k == 9 && vp.lognb == 6) return launch_vs_u<TCTX, WANT, FUSED, 9, 6>(h, ix, vp, thr, pass_in, pass_out, out);
+  if (vp.k == 12 && vp.lognb == 4) return launch_vs_u<TCTX, WANT, FUSED, 12, 4>(h, ix, vp, thr, pass_in, pass_out, out);
+  return fail(EA_ERR_STATE, "no vertical-counter kernel for this window shape");
+}
+
+template <int WANT>
+int launch_vs_w(ea_handle* h, const WinIndex& ix, const VsPlan& vp, int tctx_fused, const ThrParams& thr,
+                const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (tctx_fused) {
+    case TC_CG: return launch_vs_t<TC_CG, WANT, true>(h, ix, vp, thr, pass_in, pass_out, out);
+#ifndef EA_FAST_BUILD
+    case TC_CHG: return launch_vs_t<TC_CHG, WANT, true>(h, ix, vp, thr, pass_in, pass_out, out);
+    case TC_CHH: return launch_vs_t<TC_CHH, WANT, true>(h, ix, vp, thr, pass_in, pass_out, out);
+    case TC_CXG: return launch_vs_t<TC_CXG, WANT, true>(h, ix, vp, thr, pass_in, pass_out, out);
+    case TC_CX: return launch_vs_t<TC_CX, WANT, true>(h, ix, vp, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_vs_t<TC_NONE, WANT, false>(h, ix, vp, thr, pass_in, pass_out, out);
+  }
+}
+
+int launch_vs(ea_handle* h, const WinIndex& ix, const VsPlan& vp, int want, int tctx_fused, const ThrParams& thr,
+              const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  switch (want) {
+#ifndef EA_FAST_BUILD
+    case 1: return launch_vs_w<1>(h, ix, vp, tctx_fused, thr, pass_in, pass_out, out);
+    case 2: return launch_vs_w<2>(h, ix, vp, tctx_fused, thr, pass_in, pass_out, out);
+    case 3: return launch_vs_w<3>(h, ix, vp, tctx_fused, thr, pass_in, pass_out, out);
+    case 5: return launch_vs_w<5>(h, ix, vp, tctx_fused, thr, pass_in, pass_out, out);
+    case 6: return launch_vs_w<6>(h, ix, vp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
+    case 7: return launch_vs_w<7>(h, ix, vp, tctx_fused, thr, pass_in, pass_out, out);
+#endif
+    default: return launch_vs_w<4>(h, ix, vp, tctx_fused, thr, pass_in, pass_out, out);
   }
 }
 
@@ -1178,15 +1258,23 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
   bool wide = ix && ix->max_rows > 65535;
   const bool can_fuse = rp.threshold && rp.spec.tctx >= 0 && !wide && h->max_len <= 1024 && rp.want;
   bool fused = can_fuse && rp.mode == 0 && policy != 4;  // the long-read kernel takes the flags as an input
-  if (rp.want && policy == 0 && h->pl_ok) {
+  VsPlan vsp;
+  if (rp.want && policy == 6 && h->pl_ok) {
+    const int S = pick_vs_window(h, *ix);
+    WinIndex* ixv = ix;
+    if (S != 2048 && (rc = build_index(h, S, &ixv))) return rc;
+    vsp = plan_vs(h, *ixv, nc);
+    if (vsp.ok) ix = ixv;
+  }
+  if (rp.want && (policy == 0 || (policy == 6 && !vsp.ok)) && h->pl_ok) {
     const int S = pick_pl_window(h, *ix, nc);
     WinIndex* ixp = ix;
     if (S != 2048 && (rc = build_index(h, S, &ixp))) return rc;
     pln = plan_pl(h, *ixp, nc);
     if (pln.ok) ix = ixp;
   }
-  const bool byte_auto = (policy == 0 && !pln.ok) || policy == 5;
-  if (rp.want && !pln.ok) {
+  const bool byte_auto = ((policy == 0 || policy == 6) && !pln.ok && !vsp.ok) || policy == 5;
+  if (rp.want && !pln.ok && !vsp.ok) {
     if (byte_auto && nc == 1 && h->rows32 && ((h->max_len + 31) >> 5) <= 8) {
       const int S = pick_row_window(h, *ix);
       WinIndex* ixr = ix;
@@ -1238,16 +1326,17 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      h->report_kernel = pln.ok ? (pln.maxu ? "k_window_pl<MAXU=5> (planar call planes, row per lane, tile-coalesced 128-bit loads)" : "k_window_pl<any> (planar call planes, row per lane)") : row.ok ? "k_window_row (row per lane, 256-bit loads)" : lng.ok ? "k_window_long (warp per row, lane per 32-byte unit)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
+      h->report_kernel = vsp.ok ? (vsp.lognb == 6 ? "k_window_vs<K=9,S=2048> (planar call planes, vertical bit-sliced counters)" : "k_window_vs<K=12,S=512> (planar call planes, vertical bit-sliced counters)") : pln.ok ? (pln.maxu ? "k_window_pl<MAXU=5> (planar call planes, row per lane, tile-coalesced 128-bit loads)" : "k_window_pl<any> (planar call planes, row per lane, two sweeps)") : row.ok ? "k_window_row (row per lane, 256-bit loads)" : lng.ok ? "k_window_long (warp per row, lane per 32-byte unit)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
                                 : tpr.ok ? "k_window_tpr (thread-per-row over TMA tiles)" : "k_window (lane-group)";
-      if (pln.ok) rc = launch_pl(h, *ix, pln, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      if (vsp.ok) rc = launch_vs(h, *ix, vsp, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      else if (pln.ok) rc = launch_pl(h, *ix, pln, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (row.ok) rc = launch_row(h, *ix, row, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (lng.ok) rc = launch_long(h, *ix, lng, rp.want, pass_for_window, out);
       else if (cpl.ok) rc = launch_cpl(h, *ix, cpl, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (tpr.ok) rc = launch_tpr(h, *ix, tpr, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else rc = launch_window(h, *ix, rp.want, fused ? rp.spec.tctx : -1, wide, rp.tp, pass_for_window, h->d_pass, out);
       if (rc) return rc;
-      launches += ((pln.ok || row.ok || cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
+      launches += ((vsp.ok || pln.ok || row.ok || cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
       CU(cudaEventRecord(h->ev[2], h->stream));
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
       k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);

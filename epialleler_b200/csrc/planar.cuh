@@ -16,6 +16,9 @@
 //            exclusive prefix sum.
 //   per row: start (int32) and `ls` = len | (strand=='-') << 31 (uint32).  No per-row byte offsets.
 //
+//   long reads (data sets with rows of more than 1024 positions): tiles of ONE row, i.e. the units of a row are contiguous
+//            (toff[] has one entry per row) and a WARP walks a row, 32 consecutive units = 512 contiguous bytes per load.
+//
 // 150 bp reads: 80 bytes of call planes + 8 bytes of metadata per read (the byte rows: 160 + 13).
 //
 // The window state in shared memory, the event model and the finalize are those of win_common.cuh.
@@ -57,6 +60,16 @@ __global__ void k_pl_tile_units(const int32_t* __restrict__ len, const uint8_t* 
   }
   for (int d = 16; d >= 1; d >>= 1) nu = max(nu, __shfl_xor_sync(0xFFFFFFFFu, nu, d));
   if ((threadIdx.x & 31) == 0 && (r >> 5) <= ((n - 1) >> 5)) tile_nu[r >> 5] = nu;
+}
+
+// long-read layout: units per row (a "tile" is one row) and ls[]
+__global__ void k_pl_row_units(const int32_t* __restrict__ len, const uint8_t* __restrict__ strand, int64_t n,
+                               int64_t* __restrict__ row_nu, uint32_t* __restrict__ ls) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int l = len[r];
+  row_nu[r] = (l + 31) >> 5;
+  ls[r] = (uint32_t)l | (strand[r] == 2 ? 0x80000000u : 0u);
 }
 
 // bit b of each of the four bytes of w, gathered into bits 0..3 (byte k -> bit k)
@@ -101,6 +114,45 @@ k_planarize(const uint8_t* __restrict__ data, const int64_t* __restrict__ off, c
       }
       dst[(int64_t)j * 32] = make_uint4(P[0], P[1], P[2], P[3]);
     }
+  }
+}
+
+// 32 bytes of a padded byte row (kernels.cuh) -> one unit; b0 = first byte, l = row length, padded = padded row length
+__device__ __forceinline__ uint4 pl_unit_from_bytes(const uint8_t* __restrict__ row, int b0, int l, int padded) {
+  uint32_t P[4] = {0u, 0u, 0u, 0u};
+  if (b0 < l) {
+    const uint4 lo4 = *reinterpret_cast<const uint4*>(row + b0);
+    uint4 hi4 = make_uint4(0, 0, 0, 0);
+    if (b0 + 16 < padded) hi4 = *reinterpret_cast<const uint4*>(row + b0 + 16);
+    const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) P[b] |= gather_bit(w[k], b) << (4 * k);
+    const int nvalid = l - b0;  // pad bytes (code 3) and bytes beyond the padded row become code 0
+    if (nvalid < 32) {
+      const uint32_t keep = (1u << nvalid) - 1u;
+#pragma unroll
+      for (int b = 0; b < 4; b++) P[b] &= keep;
+    }
+  }
+  return make_uint4(P[0], P[1], P[2], P[3]);
+}
+
+// long-read layout: rows [row0, row1), one warp per row, lane l transposes units l, l + 32, ... (coalesced both ways)
+__global__ void __launch_bounds__(256)
+k_planarize_rows(const uint8_t* __restrict__ data, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
+                 const int64_t* __restrict__ toff, int64_t row0, int64_t row1, uint4* __restrict__ units) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = row0 + warp; r < row1; r += n_warps) {
+    const int l = len[r];
+    const int padded = (l + 15) & ~15;
+    const int nu = (l + 31) >> 5;
+    const uint8_t* row = data + off[r];
+    uint4* dst = units + toff[r];
+    for (int j = lane; j < nu; j += 32) dst[j] = pl_unit_from_bytes(row, 32 * j, l, padded);
   }
 }
 
@@ -159,20 +211,6 @@ __device__ __forceinline__ uint32_t pl_dashes(const uint4& v) { return v.x & v.y
 template <int NC>
 __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, uint32_t methnow, uint32_t d_addr, uint32_t t_addr,
                                           uint32_t ctx_stride, uint32_t sinc) {
-#ifdef EA_PL_MERGED_EVENTS
-  uint32_t ev = m[0] | m[1] | m[2] | iso;
-  while (ev) {
-    const int i = 31 - __clz(ev);
-    const uint32_t bit = 1u << i;
-    ev ^= bit;
-    uint32_t a = t_addr;
-    uint32_t v = (methnow & bit) ? 0x10001u : 1u;
-    if (NC > 1 && (m[1] & bit)) a = t_addr + ctx_stride;
-    if (NC > 2 && (m[2] & bit)) a = t_addr + 2u * ctx_stride;
-    if (iso & bit) { a = d_addr; v = sinc; }
-    red_shared(a + 4u * (uint32_t)i, v);
-  }
-#else
   // two loops without address / value selects: calls, then isolated '-' bytes.  A lane rarely holds more than one or two
   // events of a kind per unit: the first EA_PL_STEPS are straight-line predicated code, the loop takes the rest.
   uint32_t ev = m[0] | m[1] | m[2];
@@ -207,7 +245,6 @@ __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, 
     iso ^= 1u << i;
     red_shared(d_addr + 4u * (uint32_t)i, sinc);
   }
-#endif
 }
 
 // methylated calls of a passing row's unit (fused kernels, after the flag is known)
@@ -317,7 +354,7 @@ __device__ __forceinline__ void window_finalize_pk(uint32_t* __restrict__ W, uin
   __syncthreads();
   const long long wbase = *s_base;
   if (flags && wbase + nrows_total <= out.cap) {
-    int4* dst = out.scratch + wbase + my_off;
+    long long di = wbase + my_off;
     uint32_t pos_bits = (flags | (flags >> 16)) & 0xFFFFu;
     while (pos_bits) {  // ascending position, '+' before '-'
       const int k = __ffs(pos_bits) - 1;
@@ -342,7 +379,7 @@ __device__ __forceinline__ void window_finalize_pk(uint32_t* __restrict__ W, uin
             slot++;
           }
         }
-        *dst++ = make_int4(w0 + q0 + k, (s + 1) | (code << 8), (int)(val >> 16), (int)((val & 0xFFFFu) - (val >> 16)));
+        out.scratch[di++] = make_int4(w0 + q0 + k, (s + 1) | (code << 8), (int)(val >> 16), (int)((val & 0xFFFFu) - (val >> 16)));
       }
     }
   }
@@ -486,59 +523,58 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
           if (((Em1 & ~isom1) >> 31) && rel0 + len < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);
         }
       } else {
-        const bool pass_known = FUSED ? false : (valid && (pass_in == nullptr || pass_in[r] != 0));
-        uint32_t n_in = 0, n_inm = 0, n_out = 0, n_outm = 0;
-        uint32_t Eprev = 0;
-        bool entered = false;
-        uint4 cur, nxt;
-        if (nu > 0) cur = ldg_plunit(src);
-        for (int u = 0; u < nu; u++) {
-          if (u + 1 < nu) nxt = ldg_plunit(src + (u + 1) * 32);
-          const uint4 v = cur;
-          const int rel = rel0 + 32 * u;
-          const bool inwin = (unsigned)(rel + 31) < (unsigned)(S + 31);  // -32 < rel < S
-          if (FUSED) {
-            const uint32_t ci = cls_in<TCTX>(v.x, v.y, v.z), co = cls_out<TCTX>(v.x, v.y, v.z);
-            n_in += __popc(ci); n_inm += __popc(ci & ~v.w);
-            if (TCTX != TC_CX) { n_out += __popc(co); n_outm += __popc(co & ~v.w); }
+        // Streaming form, two sweeps over the row's units: (A, fused only) class counts of the whole row with four loads in
+        // flight -> pass flag; (B) the events of the in-window units with the flag known (the second sweep's loads hit L2).
+        bool pass = valid && (pass_in == nullptr || pass_in[r] != 0);
+        if (FUSED) {
+          uint32_t n_in = 0, n_inm = 0, n_out = 0, n_outm = 0;
+          for (int u = 0; u < nu; u += 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              v[k] = make_uint4(0, 0, 0, 0);
+              if (u + k < nu) v[k] = ldg_plunit(src + (u + k) * 32);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint32_t ci = cls_in<TCTX>(v[k].x, v[k].y, v[k].z), co = cls_out<TCTX>(v[k].x, v[k].y, v[k].z);
+              n_in += __popc(ci); n_inm += __popc(ci & ~v[k].w);
+              if (TCTX != TC_CX) { n_out += __popc(co); n_outm += __popc(co & ~v[k].w); }
+            }
           }
-          const uint32_t E = v.x & v.y & ~v.z & v.w;
-          if (inwin) {
+          __syncwarp();
+          pass = overlaps && eval_pass_staged(n_inm, n_in, n_outm, n_out, thr, s_mmin, s_omax, (uint32_t)TBL);
+          if (overlaps && rel0 >= 0) {  // the window that holds the row's start owns its flag
+            pass_out[r] = pass ? 1 : 0;
+            npass_w += pass;
+          }
+        }
+        const uint32_t passm = pass ? 0xFFFFFFFFu : 0u;
+        const int u_lo = rel0 <= -32 ? (-rel0) >> 5 : 0;           // first unit with rel > -32
+        const int u_hi = min(nu, (S - rel0 + 31) >> 5);            // first unit with rel >= S
+        const int u_first = u_lo > 0 ? u_lo - 1 : 0;               // one unit earlier: its last position decides whether a '-' run is open
+        uint32_t Eprev = 0;
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+        if (u_first < u_hi) cur = ldg_plunit(src + u_first * 32);
+        for (int u = u_first; u < u_hi; u++) {
+          if (u + 1 < u_hi) nxt = ldg_plunit(src + (u + 1) * 32);
+          const uint4 v = cur;
+          const uint32_t E = pl_dashes(v);
+          if (u >= u_lo) {
             const uint32_t off4 = 128u * (uint32_t)u;
-            if (!entered && (Eprev >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
-            entered = true;
+            if (u == u_lo && (Eprev >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
             uint32_t m[3];
             pl_want<WANT>(v, m);
             const uint32_t iso = pl_dash(E, Eprev, wq + off4, sinc, w_floor);
-            pl_events<NC>(m, iso, pass_known ? ((m[0] | m[1] | m[2]) & ~v.w) : 0u, dq + off4, tq + off4, ctx_stride, sinc);
+            pl_events<NC>(m, iso, (m[0] | m[1] | m[2]) & ~v.w & passm, dq + off4, tq + off4, ctx_stride, sinc);
           }
           Eprev = E;
           cur = nxt;
         }
-        if (overlaps) {
+        __syncwarp();
+        if (overlaps && u_hi == nu) {   // the row ends inside the window: a '-' run that reaches a row end on a unit border
           const int e = rel0 + len;
-          if ((len & 31) == 0 && (Eprev >> 31) && e < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);  // a run that reaches the row end
-        }
-        if (FUSED && overlaps) {
-          const bool pass = eval_pass_staged(n_inm, n_in, n_outm, n_out, thr, s_mmin, s_omax, (uint32_t)TBL);
-          if (rel0 >= 0) {  // the window that holds the row's start owns its flag
-            pass_out[r] = pass ? 1 : 0;
-            npass_w += pass;
-          }
-          if (pass) {
-            const int u_lo = rel0 <= -32 ? (-rel0) >> 5 : 0;
-            const int u_hi = min(nu, (S - rel0 + 31) >> 5);
-            for (int u = u_lo; u < u_hi; u++) {
-              const uint4 v = ldg_plunit(src + u * 32);
-              uint32_t m[3];
-              pl_want<WANT>(v, m);
-#pragma unroll
-              for (int c = 0; c < NC; c++) {
-                const uint32_t mm = m[c] & ~v.w;
-                if (mm) pl_push_meth(mm, tq + 128u * u + (uint32_t)c * ctx_stride);
-              }
-            }
-          }
+          if ((len & 31) == 0 && (Eprev >> 31) && e < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);
         }
       }
     }
@@ -552,6 +588,152 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
 #else
     window_finalize_pk<WANT, PER, kRowThreads, FUSED>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
 #endif
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Long-read window kernel on planar ROWS (tiles of one row): a WARP per row, rows dealt round robin, the lanes read 32
+// consecutive units of the row per step (512 contiguous bytes, the next step's units requested before the current ones
+// are processed) and push their unit's events.  Pass flags are an input (thresholding a long read needs the counts of
+// the whole read: k_threshold_plr below; the reference advises threshold.reads=FALSE for long reads anyway,
+// R/generateCytosineReport.R:97-98).  The '-' state crosses units through a shuffle (and a carried word across steps).
+// Preconditions (dispatcher): at most 32767 rows overlap a window, S a multiple of 32 and <= PER * 256.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef EA_PLR_MINB
+#define EA_PLR_MINB 5
+#endif
+template <int WANT, int PER>
+__global__ void __launch_bounds__(kRowThreads, EA_PLR_MINB)
+k_window_plr(Planar pl, WinTable wt, const uint8_t* __restrict__ pass_in, ReportOut out) {
+  constexpr int NC = n_ctx<WANT>();
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const int S = wt.S;
+  const int SG = kGuardLo + S + kGuardHi;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t s_scan[2 * kRowWarps];
+  __shared__ long long s_base;
+  __shared__ int s_npass;  // unused (no fused thresholding); the finalize takes the pointer
+
+  uint32_t* const W = reinterpret_cast<uint32_t*>(smem_raw);  // [SG]
+  uint32_t* const D = W + SG;                                 // [SG]
+  uint32_t* const T = D + SG;                                 // [NC][2][SG]
+  const int kZero4 = (NC + 1) * 2 * SG / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t w_base = smem_u32(W), d_base = smem_u32(D), t_base = smem_u32(T);
+  const uint32_t w_floor = w_base + 4u * kGuardLo;
+  const uint32_t ctx_stride = 8u * (uint32_t)SG;
+
+  for (int i = threadIdx.x; i < kZero4; i += kRowThreads) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) s_npass = 0;
+
+  for (int win = blockIdx.x; win < wt.n; win += gridDim.x) {
+    __syncthreads();
+    const int w0 = wt.pos0[win];
+    const int lo = wt.lo[win], hi = wt.hi[win];
+    for (int r = lo + warp; r < hi; r += kRowWarps) {
+      const long long u0 = pl.toff[r];                          // warp-uniform loads
+      const int start = pl.start[r];
+      const uint32_t lsv = pl.ls[r];
+      const int len = (int)(lsv & 0x7FFFFFFFu);
+      const uint32_t strand0 = lsv >> 31;
+      const int rel0 = start - w0;
+      if (len <= 0 || rel0 + len <= 0) continue;                // rel0 < S by construction of hi
+      const int nu = (len + 31) >> 5;
+      const int u_lo = rel0 <= -32 ? (-rel0) >> 5 : 0;          // first unit with rel > -32
+      const int u_hi = min(nu, (S - rel0 + 31) >> 5);           // first unit with rel >= S
+      const int u_first = u_lo > 0 ? u_lo - 1 : 0;              // one unit earlier: is a '-' run open where the row enters the window?
+      const uint32_t sinc = strand0 ? 0x10000u : 1u;
+      if (lane == 0) {  // the row's coverage deltas
+        red_shared(w_floor + 4u * (uint32_t)max(rel0, 0), sinc);
+        const int e = rel0 + len;
+        if (e < S) red_shared(w_floor + 4u * (uint32_t)e, 0u - sinc);
+      }
+      const uint32_t passm = (pass_in == nullptr || pass_in[r] != 0) ? 0xFFFFFFFFu : 0u;
+      const uint4* src = pl.units + u0;
+      const uint32_t t_row = t_base + 4u * strand0 * (uint32_t)SG;
+      uint32_t Ecarry = 0u;
+      int u = u_first + lane;
+      uint4 v = make_uint4(0, 0, 0, 0), nv = make_uint4(0, 0, 0, 0);
+      if (u < u_hi) v = ldg_plunit(src + u);
+      for (int base = u_first; base < u_hi; base += 32) {        // warp-uniform trip count
+        const int un = u + 32;
+        if (un < u_hi) nv = ldg_plunit(src + un);
+        const uint32_t E = u < u_hi ? pl_dashes(v) : 0u;
+        uint32_t Eprev = __shfl_up_sync(FULL, E, 1);
+        if (lane == 0) Eprev = Ecarry;
+        Ecarry = __shfl_sync(FULL, E, 31);
+        if (u >= u_lo && u < u_hi) {
+          const uint32_t rel4 = 4u * (uint32_t)(rel0 + 32 * u + kGuardLo);   // >= 4: rel0 + 32u > -32
+          if (u == u_lo && (Eprev >> 31)) red_shared(w_floor, 0u - sinc);    // a '-' run is open where the row enters the window
+          uint32_t m[3];
+          pl_want<WANT>(v, m);
+          const uint32_t iso = pl_dash(E, Eprev, w_base + rel4, sinc, w_floor);
+          pl_events<NC>(m, iso, (m[0] | m[1] | m[2]) & ~v.w & passm, d_base + rel4, t_row + rel4, ctx_stride, sinc);
+          if (u == nu - 1 && (len & 31) == 0 && (E >> 31) && rel0 + len < S)  // a '-' run that reaches the row end on a unit border
+            red_shared(max(w_base + 4u * (uint32_t)(rel0 + len + kGuardLo), w_floor), sinc);
+        }
+        __syncwarp();
+        v = nv; u = un;
+      }
+    }
+    __syncthreads();
+    window_finalize_pk<WANT, PER, kRowThreads, false>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
+  }
+}
+
+// Stand-alone per-read kernel on planar ROWS (long reads): a warp per row, four units in flight per lane, class counts
+// reduced with shuffles; the pass/fail chain through the staged tables where the counts fit them, else with the
+// reference's IEEE double divisions (win_common.cuh:eval_pass_staged).
+template <int TCTX>
+__global__ void __launch_bounds__(256)
+k_threshold_plr(Planar pl, ThrParams thr, ThrTables tbl, uint8_t* __restrict__ pass_out, double* __restrict__ beta_out,
+                unsigned long long* n_pass) {
+  __shared__ uint16_t s_mmin[kThrTable], s_omax[kThrTable];
+  if (pass_out) {
+    stage_thr_tables(tbl, s_mmin, s_omax, kThrTable - 1);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t my_pass = 0;
+  for (int64_t r = warp; r < pl.n; r += n_warps) {
+    const long long u0 = pl.toff[r];
+    const int nu = (int)(((pl.ls[r] & 0x7FFFFFFFu) + 31u) >> 5);
+    const uint4* src = pl.units + u0;
+    uint32_t n_in = 0, n_inm = 0, n_out = 0, n_outm = 0;
+    for (int u = lane; u < nu; u += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (u + 32 * k < nu) v[k] = ldg_plunit(src + u + 32 * k);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ci = cls_in<TCTX>(v[k].x, v[k].y, v[k].z), co = cls_out<TCTX>(v[k].x, v[k].y, v[k].z);
+        n_in += __popc(ci); n_inm += __popc(ci & ~v[k].w);
+        if (TCTX != TC_CX) { n_out += __popc(co); n_outm += __popc(co & ~v[k].w); }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      n_in += __shfl_xor_sync(0xFFFFFFFFu, n_in, d); n_inm += __shfl_xor_sync(0xFFFFFFFFu, n_inm, d);
+      n_out += __shfl_xor_sync(0xFFFFFFFFu, n_out, d); n_outm += __shfl_xor_sync(0xFFFFFFFFu, n_outm, d);
+    }
+    if (lane == 0) {
+      if (pass_out) {
+        const bool pass = eval_pass_staged(n_inm, n_in, n_outm, n_out, thr, s_mmin, s_omax, kThrTable - 1);
+        pass_out[r] = pass ? 1 : 0;
+        my_pass += pass;
+      }
+      if (beta_out) beta_out[r] = (double)n_inm / (double)(n_in ? n_in : 1u);
+    }
+  }
+  if (n_pass) {
+    for (int d = 16; d >= 1; d >>= 1) my_pass += __shfl_down_sync(0xFFFFFFFFu, my_pass, d);
+    if (lane == 0 && my_pass) atomicAdd(n_pass, (unsigned long long)my_pass);
   }
 }
 

@@ -91,22 +91,40 @@ def merge_reports(parts: List[dict]) -> dict:
     return {c: np.concatenate([p[c] for p in parts]) if parts else np.zeros(0, np.int32) for c in cols}
 
 
-def slice_bam(bam, shard: Shard):
-    """Rows [row_lo, own_hi) of a host BamData as a self-contained BamData: its strings are gathered in row
-    order (templid = 0..n-1), so nrow equals the number of strings as the per-read routines require."""
+def slice_bam(bam, shard: Shard, chunk_rows: int = 1 << 16):
+    """Rows [row_lo, own_hi) of a host BamData as a self-contained BamData: its strings in row order
+    (templid = 0..n-1), so nrow equals the number of strings as the per-read routines require.
+
+    When the rows are the strings in file order (what preprocessBam produces for sorted BAMs) the shard's
+    strings are one contiguous piece of the blob: the slice is a VIEW plus rebased offsets, no copy and
+    no per-byte temporaries.  Otherwise the strings are gathered `chunk_rows` rows at a time, so the
+    temporaries stay bounded (a few tens of MB) however large the shard is."""
     from .api import BamData
     sl = slice(shard.row_lo, shard.own_hi)
     blob, off = bam.blob()
     tid = bam.templid[sl].astype(np.int64)
-    lens = off[tid + 1] - off[tid]
-    new_off = np.zeros(tid.shape[0] + 1, dtype=np.int64)
-    np.cumsum(lens, out=new_off[1:])
-    # gather: byte i of the new blob comes from off[tid[row]] + (i - new_off[row])
-    if tid.shape[0]:
-        row_of = np.repeat(np.arange(tid.shape[0]), lens)
-        src = off[tid][row_of] + (np.arange(int(new_off[-1])) - new_off[:-1][row_of])
-        new_blob = blob[src]
+    n = tid.shape[0]
+    if n == 0:
+        return BamData(bam.rname[sl], bam.strand[sl], bam.start[sl], np.zeros(0, np.int32), np.zeros(0, np.uint8),
+                       np.zeros(1, np.int64), bam.rname_levels, bam.device)
+    if tid[-1] - tid[0] == n - 1 and (n == 1 or bool(np.all(np.diff(tid) == 1))):
+        b0 = int(off[tid[0]])
+        new_off = off[tid[0]:tid[-1] + 2] - b0
+        new_blob = blob[b0:int(off[tid[-1] + 1])]
     else:
-        new_blob = np.zeros(0, np.uint8)
-    return BamData(bam.rname[sl], bam.strand[sl], bam.start[sl], np.arange(tid.shape[0], dtype=np.int32), new_blob, new_off,
+        lens = off[tid + 1] - off[tid]
+        new_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=new_off[1:])
+        new_blob = np.empty(int(new_off[-1]), dtype=np.uint8)
+        for c0 in range(0, n, chunk_rows):
+            c1 = min(c0 + chunk_rows, n)
+            ln = lens[c0:c1]
+            tot = int(new_off[c1] - new_off[c0])
+            if tot == 0:
+                continue
+            # byte i of the chunk comes from off[tid[row]] + (i - chunk-relative start of the row)
+            row_of = np.repeat(np.arange(c1 - c0, dtype=np.int64), ln)
+            src = (off[tid[c0:c1]] - (new_off[c0:c1] - new_off[c0]))[row_of] + np.arange(tot, dtype=np.int64)
+            new_blob[new_off[c0]:new_off[c1]] = blob[src]
+    return BamData(bam.rname[sl], bam.strand[sl], bam.start[sl], np.arange(n, dtype=np.int32), new_blob, new_off,
                    bam.rname_levels, bam.device)

@@ -37,9 +37,9 @@ def crc(rep, pass_flags):
     return c
 
 
-@pytest.fixture(params=["auto", "byte-auto", "lane-group", "thread-per-row-tma", "chunk-per-lane", "long-read"])
+@pytest.fixture(params=["auto", "vertical", "byte-auto", "lane-group", "thread-per-row-tma", "chunk-per-lane", "long-read"])
 def kernel_policy(request):
-    old = N.lib().ea_set_kernel_policy({"auto": 0, "lane-group": 1, "thread-per-row-tma": 2, "chunk-per-lane": 3, "long-read": 4, "byte-auto": 5}[request.param])
+    old = N.lib().ea_set_kernel_policy({"auto": 0, "lane-group": 1, "thread-per-row-tma": 2, "chunk-per-lane": 3, "long-read": 4, "byte-auto": 5, "vertical": 6}[request.param])
     yield request.param
     N.lib().ea_set_kernel_policy(old)
 

@@ -17,12 +17,12 @@ pytestmark = pytest.mark.gpu
 CG = ("Z", "z", "XH", "xh", 2, 0.5, 0.1)
 
 
-@pytest.fixture(params=["auto", "byte-auto", "lane-group", "thread-per-row-tma", "chunk-per-lane"], autouse=True)
+@pytest.fixture(params=["auto", "vertical", "byte-auto", "lane-group", "thread-per-row-tma", "chunk-per-lane"], autouse=True)
 def kernel_policy(request):
     """Every parity test runs with each window kernel: the automatic choice (row-per-lane kernel for one-context
     reports over short 32-byte-multiple rows, else the chunk-per-lane kernel, else the lane-group kernel), the general
     lane-group kernel forced, the thread-per-row TMA kernel, and the chunk-per-lane kernel."""
-    old = N.lib().ea_set_kernel_policy({"auto": 0, "lane-group": 1, "thread-per-row-tma": 2, "chunk-per-lane": 3, "long-read": 4, "byte-auto": 5}[request.param])
+    old = N.lib().ea_set_kernel_policy({"auto": 0, "lane-group": 1, "thread-per-row-tma": 2, "chunk-per-lane": 3, "long-read": 4, "byte-auto": 5, "vertical": 6}[request.param])
     yield request.param
     N.lib().ea_set_kernel_policy(old)
 

@@ -70,3 +70,44 @@ def test_gloo_world_size_2():
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_slice_bam_large_and_shuffled():
+    """slice_bam must not build per-byte index arrays for a whole shard: 10 M rows go through the zero-copy view
+    (rows == strings in file order), and a shuffled templid goes through the chunked gather; both equal a direct gather."""
+    import tracemalloc
+    from epialleler_b200.shard import Shard, slice_bam
+    n = 10_000_000
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1, 12, n).astype(np.int64)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    blob = rng.integers(0, 256, int(off[-1]), dtype=np.uint8)
+    start = np.arange(n, dtype=np.int32)
+    ones = np.ones(n, np.int32)
+    bam = ea.BamData(ones, ones, start, np.arange(n, dtype=np.int32), blob, off)
+    sh = Shard(1, 3_000_001, 3_000_100, 9_999_999, 0, 0)
+    tracemalloc.start()
+    sub = slice_bam(bam, sh)
+    peak = tracemalloc.get_traced_memory()[1]
+    tracemalloc.stop()
+    b2, o2 = sub.blob()
+    assert peak < 4 * (sh.own_hi - sh.row_lo) * 8 + (64 << 20), "slice of contiguous strings must not copy per byte (peak %d)" % peak
+    assert np.shares_memory(b2, blob)
+    assert o2[0] == 0 and np.array_equal(np.diff(o2), lens[sh.row_lo:sh.own_hi])
+    assert np.array_equal(b2, blob[off[sh.row_lo]:off[sh.own_hi]])
+    assert np.array_equal(sub.templid, np.arange(sh.own_hi - sh.row_lo))
+    # shuffled templid: strings are not in row order
+    m = 2_000_000
+    perm = rng.permutation(m).astype(np.int32)
+    bam2 = ea.BamData(ones[:m], ones[:m], start[:m], perm, blob[:off[m]], off[:m + 1])
+    sh2 = Shard(0, 100_003, 100_003, 1_900_001, 0, 0)
+    sub2 = slice_bam(bam2, sh2)
+    b3, o3 = sub2.blob()
+    tid = perm[sh2.row_lo:sh2.own_hi].astype(np.int64)
+    assert np.array_equal(np.diff(o3), lens[tid])
+    for i in (0, 1, 777, 1_234_567, tid.shape[0] - 1):
+        assert np.array_equal(b3[o3[i]:o3[i + 1]], blob[off[tid[i]]:off[tid[i] + 1]])
+    import zlib
+    want = zlib.crc32(np.concatenate([blob[off[t]:off[t + 1]] for t in tid[:50_000]]))
+    assert zlib.crc32(b3[:o3[50_000]]) == want

@@ -38,6 +38,8 @@ CONFIGS = {
 def main():
     names = sys.argv[1:] or list(CONFIGS)
     L = N.lib()
+    import os
+    L.ea_set_kernel_policy(int(os.environ.get("EA_POLICY", "0")))
     for name in names:
         skw, rkw = CONFIGS[name]
         cfg = ea.synth_config(**skw)
