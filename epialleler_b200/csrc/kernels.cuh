@@ -559,26 +559,53 @@ __global__ void __launch_bounds__(1024) k_scan_windows(const int32_t* __restrict
 
 struct ReportCols { int32_t *rname, *strand, *pos, *ctx, *meth, *unmeth; };
 
+// A warp takes 32 consecutive windows at a time: their (count, scratch base, destination) are one coalesced load per
+// array, the rows of the 32 windows are then copied as ONE flattened run (a lane finds the window of its row with a
+// five-step shuffle search over the warp's prefix sums) - the destination rows of consecutive windows are contiguous, so
+// every store instruction writes 32 consecutive elements however few rows a window holds.
 __global__ void __launch_bounds__(128)
 k_gather_rows(const int4* __restrict__ scratch, const long long* __restrict__ w_base, const long long* __restrict__ w_dst,
               const int32_t* __restrict__ w_cnt, const int32_t* __restrict__ w_rname, int n_win, long long cap,
-              ReportCols out, int rname_shift = 0 /* entries per w_rname element, log2 (retire blocks of the streaming kernel) */) {
+              ReportCols out, int group = 32 /* windows per warp step, 1..32 (fewer when there are few windows) */) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int w = warp; w < n_win; w += n_warps) {
-    const int cnt = w_cnt[w];
-    if (!cnt) continue;
-    const long long src = w_base[w], dst = w_dst[w];
-    if (src + cnt > cap || dst + cnt > cap) continue;  // capacity overflow: the host grows the buffers and reruns
-    const int rn = w_rname[w >> rname_shift];
-    for (int i = lane; i < cnt; i += 32) {
-      const int4 v = scratch[src + i];
-      out.rname[dst + i] = rn;
-      out.strand[dst + i] = v.y & 0xFF;
-      out.pos[dst + i] = v.x;
-      out.ctx[dst + i] = v.y >> 8;
-      out.meth[dst + i] = v.z;
-      out.unmeth[dst + i] = v.w;
+  for (int w0 = warp * group; w0 < n_win; w0 += n_warps * group) {
+    const int w = w0 + lane;
+    int cnt = 0, rn = 0;
+    long long src = 0, dst = 0;
+    if (lane < group && w < n_win) {
+      cnt = w_cnt[w]; src = w_base[w]; dst = w_dst[w]; rn = w_rname[w];
+      if (src + cnt > cap || dst + cnt > cap) cnt = 0;  // capacity overflow: the host grows the buffers and reruns
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int ex = inc - cnt;
+    const int total = __shfl_sync(FULL, inc, 31);
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      int j = 0;  // the window of row c: the last lane whose exclusive count is <= c (empty windows share their successor's)
+#pragma unroll
+      for (int step = 16; step; step >>= 1) {
+        const int e = __shfl_sync(FULL, ex, j + step);
+        if (e <= c) j += step;
+      }
+      const long long sj = __shfl_sync(FULL, src, j), dj = __shfl_sync(FULL, dst, j);
+      const int ej = __shfl_sync(FULL, ex, j), rj = __shfl_sync(FULL, rn, j);
+      if (c < total) {
+        const int4 v = scratch[sj + (c - ej)];
+        const long long d = dj + (c - ej);
+        out.rname[d] = rj;
+        out.strand[d] = v.y & 0xFF;
+        out.pos[d] = v.x;
+        out.ctx[d] = v.y >> 8;
+        out.meth[d] = v.z;
+        out.unmeth[d] = v.w;
+      }
     }
   }
 }

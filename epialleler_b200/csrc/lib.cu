@@ -20,6 +20,7 @@
 
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "../../include/epialleler_b200.h"
 #include "kernels.cuh"
@@ -147,7 +148,8 @@ struct ea_handle {
   uint4* d_pl_units = nullptr;
   int64_t* d_pl_toff = nullptr;
   uint32_t* d_pl_ls = nullptr;
-  int64_t pl_tiles = 0, pl_unit_rows = 0;
+  int64_t pl_tiles = 0, pl_unit_rows = 0;   // tiles; 512-byte unit rows (tiles of 32 rows) or 16-byte units (tiles of one row)
+  int pl_th = 32;                           // rows per tile: 32 (rows of up to 1024 positions) or 1 (long reads)
   bool pl_ok = false;
   WinIndex idx[4];               // small cache of window indexes keyed by S
   cudaStream_t stream = nullptr;
@@ -524,19 +526,21 @@ Planar planar_of(const ea_handle* h) {
 
 bool planar_wanted(const ea_handle* h) {
   static const bool off = getenv("EA_NO_PLANAR") != nullptr;
-  return !off && h->n > 0 && h->max_len >= 1 && h->max_len <= 1024;
+  return !off && h->n > 0 && h->max_len >= 1;
 }
 
 // Tile table (unit rows per tile, prefix sum) and ls[] on stream s; needs d_len / d_strand.  Synchronizes s.
 int planar_tiles(ea_handle* h, cudaStream_t s) {
   int rc;
-  h->pl_tiles = (h->n + 31) >> 5;
+  h->pl_th = h->max_len <= 1024 ? 32 : 1;
+  h->pl_tiles = h->pl_th == 32 ? (h->n + 31) >> 5 : h->n;
   int64_t* d_nu = nullptr;
   if ((rc = dmalloc(&d_nu, (size_t)h->pl_tiles + 1))) return rc;
   if ((rc = dmalloc(&h->d_pl_toff, (size_t)h->pl_tiles + 1))) { pool_free_on(d_nu, s); return rc; }
   if ((rc = dmalloc(&h->d_pl_ls, (size_t)h->n))) { pool_free_on(d_nu, s); return rc; }
   CU(cudaMemsetAsync(d_nu, 0, 8 * (size_t)(h->pl_tiles + 1), s));
-  k_pl_tile_units<<<grid_for(h->n, 256), 256, 0, s>>>(h->d_len, h->d_strand, h->n, d_nu, h->d_pl_ls);
+  if (h->pl_th == 32) k_pl_tile_units<<<grid_for(h->n, 256), 256, 0, s>>>(h->d_len, h->d_strand, h->n, d_nu, h->d_pl_ls);
+  else k_pl_row_units<<<grid_for(h->n, 256), 256, 0, s>>>(h->d_len, h->d_strand, h->n, d_nu, h->d_pl_ls);
   size_t tb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_nu, h->d_pl_toff, (int)(h->pl_tiles + 1), s));
   void* tmp = nullptr;
@@ -552,7 +556,8 @@ int planar_tiles(ea_handle* h, cudaStream_t s) {
 int planar_fill(ea_handle* h, int64_t t0, int64_t t1, cudaStream_t s) {
   if (t1 <= t0) return EA_OK;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t1 - t0 + 7) / 8, (int64_t)h->sm_count * 16));
-  k_planarize<<<grid, 256, 0, s>>>(h->d_data, h->d_off, h->d_len, h->n, h->d_pl_toff, t0, t1, h->d_pl_units);
+  if (h->pl_th == 32) k_planarize<<<grid, 256, 0, s>>>(h->d_data, h->d_off, h->d_len, h->n, h->d_pl_toff, t0, t1, h->d_pl_units);
+  else k_planarize_rows<<<grid, 256, 0, s>>>(h->d_data, h->d_off, h->d_len, h->d_pl_toff, t0, t1, h->d_pl_units);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -562,7 +567,7 @@ int build_planar(ea_handle* h) {
   if (h->pl_ok || !planar_wanted(h)) return EA_OK;
   int rc;
   if ((rc = planar_tiles(h, h->stream))) return rc;
-  if ((rc = dmalloc(&h->d_pl_units, (size_t)h->pl_unit_rows * 32))) return rc;
+  if ((rc = dmalloc(&h->d_pl_units, (size_t)h->pl_unit_rows * (h->pl_th == 32 ? 32 : 1)))) return rc;
   if ((rc = planar_fill(h, 0, h->pl_tiles, h->stream))) return rc;
   CU(cudaStreamSynchronize(h->stream));
   h->pl_ok = true;
@@ -642,7 +647,8 @@ int launch_threshold_t(ea_handle* h, const ThrParams& tp, uint8_t* pass, double*
     ThrTables tb{nullptr, nullptr};
     if (pass && (rc = thr_tables(h, tp, &tb))) return rc;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((h->pl_tiles + 7) / 8, (int64_t)h->sm_count * 32));
-    k_threshold_pl<TCTX><<<blocks, 256, 0, h->stream>>>(planar_of(h), h->pl_tiles, tp, tb, pass, beta, n_pass);
+    if (h->pl_th == 32) k_threshold_pl<TCTX><<<blocks, 256, 0, h->stream>>>(planar_of(h), h->pl_tiles, tp, tb, pass, beta, n_pass);
+    else k_threshold_plr<TCTX><<<blocks, 256, 0, h->stream>>>(planar_of(h), tp, tb, pass, beta, n_pass);
     return EA_OK;
   }
   // short reads: row per lane (threshold_row.cuh); the integer tables cover counts up to 1024
@@ -666,7 +672,7 @@ int launch_threshold(ea_handle* h, const ThresholdSpec& spec, const ThrParams& t
                      unsigned long long* n_pass) {
   if (h->n == 0) return EA_OK;
   int rc = EA_OK;
-  if (spec.tctx < 0 || h->max_len > 65535) {
+  if (spec.tctx < 0 || (h->max_len > 65535 && !(h->pl_ok && (g_kernel_policy == 0 || g_kernel_policy == 6)))) {
     k_threshold_generic<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), spec.lw, tp, pass, beta, n_pass);
   } else {
     switch (spec.tctx) {
@@ -1049,12 +1055,20 @@ struct PlPlan { bool ok = false; int maxu = 0; int S = 0; size_t smem = 0; };
 // Window size: as many positions as keep EA_PL_MINB CTAs (one context) resident; more contexts take more state per position.
 int pick_pl_window(const ea_handle* h, const WinIndex& ix2048, int nc) {
   if (const char* e = getenv("EA_PL_S")) { const int v = atoi(e) & ~31; if (v >= 256 && v <= kRowMaxS) return v; }
+  if (h->pl_th == 1) return nc == 1 ? 3072 : 2048;   // long reads: few rows per window, larger windows amortise the finalize
   if (nc == 1) return pick_row_window(h, ix2048);
   return 2048;
 }
 
 PlPlan plan_pl(const ea_handle* h, const WinIndex& ix, int nc) {
   PlPlan t;
+  if (h->pl_ok && h->pl_th == 1) {   // long reads: k_window_plr
+    if (h->n == 0 || ix.n == 0 || nc < 1 || ix.max_rows > 32767 || ix.S > kRowMaxS || (ix.S & 31)) return t;
+    t.maxu = -1; t.S = ix.S;
+    t.smem = sizeof(uint32_t) * (size_t)(nc + 1) * 2 * (kGuardLo + ix.S + kGuardHi);
+    t.ok = true;
+    return t;
+  }
   if (!h->pl_ok || h->n == 0 || ix.n == 0 || nc < 1 || ix.max_rows > 32767 || ix.S > kRowMaxS || (ix.S & 31)) return t;
   const int max_nu = (h->max_len + 31) >> 5;
   t.maxu = max_nu <= 5 ? 5 : 0;
@@ -1113,8 +1127,44 @@ int launch_pl_w(ea_handle* h, const WinIndex& ix, const PlPlan& pp, int tctx_fus
   }
 }
 
+template <int WANT>
+int launch_plr_w(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const uint8_t* pass_in, const ReportOut& out) {
+  if (ix.S != pp.S) return fail(EA_ERR_STATE, "window size mismatch");
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
+  if (ix.S <= 8 * kRowThreads) {
+    auto kern = k_window_plr<WANT, 8>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
+    kern<<<grid, kRowThreads, pp.smem, h->stream>>>(planar_of(h), wt, pass_in, out);
+  } else {
+    auto kern = k_window_plr<WANT, 12>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem));
+    kern<<<grid, kRowThreads, pp.smem, h->stream>>>(planar_of(h), wt, pass_in, out);
+  }
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+int launch_plr(ea_handle* h, const WinIndex& ix, const PlPlan& pp, int want, const uint8_t* pass_in, const ReportOut& out) {
+  switch (want) {
+#ifndef EA_FAST_BUILD
+    case 1: return launch_plr_w<1>(h, ix, pp, pass_in, out);
+    case 2: return launch_plr_w<2>(h, ix, pp, pass_in, out);
+    case 3: return launch_plr_w<3>(h, ix, pp, pass_in, out);
+    case 5: return launch_plr_w<5>(h, ix, pp, pass_in, out);
+    case 6: return launch_plr_w<6>(h, ix, pp, pass_in, out);
+#endif
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
+    case 7: return launch_plr_w<7>(h, ix, pp, pass_in, out);
+#endif
+    default: return launch_plr_w<4>(h, ix, pp, pass_in, out);
+  }
+}
+
 int launch_pl(ea_handle* h, const WinIndex& ix, const PlPlan& pp, int want, int tctx_fused, const ThrParams& thr,
               const uint8_t* pass_in, uint8_t* pass_out, const ReportOut& out) {
+  if (pp.maxu < 0) return launch_plr(h, ix, pp, want, pass_in, out);
   switch (want) {
 #ifndef EA_FAST_BUILD
     case 1: return launch_pl_w<1>(h, ix, pp, tctx_fused, thr, pass_in, pass_out, out);
@@ -1141,7 +1191,7 @@ int pick_vs_window(const ea_handle* h, const WinIndex& ix2048) {
 
 VsPlan plan_vs(const ea_handle* h, const WinIndex& ix, int nc) {
   VsPlan t;
-  if (!h->pl_ok || h->n == 0 || ix.n == 0 || nc < 1 || (ix.S != 2048 && ix.S != 512)) return t;
+  if (!h->pl_ok || h->pl_th != 32 || h->n == 0 || ix.n == 0 || nc < 1 || (ix.S != 2048 && ix.S != 512)) return t;
   t.lognb = ix.S == 2048 ? 6 : 4;
   t.k = ix.S == 2048 ? 9 : 12;                  // planes per counter: 511 / 4095 rows over one window at most
   if (ix.max_rows > (1 << t.k) - 1) return t;
@@ -1208,8 +1258,55 @@ int launch_vs(ea_handle* h, const WinIndex& ix, const VsPlan& vp, int want, int 
   }
 }
 
+// ---- long reads: a warp per 1024-position window, vertical counters (window_vs.cuh: k_window_vsr) ----
+template <int WANT>
+int launch_vsr_w(ea_handle* h, const WinIndex& ix, int k, const uint8_t* pass_in, const ReportOut& out) {
+  if (ix.S != kVsrS) return fail(EA_ERR_STATE, "window size mismatch");
+  WinTable wt;
+  wt.rname = ix.rname; wt.pos0 = ix.pos0; wt.lo = ix.lo; wt.hi = ix.hi; wt.n = ix.n; wt.S = ix.S;
+  const int grid = std::max(1, std::min<int>((ix.n + kVsWarps - 1) / kVsWarps, h->sm_count * 64));
+  if (k == 6) k_window_vsr<WANT, 6><<<grid, kVsThreads, 0, h->stream>>>(planar_of(h), wt, pass_in, out);
+  else k_window_vsr<WANT, 9><<<grid, kVsThreads, 0, h->stream>>>(planar_of(h), wt, pass_in, out);
+  CU(cudaGetLastError());
+  return EA_OK;
+}
+
+int launch_vsr(ea_handle* h, const WinIndex& ix, int k, int want, const uint8_t* pass_in, const ReportOut& out) {
+  switch (want) {
+#ifndef EA_FAST_BUILD
+    case 1: return launch_vsr_w<1>(h, ix, k, pass_in, out);
+    case 2: return launch_vsr_w<2>(h, ix, k, pass_in, out);
+    case 3: return launch_vsr_w<3>(h, ix, k, pass_in, out);
+    case 5: return launch_vsr_w<5>(h, ix, k, pass_in, out);
+    case 6: return launch_vsr_w<6>(h, ix, k, pass_in, out);
+#endif
+#if !defined(EA_FAST_BUILD) || defined(EA_FAST_CX)
+    case 7: return launch_vsr_w<7>(h, ix, k, pass_in, out);
+#endif
+    default: return launch_vsr_w<4>(h, ix, k, pass_in, out);
+  }
+}
+
 int ensure_pass(ea_handle* h) {
   if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
+  return EA_OK;
+}
+
+// exclusive prefix sum of the windows' row counts: one CTA for small indexes, CUB's multi-block scan beyond (the one-CTA
+// kernel takes ~110 us for the 123 k windows of config 2, latency-bound on a single SM)
+struct I32ToI64 { __host__ __device__ __forceinline__ long long operator()(const int32_t& v) const { return (long long)v; } };
+int scan_windows(ea_handle* h, const WinIndex& ix) {
+  if (ix.n <= 4096) {
+    k_scan_windows<<<1, 1024, 0, h->stream>>>(ix.w_cnt, ix.w_dst, ix.n);
+    return EA_OK;
+  }
+  auto in = thrust::make_transform_iterator(static_cast<const int32_t*>(ix.w_cnt), I32ToI64());
+  size_t tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, ix.w_dst, ix.n, h->stream));
+  void* tmp = nullptr;
+  CU(cudaMallocAsync(&tmp, std::max<size_t>(tb, 1), h->stream));
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tb, in, ix.w_dst, ix.n, h->stream));
+  CU(cudaFreeAsync(tmp, h->stream));
   return EA_OK;
 }
 
@@ -1266,15 +1363,21 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
     vsp = plan_vs(h, *ixv, nc);
     if (vsp.ok) ix = ixv;
   }
-  if (rp.want && (policy == 0 || (policy == 6 && !vsp.ok)) && h->pl_ok) {
+  int vsr_k = 0;   // long reads: k_window_vsr when at most 511 rows overlap a 1024-position window
+  if (rp.want && (policy == 0 || policy == 6) && h->pl_ok && h->pl_th == 1 && !getenv("EA_NO_VSR")) {
+    WinIndex* ixr = nullptr;
+    if ((rc = build_index(h, kVsrS, &ixr))) return rc;
+    if (ixr->n > 0 && ixr->max_rows <= 511) { vsr_k = ixr->max_rows <= 63 ? 6 : 9; ix = ixr; }
+  }
+  if (rp.want && !vsr_k && (policy == 0 || (policy == 6 && !vsp.ok)) && h->pl_ok) {
     const int S = pick_pl_window(h, *ix, nc);
     WinIndex* ixp = ix;
     if (S != 2048 && (rc = build_index(h, S, &ixp))) return rc;
     pln = plan_pl(h, *ixp, nc);
     if (pln.ok) ix = ixp;
   }
-  const bool byte_auto = ((policy == 0 || policy == 6) && !pln.ok && !vsp.ok) || policy == 5;
-  if (rp.want && !pln.ok && !vsp.ok) {
+  const bool byte_auto = ((policy == 0 || policy == 6) && !pln.ok && !vsp.ok && !vsr_k) || policy == 5;
+  if (rp.want && !pln.ok && !vsp.ok && !vsr_k) {
     if (byte_auto && nc == 1 && h->rows32 && ((h->max_len + 31) >> 5) <= 8) {
       const int S = pick_row_window(h, *ix);
       WinIndex* ixr = ix;
@@ -1326,9 +1429,10 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       ReportOut out;
       out.scratch = h->d_scratch; out.cap = h->cap_rows; out.cursor = h->d_counters; out.w_base = ix->w_base;
       out.w_cnt = ix->w_cnt; out.n_pass = h->d_counters + 1;
-      h->report_kernel = vsp.ok ? (vsp.lognb == 6 ? "k_window_vs<K=9,S=2048> (planar call planes, vertical bit-sliced counters)" : "k_window_vs<K=12,S=512> (planar call planes, vertical bit-sliced counters)") : pln.ok ? (pln.maxu ? "k_window_pl<MAXU=5> (planar call planes, row per lane, tile-coalesced 128-bit loads)" : "k_window_pl<any> (planar call planes, row per lane, two sweeps)") : row.ok ? "k_window_row (row per lane, 256-bit loads)" : lng.ok ? "k_window_long (warp per row, lane per 32-byte unit)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
+      h->report_kernel = vsr_k ? "k_window_vsr (planar call planes, warp per 1024-position window, vertical bit-sliced counters)" : (pln.ok && pln.maxu < 0) ? "k_window_plr (planar call planes, warp per row, 512-byte coalesced loads)" : vsp.ok ? (vsp.lognb == 6 ? "k_window_vs<K=9,S=2048> (planar call planes, vertical bit-sliced counters)" : "k_window_vs<K=12,S=512> (planar call planes, vertical bit-sliced counters)") : pln.ok ? (pln.maxu ? "k_window_pl<MAXU=5> (planar call planes, row per lane, tile-coalesced 128-bit loads)" : "k_window_pl<any> (planar call planes, row per lane, two sweeps)") : row.ok ? "k_window_row (row per lane, 256-bit loads)" : lng.ok ? "k_window_long (warp per row, lane per 32-byte unit)" : cpl.ok ? (cpl.ub == 32 ? "k_window_cpl<UB=32> (chunk-per-lane, 256-bit loads)" : "k_window_cpl<UB=16> (chunk-per-lane)")
                                 : tpr.ok ? "k_window_tpr (thread-per-row over TMA tiles)" : "k_window (lane-group)";
-      if (vsp.ok) rc = launch_vs(h, *ix, vsp, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
+      if (vsr_k) rc = launch_vsr(h, *ix, vsr_k, rp.want, pass_for_window, out);
+      else if (vsp.ok) rc = launch_vs(h, *ix, vsp, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (pln.ok) rc = launch_pl(h, *ix, pln, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (row.ok) rc = launch_row(h, *ix, row, rp.want, fused ? rp.spec.tctx : -1, rp.tp, pass_for_window, h->d_pass, out);
       else if (lng.ok) rc = launch_long(h, *ix, lng, rp.want, pass_for_window, out);
@@ -1339,9 +1443,14 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       launches += ((vsp.ok || pln.ok || row.ok || cpl.ok || tpr.ok) && fused) ? 2 : 1;  // the short-read kernels are preceded by the threshold-table kernel
       CU(cudaEventRecord(h->ev[2], h->stream));
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
-      k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
-      k_gather_rows<<<std::max(1, std::min(ix->n / 4 + 1, h->sm_count * 16)), 128, 0, h->stream>>>(
-          h->d_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, h->cap_rows, cols);
+      if ((rc = scan_windows(h, *ix))) return rc;
+      {  // windows per warp step: 32 when there are plenty of windows, fewer so that a small index still fills the GPU
+        int group = 32;
+        while (group > 1 && (int64_t)ix->n / group < (int64_t)h->sm_count * 32) group >>= 1;
+        const int warps = (ix->n + group - 1) / group;
+        k_gather_rows<<<std::max(1, std::min((warps + 3) / 4, h->sm_count * 16)), 128, 0, h->stream>>>(
+            h->d_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, h->cap_rows, cols, group);
+      }
       launches += 2;
       CU(cudaGetLastError());
     } else {

@@ -338,4 +338,137 @@ k_window_vs(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Long reads (planar rows, tiles of one row): a WARP per window of 1024 positions, lane b owns block b of the window.
+// Every row that crosses the window is warp-uniform work: its metadata are uniform loads, lane b reads the unit that
+// holds its block's first position (the 32 lanes read 512 contiguous bytes), takes the next unit from its neighbour with
+// a shuffle, aligns the four planes with funnel shifts and adds `not '-'`, `call` and `methylated call of a passing row`
+// into the bit-sliced counters of the row's strand (a warp-uniform branch).  No shared memory, no barriers, no atomics
+// but the window's claim on the scratch rows; coverage is counted directly, so nothing is proportional to the number of
+// POSITIONS except one comparator pass per block - on 10-30 kb reads at a few-fold depth the per-position finalize of the
+// event kernels is 40 % of their instructions.  Pass flags are an input (k_threshold_plr).
+// K planes per counter: at most 2^K - 1 rows may overlap a window (dispatcher).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kVsrS = 1024;
+#ifndef EA_VSR_MINB
+#define EA_VSR_MINB 3
+#endif
+
+template <int K>
+__device__ __forceinline__ void vs_add1(VsCounter<K>& c, uint32_t x) {
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    const uint32_t carry = c.p[i] & x;
+    c.p[i] ^= x;
+    x = carry;
+  }
+}
+
+template <int WANT, int K>
+struct VsrStrand {
+  VsCounter<K> cov, tot[n_ctx<WANT>()], meth[n_ctx<WANT>()];
+  __device__ __forceinline__ void clear() {
+    cov.clear();
+#pragma unroll
+    for (int c = 0; c < n_ctx<WANT>(); c++) { tot[c].clear(); meth[c].clear(); }
+  }
+  __device__ __forceinline__ void add(const uint4& v, uint32_t passm) {
+    vs_add1<K>(cov, v.z | (v.y & ~(v.x & v.w)));   // code neither 0 (outside the row) nor 11 ('-')
+    uint32_t m[3];
+    pl_want<WANT>(v, m);
+#pragma unroll
+    for (int c = 0; c < n_ctx<WANT>(); c++) { vs_add1<K>(tot[c], m[c]); vs_add1<K>(meth[c], m[c] & ~v.w & passm); }
+  }
+};
+
+template <int WANT, int K>
+__global__ void __launch_bounds__(kVsThreads, EA_VSR_MINB)
+k_window_vsr(Planar pl, WinTable wt, const uint8_t* __restrict__ pass_in, ReportOut out) {
+  constexpr int NC = n_ctx<WANT>();
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int pb = 32 * lane;
+  const int gw = (int)((blockIdx.x * (unsigned)kVsThreads + threadIdx.x) >> 5), n_gw = (int)((gridDim.x * (unsigned)kVsThreads) >> 5);
+  for (int win = gw; win < wt.n; win += n_gw) {
+    const int w0 = wt.pos0[win];
+    const int lo = wt.lo[win], hi = wt.hi[win];
+    VsrStrand<WANT, K> sp, sm;   // '+' and '-' strand
+    sp.clear(); sm.clear();
+    for (int r = lo; r < hi; r++) {
+      const long long u0 = pl.toff[r];
+      const int start = pl.start[r];
+      const uint32_t lsv = pl.ls[r];
+      const int len = (int)(lsv & 0x7FFFFFFFu);
+      const int rel0 = start - w0;
+      if (len <= 0 || rel0 + len <= 0) continue;              // warp-uniform; rel0 < S by construction of hi
+      const int nu = (len + 31) >> 5;
+      const int o = pb - rel0;                                // position within the row of this lane's first position
+      const int j = o >> 5;                                   // (floor) unit that holds it; lane b+1 looks at unit j+1
+      const uint32_t sh = (uint32_t)o & 31u;                  // the same in every lane
+      uint4 lo4 = make_uint4(0, 0, 0, 0);
+      if (j >= 0 && j < nu) lo4 = ldg_plunit(pl.units + u0 + j);
+      uint4 hi4;
+      hi4.x = __shfl_down_sync(FULL, lo4.x, 1); hi4.y = __shfl_down_sync(FULL, lo4.y, 1);
+      hi4.z = __shfl_down_sync(FULL, lo4.z, 1); hi4.w = __shfl_down_sync(FULL, lo4.w, 1);
+      if (lane == 31) {
+        hi4 = make_uint4(0, 0, 0, 0);
+        if (sh != 0u && j + 1 >= 0 && j + 1 < nu) hi4 = ldg_plunit(pl.units + u0 + j + 1);
+      }
+      uint4 v;
+      v.x = __funnelshift_r(lo4.x, hi4.x, sh); v.y = __funnelshift_r(lo4.y, hi4.y, sh);
+      v.z = __funnelshift_r(lo4.z, hi4.z, sh); v.w = __funnelshift_r(lo4.w, hi4.w, sh);
+      const uint32_t passm = (pass_in == nullptr || pass_in[r] != 0) ? 0xFFFFFFFFu : 0u;
+      if (lsv >> 31) sm.add(v, passm); else sp.add(v, passm);   // warp-uniform branch
+    }
+    // ---- rows of the window: bit-sliced majority test, ordered compaction within the warp ----
+    uint32_t win_p[NC], win_m[NC], rows_p = 0u, rows_m = 0u;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      win_p[c] = vs_majority<K>(sp.tot[c], sp.cov); rows_p |= win_p[c];
+      win_m[c] = vs_majority<K>(sm.tot[c], sm.cov); rows_m |= win_m[c];
+    }
+    const int mine = __popc(rows_p) + __popc(rows_m);
+    int inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int total = __shfl_sync(FULL, inc, 31);
+    unsigned long long bb = 0ull;
+    if (lane == 0) {
+      bb = total ? atomicAdd(out.cursor, (unsigned long long)total) : 0ull;
+      out.w_base[win] = (long long)bb;
+      out.w_cnt[win] = total;
+    }
+    bb = __shfl_sync(FULL, bb, 0);
+    if (mine && (long long)bb + total <= out.cap) {
+      int4* dst = out.scratch + bb + (inc - mine);
+      uint32_t both = rows_p | rows_m;
+      while (both) {  // ascending position, '+' before '-'
+        const int p = __ffs(both) - 1;
+        both &= both - 1u;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          if (!(((s ? rows_m : rows_p) >> p) & 1u)) continue;
+          int code = (WANT & W_CHH) ? 2 : ((WANT & W_CHG) ? 6 : 7);
+          uint32_t tot = 0u, meth = 0u;
+          int slot = 0;
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            if (!((WANT >> cc) & 1)) continue;
+            if (((s ? win_m[slot] : win_p[slot]) >> p) & 1u) {
+              code = cc == 0 ? 2 : (cc == 1 ? 6 : 7);
+              tot = s ? sm.tot[slot].value_at(p) : sp.tot[slot].value_at(p);
+              meth = s ? sm.meth[slot].value_at(p) : sp.meth[slot].value_at(p);
+            }
+            slot++;
+          }
+          *dst++ = make_int4(w0 + pb + p, (s + 1) | (code << 8), (int)meth, (int)(tot - meth));
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ea
