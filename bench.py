@@ -189,7 +189,7 @@ def run_ours(args):
     thr_alg = int(dev.nbytes) + 9 * int(dev.nrow)  # rcpp_threshold_reads alone: every XM byte once, 8 B offset read + 1 B flag written per row
     two_pass = dict(total_ms=round(tm.total_ms, 4), threshold_ms=round(tm.kernel_ms[0], 4), window_ms=round(tm.kernel_ms[1], 4),
                     rows=int(tm.n_rows), n_pass=int(tm.n_pass),
-                    threshold_kernel={"what": "rcpp_threshold_reads stand-alone (k_threshold_row + thr tables)", "algorithmic_bytes": thr_alg,
+                    threshold_kernel={"what": "rcpp_threshold_reads stand-alone (k_threshold_pl on the planar call planes + thr tables)", "algorithmic_bytes": thr_alg,
                                       "achieved_gbs": round(thr_alg / max(tm.kernel_ms[0], 1e-9) / 1e6, 1),
                                       "frac_of_hbm_peak": round(thr_alg / max(tm.kernel_ms[0], 1e-9) / 1e6 / measured_peak()[0], 4)})
 
@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--reads", type=int, default=READS_PER_GPU, help="reads per GPU (default: BASELINE configs[1])")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000)
     ap.add_argument("--ref-rows", type=int, default=500_000)
-    ap.add_argument("--policy", type=int, default=0, help="kernel policy for A/B runs: 0 automatic, 1 lane-group, 2 thread-per-row TMA")
+    ap.add_argument("--policy", type=int, default=0, help="kernel policy for A/B runs: 0 automatic (planar call planes), 5 automatic over the byte rows (round-1 kernels), 6 vertical counters, 1-4 single byte-row kernels")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

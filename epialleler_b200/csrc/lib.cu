@@ -72,32 +72,62 @@ struct Trace {
   void mark(const char* stage) { if (on) { cudaDeviceSynchronize(); const double t = now(); fprintf(stderr, "[ea]   %-28s %8.2f ms\n", stage, t - t0); t0 = t; } }
 };
 
-// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync) with an unlimited release threshold:
-// a handle packs and frees tens of GB per call, and plain cudaMalloc/cudaFree of such blocks costs tens to hundreds of
-// milliseconds (measured, EA_TRACE) while the pool hands the cached blocks back in microseconds.  ea_trim() returns the
-// cached memory to the driver.  Allocation and free are made synchronous here (the callers' work runs on other streams).
+// Device memory comes from a PRIVATE stream-ordered pool per device (cudaMemPoolCreate, unlimited release threshold; the
+// device's default pool, which other users of cudaMallocAsync in the process share, e.g. PyTorch, is left alone): a handle
+// packs and frees tens of GB per call, and plain cudaMalloc/cudaFree of such blocks costs tens to hundreds of milliseconds
+// (measured, EA_TRACE) while the pool hands the cached blocks back in microseconds.  ea_trim() returns the cached memory to
+// the driver.  Allocation is made synchronous here (the callers' work runs on other streams).
+constexpr int kMaxDevices = 64;
+cudaMemPool_t g_pools[kMaxDevices] = {};
+std::mutex g_pool_mu;
+
+cudaError_t ea_pool(int dev, cudaMemPool_t* out) {
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    cudaError_t e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    g_pools[dev] = pool;
+  }
+  *out = g_pools[dev];
+  return cudaSuccess;
+}
+
 cudaError_t pool_malloc(void** p, size_t bytes) {
-  static thread_local int configured_for = -1;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (configured_for != dev) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    configured_for = dev;
-  }
-  e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+  cudaMemPool_t pool;
+  if ((e = ea_pool(dev, &pool)) != cudaSuccess) return e;
+  e = cudaMallocFromPoolAsync(p, bytes, pool, cudaStreamPerThread);
   if (e != cudaSuccess) return e;
   return cudaStreamSynchronize(cudaStreamPerThread);
 }
 template <class T>
 cudaError_t pool_malloc(T** p, size_t bytes) { return pool_malloc(reinterpret_cast<void**>(p), bytes); }
+
+// Freeing a block that any stream may still use needs a device-wide synchronisation first (like cudaFree).  Code that
+// frees many blocks in a row opens a FreeScope: the first pool_free inside it synchronises, the others only free.
+thread_local int g_free_scope_depth = 0;
+thread_local bool g_free_scope_synced = false;
+struct FreeScope {
+  FreeScope() { if (g_free_scope_depth++ == 0) g_free_scope_synced = false; }
+  ~FreeScope() { --g_free_scope_depth; }
+};
 void pool_free(void* p) {
   if (!p) return;
-  cudaDeviceSynchronize();  // like cudaFree: nothing on any stream may still use the block
+  if (!(g_free_scope_depth > 0 && g_free_scope_synced)) {
+    cudaDeviceSynchronize();  // nothing on any stream may still use the block
+    g_free_scope_synced = true;
+  }
   cudaFreeAsync(p, cudaStreamPerThread);
 }
 
@@ -105,6 +135,15 @@ void pool_free(void* p) {
 void pool_free_on(void* p, cudaStream_t s) {
   if (p) cudaFreeAsync(p, s);
 }
+
+// temporaries of one call, all used on one stream: freed stream-ordered when the scope ends, early returns included
+struct StreamTmp {
+  cudaStream_t s;
+  std::vector<void*> v;
+  explicit StreamTmp(cudaStream_t stream) : s(stream) {}
+  ~StreamTmp() { for (void* p : v) pool_free_on(p, s); }
+  template <class T> T* keep(T* p) { v.push_back(p); return p; }
+};
 
 template <class T>
 int dmalloc(T** p, size_t n) {
@@ -121,6 +160,7 @@ struct WinIndex {
   int32_t* w_cnt = nullptr;
   int32_t max_rows = 0;  // largest hi-lo
   void release() {
+    FreeScope fs;
     pool_free(rname); pool_free(pos0); pool_free(lo); pool_free(hi); pool_free(w_base); pool_free(w_dst); pool_free(w_cnt);
     *this = WinIndex();
   }
@@ -449,8 +489,11 @@ int finish_handle(ea_handle* h) {
   if ((rc = dmalloc(&h->d_maxend, (size_t)h->n))) return rc;
   if ((rc = dmalloc(&h->d_sp, (size_t)h->n))) return rc;
   unsigned* d_flags; int32_t* d_maxlen;
+  StreamTmp tmps(h->stream);
   if ((rc = dmalloc(&d_flags, 1))) return rc;
+  tmps.keep(d_flags);
   if ((rc = dmalloc(&d_maxlen, 1))) return rc;
+  tmps.keep(d_maxlen);
   CU(cudaMemsetAsync(d_flags, 0, 4, h->stream));
   CU(cudaMemsetAsync(d_maxlen, 0, 4, h->stream));
   if (h->n > 0) {
@@ -458,14 +501,13 @@ int finish_handle(ea_handle* h) {
     size_t tb = 0;
     CU(cub::DeviceScan::InclusiveScan(nullptr, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
     void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
+    tmps.keep(tmp);
     CU(cub::DeviceScan::InclusiveScan(tmp, tb, h->d_maxend, h->d_maxend, MaxU64(), (int)h->n, h->stream));
-    pool_free_on(tmp, h->stream);
   }
   unsigned f = 0;
   CU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(&h->max_len, d_maxlen, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  pool_free_on(d_flags, h->stream); pool_free_on(d_maxlen, h->stream);
   CU(cudaGetLastError());
   h->rows32 = !(f & F_ODDCHUNKS);
   return flags_error(f & ~(unsigned)F_ODDCHUNKS);
@@ -482,19 +524,23 @@ int build_index(ea_handle* h, int S, WinIndex** out) {
   if (h->n == 0) return EA_OK;
   int rc;
   int32_t *d_cnt, *d_woff, *d_max;
+  StreamTmp tmps(h->stream);
   if ((rc = dmalloc(&d_cnt, (size_t)h->n))) return rc;
+  tmps.keep(d_cnt);
   if ((rc = dmalloc(&d_woff, (size_t)h->n))) return rc;
+  tmps.keep(d_woff);
   if ((rc = dmalloc(&d_max, 1))) return rc;
+  tmps.keep(d_max);
   k_count_windows<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), h->d_maxend, S, d_cnt);
   size_t tb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt, d_woff, (int)h->n, h->stream));
   void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
+  tmps.keep(tmp);
   CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_cnt, d_woff, (int)h->n, h->stream));
   int32_t last_off = 0, last_cnt = 0;
   CU(cudaMemcpyAsync(&last_off, d_woff + h->n - 1, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(&last_cnt, d_cnt + h->n - 1, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  pool_free(tmp);
   ix->n = last_off + last_cnt;
   if ((rc = dmalloc(&ix->rname, (size_t)ix->n))) return rc;
   if ((rc = dmalloc(&ix->pos0, (size_t)ix->n))) return rc;
@@ -510,7 +556,6 @@ int build_index(ea_handle* h, int S, WinIndex** out) {
   }
   CU(cudaMemcpyAsync(&ix->max_rows, d_max, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  pool_free(d_cnt); pool_free(d_woff); pool_free(d_max);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -1304,9 +1349,9 @@ int scan_windows(ea_handle* h, const WinIndex& ix) {
   size_t tb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, ix.w_dst, ix.n, h->stream));
   void* tmp = nullptr;
-  CU(cudaMallocAsync(&tmp, std::max<size_t>(tb, 1), h->stream));
+  CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
   CU(cub::DeviceScan::ExclusiveSum(tmp, tb, in, ix.w_dst, ix.n, h->stream));
-  CU(cudaFreeAsync(tmp, h->stream));
+  pool_free_on(tmp, h->stream);
   return EA_OK;
 }
 
@@ -1510,8 +1555,11 @@ int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_
                           const int32_t* d_templid /* null = identity */) {
   int rc;
   unsigned* d_flags; int64_t* d_padded;
+  StreamTmp tmps(nullptr);   // every kernel of this function runs on the default stream
   if ((rc = dmalloc(&d_flags, 1))) return rc;
+  tmps.keep(d_flags);
   if ((rc = dmalloc(&d_padded, (size_t)h->n + 1))) return rc;
+  tmps.keep(d_padded);
   if ((rc = dmalloc(&h->d_len, (size_t)h->n))) return rc;
   if ((rc = dmalloc(&h->d_off, (size_t)h->n + 1))) return rc;
   CU(cudaMemset(d_flags, 0, 4));
@@ -1525,29 +1573,30 @@ int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_
   size_t tb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_padded, h->d_off, (int)(h->n + 1)));
   void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
+  tmps.keep(tmp);
   CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_padded, h->d_off, (int)(h->n + 1)));
   unsigned f = 0;
   CU(cudaMemcpy(&f, d_flags, 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(&h->npadded, h->d_off + h->n, 8, cudaMemcpyDeviceToHost));
-  pool_free(tmp);
-  if (f) { pool_free(d_flags); pool_free(d_padded); return flags_error(f); }
+  if (f) return flags_error(f);
   // true byte total
   {
     int64_t* d_l64; int64_t* d_sum;
     if ((rc = dmalloc(&d_l64, (size_t)h->n))) return rc;
+    tmps.keep(d_l64);
     if ((rc = dmalloc(&d_sum, 1))) return rc;
+    tmps.keep(d_sum);
     if (h->n > 0) k_len_i64<<<grid_for(h->n, 256), 256>>>(h->d_len, h->n, d_l64);
     size_t tb2 = 0;
     CU(cub::DeviceReduce::Sum(nullptr, tb2, d_l64, d_sum, (int)h->n));
     void* tmp2; CU(pool_malloc(&tmp2, std::max<size_t>(tb2, 1)));
+    tmps.keep(tmp2);
     CU(cub::DeviceReduce::Sum(tmp2, tb2, d_l64, d_sum, (int)h->n));
     CU(cudaMemcpy(&h->nbytes, d_sum, 8, cudaMemcpyDeviceToHost));
-    pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
   }
   if ((rc = dmalloc(&h->d_data, (size_t)h->npadded + 16))) return rc;
   if (h->n > 0) k_repack<<<std::max(1, std::min(grid_for(h->n, 256), h->sm_count * 8)), 256>>>(d_blob, d_soff, d_templid, 0, h->n, h->d_off, h->d_len, h->d_data);
   CU(cudaDeviceSynchronize());
-  pool_free(d_flags); pool_free(d_padded);
   CU(cudaGetLastError());
   return EA_OK;
 }
@@ -1618,6 +1667,7 @@ void ea_free(ea_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   Trace tr("ea_free");
+  FreeScope fs;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->owns) {
     pool_free(h->d_rname); pool_free(h->d_strand); pool_free(h->d_start); pool_free(h->d_off); pool_free(h->d_data);
@@ -1675,11 +1725,24 @@ void* ea_host_alloc(size_t bytes) {
 
 void ea_host_free(void* p) {
   if (!p) return;
-  std::lock_guard<std::mutex> lk(g_host_mu);
-  auto it = g_host_live.find(p);
-  if (it == g_host_live.end()) return;
-  g_host_free.push_back(HostBlock{p, it->second});
-  g_host_live.erase(it);
+  std::vector<HostBlock> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host_live.find(p);
+    if (it == g_host_live.end()) return;
+    g_host_free.push_back(HostBlock{p, it->second});
+    g_host_live.erase(it);
+    // the cache of unused page-locked blocks is bounded (EA_PINNED_CACHE_MB, default 16 GiB): the oldest blocks go first
+    static const size_t cap = []() { const char* e = getenv("EA_PINNED_CACHE_MB"); return (size_t)(e ? std::max<long long>(0, atoll(e)) : 16384) << 20; }();
+    size_t held = 0;
+    for (auto& b : g_host_free) held += b.bytes;
+    while (held > cap && !g_host_free.empty()) {
+      held -= g_host_free.front().bytes;
+      drop.push_back(g_host_free.front());
+      g_host_free.erase(g_host_free.begin());
+    }
+  }
+  for (auto& b : drop) cudaFreeHost(b.p);
 }
 
 int ea_trim(int device) {
@@ -1687,7 +1750,7 @@ int ea_trim(int device) {
   if ((rc = pick_device(device))) return rc;
   cudaMemPool_t pool;
   CU(cudaDeviceSynchronize());
-  CU(cudaDeviceGetDefaultMemPool(&pool, device));
+  CU(ea_pool(device, &pool));
   CU(cudaMemPoolTrimTo(pool, 0));
   std::vector<HostBlock> blocks;
   {
@@ -1747,7 +1810,7 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   cudaStream_t sc = nullptr, sk = nullptr;
   cudaEvent_t ev_meta = nullptr, ev_chunk[kMaxChunks] = {};
   auto cleanup = [&]() {
-    cudaDeviceSynchronize();
+    FreeScope fs;
     pool_free(d_strand32); pool_free(d_templid); pool_free(d_soff); pool_free(d_blob); pool_free(d_flags); pool_free(d_padded); pool_free(d_tmp);
     if (sc) cudaStreamDestroy(sc);
     if (sk) cudaStreamDestroy(sk);
@@ -1814,6 +1877,13 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   TRY(dmalloc(&h->d_data, (size_t)h->npadded + 16));
   rc = finish_handle(h);  // validation + row keys on the handle's own stream, while the blob is in flight
   if (rc != EA_OK) { cleanup(); ea_free(h); return rc; }
+  // the planar call planes (planar.cuh) are filled tile by tile behind the repack of every chunk, like the byte rows
+  const bool planar = planar_wanted(h);
+  if (planar) {
+    TRY(planar_tiles(h, sk));
+    TRY(dmalloc(&h->d_pl_units, (size_t)h->pl_unit_rows * (h->pl_th == 32 ? 32 : 1)));
+  }
+  int64_t tiles_done = 0;
   const int rp_grid = std::max(1, h->sm_count * 8);
   for (int k = 0; k < n_chunks; k++) {
     const int64_t b0 = nstr > 0 ? off[s_begin[k]] : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] : 0;
@@ -1822,10 +1892,17 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
     if (by_chunk) {
       const int64_t r0 = std::min(s_begin[k], nrow), r1 = std::min(s_begin[k + 1], nrow);
       if (r1 > r0) k_repack<<<std::min(grid_for(r1 - r0, 256), rp_grid), 256, 0, sk>>>(d_blob, d_soff, nullptr, r0, r1, h->d_off, h->d_len, h->d_data);
+      if (planar) {  // the tiles whose rows are all repacked by now
+        const int64_t t1 = (k == n_chunks - 1 || r1 >= nrow) ? h->pl_tiles : (h->pl_th == 32 ? r1 >> 5 : r1);
+        TRY(planar_fill(h, tiles_done, t1, sk));
+        tiles_done = std::max(tiles_done, t1);
+      }
     }
   }
-  if (!by_chunk && nrow > 0)
+  if (!by_chunk && nrow > 0) {
     k_repack<<<std::min(grid_for(nrow, 256), rp_grid), 256, 0, sk>>>(d_blob, d_soff, d_templid, 0, nrow, h->d_off, h->d_len, h->d_data);
+    if (planar) TRY(planar_fill(h, 0, h->pl_tiles, sk));
+  }
   TRYCU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, sk));
   TRYCU(cudaStreamSynchronize(sk));
   TRYCU(cudaGetLastError());
@@ -1846,8 +1923,7 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
     TRYCU(cudaStreamSynchronize(sk));
     pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
   }
-  TRY(build_planar(h));
-  tr.mark("planar call planes");
+  h->pl_ok = planar;   // filled on sk, which has been synchronized above
   cleanup();
   tr.mark("free staging");
 #undef TRY
@@ -1956,7 +2032,7 @@ struct BedDev {
   int64_t *s_key = nullptr, *e_key = nullptr;
   int32_t *s_start = nullptr, *s_end = nullptr, *s_pmax = nullptr, *s_idx = nullptr, *e_idx = nullptr;
   int32_t n = 0;
-  void release() { pool_free(s_key); pool_free(e_key); pool_free(s_start); pool_free(s_end); pool_free(s_pmax); pool_free(s_idx); pool_free(e_idx); }
+  void release() { FreeScope fs; pool_free(s_key); pool_free(e_key); pool_free(s_start); pool_free(s_end); pool_free(s_pmax); pool_free(s_idx); pool_free(e_idx); }
 };
 
 // Sort the BED rows whose chromosome the BAM knows by (chr, start) and by (chr, end); file order index kept.
@@ -2048,7 +2124,7 @@ int ea_base_freqs(ea_handle* h, const uint8_t* pass, const int32_t* vcf_chr, con
   const size_t cells = (size_t)n_vcf * 20;
   unsigned int* d_counts = nullptr; double* d_out = nullptr; uint64_t* d_keys = nullptr; int32_t* d_idx = nullptr; uint8_t* d_p = nullptr;
   uint64_t* d_na_key = nullptr; int32_t* d_na_limit = nullptr; int32_t* d_limit = nullptr;
-  auto cleanup = [&]() { pool_free(d_counts); pool_free(d_out); pool_free(d_keys); pool_free(d_idx); pool_free(d_p); pool_free(d_na_key); pool_free(d_na_limit); pool_free(d_limit); };
+  auto cleanup = [&]() { FreeScope fs; pool_free(d_counts); pool_free(d_out); pool_free(d_keys); pool_free(d_idx); pool_free(d_p); pool_free(d_na_key); pool_free(d_na_limit); pool_free(d_limit); };
 #define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); return rc; } } while (0)
 #define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   TRY(dmalloc(&d_counts, cells));
@@ -2339,7 +2415,7 @@ int ea_cx_report_text(ea_handle* h, const char* const* rname_levels, int32_t n_l
   pool_free(h->d_text); h->d_text = nullptr; h->text_bytes = -1;
   const int64_t n = h->n_rows;
   char* d_chars = nullptr; int32_t* d_off = nullptr; int64_t* d_len = nullptr; int64_t* d_pos = nullptr; void* d_tmp = nullptr;
-  auto cleanup = [&]() { pool_free(d_chars); pool_free(d_off); pool_free(d_len); pool_free(d_pos); pool_free(d_tmp); };
+  auto cleanup = [&]() { FreeScope fs; pool_free(d_chars); pool_free(d_off); pool_free(d_len); pool_free(d_pos); pool_free(d_tmp); };
 #define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); return rc; } } while (0)
 #define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   TRY(dmalloc(&d_chars, chars.size()));
@@ -2519,23 +2595,26 @@ int ea_export_host(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* start
   }
   if (off || blob) {
     int64_t *d_l64, *d_toff;
+    StreamTmp tmps(nullptr);   // default-stream work below
     if ((rc = dmalloc(&d_l64, (size_t)n + 1))) return rc;
+    tmps.keep(d_l64);
     if ((rc = dmalloc(&d_toff, (size_t)n + 1))) return rc;
+    tmps.keep(d_toff);
     CU(cudaMemset(d_l64, 0, 8 * (size_t)(n + 1)));
     k_len_i64<<<grid_for(n, 256), 256>>>(h->d_len, n, d_l64);
     size_t tb = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_l64, d_toff, (int)(n + 1)));
     void* tmp; CU(pool_malloc(&tmp, std::max<size_t>(tb, 1)));
+    tmps.keep(tmp);
     CU(cub::DeviceScan::ExclusiveSum(tmp, tb, d_l64, d_toff, (int)(n + 1)));
     if (off) CU(cudaMemcpy(off, d_toff, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost));
     if (blob && h->nbytes > 0) {
       uint8_t* d_tight;
       if ((rc = dmalloc(&d_tight, (size_t)h->nbytes))) return rc;
+      tmps.keep(d_tight);
       k_unpad<<<std::max(1, std::min(grid_for(n * 32, 256), h->sm_count * 32)), 256>>>(h->d_data, h->d_off, h->d_len, d_toff, n, d_tight);
       CU(cudaMemcpy(blob, d_tight, (size_t)h->nbytes, cudaMemcpyDeviceToHost));
-      pool_free(d_tight);
     }
-    pool_free(tmp); pool_free(d_l64); pool_free(d_toff);
   }
   CU(cudaGetLastError());
   return EA_OK;

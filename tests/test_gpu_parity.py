@@ -88,6 +88,11 @@ SYNTH = {
     "long_reads": dict(seed=20261020, n_reads=300, chr_len=[900000, 500000], len_min=10000, len_max=30000),
     "tiny_reads": dict(seed=9, n_reads=30000, chr_len=[30000], len_min=1, len_max=40),
     "deep_amplicon": dict(seed=11, n_reads=70000, chr_len=[20000], len_min=120, len_max=260, n_islands=1, island_len=600),
+    # 32768..65535 rows over one 2048-position window: fused thresholds on the lane-group kernel's 16|16-bit counters
+    "amplicon_45k": dict(seed=12, n_reads=45000, chr_len=[20000], len_min=120, len_max=260, n_islands=1, island_len=600),
+    # long reads at ~400x: k_window_vsr with 9 planes per counter; at ~1000x: more rows per window than it takes -> k_window_plr
+    "long_reads_400x": dict(seed=13, n_reads=2000, chr_len=[100000], len_min=10000, len_max=30000),
+    "long_reads_1000x": dict(seed=14, n_reads=1500, chr_len=[40000], len_min=10000, len_max=30000),
 }
 SYNTH_CASES = [(True, "CG", 2, 0.5, 0.1, "CG"), (False, "CG", 2, 0.5, 0.1, "CX"), (True, "CHH", 1, 0.02, 0.9, "CxG"),
                (True, "CX", 3, 0.04, 0.1, "CHG")]
