@@ -147,6 +147,11 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit("launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
     host_affinity = bind_host_to_gpu(local) if world > 1 else "not set (single GPU)"
+    if world > 1:  # the ranks share the host's cores: the host-side transposition only pays with enough threads per rank
+        per_rank = max(1, (os.cpu_count() or 1) // world)
+        os.environ.setdefault("EA_HOST_PACK_THREADS", str(per_rank))
+        if per_rank < 8:
+            os.environ.setdefault("EA_HOST_PACK", "0")
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -254,6 +259,8 @@ def run_ours(args):
             t1 = time.perf_counter()
             b = ea.BamData(rn, st, sa, tid, blob, off, device=local)
             pass_flags, rep = ea.generateCytosineReport(b, return_pass=True, **THRESH)
+            h2d_actual = int(L.ea_pack_h2d_bytes(b.handle(need_bases=False)))
+            calls_only = not bool(L.ea_has_bytes(b.handle(need_bases=False)))
             b.close()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t1
@@ -261,9 +268,10 @@ def run_ours(args):
                 times.append(dt)
             rows_e2e = rep["pos"].shape[0]
         e2e_s = float(np.median(times))  # a pack allocates and frees ~20 GB: single outliers of the allocator are not the path's speed
-        h2d = int(blob.nbytes + off.nbytes + rn.nbytes + st.nbytes + sa.nbytes + tid.nbytes)
+        h2d_input = int(blob.nbytes + off.nbytes + rn.nbytes + st.nbytes + sa.nbytes + tid.nbytes)
         d2h = int(n_loc + 24 * rows_e2e)
-        e2e = dict(seconds=e2e_s, h2d=h2d, d2h=d2h, pinned=pinned, steps=e2e_steps, rows=rows_e2e, n_pass=int(pass_flags.sum()))
+        e2e = dict(seconds=e2e_s, h2d=h2d_actual, h2d_input=h2d_input, calls_only=calls_only, d2h=d2h, pinned=pinned, steps=e2e_steps,
+                   rows=rows_e2e, n_pass=int(pass_flags.sum()))
 
     ms_step = tot / args.steps
     stats = torch.tensor([ms_step, wall_ms / args.steps, win / args.steps, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device="cuda")
@@ -311,7 +319,11 @@ def run_ours(args):
         if e2e:
             line["e2e"] = {"value": tot_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "seconds_per_step": e2e_s, "pinned_host_memory": e2e["pinned"], "host_affinity": host_affinity, "steps": e2e["steps"],
-                           "what": "ea_pack_blob (H2D + device repack + validation + window index) + fused report + D2H of pass flags and rows + free"}
+                           "host_input_bytes_per_step": e2e["h2d_input"], "host_threads": os.environ.get("EA_HOST_PACK_THREADS", str(os.cpu_count())),
+                           "what": ("ea_pack_blob_calls (host threads transpose the strings of the pinned input into 4-bit call planes chunk by chunk while the previous chunk "
+                                    "crosses PCIe; validation + window index on the device) + fused report + D2H of pass flags and rows + free"
+                                    if e2e["calls_only"] else
+                                    "ea_pack_blob (H2D + device repack + validation + window index) + fused report + D2H of pass flags and rows + free")}
         if cpu:
             line["cpu_baseline"] = cpu
         if widened:

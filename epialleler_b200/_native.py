@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("EA_LIB_PATH") or os.path.join(HERE, "lib", "libepiall
 
 EA_SYNTH_MAX_CHR = 32
 
-ERRORS = {-1: "EA_ERR_ARG", -2: "EA_ERR_CUDA", -3: "EA_ERR_UNSORTED", -4: "EA_ERR_DOMAIN", -5: "EA_ERR_NODEVICE",
+EA_ERR_NEEDS_BYTES = -8
+ERRORS = {-8: "EA_ERR_NEEDS_BYTES", -1: "EA_ERR_ARG", -2: "EA_ERR_CUDA", -3: "EA_ERR_UNSORTED", -4: "EA_ERR_DOMAIN", -5: "EA_ERR_NODEVICE",
           -6: "EA_ERR_INTERRUPT", -7: "EA_ERR_STATE"}
 
 
@@ -58,6 +59,9 @@ SIGNATURES = {
     "ea_bed_report": (C.c_int, [_H, C.c_int, _I32P, _I32P, _I32P, C.c_int64, C.c_int32, C.POINTER(ReportParams), _U8P, _I32P, _U8P, _I64P]),
     "ea_pack": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_void_p), _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
     "ea_pack_blob": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, _U8P, _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
+    "ea_pack_blob_calls": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, _U8P, _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
+    "ea_has_bytes": (C.c_int, [_H]),
+    "ea_pack_h2d_bytes": (C.c_int64, [_H]),
     "ea_attach_device": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.POINTER(_H)]),
     "ea_free": (None, [_H]),
     "ea_trim": (C.c_int, [C.c_int]),

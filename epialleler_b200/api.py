@@ -6,6 +6,7 @@ function); the bodies only marshal numpy arrays across the C ABI (epialleler_b20
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 import gzip as _gzip
 from typing import Optional, Sequence
@@ -46,6 +47,7 @@ class BamData:
         self.rname_levels = list(rname_levels)
         self.device = device
         self._h = None
+        self._has_bases = True
         n = self.rname.shape[0]
         if not (self.strand.shape[0] == self.start.shape[0] == self.templid.shape[0] == n):
             raise ValueError("rname/strand/start/templid must have the same length")
@@ -70,15 +72,24 @@ class BamData:
         return self._blob, self._off
 
     # -- device handle ------------------------------------------------------------------------
-    def handle(self):
+    def handle(self, need_bases: bool = True):
+        """The packed device copy.  need_bases=False (the cytosine-report path: thresholds, betas, reports, BED matching) lets
+        the library pack the call codes only (ea_pack_blob_calls: the host transposes the strings into the bit-sliced call
+        planes while they cross PCIe, half the bytes); a later call that needs the byte rows (VCF, lMHL reports) repacks."""
+        L = N.lib()
+        if self._h is not None and need_bases and not self._has_bases:
+            self.close()
         if self._h is None:
-            L = N.lib()
             h = C.c_void_p()
             blob = self._blob if self._blob.shape[0] else np.zeros(1, np.uint8)
-            N.check(L.ea_pack_blob(_p(self.rname, C.c_int32), _p(self.strand, C.c_int32), _p(self.start, C.c_int32),
-                                   _p(self.templid, C.c_int32), self.nrow, _p(blob, C.c_uint8), _p(self._off, C.c_int64),
-                                   self.nstr, self.device, C.byref(h)))
+            calls_only = (not need_bases and os.environ.get("EA_HOST_PACK", "1") != "0" and L.ea_set_kernel_policy(-1) == 0
+                          and self.nrow == self.nstr and self.nrow > 0)
+            pack = L.ea_pack_blob_calls if calls_only else L.ea_pack_blob
+            N.check(pack(_p(self.rname, C.c_int32), _p(self.strand, C.c_int32), _p(self.start, C.c_int32),
+                         _p(self.templid, C.c_int32), self.nrow, _p(blob, C.c_uint8), _p(self._off, C.c_int64),
+                         self.nstr, self.device, C.byref(h)))
             self._h = h
+            self._has_bases = bool(L.ea_has_bytes(h))
         return self._h
 
     def close(self):
@@ -101,7 +112,7 @@ class DeviceBam:
         self.device = device
         self.rname_levels = []
 
-    def handle(self):
+    def handle(self, need_bases: bool = True):
         return self._h
 
     @property
@@ -146,6 +157,18 @@ def preprocessBam(bam_file, **kwargs):
                               "(BamData) as the reference allows (R/preprocessBam.R:226-235)")
 
 
+def _on_calls(df, fn):
+    """Run fn(handle) on a handle that may hold the call planes only; a request the planes cannot serve (unusual letter
+    sets, more than 65535 rows over a window, a non-default kernel policy) makes the library answer EA_ERR_NEEDS_BYTES:
+    pack again with the byte rows and repeat."""
+    try:
+        return fn(df.handle(need_bases=False))
+    except N.EaError as e:
+        if e.code != N.EA_ERR_NEEDS_BYTES:
+            raise
+        return fn(df.handle(need_bases=True))
+
+
 def _check_nrow(df):
     # the reference sizes its result by the number of strings and indexes templid by row
     # (src/rcpp_threshold_reads.cpp:27-33): anything else is out of contract
@@ -158,8 +181,8 @@ def rcpp_threshold_reads(df, ctx_meth, ctx_unmeth, ooctx_meth, ooctx_unmeth, min
     _check_nrow(df)
     L = N.lib()
     out = np.zeros(max(df.nrow, 1), np.uint8)
-    N.check(L.ea_threshold_reads(df.handle(), ctx_meth.encode(), ctx_unmeth.encode(), ooctx_meth.encode(), ooctx_unmeth.encode(),
-                                 int(min_n_ctx) & 0xFFFFFFFF, float(min_ctx_meth_frac), float(max_ooctx_meth_frac), _p(out, C.c_uint8)))
+    _on_calls(df, lambda h: N.check(L.ea_threshold_reads(h, ctx_meth.encode(), ctx_unmeth.encode(), ooctx_meth.encode(), ooctx_unmeth.encode(),
+                                                         int(min_n_ctx) & 0xFFFFFFFF, float(min_ctx_meth_frac), float(max_ooctx_meth_frac), _p(out, C.c_uint8))))
     return out[:df.nrow].astype(bool)
 
 
@@ -168,7 +191,7 @@ def rcpp_get_xm_beta(df, ctx_meth, ctx_unmeth):
     _check_nrow(df)
     L = N.lib()
     out = np.zeros(max(df.nrow, 1), np.float64)
-    N.check(L.ea_get_xm_beta(df.handle(), ctx_meth.encode(), ctx_unmeth.encode(), _p(out, C.c_double)))
+    _on_calls(df, lambda h: N.check(L.ea_get_xm_beta(h, ctx_meth.encode(), ctx_unmeth.encode(), _p(out, C.c_double))))
     return out[:df.nrow]
 
 
@@ -196,7 +219,7 @@ def _host_out(n, dtype):
 def _fetch_report(df, nrow):
     L = N.lib()
     cols = [_host_out(nrow, np.int32) for _ in range(6)]
-    N.check(L.ea_cx_report_fetch(df.handle(), *[_p(c, C.c_int32) for c in cols]))
+    N.check(L.ea_cx_report_fetch(df.handle(need_bases=False), *[_p(c, C.c_int32) for c in cols]))
     names = ("rname", "strand", "pos", "context", "meth", "unmeth")
     rep = {k: c[:nrow] for k, c in zip(names, cols)}
     rep["levels"] = {"rname": list(df.rname_levels), "strand": list(STRAND_LEVELS), "context": list(CONTEXT_LEVELS)}
@@ -215,7 +238,7 @@ def rcpp_cx_report(df, pass_, ctx):
         if pv.shape[0] != df.nrow:
             raise ValueError("length(pass) must equal nrow(bam)")
         pp = _p(pv if pv.shape[0] else np.zeros(1, np.uint8), C.c_uint8)
-    N.check(L.ea_cx_report(df.handle(), pp, ctx.encode(), C.byref(nrow)))
+    _on_calls(df, lambda h: N.check(L.ea_cx_report(h, pp, ctx.encode(), C.byref(nrow))))
     return _fetch_report(df, nrow.value)
 
 
@@ -250,7 +273,7 @@ def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshol
     p = _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, report_context)
     nrow = C.c_int64(0)
     pass_out = _host_out(bam.nrow, np.uint8) if return_pass else None
-    N.check(L.ea_cytosine_report(bam.handle(), C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow)))
+    _on_calls(bam, lambda h: N.check(L.ea_cytosine_report(h, C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow))))
     if report_file is not None:  # formatted on the device, the rows never become Python objects
         _write_report_text(report_text(bam), report_file, gzip)
         return None
@@ -316,7 +339,7 @@ def _bedp(a):
 def _match_target(df, mode, bed, param):
     c, s, e = _bed_cols(bed)
     out = np.empty(max(df.nrow, 1), np.int32)
-    N.check(N.lib().ea_match_target(df.handle(), mode, _bedp(c), _bedp(s), _bedp(e), c.shape[0], int(param), _p(out, C.c_int32)))
+    N.check(N.lib().ea_match_target(df.handle(need_bases=False), mode, _bedp(c), _bedp(s), _bedp(e), c.shape[0], int(param), _p(out, C.c_int32)))
     return out[:df.nrow]
 
 
@@ -363,9 +386,9 @@ def generateBedReport(bam, bed, report_file=None, bed_type="amplicon", match_tol
     p = _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, threshold_context)
     counts = np.zeros((nbed + 1) * 4, np.int64)
     match = np.empty(max(bam.nrow, 1), np.int32) if return_match else None
-    N.check(N.lib().ea_bed_report(bam.handle(), 0 if bed_type == "amplicon" else 1, _bedp(c), _bedp(s), _bedp(e), nbed,
-                                  int(match_tolerance if bed_type == "amplicon" else match_min_overlap), C.byref(p), None,
-                                  _p(match, C.c_int32) if return_match else None, None, _p(counts, C.c_int64)))
+    _on_calls(bam, lambda h: N.check(N.lib().ea_bed_report(h, 0 if bed_type == "amplicon" else 1, _bedp(c), _bedp(s), _bedp(e), nbed,
+                                                           int(match_tolerance if bed_type == "amplicon" else match_min_overlap), C.byref(p), None,
+                                                           _p(match, C.c_int32) if return_match else None, None, _p(counts, C.c_int64))))
     rep = _bed_table(counts, nbed)
     if not threshold_reads:
         rep["VEF"] = np.full(rep["VEF"].shape, np.nan)  # R/generateBedReport.R:264
@@ -581,10 +604,10 @@ def report_text(df, header=True):
     names = [str(x).encode() for x in df.rname_levels]
     arr = (C.c_char_p * max(len(names), 1))(*names)
     nbytes = C.c_int64(0)
-    N.check(L.ea_cx_report_text(df.handle(), arr, len(names), 1 if header else 0, C.byref(nbytes)))
+    N.check(L.ea_cx_report_text(df.handle(need_bases=False), arr, len(names), 1 if header else 0, C.byref(nbytes)))
     out = _host_out(nbytes.value, np.uint8)
     if nbytes.value:
-        N.check(L.ea_cx_report_text_fetch(df.handle(), out.ctypes.data_as(C.c_void_p)))
+        N.check(L.ea_cx_report_text_fetch(df.handle(need_bases=False), out.ctypes.data_as(C.c_void_p)))
     return out[:nbytes.value]
 
 

@@ -1,0 +1,163 @@
+// Host half of the "calls only" packer (ea_pack_blob_calls): turns the caller's byte-per-position strings into the planar
+// call planes of planar.cuh ON THE HOST, with all cores, so that 4 bits per position cross PCIe instead of 8.  The base
+// nibble (high nibble) is dropped - the cytosine-report path never reads it (`& 15`, src/rcpp_cx_report.cpp:117,
+// src/rcpp_threshold_reads.cpp:34).  One AVX2 instruction pair per bit plane: shift the wanted bit of every byte into
+// the byte's top bit, VPMOVMSKB gathers the 32 top bits = one plane word of a unit.
+// Plain C++ (g++), no CUDA: the library's C ABI functions in lib.cu drive it.
+#include "hostpack.h"
+
+#include <immintrin.h>
+
+#include <cstdint>
+#include <cstring>
+
+namespace eahp {
+
+namespace {
+
+inline bool valid_code(unsigned c) { return (0xFCE4u >> (c & 15u)) & 1u; }  // {2,5,6,7,10..15}
+
+// scalar: 32 bytes (n valid) -> one unit; returns false if a valid position holds a code outside the domain
+bool unit_scalar(const uint8_t* p, int n, uint32_t out[4]) {
+  uint32_t a = 0, b = 0, c = 0, d = 0;
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    const unsigned v = p[k] & 15u;
+    ok &= valid_code(v);
+    a |= (v & 1u) << k; b |= ((v >> 1) & 1u) << k; c |= ((v >> 2) & 1u) << k; d |= ((v >> 3) & 1u) << k;
+  }
+  out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+  return ok;
+}
+
+__attribute__((target("avx2"))) bool unit_avx2(const uint8_t* p, int n, uint32_t out[4]) {
+  __m256i v;
+  if (n >= 32) {
+    v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+  } else {  // the row's last unit: never read past the row
+    alignas(32) uint8_t tmp[32] = {0};
+    memcpy(tmp, p, (size_t)n);
+    v = _mm256_load_si256(reinterpret_cast<const __m256i*>(tmp));
+  }
+  const uint32_t keep = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+  out[0] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 7)) & keep;
+  out[1] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6)) & keep;
+  out[2] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5)) & keep;
+  out[3] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 4)) & keep;
+  // domain check: table lookup on the low nibbles, 0x80 for the codes the reference's readers emit
+  const __m256i tbl = _mm256_setr_epi8(0, 0, (char)0x80, 0, 0, (char)0x80, (char)0x80, (char)0x80, 0, 0, (char)0x80, (char)0x80, (char)0x80, (char)0x80,
+                                       (char)0x80, (char)0x80, 0, 0, (char)0x80, 0, 0, (char)0x80, (char)0x80, (char)0x80, 0, 0, (char)0x80, (char)0x80,
+                                       (char)0x80, (char)0x80, (char)0x80, (char)0x80);
+  const uint32_t okm = (uint32_t)_mm256_movemask_epi8(_mm256_shuffle_epi8(tbl, _mm256_and_si256(v, _mm256_set1_epi8(0x0F))));
+  return (okm & keep) == keep;
+}
+
+bool have_avx2() {
+  static const bool v = __builtin_cpu_supports("avx2");
+  return v;
+}
+
+}  // namespace
+
+unsigned scan_rows(const Job& job, int64_t t0, int64_t t1, uint32_t* ls, int32_t* tile_nu) {
+  unsigned flags = 0;
+  for (int64_t t = t0; t < t1; t++) {
+    int mx = 0;
+    const int64_t r1 = (t * 32 + 32 < job.n) ? t * 32 + 32 : job.n;
+    for (int64_t r = t * 32; r < r1; r++) {
+      if (job.templid && job.templid[r] != (int32_t)r) flags |= kNotIdentity;
+      const int64_t l = job.off[r + 1] - job.off[r];
+      if (l < 0 || l > 0x7FFFFFF0ll) { flags |= kBadLength; ls[r] = 0; continue; }
+      const int32_t s = job.strand[r];
+      if (s != 1 && s != 2) flags |= kBadStrand;
+      ls[r] = (uint32_t)l | (s == 2 ? 0x80000000u : 0u);
+      const int nu = (int)((l + 31) >> 5);
+      if (nu > mx) mx = nu;
+    }
+    tile_nu[t] = mx;
+  }
+  return flags;
+}
+
+// unit without the domain check (the device validates the planes it receives): full 32-byte load, garbage beyond n masked
+__attribute__((target("avx2"))) static inline void unit_avx2_fast(const uint8_t* p, int n, __m128i* dst) {
+  const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+  const uint32_t keep = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+  const uint32_t a = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 7)) & keep;
+  const uint32_t b = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6)) & keep;
+  const uint32_t c = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5)) & keep;
+  const uint32_t d = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 4)) & keep;
+  _mm_stream_si128(dst, _mm_set_epi32((int)d, (int)c, (int)b, (int)a));   // written once, read by the DMA engine only
+}
+
+__attribute__((target("avx2"))) static void pack_tiles_avx2(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst) {
+  const uint8_t* const safe_end = job.blob + job.off[job.n] - 32;   // a full 32-byte load at or below this address stays inside the blob
+  for (int64_t t = t0; t < t1; t++) {
+    __m128i* tile = reinterpret_cast<__m128i*>(dst + (toff[t] - toff[t0]) * 512);
+    const int nu_t = (int)(toff[t + 1] - toff[t]);
+    const uint8_t* row[32];
+    int len[32];
+    for (int l = 0; l < 32; l++) {
+      const int64_t r = t * 32 + l;
+      if (r < job.n) { row[l] = job.blob + job.off[r]; len[l] = (int)(job.off[r + 1] - job.off[r]); }
+      else { row[l] = job.blob; len[l] = 0; }
+    }
+    for (int j = 0; j < nu_t; j++) {   // unit-major: the tile's 512-byte unit rows are written front to back
+      for (int l = 0; l < 32; l++) {
+        const int n = len[l] - 32 * j;
+        const uint8_t* p = row[l] + 32 * j;
+        if (n <= 0) { _mm_stream_si128(tile + j * 32 + l, _mm_setzero_si128()); continue; }
+        if (p <= safe_end) { unit_avx2_fast(p, n, tile + j * 32 + l); continue; }
+        alignas(32) uint8_t tmp[32] = {0};
+        memcpy(tmp, p, (size_t)(n < 32 ? n : 32));
+        unit_avx2_fast(tmp, n, tile + j * 32 + l);
+      }
+    }
+  }
+  _mm_sfence();
+}
+
+unsigned pack_tiles(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst) {
+  if (have_avx2() && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) { pack_tiles_avx2(job, toff, t0, t1, dst); return 0u; }
+  bool ok = true;
+  for (int64_t t = t0; t < t1; t++) {
+    uint8_t* tile = dst + (toff[t] - toff[t0]) * 512;
+    const int nu_t = (int)(toff[t + 1] - toff[t]);
+    for (int l = 0; l < 32; l++) {
+      const int64_t r = t * 32 + l;
+      int64_t len = 0;
+      const uint8_t* row = nullptr;
+      if (r < job.n) { len = job.off[r + 1] - job.off[r]; row = job.blob + job.off[r]; }
+      const int nu = (int)((len + 31) >> 5);
+      for (int j = 0; j < nu_t; j++) {
+        uint32_t u[4] = {0, 0, 0, 0};
+        if (j < nu) {
+          const int n = (int)(len - 32 * (int64_t)j < 32 ? len - 32 * (int64_t)j : 32);
+          ok &= unit_scalar(row + 32 * j, n, u);
+        }
+        memcpy(tile + ((size_t)j * 32 + l) * 16, u, 16);
+      }
+    }
+  }
+  return ok ? 0u : kBadCode;
+}
+
+unsigned pack_rows(const Job& job, const int64_t* uoff, int64_t r0, int64_t r1, uint8_t* dst) {
+  const bool avx2 = have_avx2();
+  bool ok = true;
+  for (int64_t r = r0; r < r1; r++) {
+    const int64_t len = job.off[r + 1] - job.off[r];
+    const uint8_t* row = job.blob + job.off[r];
+    uint8_t* d = dst + (uoff[r] - uoff[r0]) * 16;
+    const int64_t nu = (len + 31) >> 5;
+    for (int64_t j = 0; j < nu; j++) {
+      uint32_t u[4];
+      const int n = (int)(len - 32 * j < 32 ? len - 32 * j : 32);
+      ok &= avx2 ? unit_avx2(row + 32 * j, n, u) : unit_scalar(row + 32 * j, n, u);
+      memcpy(d + j * 16, u, 16);
+    }
+  }
+  return ok ? 0u : kBadCode;
+}
+
+}  // namespace eahp

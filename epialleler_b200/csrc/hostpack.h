@@ -1,0 +1,25 @@
+// Host half of the "calls only" packer, see hostpack.cpp.  Internal to the library.
+#pragma once
+#include <cstdint>
+
+namespace eahp {
+
+struct Job {
+  const uint8_t* blob;      // the strings, one after the other (file order == row order)
+  const int64_t* off;       // n + 1 offsets
+  const int32_t* strand;    // 1 '+', 2 '-'
+  const int32_t* templid;   // nullptr or the identity
+  int64_t n;
+};
+
+enum : unsigned { kNotIdentity = 1u, kBadLength = 2u, kBadStrand = 4u, kBadCode = 8u };
+
+// pass 1 over the rows of tiles [t0, t1) (tiles of 32 rows): ls[r] = length | (strand == '-') << 31, tile_nu[t] = unit rows
+// of tile t (max over its rows of ceil(length / 32)); returns the OR of the flags above
+unsigned scan_rows(const Job& job, int64_t t0, int64_t t1, uint32_t* ls, int32_t* tile_nu);
+// planar units of tiles [t0, t1) in the tile-interleaved layout of planar.cuh; dst = where tile t0 starts
+unsigned pack_tiles(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst);
+// long-read layout (units of a row contiguous): rows [r0, r1), uoff = per-row unit offsets; dst = where row r0 starts
+unsigned pack_rows(const Job& job, const int64_t* uoff, int64_t r0, int64_t r1, uint8_t* dst);
+
+}  // namespace eahp

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -36,6 +38,7 @@
 #include "planar.cuh"
 #include "window_vs.cuh"
 #include "synth.h"
+#include "hostpack.h"
 
 namespace {
 
@@ -175,6 +178,8 @@ struct ea_handle {
   int64_t npadded = 0;  // bytes of the padded data array
   int32_t max_len = 0;
   bool rows32 = false;  // every padded row is a multiple of 32 bytes (pairs of chunks can be handled as one unit)
+  bool has_bytes = true;   // false: packed by ea_pack_blob_calls - call planes only, no byte rows (base codes dropped)
+  int64_t h2d_bytes = 0;   // bytes the packer sent over PCIe
   bool owns = true;
   int32_t* d_rname = nullptr;
   uint8_t* d_strand = nullptr;
@@ -560,6 +565,54 @@ int build_index(ea_handle* h, int S, WinIndex** out) {
   return EA_OK;
 }
 
+__global__ void k_unpack_ls(const uint32_t* __restrict__ ls, int64_t n, int32_t* __restrict__ len, uint8_t* __restrict__ strand) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t v = ls[r];
+  len[r] = (int32_t)(v & 0x7FFFFFFFu);
+  strand[r] = (uint8_t)(1u + (v >> 31));
+}
+
+// call planes that came from the host (ea_pack_blob_calls): every position inside a row must hold one of the codes the
+// reference's readers emit {2,5,6,7,10..15}, every position beyond the row's end code 0
+__global__ void k_validate_planes(Planar pl, int64_t n_tiles, int th, unsigned* flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  bool bad = false;
+  for (int64_t t = warp; t < n_tiles; t += n_warps) {
+    const int64_t u0 = pl.toff[t];
+    const int nu_t = (int)(pl.toff[t + 1] - u0);
+    if (th == 32) {
+      const int64_t r = t * 32 + lane;
+      const int len = r < pl.n ? (int)(pl.ls[r] & 0x7FFFFFFFu) : 0;
+      for (int j = 0; j < nu_t; j++) {
+        const uint4 v = ldg_plunit(pl.units + (u0 + j) * 32 + lane);
+        const int nv = len - 32 * j;
+        const uint32_t in = nv >= 32 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : (1u << nv) - 1u);
+        const uint32_t valid = (v.w & (v.z | v.y)) | (~v.w & ((v.z & (v.x | v.y)) | (~v.z & v.y & ~v.x)));
+        bad |= ((~valid & in) | ((v.x | v.y | v.z | v.w) & ~in)) != 0u;
+      }
+    } else {
+      const int len = (int)(pl.ls[t] & 0x7FFFFFFFu);
+      for (int j = lane; j < nu_t; j += 32) {
+        const uint4 v = ldg_plunit(pl.units + u0 + j);
+        const int nv = len - 32 * j;
+        const uint32_t in = nv >= 32 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : (1u << nv) - 1u);
+        const uint32_t valid = (v.w & (v.z | v.y)) | (~v.w & ((v.z & (v.x | v.y)) | (~v.z & v.y & ~v.x)));
+        bad |= ((~valid & in) | ((v.x | v.y | v.z | v.w) & ~in)) != 0u;
+      }
+    }
+  }
+  if (bad) atomicOr(flags, (unsigned)F_DOMAIN);
+}
+
+#define NEED_BYTES(h)                                                                                                   \
+  do {                                                                                                                  \
+    if (!(h)->has_bytes)                                                                                                \
+      return fail(EA_ERR_NEEDS_BYTES, "this handle holds the call planes only (ea_pack_blob_calls): pack with ea_pack_blob for this call"); \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // planar call planes (planar.cuh): built once per handle from the padded byte rows
 // ---------------------------------------------------------------------------------------------
@@ -717,6 +770,8 @@ int launch_threshold(ea_handle* h, const ThresholdSpec& spec, const ThrParams& t
                      unsigned long long* n_pass) {
   if (h->n == 0) return EA_OK;
   int rc = EA_OK;
+  const bool planar_ok = h->pl_ok && (g_kernel_policy == 0 || g_kernel_policy == 6);
+  if (!(planar_ok && spec.tctx >= 0)) NEED_BYTES(h);   // the generic letter-set kernel and the byte-row kernels read the byte rows
   if (spec.tctx < 0 || (h->max_len > 65535 && !(h->pl_ok && (g_kernel_policy == 0 || g_kernel_policy == 6)))) {
     k_threshold_generic<<<grid_for(h->n, 256), 256, 0, h->stream>>>(csr_of(h), spec.lw, tp, pass, beta, n_pass);
   } else {
@@ -1422,6 +1477,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
     if (pln.ok) ix = ixp;
   }
   const bool byte_auto = ((policy == 0 || policy == 6) && !pln.ok && !vsp.ok && !vsr_k) || policy == 5;
+  if (rp.want && !pln.ok && !vsp.ok && !vsr_k) NEED_BYTES(h);   // the byte-row kernels
   if (rp.want && !pln.ok && !vsp.ok && !vsr_k) {
     if (byte_auto && nc == 1 && h->rows32 && ((h->max_len + 31) >> 5) <= 8) {
       const int S = pick_row_window(h, *ix);
@@ -1661,7 +1717,7 @@ int ea_device_count(void) {
   return n;
 }
 void ea_set_poll(ea_poll_fn fn) { g_poll = fn; }
-int ea_set_kernel_policy(int policy) { const int old = g_kernel_policy; g_kernel_policy = policy; return old; }
+int ea_set_kernel_policy(int policy) { const int old = g_kernel_policy; if (policy >= 0) g_kernel_policy = policy; return old; }
 
 void ea_free(ea_handle* h) {
   if (!h) return;
@@ -1924,6 +1980,7 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
     pool_free(tmp2); pool_free(d_l64); pool_free(d_sum);
   }
   h->pl_ok = planar;   // filled on sk, which has been synchronized above
+  h->h2d_bytes = total + 8 * (nstr + 1) + 4 * nrow * (templid ? 4 : 3);
   cleanup();
   tr.mark("free staging");
 #undef TRY
@@ -1932,6 +1989,215 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   return EA_OK;
 }
 }  // namespace
+
+// Calls-only packer: the host transposes the strings into the planar call planes (hostpack.cpp, all cores, AVX2) chunk by
+// chunk into a ring of page-locked staging blocks while the previous chunk crosses PCIe, so 4 bits per position travel
+// instead of 8 and the device does no repacking at all.  The handle has no byte rows (has_bytes = false): everything on
+// the cytosine-report path works on it (thresholds, betas, reports, BED matching), the base-level paths (VCF, lMHL,
+// ea_export_host) answer EA_ERR_NEEDS_BYTES.  Falls back to ea_pack_blob when rows are not the strings in file order.
+namespace {
+// worker threads that live for one pack call: run(fn) executes fn(thread index) on all of them and returns when all are done
+class PackPool {
+ public:
+  explicit PackPool(int n) : n_(n) {
+    for (int t = 0; t < n_; t++) th_.emplace_back([this, t]() { loop(t); });
+  }
+  ~PackPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+    cv_start_.notify_all();
+    for (auto& x : th_) x.join();
+  }
+  void run(const std::function<void(int)>& fn) {
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn; pending_ = n_; gen_++;
+    cv_start_.notify_all();
+    cv_done_.wait(lk, [this]() { return pending_ == 0; });
+  }
+  // [lo, hi) in pieces of `grain`, handed out dynamically
+  void parallel_for(int64_t lo, int64_t hi, int64_t grain, const std::function<void(int64_t, int64_t)>& body) {
+    std::atomic<int64_t> next{lo};
+    run([&](int) {
+      for (;;) {
+        const int64_t a = next.fetch_add(grain);
+        if (a >= hi) break;
+        body(a, std::min(hi, a + grain));
+      }
+    });
+  }
+
+ private:
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_start_.wait(lk, [&]() { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        fn = fn_;
+      }
+      (*fn)(t);
+      { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) cv_done_.notify_one(); }
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_start_, cv_done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+}  // namespace
+
+int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                       int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out) {
+  if (!out) return fail(EA_ERR_ARG, "null out");
+  *out = nullptr;
+  if (nrow != nstr || nrow <= 0) return ea_pack_blob(rname, strand, start, templid, nrow, blob, off, nstr, device, out);
+  if (!rname || !strand || !start || !off) return fail(EA_ERR_ARG, "null column");
+  if (off[0] != 0) return fail(EA_ERR_ARG, "string offsets must start at 0");
+  const int64_t total = off[nstr];
+  if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
+  if (nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row/string count");
+  int rc;
+  if ((rc = pick_device(device))) return rc;
+  Trace tr("ea_pack_blob_calls");
+  int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  if (const char* e = getenv("EA_HOST_PACK_THREADS")) nt = std::max(1, atoi(e));
+  PackPool pool(nt);
+  const eahp::Job job{blob, off, strand, templid, nrow};
+  const int64_t n_tiles32 = (nrow + 31) >> 5;
+
+  ea_handle* h = new ea_handle;
+  h->device = device; h->n = nrow; h->has_bytes = false; h->nbytes = total; h->npadded = 0;
+  constexpr int kSlots = 3;
+  cudaStream_t sc = nullptr;
+  cudaEvent_t ev_slot[kSlots] = {};
+  uint8_t* stage[kSlots] = {};
+  uint32_t* ls = nullptr; int32_t* tile_nu = nullptr; int64_t* toff = nullptr;
+  unsigned* d_flags = nullptr;
+  auto cleanup = [&]() {
+    if (sc) { cudaStreamSynchronize(sc); cudaStreamDestroy(sc); }
+    for (auto& e : ev_slot) if (e) cudaEventDestroy(e);
+    for (auto& p : stage) ea_host_free(p);
+    ea_host_free(ls); ea_host_free(tile_nu); ea_host_free(toff);
+    pool_free(d_flags);
+  };
+#define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); ea_free(h); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  TRYCU(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+  for (auto& e : ev_slot) TRYCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  // ---- the two columns the device takes as they are travel while the host makes its first pass over the rows ----
+  TRY(dmalloc(&h->d_rname, (size_t)nrow));
+  TRY(dmalloc(&h->d_start, (size_t)nrow));
+  TRYCU(cudaMemcpyAsync(h->d_rname, rname, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
+  TRYCU(cudaMemcpyAsync(h->d_start, start, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
+  // ---- pass 1: lengths, strands, unit rows per tile ----
+  ls = static_cast<uint32_t*>(ea_host_alloc(4 * (size_t)nrow));
+  tile_nu = static_cast<int32_t*>(ea_host_alloc(4 * (size_t)n_tiles32));
+  if (!ls || !tile_nu) { cleanup(); ea_free(h); return EA_ERR_CUDA; }
+  std::atomic<unsigned> flags{0};
+  std::atomic<int64_t> true_max{0};
+  pool.parallel_for(0, n_tiles32, 4096, [&](int64_t a, int64_t b) {
+    flags |= eahp::scan_rows(job, a, b, ls, tile_nu);
+    int64_t m = 0;
+    for (int64_t r = a * 32; r < std::min(b * 32, nrow); r++) m = std::max<int64_t>(m, ls[r] & 0x7FFFFFFFu);
+    int64_t cur = true_max.load();
+    while (m > cur && !true_max.compare_exchange_weak(cur, m)) {}
+  });
+  const int64_t max_l = true_max.load();
+  if ((flags & eahp::kNotIdentity) || max_l < 1) {   // rows are not the strings in file order (or there is nothing to pack): the general packer
+    cleanup(); ea_free(h);
+    return ea_pack_blob(rname, strand, start, templid, nrow, blob, off, nstr, device, out);
+  }
+  if (flags & eahp::kBadLength) { cleanup(); ea_free(h); return fail(EA_ERR_ARG, "string length / end position does not fit 31 bits"); }
+  if (flags & eahp::kBadStrand) { cleanup(); ea_free(h); return fail(EA_ERR_ARG, "strand must be 1 ('+') or 2 ('-')"); }
+  const int th = max_l <= 1024 ? 32 : 1;
+  const int64_t n_tiles = th == 32 ? n_tiles32 : nrow;
+  toff = static_cast<int64_t*>(ea_host_alloc(8 * (size_t)(n_tiles + 1)));
+  if (!toff) { cleanup(); ea_free(h); return EA_ERR_CUDA; }
+  toff[0] = 0;
+  if (th == 32) for (int64_t t = 0; t < n_tiles; t++) toff[t + 1] = toff[t] + tile_nu[t];
+  else for (int64_t r = 0; r < nrow; r++) toff[r + 1] = toff[r] + (((ls[r] & 0x7FFFFFFFu) + 31u) >> 5);
+  const int64_t unit_bytes = th == 32 ? 512 : 16;     // bytes per toff step
+  const int64_t total_units_bytes = toff[n_tiles] * unit_bytes;
+  h->pl_th = th; h->pl_tiles = n_tiles; h->pl_unit_rows = toff[n_tiles];
+  tr.mark("host pass 1");
+
+  TRY(dmalloc(&h->d_strand, (size_t)nrow));
+  TRY(dmalloc(&h->d_len, (size_t)nrow));
+  TRY(dmalloc(&h->d_pl_ls, (size_t)nrow));
+  TRY(dmalloc(&h->d_pl_toff, (size_t)n_tiles + 1));
+  TRY(dmalloc(&h->d_pl_units, (size_t)(total_units_bytes / 16)));
+  TRY(dmalloc(&d_flags, 1));
+  TRYCU(cudaMemsetAsync(d_flags, 0, 4, sc));
+  TRYCU(cudaMemcpyAsync(h->d_pl_ls, ls, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
+  TRYCU(cudaMemcpyAsync(h->d_pl_toff, toff, 8 * (size_t)(n_tiles + 1), cudaMemcpyHostToDevice, sc));
+  k_unpack_ls<<<grid_for(nrow, 256), 256, 0, sc>>>(h->d_pl_ls, nrow, h->d_len, h->d_strand);
+  h->h2d_bytes = 12 * nrow + 8 * (n_tiles + 1) + total_units_bytes;
+  // ---- the planes, chunk by chunk: all threads transpose chunk k into a staging block while chunk k-1 is in flight ----
+  int64_t chunk_bytes = 128ll << 20;
+  if (const char* e = getenv("EA_PACK_CHUNK_MB")) chunk_bytes = std::max<int64_t>(1, atoll(e)) << 20;
+  int64_t stage_bytes = 0;
+  std::vector<int64_t> cuts{0};
+  for (int64_t t = 0; t < n_tiles;) {   // the largest run of tiles that fits a chunk (binary search on the prefix sums; at least one tile)
+    int64_t a = t + 1, b = n_tiles;
+    while (a < b) {
+      const int64_t m = (a + b + 1) >> 1;
+      if ((toff[m] - toff[t]) * unit_bytes <= chunk_bytes) a = m; else b = m - 1;
+    }
+    stage_bytes = std::max(stage_bytes, (toff[a] - toff[t]) * unit_bytes);
+    cuts.push_back(a);
+    t = a;
+  }
+  for (auto& p : stage) { p = static_cast<uint8_t*>(ea_host_alloc((size_t)std::max<int64_t>(stage_bytes, 1))); if (!p) { cleanup(); ea_free(h); return EA_ERR_CUDA; } }
+  bool finished = false;
+  for (size_t k = 0; k + 1 < cuts.size(); k++) {
+    const int slot = (int)(k % kSlots);
+    const int64_t t0 = cuts[k], t1 = cuts[k + 1];
+    if (k >= (size_t)kSlots) TRYCU(cudaEventSynchronize(ev_slot[slot]));   // the copy that last used this block is done
+    uint8_t* dst = stage[slot];
+    const int64_t grain = std::max<int64_t>(1, th == 32 ? 512 : 4096 / std::max<int64_t>(1, (max_l + 31) >> 5));
+    pool.parallel_for(t0, t1, grain, [&](int64_t a, int64_t b) {
+      uint8_t* d = dst + (toff[a] - toff[t0]) * unit_bytes;
+      flags |= th == 32 ? eahp::pack_tiles(job, toff, a, b, d) : eahp::pack_rows(job, toff, a, b, d);
+    });
+    const int64_t bytes = (toff[t1] - toff[t0]) * unit_bytes;
+    if (bytes > 0) TRYCU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->d_pl_units) + toff[t0] * unit_bytes, dst, (size_t)bytes, cudaMemcpyHostToDevice, sc));
+    TRYCU(cudaEventRecord(ev_slot[slot], sc));
+    if (!finished && k >= 1) {   // the metadata have landed long ago: validation + row keys on the handle's own stream, overlapped
+      TRYCU(cudaEventSynchronize(ev_slot[0]));
+      rc = finish_handle(h);
+      if (rc != EA_OK) { cleanup(); ea_free(h); return rc; }
+      finished = true;
+    }
+  }
+  // the device checks what it received: codes inside the domain, nothing beyond the rows' ends
+  {
+    Planar pl; pl.units = h->d_pl_units; pl.toff = h->d_pl_toff; pl.ls = h->d_pl_ls; pl.start = h->d_start; pl.n = nrow;
+    k_validate_planes<<<(int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + 7) / 8, 148 * 32)), 256, 0, sc>>>(pl, n_tiles, th, d_flags);
+  }
+  unsigned dflags = 0;
+  TRYCU(cudaMemcpyAsync(&dflags, d_flags, 4, cudaMemcpyDeviceToHost, sc));
+  TRYCU(cudaStreamSynchronize(sc));
+  TRYCU(cudaGetLastError());
+  tr.mark("host transposition + H2D");
+  if (!finished) { rc = finish_handle(h); if (rc != EA_OK) { cleanup(); ea_free(h); return rc; } }
+  if ((flags & eahp::kBadCode) || (dflags & F_DOMAIN)) { cleanup(); ea_free(h); return flags_error(F_DOMAIN); }
+  if (h->max_len != (int32_t)max_l) { cleanup(); ea_free(h); return fail(EA_ERR_STATE, "length bookkeeping mismatch"); }
+  h->pl_ok = true;
+  cleanup();
+#undef TRY
+#undef TRYCU
+  *out = h;
+  return EA_OK;
+}
+
+int ea_has_bytes(const ea_handle* h) { return h && h->has_bytes ? 1 : 0; }
+int64_t ea_pack_h2d_bytes(const ea_handle* h) { return h ? h->h2d_bytes : -1; }
 
 int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
             const uint8_t* const* str, const int64_t* len, int64_t nstr, int device, ea_handle** out) {
@@ -2106,6 +2372,7 @@ int ea_base_freqs(ea_handle* h, const uint8_t* pass, const int32_t* vcf_chr, con
   if (n_vcf < 0 || n_vcf > 0x7FFFFFFFll || (n_vcf > 0 && (!vcf_chr || !vcf_pos || !freqs_out))) return fail(EA_ERR_ARG, "bad VCF table");
   if (n_vcf == 0) return EA_OK;
   int rc;
+  NEED_BYTES(h);   // base codes are the HIGH nibble
   CU(cudaSetDevice(h->device));
   std::vector<uint64_t> keys, na_key;     // valid entries; per NA entry the key of the last valid entry in front of it
   std::vector<int32_t> idx, na_after;     // row in the caller's table; per NA entry the number of valid entries in front of it
@@ -2269,6 +2536,7 @@ int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, dou
   int rc;
   CU(cudaSetDevice(h->device));
   h->mhl_rows = -1;
+  NEED_BYTES(h);
   if (h->max_len > 65535) return fail(EA_ERR_ARG, "lMHL report: rows longer than 65535 bytes are not supported (the reference's lookup table ends there)");
   MhlParams prm;
   prm.ctx_mask = 0;
@@ -2586,6 +2854,7 @@ int ea_export_host(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* start
   const int64_t n = h->n;
   if (n == 0) { if (off) off[0] = 0; return EA_OK; }
   int rc;
+  if (off || blob) NEED_BYTES(h);
   if (rname) CU(cudaMemcpy(rname, h->d_rname, 4 * (size_t)n, cudaMemcpyDeviceToHost));
   if (start) CU(cudaMemcpy(start, h->d_start, 4 * (size_t)n, cudaMemcpyDeviceToHost));
   if (strand) {

@@ -51,6 +51,7 @@ extern "C" {
 #define EA_ERR_NODEVICE (-5) /* no CUDA device: there is NO CPU fallback */
 #define EA_ERR_INTERRUPT (-6)/* the poll callback asked to stop */
 #define EA_ERR_STATE (-7)    /* call order (e.g. fetch before report) */
+#define EA_ERR_NEEDS_BYTES (-8) /* the handle was packed by ea_pack_blob_calls (call planes only): this call needs ea_pack_blob */
 
 typedef struct ea_handle ea_handle;
 
@@ -67,7 +68,9 @@ void ea_set_poll(ea_poll_fn fn);
  * kernel (flags from the stand-alone threshold pass), else - more than 32767 rows over one window - the general
  * lane-group kernel), 1 always the lane-group kernel, 2 prefer the thread-per-row TMA kernel (reads up to 512 bytes),
  * 3 prefer the chunk-per-lane kernel, 4 prefer the long-read kernel (any read length; thresholding runs as its own pass).
- * Returns the previous policy.  Results are identical either way; used by the parity tests and A/B timing. */
+ * 5 automatic over the byte rows only, 6 prefer the vertical-counter kernel; 0 (default) prefers the kernels on the planar
+ * call planes.  A negative value only queries.  Returns the previous policy.  Results are identical either way; used by the
+ * parity tests and A/B timing. */
 int ea_set_kernel_policy(int policy);
 
 /* ---- packer: host bam.data -> device-resident CSR (row order) ------------------------------ */
@@ -82,6 +85,19 @@ int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, c
 int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                  int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device,
                  ea_handle** out);
+
+/* Calls-only variant of ea_pack_blob for the cytosine-report path (thresholds, betas, reports, BED matching): the host
+ * transposes the strings into the library's bit-sliced call planes with all its cores while the previous chunk crosses
+ * PCIe, so 4 bits per position travel instead of 8 (the base code in the high nibble, which this path never reads -
+ * `& 15`, src/rcpp_cx_report.cpp:117 - is dropped).  Needs rows == strings in file order (templid NULL or the identity, what
+ * preprocessBam produces); anything else is handed to ea_pack_blob.  Calls that need the byte rows (ea_base_freqs,
+ * ea_mhl_report, ea_export_host, non-default kernel policies, unusual letter sets) return EA_ERR_NEEDS_BYTES on such a
+ * handle.  EA_HOST_PACK_THREADS overrides the number of host threads (default: all, at most 32). */
+int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                       int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device,
+                       ea_handle** out);
+int ea_has_bytes(const ea_handle* h);            /* 1: byte rows present (ea_pack, ea_pack_blob, ...), 0: call planes only */
+int64_t ea_pack_h2d_bytes(const ea_handle* h);   /* bytes the packer copied host -> device for this handle */
 
 /* Adopt CSR arrays that already live on `device` in ROW order (d_off: nrow+1 int64, d_strand: 1|2 as
  * uint8).  The handle takes ownership iff take_ownership != 0 (pointers must come from cudaMalloc). */
