@@ -2067,35 +2067,79 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   Trace tr("ea_pack_blob_calls");
   int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
   if (const char* e = getenv("EA_HOST_PACK_THREADS")) nt = std::max(1, atoi(e));
+  if (nt < 6 && !getenv("EA_HOST_PACK_FORCE"))   // too few cores for the host half to pay: the general packer (all bytes over PCIe)
+    return ea_pack_blob(rname, strand, start, templid, nrow, blob, off, nstr, device, out);
   PackPool pool(nt);
   const eahp::Job job{blob, off, strand, templid, nrow};
   const int64_t n_tiles32 = (nrow + 31) >> 5;
 
+  // Chunks of whole 32-row tiles, ~192 MB of strings each.  The chunks are worked off FROM BOTH ENDS: this thread sends
+  // chunks from the front as they are (raw bytes, transposed on the device, k_planarize_tight), a second thread lets the
+  // pool transpose chunks from the back on the host and sends the planes (half the bytes).  PCIe and the host's cores are
+  // both kept busy and the split between them finds itself, whatever the number of cores this process may use.
+  int64_t raw_chunk = 192ll << 20;
+  if (const char* e = getenv("EA_PACK_CHUNK_MB")) raw_chunk = std::max<int64_t>(1, atoll(e)) << 20;
+  const int64_t avg_len = std::max<int64_t>(1, total / nrow);
+  const int64_t rows_per_chunk = std::max<int64_t>(32, (raw_chunk / avg_len) & ~31ll);
+  const int n_chunks = (int)((nrow + rows_per_chunk - 1) / rows_per_chunk);
+  auto chunk_rows = [&](int c, int64_t& r0, int64_t& r1) { r0 = (int64_t)c * rows_per_chunk; r1 = std::min(nrow, r0 + rows_per_chunk); };
+  int64_t max_raw = 0;
+  for (int c = 0; c < n_chunks; c++) { int64_t r0, r1; chunk_rows(c, r0, r1); max_raw = std::max(max_raw, off[r1] - off[r0]); }
+
   ea_handle* h = new ea_handle;
   h->device = device; h->n = nrow; h->has_bytes = false; h->nbytes = total; h->npadded = 0;
-  constexpr int kSlots = 3;
-  cudaStream_t sc = nullptr;
-  cudaEvent_t ev_slot[kSlots] = {};
+  constexpr int kSlots = 2;                                // page-locked staging blocks of host-packed chunks
+  constexpr int kRawSlots = 4;                             // raw chunks on the device (four keep PCIe busy during the host's first pass)
+  cudaStream_t sr = nullptr, sh = nullptr;                 // raw chunks + metadata / host-packed chunks
+  cudaEvent_t ev_raw[kRawSlots] = {}, ev_host[kSlots] = {}, ev_meta = nullptr;
   uint8_t* stage[kSlots] = {};
+  uint8_t* d_raw[kRawSlots] = {}; int64_t* d_soff[kRawSlots] = {};
   uint32_t* ls = nullptr; int32_t* tile_nu = nullptr; int64_t* toff = nullptr;
   unsigned* d_flags = nullptr;
   auto cleanup = [&]() {
-    if (sc) { cudaStreamSynchronize(sc); cudaStreamDestroy(sc); }
-    for (auto& e : ev_slot) if (e) cudaEventDestroy(e);
+    if (sr) { cudaStreamSynchronize(sr); cudaStreamDestroy(sr); }
+    if (sh) { cudaStreamSynchronize(sh); cudaStreamDestroy(sh); }
+    for (auto& e : ev_raw) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_host) if (e) cudaEventDestroy(e);
+    if (ev_meta) cudaEventDestroy(ev_meta);
     for (auto& p : stage) ea_host_free(p);
     ea_host_free(ls); ea_host_free(tile_nu); ea_host_free(toff);
+    FreeScope fs;
+    for (auto& p : d_raw) pool_free(p);
+    for (auto& p : d_soff) pool_free(p);
     pool_free(d_flags);
   };
 #define TRY(x) do { rc = (x); if (rc != EA_OK) { cleanup(); ea_free(h); return rc; } } while (0)
 #define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ea_free(h); return fail(EA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
-  TRYCU(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-  for (auto& e : ev_slot) TRYCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  // ---- the two columns the device takes as they are travel while the host makes its first pass over the rows ----
+  TRYCU(cudaStreamCreateWithFlags(&sr, cudaStreamNonBlocking));
+  TRYCU(cudaStreamCreateWithFlags(&sh, cudaStreamNonBlocking));
+  for (auto& e : ev_raw) TRYCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+  for (auto& e : ev_host) TRYCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+  TRYCU(cudaEventCreateWithFlags(&ev_meta, cudaEventDisableTiming | cudaEventBlockingSync));
   TRY(dmalloc(&h->d_rname, (size_t)nrow));
   TRY(dmalloc(&h->d_start, (size_t)nrow));
-  TRYCU(cudaMemcpyAsync(h->d_rname, rname, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
-  TRYCU(cudaMemcpyAsync(h->d_start, start, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
-  // ---- pass 1: lengths, strands, unit rows per tile ----
+  for (int i = 0; i < kRawSlots; i++) {
+    TRY(dmalloc(&d_raw[i], (size_t)max_raw + 64));
+    TRY(dmalloc(&d_soff[i], (size_t)rows_per_chunk + 1));
+  }
+  // ---- PCIe starts right away: the two columns the device takes as they are, then the first raw chunks ----
+  TRYCU(cudaMemcpyAsync(h->d_rname, rname, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sr));
+  TRYCU(cudaMemcpyAsync(h->d_start, start, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sr));
+  std::mutex qmu;
+  int front = 0, back = n_chunks - 1;                      // next chunk from the front (raw) / from the back (host-packed)
+  auto claim_front = [&]() { std::lock_guard<std::mutex> lk(qmu); return front <= back ? front++ : -1; };
+  auto claim_back = [&]() { std::lock_guard<std::mutex> lk(qmu); return back >= front ? back-- : -1; };
+  std::vector<int> raw_chunks;                             // chunks whose bytes are on their way; their kernels follow once toff is known
+  auto send_raw = [&](int c, int slot) -> cudaError_t {
+    int64_t r0, r1; chunk_rows(c, r0, r1);
+    cudaError_t e = cudaSuccess;
+    if (off[r1] > off[r0]) e = cudaMemcpyAsync(d_raw[slot], blob + off[r0], (size_t)(off[r1] - off[r0]), cudaMemcpyHostToDevice, sr);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_soff[slot], off + r0, 8 * (size_t)(r1 - r0 + 1), cudaMemcpyHostToDevice, sr);
+    return e;
+  };
+  const int n_early = std::min(kRawSlots, std::max(0, n_chunks - 1));   // (at least one chunk stays for the host side)
+  for (int i = 0; i < n_early; i++) { const int c = claim_front(); if (c < 0) break; TRYCU(send_raw(c, (int)raw_chunks.size() % kRawSlots)); raw_chunks.push_back(c); }
+  // ---- pass 1 on the host meanwhile: lengths, strands, unit rows per tile ----
   ls = static_cast<uint32_t*>(ea_host_alloc(4 * (size_t)nrow));
   tile_nu = static_cast<int32_t*>(ea_host_alloc(4 * (size_t)n_tiles32));
   if (!ls || !tile_nu) { cleanup(); ea_free(h); return EA_ERR_CUDA; }
@@ -2125,6 +2169,9 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   const int64_t unit_bytes = th == 32 ? 512 : 16;     // bytes per toff step
   const int64_t total_units_bytes = toff[n_tiles] * unit_bytes;
   h->pl_th = th; h->pl_tiles = n_tiles; h->pl_unit_rows = toff[n_tiles];
+  auto chunk_tiles = [&](int c, int64_t& t0, int64_t& t1) { int64_t r0, r1; chunk_rows(c, r0, r1); t0 = th == 32 ? r0 >> 5 : r0; t1 = th == 32 ? (r1 + 31) >> 5 : r1; };
+  int64_t stage_bytes = 0;
+  for (int c = 0; c < n_chunks; c++) { int64_t t0, t1; chunk_tiles(c, t0, t1); stage_bytes = std::max(stage_bytes, (toff[t1] - toff[t0]) * unit_bytes); }
   tr.mark("host pass 1");
 
   TRY(dmalloc(&h->d_strand, (size_t)nrow));
@@ -2133,59 +2180,72 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   TRY(dmalloc(&h->d_pl_toff, (size_t)n_tiles + 1));
   TRY(dmalloc(&h->d_pl_units, (size_t)(total_units_bytes / 16)));
   TRY(dmalloc(&d_flags, 1));
-  TRYCU(cudaMemsetAsync(d_flags, 0, 4, sc));
-  TRYCU(cudaMemcpyAsync(h->d_pl_ls, ls, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sc));
-  TRYCU(cudaMemcpyAsync(h->d_pl_toff, toff, 8 * (size_t)(n_tiles + 1), cudaMemcpyHostToDevice, sc));
-  k_unpack_ls<<<grid_for(nrow, 256), 256, 0, sc>>>(h->d_pl_ls, nrow, h->d_len, h->d_strand);
-  h->h2d_bytes = 12 * nrow + 8 * (n_tiles + 1) + total_units_bytes;
-  // ---- the planes, chunk by chunk: all threads transpose chunk k into a staging block while chunk k-1 is in flight ----
-  int64_t chunk_bytes = 128ll << 20;
-  if (const char* e = getenv("EA_PACK_CHUNK_MB")) chunk_bytes = std::max<int64_t>(1, atoll(e)) << 20;
-  int64_t stage_bytes = 0;
-  std::vector<int64_t> cuts{0};
-  for (int64_t t = 0; t < n_tiles;) {   // the largest run of tiles that fits a chunk (binary search on the prefix sums; at least one tile)
-    int64_t a = t + 1, b = n_tiles;
-    while (a < b) {
-      const int64_t m = (a + b + 1) >> 1;
-      if ((toff[m] - toff[t]) * unit_bytes <= chunk_bytes) a = m; else b = m - 1;
-    }
-    stage_bytes = std::max(stage_bytes, (toff[a] - toff[t]) * unit_bytes);
-    cuts.push_back(a);
-    t = a;
-  }
   for (auto& p : stage) { p = static_cast<uint8_t*>(ea_host_alloc((size_t)std::max<int64_t>(stage_bytes, 1))); if (!p) { cleanup(); ea_free(h); return EA_ERR_CUDA; } }
-  bool finished = false;
-  for (size_t k = 0; k + 1 < cuts.size(); k++) {
-    const int slot = (int)(k % kSlots);
-    const int64_t t0 = cuts[k], t1 = cuts[k + 1];
-    if (k >= (size_t)kSlots) TRYCU(cudaEventSynchronize(ev_slot[slot]));   // the copy that last used this block is done
-    uint8_t* dst = stage[slot];
-    const int64_t grain = std::max<int64_t>(1, th == 32 ? 512 : 4096 / std::max<int64_t>(1, (max_l + 31) >> 5));
-    pool.parallel_for(t0, t1, grain, [&](int64_t a, int64_t b) {
-      uint8_t* d = dst + (toff[a] - toff[t0]) * unit_bytes;
-      flags |= th == 32 ? eahp::pack_tiles(job, toff, a, b, d) : eahp::pack_rows(job, toff, a, b, d);
-    });
-    const int64_t bytes = (toff[t1] - toff[t0]) * unit_bytes;
-    if (bytes > 0) TRYCU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->d_pl_units) + toff[t0] * unit_bytes, dst, (size_t)bytes, cudaMemcpyHostToDevice, sc));
-    TRYCU(cudaEventRecord(ev_slot[slot], sc));
-    if (!finished && k >= 1) {   // the metadata have landed long ago: validation + row keys on the handle's own stream, overlapped
-      TRYCU(cudaEventSynchronize(ev_slot[0]));
-      rc = finish_handle(h);
-      if (rc != EA_OK) { cleanup(); ea_free(h); return rc; }
-      finished = true;
+  TRYCU(cudaMemsetAsync(d_flags, 0, 4, sh));
+  TRYCU(cudaMemcpyAsync(h->d_pl_ls, ls, 4 * (size_t)nrow, cudaMemcpyHostToDevice, sh));
+  TRYCU(cudaMemcpyAsync(h->d_pl_toff, toff, 8 * (size_t)(n_tiles + 1), cudaMemcpyHostToDevice, sh));
+  k_unpack_ls<<<grid_for(nrow, 256), 256, 0, sh>>>(h->d_pl_ls, nrow, h->d_len, h->d_strand);
+  TRYCU(cudaEventRecord(ev_meta, sh));
+  TRYCU(cudaStreamWaitEvent(sr, ev_meta, 0));            // the raw chunks' kernels need toff
+  int64_t h2d = 12 * nrow + 8 * (n_tiles + 1);
+
+  // ---- host side: chunks from the back, transposed by the pool, planes sent on sh ----
+  std::atomic<int64_t> h2d_host{0};
+  std::atomic<int> host_err{0};
+  std::thread host_thread([&]() {
+    cudaSetDevice(device);
+    for (int k = 0;; k++) {
+      const int c = claim_back();
+      if (c < 0) break;
+      const int slot = k % kSlots;
+      if (k >= kSlots && cudaEventSynchronize(ev_host[slot]) != cudaSuccess) { host_err = 1; break; }
+      int64_t t0, t1; chunk_tiles(c, t0, t1);
+      uint8_t* dst = stage[slot];
+      const int64_t grain = std::max<int64_t>(1, th == 32 ? 512 : 4096 / std::max<int64_t>(1, (max_l + 31) >> 5));
+      pool.parallel_for(t0, t1, grain, [&](int64_t a, int64_t b) {
+        uint8_t* d = dst + (toff[a] - toff[t0]) * unit_bytes;
+        flags |= th == 32 ? eahp::pack_tiles(job, toff, a, b, d) : eahp::pack_rows(job, toff, a, b, d);
+      });
+      const int64_t bytes = (toff[t1] - toff[t0]) * unit_bytes;
+      if (bytes > 0 && cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->d_pl_units) + toff[t0] * unit_bytes, dst, (size_t)bytes, cudaMemcpyHostToDevice, sh) != cudaSuccess) { host_err = 1; break; }
+      if (cudaEventRecord(ev_host[slot], sh) != cudaSuccess) { host_err = 1; break; }
+      h2d_host += bytes;
     }
+  });
+  // ---- this thread: raw chunks from the front ----
+  cudaError_t raw_err = cudaSuccess;
+  auto launch_tight = [&](int c, int slot) {
+    int64_t r0, r1, t0, t1; chunk_rows(c, r0, r1); chunk_tiles(c, t0, t1);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t1 - t0 + 7) / 8, (int64_t)148 * 16));
+    k_planarize_tight<<<grid, 256, 0, sr>>>(d_raw[slot], off[r0], d_soff[slot], r0, nrow, h->d_pl_toff, t0, t1, th, h->d_pl_units);
+    h2d += (off[r1] - off[r0]) + 8 * (r1 - r0 + 1);
+    return cudaEventRecord(ev_raw[slot], sr);
+  };
+  for (size_t i = 0; i < raw_chunks.size() && raw_err == cudaSuccess; i++) raw_err = launch_tight(raw_chunks[i], (int)i % kRawSlots);
+  for (int k = (int)raw_chunks.size(); raw_err == cudaSuccess; k++) {
+    const int slot = k % kRawSlots;
+    if ((raw_err = cudaEventSynchronize(ev_raw[slot])) != cudaSuccess) break;   // the chunk that used this slot has been transposed
+    const int c = claim_front();
+    if (c < 0) break;
+    if ((raw_err = send_raw(c, slot)) != cudaSuccess) break;
+    raw_err = launch_tight(c, slot);
   }
-  // the device checks what it received: codes inside the domain, nothing beyond the rows' ends
+  host_thread.join();
+  if (raw_err != cudaSuccess || host_err) { cleanup(); ea_free(h); return fail(EA_ERR_CUDA, "pack pipeline: %s", cudaGetErrorString(raw_err != cudaSuccess ? raw_err : cudaGetLastError())); }
+  TRYCU(cudaStreamSynchronize(sr));
+  h->h2d_bytes = h2d + h2d_host.load();
+  // the device checks what it has: codes inside the domain, nothing beyond the rows' ends (covers both ways in)
   {
     Planar pl; pl.units = h->d_pl_units; pl.toff = h->d_pl_toff; pl.ls = h->d_pl_ls; pl.start = h->d_start; pl.n = nrow;
-    k_validate_planes<<<(int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + 7) / 8, 148 * 32)), 256, 0, sc>>>(pl, n_tiles, th, d_flags);
+    k_validate_planes<<<(int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + 7) / 8, 148 * 32)), 256, 0, sh>>>(pl, n_tiles, th, d_flags);
   }
   unsigned dflags = 0;
-  TRYCU(cudaMemcpyAsync(&dflags, d_flags, 4, cudaMemcpyDeviceToHost, sc));
-  TRYCU(cudaStreamSynchronize(sc));
+  TRYCU(cudaMemcpyAsync(&dflags, d_flags, 4, cudaMemcpyDeviceToHost, sh));
+  rc = finish_handle(h);   // sortedness, row keys (own stream) while the validation runs
+  if (rc != EA_OK) { cleanup(); ea_free(h); return rc; }
+  TRYCU(cudaStreamSynchronize(sh));
   TRYCU(cudaGetLastError());
-  tr.mark("host transposition + H2D");
-  if (!finished) { rc = finish_handle(h); if (rc != EA_OK) { cleanup(); ea_free(h); return rc; } }
+  tr.mark("transposition (host + device) + H2D");
   if ((flags & eahp::kBadCode) || (dflags & F_DOMAIN)) { cleanup(); ea_free(h); return flags_error(F_DOMAIN); }
   if (h->max_len != (int32_t)max_l) { cleanup(); ea_free(h); return fail(EA_ERR_STATE, "length bookkeeping mismatch"); }
   h->pl_ok = true;

@@ -156,6 +156,81 @@ k_planarize_rows(const uint8_t* __restrict__ data, const int64_t* __restrict__ o
   }
 }
 
+// 32 code bytes given as eight 32-bit words -> one unit, the first nvalid positions kept
+__device__ __forceinline__ uint4 pl_unit_from_words(const uint32_t (&w)[8], int nvalid) {
+  uint32_t P[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) P[b] |= gather_bit(w[k], b) << (4 * k);
+  if (nvalid < 32) {
+    const uint32_t keep = nvalid <= 0 ? 0u : (1u << nvalid) - 1u;
+#pragma unroll
+    for (int b = 0; b < 4; b++) P[b] &= keep;
+  }
+  return make_uint4(P[0], P[1], P[2], P[3]);
+}
+
+// Tiles [tile0, tile1) straight from TIGHT strings (a chunk of the caller's blob as it arrived, no padded copy): `raw` holds
+// the bytes from string offset `raw_base` on, soff[r - row0] is the offset of row r's string.  One warp per tile, lane l
+// transposes row l; the unaligned source is read as aligned 32-bit words and assembled with funnel shifts.  The buffer
+// behind `raw` must be readable 8 bytes past the chunk's last byte.
+__global__ void __launch_bounds__(256)
+k_planarize_tight(const uint8_t* __restrict__ raw, int64_t raw_base, const int64_t* __restrict__ soff, int64_t row0, int64_t n,
+                  const int64_t* __restrict__ toff, int64_t tile0, int64_t tile1, int th, uint4* __restrict__ units) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = tile0 + warp; t < tile1; t += n_warps) {
+    const int64_t u0 = toff[t];
+    const int nu_t = (int)(toff[t + 1] - u0);
+    if (th == 32) {
+      const int64_t r = t * 32 + lane;
+      long long so = 0;
+      int l = 0;
+      if (r < n) { so = soff[r - row0]; l = (int)(soff[r - row0 + 1] - so); }
+      const uint8_t* src = raw + (so - raw_base);
+      uint4* dst = units + u0 * 32 + lane;
+      for (int j = 0; j < nu_t; j++) {
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int nv = l - 32 * j;
+        if (nv > 0) {
+          const uintptr_t p = reinterpret_cast<uintptr_t>(src + 32 * j);
+          const uint32_t sh = (uint32_t)(p & 3) * 8u;
+          const uint32_t* a = reinterpret_cast<const uint32_t*>(p & ~(uintptr_t)3);
+          const int need = (int)(p & 3) + min(nv, 32);   // bytes of the aligned words that belong to this unit
+          uint32_t x[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) x[k] = 4 * k < need ? a[k] : 0u;
+#pragma unroll
+          for (int k = 0; k < 8; k++) w[k] = __funnelshift_r(x[k], x[k + 1], sh);
+        }
+        dst[(int64_t)j * 32] = pl_unit_from_words(w, nv);
+      }
+    } else {  // long reads: a tile is a row, the lanes take its units in turn
+      const long long so = soff[t - row0];
+      const int l = (int)(soff[t - row0 + 1] - so);
+      const uint8_t* src = raw + (so - raw_base);
+      for (int j = lane; j < nu_t; j += 32) {
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int nv = l - 32 * j;
+        if (nv > 0) {
+          const uintptr_t p = reinterpret_cast<uintptr_t>(src + 32ll * j);
+          const uint32_t sh = (uint32_t)(p & 3) * 8u;
+          const uint32_t* a = reinterpret_cast<const uint32_t*>(p & ~(uintptr_t)3);
+          const int need = (int)(p & 3) + min(nv, 32);
+          uint32_t x[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) x[k] = 4 * k < need ? a[k] : 0u;
+#pragma unroll
+          for (int k = 0; k < 8; k++) w[k] = __funnelshift_r(x[k], x[k + 1], sh);
+        }
+        units[u0 + j] = pl_unit_from_words(w, nv);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // events of one unit (32 positions) on the shared-memory window state
 // ---------------------------------------------------------------------------------------------------------------

@@ -241,6 +241,59 @@ def test_pack_pipeline_chunks_and_shuffled_strings(monkeypatch):
     a.close(); b.close(); host.close()
 
 
+def test_calls_only_packer(monkeypatch, kernel_policy):
+    """ea_pack_blob_calls: the host transposes chunks from the back (AVX2), the device transposes raw chunks from the front,
+    both into the same call planes.  Many small chunks, 1 / 3 / 16 host threads, short ragged reads and long reads: reports,
+    flags and betas equal the oracle; what the planes cannot serve repacks with the byte rows; bad inputs are rejected."""
+    if kernel_policy != "auto":
+        pytest.skip("the calls-only packer is used with the default kernel policy")
+    L = N.lib()
+    monkeypatch.setenv("EA_PACK_CHUNK_MB", "1")
+    monkeypatch.setenv("EA_HOST_PACK_FORCE", "1")
+    shapes = [ea.synth_config(77, 60000, [250000, 100000], 1, 333), ea.synth_config(20261020, 120, [900000, 500000], 10000, 30000)]
+    for cfg in shapes:
+        host = ea.synth_host(cfg)
+        blob, off = host.blob()
+        oracle = PortCpu(host)
+        want_p, want = oracle.generateCytosineReport(True, "CG", 2, 0.5, 0.1, "CX")
+        for nthreads in ("1", "3", "16"):
+            monkeypatch.setenv("EA_HOST_PACK_THREADS", nthreads)
+            b = ea.BamData(host.rname, host.strand, host.start, np.arange(host.nrow, dtype=np.int32), blob, off)
+            assert L.ea_has_bytes(b.handle(need_bases=False)) == 0
+            assert 0 < L.ea_pack_h2d_bytes(b.handle(need_bases=False)) < blob.nbytes + 24 * host.nrow + 65536
+            p, rep = ea.generateCytosineReport(b, report_context="CX", return_pass=True)
+            assert np.array_equal(p, want_p)
+            assert_report_equal(rep, want, "calls-only pack, %s threads" % nthreads)
+            assert np.array_equal(ea.rcpp_get_xm_beta(b, "ZX", "zx"), oracle.rcpp_get_xm_beta("ZX", "zx"))
+            assert L.ea_has_bytes(b.handle(need_bases=False)) == 0
+            # a letter set outside the named contexts needs the byte rows: transparent repack
+            assert np.array_equal(ea.rcpp_threshold_reads(b, "ZU", "z", "X", "x", 1, 0.2, 0.5), oracle.rcpp_threshold_reads("ZU", "z", "X", "x", 1, 0.2, 0.5))
+            assert L.ea_has_bytes(b.handle(need_bases=False)) == 1
+            b.close()
+        host.close()
+    # invalid inputs through the calls-only packer
+    def pack(rn, st, sa, strs, tid=None):
+        b = ea.BamData.from_strings(rn, st, sa, tid if tid is not None else list(range(len(strs))), strs)
+        try:
+            return b, L.ea_has_bytes(b.handle(need_bases=False))
+        finally:
+            b.close()
+    ok = bytes([0x1C]) * 70
+    for bad_at in (0, 31, 32, 69):   # first unit, unit border, last (partial) unit
+        s = bytearray(ok); s[bad_at] = 0x13
+        with pytest.raises(ea.EaError) as e:
+            pack([1, 1], [1, 2], [5, 6], [ok, bytes(s)])
+        assert e.value.code == -4, bad_at
+    with pytest.raises(ea.EaError) as e:
+        pack([1, 1], [1, 1], [10, 5], [ok, ok])
+    assert e.value.code == -3
+    with pytest.raises(ea.EaError) as e:
+        pack([1, 1], [1, 3], [5, 6], [ok, ok])
+    assert e.value.code == -1
+    assert pack([1, 1], [1, 2], [5, 6], [ok, ok])[1] == 0
+    assert pack([1, 1], [1, 2], [5, 6], [ok, ok], tid=[1, 0])[1] == 1   # rows are not the strings in file order: the general packer
+
+
 def test_row_capacity_retry_on_sparse_coverage():
     """A CX report over ~1x coverage has about one row per five bytes of calls, far above the first capacity guess:
     the window kernel only counts, the pipeline re-runs with the exact capacity, and the rows are still bit-exact."""
