@@ -309,10 +309,15 @@ def run_ours(args):
             "xm_gbs": tot_xm / 1e9 / (ms_step / 1e3),
             "wall_ms_per_step": wall_step,
             "gpu_launches": launches * args.steps,
-            "kernels_per_step": {"thr_tables": 1, "window(fused threshold+aggregate)": 1, "scan_windows": 1, "gather_rows": 1},
+            "kernels_per_step": {"thr_tables": 1, "window(fused threshold+aggregate)": 1, "scan_windows (cub: init + scan)": 2, "gather_rows": 1},
             "roofline": {"bound": "hbm", "kernel": kernel_name + ", fused", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": win_step, "formula": "sum(L) + 14 N + 24 R"},
+                         "kernel_ms": win_step, "formula": "sum(L) + 14 N + 24 R",
+                         "device_format": ("the kernel reads the packer's 4-bit bit-sliced call planes (16 bytes per 32 positions, tiles of 32 rows) plus 8 bytes "
+                                           "of metadata per read, not the reference's byte per position: DRAM traffic per launch (`traffic`) is about half the "
+                                           "algorithmic bytes, which are counted on the reference's format as SURVEY.md 8(d) defines them"),
+                         "dram_gbs": (traffic / 1e9) / (win_step / 1e3) if traffic else None,
+                         "dram_frac_of_peak": ((traffic / 1e9) / (win_step / 1e3) / peak) if traffic else None},
             "two_pass_variant": two_pass,
             "clocks": clocks,
         }

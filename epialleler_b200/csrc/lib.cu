@@ -1545,6 +1545,7 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       CU(cudaEventRecord(h->ev[2], h->stream));
       ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
       if ((rc = scan_windows(h, *ix))) return rc;
+      launches += ix->n > 4096 ? 1 : 0;   // the multi-block scan is two kernels (CUB: tile-state init + scan)
       {  // windows per warp step: 32 when there are plenty of windows, fewer so that a small index still fills the GPU
         int group = 32;
         while (group > 1 && (int64_t)ix->n / group < (int64_t)h->sm_count * 32) group >>= 1;
