@@ -23,6 +23,7 @@
 //
 // The window state in shared memory, the event model and the finalize are those of win_common.cuh.
 #pragma once
+#include <type_traits>
 #include "win_common.cuh"
 #include "window_row.cuh"  // kRowThreads, kRowWarps, kRowPer, kRowMaxS
 
@@ -505,7 +506,12 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
   uint32_t* const T = D + SG;                                 // [NC][2][SG]
   const int kZero4 = (NC + 1) * 2 * SG / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t w_base = smem_u32(W), d_base = smem_u32(D), t_base = smem_u32(T);
+  // the 32-bit shared address of the window state, taken ONCE through an opaque asm: left to itself the compiler
+  // rematerialises the generic->shared conversion (S2R + LEA + ...) at every use instead of spending a register (3 % of
+  // the kernel's instructions in round 2's first profile)
+  uint32_t w_base = smem_u32(W);
+  asm volatile("mov.u32 %0, %0;" : "+r"(w_base));
+  const uint32_t d_base = w_base + 4u * (uint32_t)SG, t_base = w_base + 8u * (uint32_t)SG;
   const uint32_t w_floor = w_base + 4u * kGuardLo;
   const uint32_t ctx_stride = 8u * (uint32_t)SG;  // bytes between T[c][s] and T[c+1][s]
 
@@ -568,34 +574,49 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
             n_in += __popc(ci); n_inm += __popc(ci & ~v[u].w);
             if (TCTX != TC_CX) { n_out += __popc(co); n_outm += __popc(co & ~v[u].w); }
           }
-          pass = n_inm != 0u && n_in >= thr.min_n && n_inm >= (uint32_t)s_mmin[n_in] && (n_outm == 0u || n_outm <= (uint32_t)s_omax[n_out]);
+          // the reference's chain (src/rcpp_threshold_reads.cpp:39-70) without its short circuits: both table entries are
+          // always inside the staged range, so all four conditions can be evaluated for 32 rows without a branch
+          const uint32_t t_m = s_mmin[n_in], t_o = s_omax[n_out];
+          pass = (n_inm != 0u) & (n_in >= thr.min_n) & (n_inm >= t_m) & ((n_outm == 0u) | (n_outm <= t_o));
           if (overlaps && rel0 >= 0) {  // the window that holds the row's start owns its flag
             pass_out[r] = pass ? 1 : 0;
             npass_w += pass;
           }
         }
         const uint32_t passm = pass ? 0xFFFFFFFFu : 0u;
-        // '-' masks with exact neighbours across unit borders: E of the previous / this / the next unit are all in registers
-        uint32_t Em1 = 0u, isom1 = 0u, E = pl_dashes(v[0]);
+        // '-' masks with exact neighbours across unit borders: E of the previous / this / the next unit are all in registers.
+        // ALLIN: every row of the tile lies completely inside the window (the common case: only the tiles at a window's
+        // edges hold rows that cross it) - no per-unit window test, no entry rule.
+        auto sweep = [&](auto allin_t) {
+          constexpr bool ALLIN = decltype(allin_t)::value;
+          uint32_t Em1 = 0u, isom1 = 0u, E = pl_dashes(v[0]);
 #pragma unroll
-        for (int u = 0; u < KU; u++) {
-          const uint32_t Enext = u + 1 < KU ? pl_dashes(v[u + 1 < KU ? u + 1 : u]) : 0u;
-          const uint32_t prev = __funnelshift_l(Em1, E, 1), next = __funnelshift_r(E, Enext, 1);
-          const uint32_t iso = E & ~prev & ~next;
-          const uint32_t ed = (E ^ prev) & ~(iso | __funnelshift_l(isom1, iso, 1));
-          const int rel = rel0 + 32 * u;
-          if ((unsigned)(rel + 31) < (unsigned)(S + 31)) {  // -32 < rel < S (units of lanes without a row are zero: no events)
-            const uint32_t off4 = 128u * (uint32_t)u;
-            if (u > 0 && rel <= 0 && ((Em1 & ~isom1) >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
-            uint32_t m[3];
-            pl_want<WANT>(v[u], m);
-            pl_edges(ed, E, wq + off4, sinc, w_floor);
-            pl_events<NC>(m, iso, (m[0] | m[1] | m[2]) & ~v[u].w & passm, dq + off4, tq + off4, ctx_stride, sinc);
+          for (int u = 0; u < KU; u++) {
+            const uint32_t Enext = u + 1 < KU ? pl_dashes(v[u + 1 < KU ? u + 1 : u]) : 0u;
+            const uint32_t prev = __funnelshift_l(Em1, E, 1), next = __funnelshift_r(E, Enext, 1);
+            const uint32_t iso = E & ~prev & ~next;
+            const uint32_t ed = (E ^ prev) & ~(iso | __funnelshift_l(isom1, iso, 1));
+            const int rel = rel0 + 32 * u;
+            if (ALLIN || (unsigned)(rel + 31) < (unsigned)(S + 31)) {  // -32 < rel < S (units of lanes without a row are zero: no events)
+              const uint32_t off4 = 128u * (uint32_t)u;
+              if (!ALLIN && u > 0 && rel <= 0 && ((Em1 & ~isom1) >> 31)) red_shared(w_floor, 0u - sinc);  // a '-' run is open where the row enters the window
+              uint32_t m[3];
+              pl_want<WANT>(v[u], m);
+              pl_edges(ed, E, wq + off4, sinc, w_floor);
+              pl_events<NC>(m, iso, (m[0] | m[1] | m[2]) & ~v[u].w & passm, dq + off4, tq + off4, ctx_stride, sinc);
+            }
+            Em1 = E; isom1 = iso; E = Enext;
           }
-          Em1 = E; isom1 = iso; E = Enext;
-        }
+          return (Em1 & ~isom1) >> 31;   // the row's last position is the end of a '-' run
+        };
+#ifndef EA_PL_NO_ALLIN
+        const bool allin = __all_sync(0xFFFFFFFFu, !overlaps || (rel0 >= 0 && rel0 + 32 * KU < S));
+#else
+        const bool allin = false;
+#endif
+        const uint32_t tail_run = allin ? sweep(std::true_type{}) : sweep(std::false_type{});
         if (overlaps && nu == KU && (len & 31) == 0) {  // a '-' run that reaches the end of a row filling all KU units
-          if (((Em1 & ~isom1) >> 31) && rel0 + len < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);
+          if (tail_run && rel0 + len < S) red_shared(max(wq + 4u * (uint32_t)len, w_floor), sinc);
         }
       } else {
         // Streaming form, two sweeps over the row's units: (A, fused only) class counts of the whole row with four loads in
