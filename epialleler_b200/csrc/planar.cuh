@@ -377,8 +377,16 @@ __device__ __forceinline__ void window_finalize_pk(uint32_t* __restrict__ W, uin
   if (lane == 31) s_scan[warp] = inc;
   __syncthreads();
   uint32_t ex = inc - run;
+  {  // + the coverage of the warps in front: a shuffle scan over the NW per-warp totals instead of NW loads per thread
+    const uint32_t v = lane < NW ? s_scan[lane] : 0u;
+    uint32_t vi = v;
 #pragma unroll
-  for (int w = 0; w < NW; w++) ex += (w < warp) ? s_scan[w] : 0u;
+    for (int d = 1; d < NW; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(FULL, vi, d);
+      if (lane >= d) vi += o;
+    }
+    ex += __shfl_sync(FULL, vi - v, warp);
+  }
 
   uint32_t flags = 0;
 #pragma unroll
@@ -410,12 +418,17 @@ __device__ __forceinline__ void window_finalize_pk(uint32_t* __restrict__ W, uin
   }
   if (lane == 31) s_scan[NW + warp] = (uint32_t)rinc;
   __syncthreads();
-  int my_off = rinc - mine, nrows_total = 0;
+  int my_off = rinc - mine, nrows_total;
+  {
+    const int v = lane < NW ? (int)s_scan[NW + lane] : 0;
+    int vi = v;
 #pragma unroll
-  for (int w = 0; w < NW; w++) {
-    const int c = (int)s_scan[NW + w];
-    nrows_total += c;
-    my_off += (w < warp) ? c : 0;
+    for (int d = 1; d < NW; d <<= 1) {
+      const int o = __shfl_up_sync(FULL, vi, d);
+      if (lane >= d) vi += o;
+    }
+    my_off += __shfl_sync(FULL, vi - v, warp);
+    nrows_total = __shfl_sync(FULL, vi, NW - 1);
   }
   if (threadIdx.x == 0) {
     const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
