@@ -323,15 +323,6 @@ __device__ __forceinline__ void pl_events(const uint32_t (&m)[3], uint32_t iso, 
   }
 }
 
-// methylated calls of a passing row's unit (fused kernels, after the flag is known)
-__device__ __forceinline__ void pl_push_meth(uint32_t mm, uint32_t t_addr) {
-  while (mm) {
-    const int i = 31 - __clz(mm);
-    mm ^= 1u << i;
-    red_shared(t_addr + 4u * (uint32_t)i, 0x10000u);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Finalize of one window, packed-compare form of window_finalize_rt (win_common.cuh): same state, same three barriers, same
 // ordered compaction, leaves the state zeroed.  The row test `total_ctx > floor(cov/2)` (src/rcpp_cx_report.cpp:58-85) is
@@ -692,11 +683,7 @@ k_window_pl(Planar pl, WinTable wt, ThrParams thr, ThrTables tbl, const uint8_t*
       if (lane == 0 && npass_w) atomicAdd(&s_npass, npass_w);
     }
     __syncthreads();
-#ifdef EA_PL_OLD_FINALIZE
-    window_finalize_rt<WANT, PER, kRowThreads, FUSED>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
-#else
     window_finalize_pk<WANT, PER, kRowThreads, FUSED>(W, D, T, S, w0, win, out, s_scan, &s_base, &s_npass);
-#endif
   }
 }
 
