@@ -2193,9 +2193,10 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   // ---- host side: chunks from the back, transposed by the pool, planes sent on sh ----
   std::atomic<int64_t> h2d_host{0};
   std::atomic<int> host_err{0};
+  std::atomic<bool> abort_pack{false};
   std::thread host_thread([&]() {
     cudaSetDevice(device);
-    for (int k = 0;; k++) {
+    for (int k = 0; !abort_pack; k++) {
       const int c = claim_back();
       if (c < 0) break;
       const int slot = k % kSlots;
@@ -2223,7 +2224,22 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
     return cudaEventRecord(ev_raw[slot], sr);
   };
   for (size_t i = 0; i < raw_chunks.size() && raw_err == cudaSuccess; i++) raw_err = launch_tight(raw_chunks[i], (int)i % kRawSlots);
-  for (int k = (int)raw_chunks.size(); raw_err == cudaSuccess; k++) {
+  // While the early raw chunks and the first host-packed chunk travel: validation + row keys (finish_handle) and the window
+  // indexes a one-context report will ask for - they only need the metadata, which is on the device by now.
+  int rc_meta = EA_OK;
+  if (raw_err == cudaSuccess) raw_err = cudaEventSynchronize(ev_meta);
+  if (raw_err == cudaSuccess) {
+    rc_meta = finish_handle(h);
+    WinIndex* ixp = nullptr;
+    if (rc_meta == EA_OK && h->max_len != (int32_t)max_l) rc_meta = fail(EA_ERR_STATE, "length bookkeeping mismatch");
+    if (rc_meta == EA_OK) rc_meta = build_index(h, h->pl_th == 32 ? 2048 : kVsrS, &ixp);
+    if (rc_meta == EA_OK && h->pl_th == 32) {
+      const int S = pick_pl_window(h, *ixp, 1);
+      if (S != 2048) rc_meta = build_index(h, S, &ixp);
+    }
+    if (rc_meta != EA_OK) abort_pack = true;
+  }
+  for (int k = (int)raw_chunks.size(); raw_err == cudaSuccess && rc_meta == EA_OK; k++) {
     const int slot = k % kRawSlots;
     if ((raw_err = cudaEventSynchronize(ev_raw[slot])) != cudaSuccess) break;   // the chunk that used this slot has been transposed
     const int c = claim_front();
@@ -2232,6 +2248,7 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
     raw_err = launch_tight(c, slot);
   }
   host_thread.join();
+  if (rc_meta != EA_OK) { const std::string msg = g_err; cleanup(); ea_free(h); g_err = msg; return rc_meta; }
   if (raw_err != cudaSuccess || host_err) { cleanup(); ea_free(h); return fail(EA_ERR_CUDA, "pack pipeline: %s", cudaGetErrorString(raw_err != cudaSuccess ? raw_err : cudaGetLastError())); }
   TRYCU(cudaStreamSynchronize(sr));
   h->h2d_bytes = h2d + h2d_host.load();
@@ -2242,13 +2259,10 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   }
   unsigned dflags = 0;
   TRYCU(cudaMemcpyAsync(&dflags, d_flags, 4, cudaMemcpyDeviceToHost, sh));
-  rc = finish_handle(h);   // sortedness, row keys (own stream) while the validation runs
-  if (rc != EA_OK) { cleanup(); ea_free(h); return rc; }
   TRYCU(cudaStreamSynchronize(sh));
   TRYCU(cudaGetLastError());
   tr.mark("transposition (host + device) + H2D");
   if ((flags & eahp::kBadCode) || (dflags & F_DOMAIN)) { cleanup(); ea_free(h); return flags_error(F_DOMAIN); }
-  if (h->max_len != (int32_t)max_l) { cleanup(); ea_free(h); return fail(EA_ERR_STATE, "length bookkeeping mismatch"); }
   h->pl_ok = true;
   cleanup();
 #undef TRY

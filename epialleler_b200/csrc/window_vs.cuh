@@ -394,31 +394,53 @@ k_window_vsr(Planar pl, WinTable wt, const uint8_t* __restrict__ pass_in, Report
     const int lo = wt.lo[win], hi = wt.hi[win];
     VsrStrand<WANT, K> sp, sm;   // '+' and '-' strand
     sp.clear(); sm.clear();
-    for (int r = lo; r < hi; r++) {
-      const long long u0 = pl.toff[r];
-      const int start = pl.start[r];
-      const uint32_t lsv = pl.ls[r];
-      const int len = (int)(lsv & 0x7FFFFFFFu);
-      const int rel0 = start - w0;
-      if (len <= 0 || rel0 + len <= 0) continue;              // warp-uniform; rel0 < S by construction of hi
+    // Software pipeline over the window's rows: the metadata of row r+2 and the units of row r+1 are requested before row r
+    // is added up (a window holds few rows, each costing a dependent metadata -> unit round trip; with three CTAs of
+    // registers per SM there are not enough warps to hide it otherwise).
+    struct Meta { long long u0; int start; uint32_t lsv; uint32_t passm; };
+    auto load_meta = [&](int r) {
+      Meta m;
+      m.u0 = 0; m.start = 0; m.lsv = 0u; m.passm = 0u;
+      if (r < hi) {
+        m.u0 = pl.toff[r]; m.start = pl.start[r]; m.lsv = pl.ls[r];
+        m.passm = (pass_in == nullptr || pass_in[r] != 0) ? 0xFFFFFFFFu : 0u;
+      }
+      return m;
+    };
+    struct Units { uint4 lo4, hi31; uint32_t sh; bool live; uint32_t strand, passm; };
+    auto issue = [&](const Meta& m) {   // request the units of a row: lane b the one that holds its block's first position
+      Units u;
+      u.lo4 = make_uint4(0, 0, 0, 0); u.hi31 = make_uint4(0, 0, 0, 0);
+      const int len = (int)(m.lsv & 0x7FFFFFFFu);
+      const int rel0 = m.start - w0;
+      u.live = len > 0 && rel0 + len > 0;                     // warp-uniform; rel0 < S by construction of hi
+      u.strand = m.lsv >> 31; u.passm = m.passm;
       const int nu = (len + 31) >> 5;
       const int o = pb - rel0;                                // position within the row of this lane's first position
       const int j = o >> 5;                                   // (floor) unit that holds it; lane b+1 looks at unit j+1
-      const uint32_t sh = (uint32_t)o & 31u;                  // the same in every lane
-      uint4 lo4 = make_uint4(0, 0, 0, 0);
-      if (j >= 0 && j < nu) lo4 = ldg_plunit(pl.units + u0 + j);
-      uint4 hi4;
-      hi4.x = __shfl_down_sync(FULL, lo4.x, 1); hi4.y = __shfl_down_sync(FULL, lo4.y, 1);
-      hi4.z = __shfl_down_sync(FULL, lo4.z, 1); hi4.w = __shfl_down_sync(FULL, lo4.w, 1);
-      if (lane == 31) {
-        hi4 = make_uint4(0, 0, 0, 0);
-        if (sh != 0u && j + 1 >= 0 && j + 1 < nu) hi4 = ldg_plunit(pl.units + u0 + j + 1);
+      u.sh = (uint32_t)o & 31u;                               // the same in every lane
+      if (u.live) {
+        if (j >= 0 && j < nu) u.lo4 = ldg_plunit(pl.units + m.u0 + j);
+        if (lane == 31 && u.sh != 0u && j + 1 >= 0 && j + 1 < nu) u.hi31 = ldg_plunit(pl.units + m.u0 + j + 1);
       }
-      uint4 v;
-      v.x = __funnelshift_r(lo4.x, hi4.x, sh); v.y = __funnelshift_r(lo4.y, hi4.y, sh);
-      v.z = __funnelshift_r(lo4.z, hi4.z, sh); v.w = __funnelshift_r(lo4.w, hi4.w, sh);
-      const uint32_t passm = (pass_in == nullptr || pass_in[r] != 0) ? 0xFFFFFFFFu : 0u;
-      if (lsv >> 31) sm.add(v, passm); else sp.add(v, passm);   // warp-uniform branch
+      return u;
+    };
+    Meta m1 = load_meta(lo), m2 = load_meta(lo + 1);
+    Units cur = issue(m1);
+    for (int r = lo; r < hi; r++) {
+      const Meta m3 = load_meta(r + 2);
+      const Units nxt = issue(m2);
+      if (cur.live) {
+        uint4 hi4;
+        hi4.x = __shfl_down_sync(FULL, cur.lo4.x, 1); hi4.y = __shfl_down_sync(FULL, cur.lo4.y, 1);
+        hi4.z = __shfl_down_sync(FULL, cur.lo4.z, 1); hi4.w = __shfl_down_sync(FULL, cur.lo4.w, 1);
+        if (lane == 31) hi4 = cur.hi31;
+        uint4 v;
+        v.x = __funnelshift_r(cur.lo4.x, hi4.x, cur.sh); v.y = __funnelshift_r(cur.lo4.y, hi4.y, cur.sh);
+        v.z = __funnelshift_r(cur.lo4.z, hi4.z, cur.sh); v.w = __funnelshift_r(cur.lo4.w, hi4.w, cur.sh);
+        if (cur.strand) sm.add(v, cur.passm); else sp.add(v, cur.passm);   // warp-uniform branch
+      }
+      cur = nxt; m2 = m3;
     }
     // ---- rows of the window: bit-sliced majority test, ordered compaction within the warp ----
     uint32_t win_p[NC], win_m[NC], rows_p = 0u, rows_m = 0u;

@@ -18,6 +18,9 @@ CONFIGS = {
     # name: (synth_config kwargs, report kwargs)
     "cfg2_wgbs150": (dict(seed=20261018, n_reads=50_000_000, chr_len=[248956422], len_min=150),
                      dict(threshold_reads=True, threshold_context="CG", report_context="CG")),
+    # the per-GPU shard of config 5 (1 B reads x 150 bp over hg38 on 8 GPUs): 125 M reads over an eighth of the genome, ~48x
+    "cfg5_shard": (dict(seed=20261021, n_reads=125_000_000, chr_len=[248956422, 114364328, 25000000], len_min=150),
+                   dict(threshold_reads=True, threshold_context="CG", report_context="CG")),
     "cfg2b_pe_merged": (dict(seed=20261018, n_reads=25_000_000, chr_len=[248956422], len_min=150, len_max=450),
                         dict(threshold_reads=True, threshold_context="CG", report_context="CG")),
     "cfg3_capture_cx": (dict(seed=20261019, n_reads=50_000_000, chr_len=HG38, len_min=100, len_max=417, n_islands=5000, island_len=2000),
