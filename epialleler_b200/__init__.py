@@ -10,4 +10,5 @@ from .api import (BamData, CONTEXT_TO_BASES, generateCytosineReport, preprocessB
 from .api import (generateBedReport, generateAmpliconReport, generateCaptureReport, generateBedEcdf, ecdf_at,  # noqa: F401
                   rcpp_match_amplicon, rcpp_match_capture, rcpp_mhl_report, generateMhlReport)
 from .api import generateVcfReport, rcpp_get_base_freqs, rcpp_fep, read_vcf, report_text  # noqa: F401
+from .api import Ingest, MultiBam  # noqa: F401
 from ._native import EaError  # noqa: F401

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("EA_LIB_PATH") or os.path.join(HERE, "lib", "libepiall
 EA_SYNTH_MAX_CHR = 32
 
 EA_ERR_NEEDS_BYTES = -8
+EA_ERR_ARG, EA_ERR_CUDA, EA_ERR_UNSORTED, EA_ERR_DOMAIN, EA_ERR_NODEVICE, EA_ERR_INTERRUPT, EA_ERR_STATE = -1, -2, -3, -4, -5, -6, -7
 ERRORS = {-8: "EA_ERR_NEEDS_BYTES", -1: "EA_ERR_ARG", -2: "EA_ERR_CUDA", -3: "EA_ERR_UNSORTED", -4: "EA_ERR_DOMAIN", -5: "EA_ERR_NODEVICE",
           -6: "EA_ERR_INTERRUPT", -7: "EA_ERR_STATE"}
 
@@ -40,6 +41,11 @@ class SynthCfg(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_reads", C.c_int64), ("n_chr", C.c_int32), ("len_min", C.c_int32),
                 ("len_max", C.c_int32), ("n_islands", C.c_int32), ("island_len", C.c_int32), ("reserved", C.c_int32),
                 ("chr_len", C.c_int64 * EA_SYNTH_MAX_CHR)]
+
+
+class Shard(C.Structure):
+    """ea_shard: rows [row_lo, own_hi) packed (halo = [row_lo, own_lo)), keys [key_lo, key_hi) owned."""
+    _fields_ = [("row_lo", C.c_int64), ("own_lo", C.c_int64), ("own_hi", C.c_int64), ("key_lo", C.c_int64), ("key_hi", C.c_int64)]
 
 
 _I32P, _U8P, _I64P, _F64P = C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_int64), C.POINTER(C.c_double)
@@ -85,6 +91,20 @@ SIGNATURES = {
     "ea_synth_device": (C.c_int, [C.POINTER(SynthCfg), C.c_int64, C.c_int64, C.c_int, C.POINTER(_H)]),
     "ea_synth_host": (C.c_int, [C.POINTER(SynthCfg), C.c_int64, C.c_int64, _I32P, _I32P, _I32P, _I64P, _U8P]),
     "ea_export_host": (C.c_int, [_H, _I32P, _I32P, _I32P, _I64P, _U8P]),
+    "ea_pack_calls": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_void_p), _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
+    "ea_ingest_begin": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_H)]),
+    "ea_ingest_append": (C.c_int64, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "ea_ingest_finish": (C.c_int, [_H, _I32P, _I32P, _I32P, _I32P, C.POINTER(_H)]),
+    "ea_ingest_abort": (None, [_H]),
+    "ea_plan_shards": (C.c_int, [_I32P, _I32P, _I32P, C.c_int64, _I64P, C.c_int64, C.c_int, C.POINTER(Shard)]),
+    "ea_set_owned_range": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64]),
+    "ea_pack_multi": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, _U8P, _I64P, C.c_int64, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(_H)]),
+    "ea_multi_ndev": (C.c_int, [_H]),
+    "ea_multi_handle": (_H, [_H, C.c_int]),
+    "ea_multi_shard": (C.c_int, [_H, C.c_int, C.POINTER(Shard)]),
+    "ea_multi_cytosine_report": (C.c_int, [_H, C.POINTER(ReportParams), _U8P, _I64P]),
+    "ea_multi_report_fetch": (C.c_int, [_H] + [_I32P] * 6),
+    "ea_multi_free": (None, [_H]),
 }
 
 _lib = None

@@ -48,6 +48,7 @@ class BamData:
         self.device = device
         self._h = None
         self._has_bases = True
+        self._owned = None
         n = self.rname.shape[0]
         if not (self.strand.shape[0] == self.start.shape[0] == self.templid.shape[0] == n):
             raise ValueError("rname/strand/start/templid must have the same length")
@@ -90,7 +91,20 @@ class BamData:
                          self.nstr, self.device, C.byref(h)))
             self._h = h
             self._has_bases = bool(L.ea_has_bytes(h))
+            if self._owned is not None:
+                N.check(L.ea_set_owned_range(h, *self._owned))
         return self._h
+
+    def set_owned(self, key_lo, key_hi, own_row_lo):
+        """These rows are one range shard (epialleler_b200/shard.py): reports keep the rows with key rname<<32|pos in
+        [key_lo, key_hi) - filtered on the device - and pass flags are returned for rows [own_row_lo, nrow)."""
+        self._owned = (int(key_lo), int(key_hi), int(own_row_lo))
+        if self._h is not None:
+            N.check(N.lib().ea_set_owned_range(self._h, *self._owned))
+
+    @property
+    def n_owned(self) -> int:
+        return self.nrow - (self._owned[2] if self._owned else 0)
 
     def close(self):
         if self._h is not None:
@@ -111,9 +125,18 @@ class DeviceBam:
         self._h = h
         self.device = device
         self.rname_levels = []
+        self._owned = None
 
     def handle(self, need_bases: bool = True):
         return self._h
+
+    def set_owned(self, key_lo, key_hi, own_row_lo):
+        self._owned = (int(key_lo), int(key_hi), int(own_row_lo))
+        N.check(N.lib().ea_set_owned_range(self._h, *self._owned))
+
+    @property
+    def n_owned(self):
+        return self.nrow - (self._owned[2] if self._owned else 0)
 
     @property
     def nrow(self):
@@ -151,7 +174,7 @@ class DeviceBam:
 def preprocessBam(bam_file, **kwargs):
     """R/preprocessBam.R:197-237.  Already preprocessed reads pass through unchanged; decoding a BAM
     file stays on the host with HTSlib (BASELINE.json north_star) and is not part of this package."""
-    if isinstance(bam_file, (BamData, DeviceBam)):
+    if isinstance(bam_file, (BamData, DeviceBam, MultiBam)):
         return bam_file
     raise NotImplementedError("BAM decoding (HTSlib) is outside the B200 hot path: pass preprocessed reads "
                               "(BamData) as the reference allows (R/preprocessBam.R:226-235)")
@@ -272,16 +295,113 @@ def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshol
     L = N.lib()
     p = _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, report_context)
     nrow = C.c_int64(0)
-    pass_out = _host_out(bam.nrow, np.uint8) if return_pass else None
+    if isinstance(bam, MultiBam):
+        return bam._report(p, report_file, return_pass)
+    n_flags = getattr(bam, "n_owned", bam.nrow)   # a range shard reports the flags of the rows it owns
+    pass_out = _host_out(n_flags, np.uint8) if return_pass else None
     _on_calls(bam, lambda h: N.check(L.ea_cytosine_report(h, C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow))))
     if report_file is not None:  # formatted on the device, the rows never become Python objects
         _write_report_text(report_text(bam), report_file, gzip)
         return None
     rep = _fetch_report(bam, nrow.value)
     if return_pass:
-        return pass_out[:bam.nrow].view(np.bool_), rep  # the library writes 0/1 bytes
+        return pass_out[:n_flags].view(np.bool_), rep  # the library writes 0/1 bytes
     return rep
 
+
+class MultiBam:
+    """One process, several GPUs (ea_pack_multi): the host `bam` is cut into contiguous genomic ranges with halo rows,
+    shard i is packed on devices[i] by its own host thread, generateCytosineReport runs on all devices at once and the
+    owned rows come back concatenated in genomic order - the result equals the single-GPU report bit for bit."""
+
+    def __init__(self, bam: BamData, devices: Sequence[int], calls_only: bool = True):
+        L = N.lib()
+        self.bam = bam
+        self.rname_levels = bam.rname_levels
+        self.devices = list(devices)
+        dv = (C.c_int * len(self.devices))(*self.devices)
+        m = C.c_void_p()
+        blob, off = bam.blob()
+        blob = blob if blob.shape[0] else np.zeros(1, np.uint8)
+        N.check(L.ea_pack_multi(_p(bam.rname, C.c_int32), _p(bam.strand, C.c_int32), _p(bam.start, C.c_int32), _p(bam.templid, C.c_int32),
+                                bam.nrow, _p(blob, C.c_uint8), _p(off, C.c_int64), bam.nstr, dv, len(self.devices), 1 if calls_only else 0, C.byref(m)))
+        self._m = m
+
+    @property
+    def nrow(self):
+        return self.bam.nrow
+
+    def shards(self):
+        L = N.lib()
+        out = []
+        for i in range(L.ea_multi_ndev(self._m)):
+            s = N.Shard()
+            N.check(L.ea_multi_shard(self._m, i, C.byref(s)))
+            out.append(s)
+        return out
+
+    def _report(self, p, report_file, return_pass):
+        L = N.lib()
+        if report_file is not None:
+            raise NotImplementedError("report_file with several devices: fetch the report and write it")
+        nrow = C.c_int64(0)
+        pass_out = _host_out(self.nrow, np.uint8) if return_pass else None
+        N.check(L.ea_multi_cytosine_report(self._m, C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow)))
+        n = nrow.value
+        cols = [_host_out(n, np.int32) for _ in range(6)]
+        N.check(L.ea_multi_report_fetch(self._m, *[_p(c, C.c_int32) for c in cols]))
+        rep = {k: c[:n] for k, c in zip(("rname", "strand", "pos", "context", "meth", "unmeth"), cols)}
+        rep["levels"] = {"rname": list(self.rname_levels), "strand": list(STRAND_LEVELS), "context": list(CONTEXT_LEVELS)}
+        if return_pass:
+            return pass_out[:self.nrow].view(np.bool_), rep
+        return rep
+
+    def close(self):
+        if self._m is not None:
+            N.lib().ea_multi_free(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+
+class Ingest:
+    """Streaming ingestion (ea_ingest_*): what the reader loop (src/rcpp_read_bam.cpp:61-69, push_template) would call
+    instead of seqxm->emplace_back.  append() takes one template in FILE order; finish() sorts the rows by (rname,start)
+    on the device (stable, like R's setorder) and returns (DeviceBam, columns) - columns = the sorted bam.data columns
+    rname/strand/start/templid the reference's data.table would hold."""
+
+    def __init__(self, device=0, expected_templates=0):
+        g = C.c_void_p()
+        N.check(N.lib().ea_ingest_begin(device, expected_templates, C.byref(g)))
+        self._g, self.device, self.n = g, device, 0
+
+    def append(self, rname, strand, start, seqxm: bytes):
+        buf = np.frombuffer(seqxm, dtype=np.uint8) if len(seqxm) else np.zeros(1, np.uint8)
+        r = N.lib().ea_ingest_append(self._g, int(rname), int(strand), int(start), buf.ctypes.data, len(seqxm))
+        if r < 0:
+            N.check(int(r))
+        self.n += 1
+        return int(r)
+
+    def finish(self):
+        n = self.n
+        cols = [np.zeros(max(n, 1), np.int32) for _ in range(4)]
+        h = C.c_void_p()
+        g, self._g = self._g, None
+        N.check(N.lib().ea_ingest_finish(g, *[_p(c, C.c_int32) for c in cols], C.byref(h)))
+        return DeviceBam(h, self.device), dict(zip(("rname", "strand", "start", "templid"), (c[:n] for c in cols)))
+
+    def abort(self):
+        if self._g is not None:
+            N.lib().ea_ingest_abort(self._g)
+            self._g = None
+
+    __del__ = abort
 
 
 # ---- lMHL report (SURVEY.md 8f rank 1) ---------------------------------------------------------------

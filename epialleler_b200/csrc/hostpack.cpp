@@ -66,7 +66,7 @@ unsigned scan_rows(const Job& job, int64_t t0, int64_t t1, uint32_t* ls, int32_t
     const int64_t r1 = (t * 32 + 32 < job.n) ? t * 32 + 32 : job.n;
     for (int64_t r = t * 32; r < r1; r++) {
       if (job.templid && job.templid[r] != (int32_t)r) flags |= kNotIdentity;
-      const int64_t l = job.off[r + 1] - job.off[r];
+      const int64_t l = job.row_len(r);
       if (l < 0 || l > 0x7FFFFFF0ll) { flags |= kBadLength; ls[r] = 0; continue; }
       const int32_t s = job.strand[r];
       if (s != 1 && s != 2) flags |= kBadStrand;
@@ -91,7 +91,9 @@ __attribute__((target("avx2"))) static inline void unit_avx2_fast(const uint8_t*
 }
 
 __attribute__((target("avx2"))) static void pack_tiles_avx2(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst) {
-  const uint8_t* const safe_end = job.blob + job.off[job.n] - 32;   // a full 32-byte load at or below this address stays inside the blob
+  // a full 32-byte load at or below safe_end stays inside the blob; scattered strings: only full units are loaded directly
+  const uint8_t* const safe_end = job.str ? nullptr : job.blob + job.off[job.n] - 32;
+  static const uint8_t kNone[1] = {0};
   for (int64_t t = t0; t < t1; t++) {
     __m128i* tile = reinterpret_cast<__m128i*>(dst + (toff[t] - toff[t0]) * 512);
     const int nu_t = (int)(toff[t + 1] - toff[t]);
@@ -99,15 +101,15 @@ __attribute__((target("avx2"))) static void pack_tiles_avx2(const Job& job, cons
     int len[32];
     for (int l = 0; l < 32; l++) {
       const int64_t r = t * 32 + l;
-      if (r < job.n) { row[l] = job.blob + job.off[r]; len[l] = (int)(job.off[r + 1] - job.off[r]); }
-      else { row[l] = job.blob; len[l] = 0; }
+      if (r < job.n) { row[l] = job.row_ptr(r); len[l] = (int)job.row_len(r); }
+      else { row[l] = kNone; len[l] = 0; }
     }
     for (int j = 0; j < nu_t; j++) {   // unit-major: the tile's 512-byte unit rows are written front to back
       for (int l = 0; l < 32; l++) {
         const int n = len[l] - 32 * j;
         const uint8_t* p = row[l] + 32 * j;
         if (n <= 0) { _mm_stream_si128(tile + j * 32 + l, _mm_setzero_si128()); continue; }
-        if (p <= safe_end) { unit_avx2_fast(p, n, tile + j * 32 + l); continue; }
+        if (safe_end ? p <= safe_end : n >= 32) { unit_avx2_fast(p, n, tile + j * 32 + l); continue; }
         alignas(32) uint8_t tmp[32] = {0};
         memcpy(tmp, p, (size_t)(n < 32 ? n : 32));
         unit_avx2_fast(tmp, n, tile + j * 32 + l);
@@ -127,7 +129,7 @@ unsigned pack_tiles(const Job& job, const int64_t* toff, int64_t t0, int64_t t1,
       const int64_t r = t * 32 + l;
       int64_t len = 0;
       const uint8_t* row = nullptr;
-      if (r < job.n) { len = job.off[r + 1] - job.off[r]; row = job.blob + job.off[r]; }
+      if (r < job.n) { len = job.row_len(r); row = job.row_ptr(r); }
       const int nu = (int)((len + 31) >> 5);
       for (int j = 0; j < nu_t; j++) {
         uint32_t u[4] = {0, 0, 0, 0};
@@ -146,8 +148,8 @@ unsigned pack_rows(const Job& job, const int64_t* uoff, int64_t r0, int64_t r1, 
   const bool avx2 = have_avx2();
   bool ok = true;
   for (int64_t r = r0; r < r1; r++) {
-    const int64_t len = job.off[r + 1] - job.off[r];
-    const uint8_t* row = job.blob + job.off[r];
+    const int64_t len = job.row_len(r);
+    const uint8_t* row = job.row_ptr(r);
     uint8_t* d = dst + (uoff[r] - uoff[r0]) * 16;
     const int64_t nu = (len + 31) >> 5;
     for (int64_t j = 0; j < nu; j++) {

@@ -10,6 +10,11 @@ struct Job {
   const int32_t* strand;    // 1 '+', 2 '-'
   const int32_t* templid;   // nullptr or the identity
   int64_t n;
+  // scattered form (ea_pack_calls: the reference's std::vector<std::string>): row r = str[r][0 .. len[r]); blob/off unused
+  const uint8_t* const* str = nullptr;
+  const int64_t* len = nullptr;
+  const uint8_t* row_ptr(int64_t r) const { return str ? str[r] : blob + off[r]; }
+  int64_t row_len(int64_t r) const { return str ? len[r] : off[r + 1] - off[r]; }
 };
 
 enum : unsigned { kNotIdentity = 1u, kBadLength = 2u, kBadStrand = 4u, kBadCode = 8u };

@@ -14,12 +14,14 @@
 #include <functional>
 #include <cstdlib>
 #include <ctime>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
@@ -43,6 +45,7 @@
 namespace {
 
 thread_local std::string g_err;
+thread_local int g_pack_threads = 0;   // > 0: host threads a packer called from this thread may use (ea_pack_multi)
 ea_poll_fn g_poll = nullptr;
 int g_kernel_policy = 0;
 
@@ -214,6 +217,11 @@ struct ea_handle {
   int32_t* d_cols[6] = {};
   int64_t cap_rows = 0;
   int64_t n_rows = -1;
+  // range sharding (ea_set_owned_range): the report keeps the rows whose key rname<<32|pos lies in [own_key_lo, own_key_hi)
+  // - found on the device by two binary searches over the ordered columns - and pass flags are reported from own_row_lo on
+  bool own_set = false;
+  int64_t own_key_lo = 0, own_key_hi = 0, own_row_lo = 0;
+  int64_t row_first = 0;           // first owned row of the last report inside d_cols
   int32_t report_n_launches = 0;
   const char* report_kernel = "";  // which window kernel the last report ran
   char* d_text = nullptr;      // last formatted report (ea_cx_report_text)
@@ -1189,7 +1197,8 @@ int launch_pl_u(ea_handle* h, const WinIndex& ix, const PlPlan& pp, const ThrPar
   ThrTables tb{nullptr, nullptr};
   int rc;
   if (FUSED && (rc = thr_tables(h, thr, &tb))) return rc;
-  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * 64));
+  static const int grid_mult = []() { const char* e = getenv("EA_PL_GRID"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 64; }();
+  const int grid = std::max(1, std::min<int>(ix.n, h->sm_count * grid_mult));
   kern<<<grid, kRowThreads, pp.smem, h->stream>>>(planar_of(h), wt, thr, tb, pass_in, pass_out, out);
   CU(cudaGetLastError());
   return EA_OK;
@@ -1387,6 +1396,22 @@ int launch_vsr(ea_handle* h, const WinIndex& ix, int k, int want, const uint8_t*
   }
 }
 
+// Ownership filter of a range shard: the report is ordered by (rname,pos), so the rows a shard owns are ONE contiguous run
+// [a,b) of it; counters[2] = a, counters[3] = b.  counters[0] = rows written (read on the device: no host round trip).
+__global__ void k_owned_rows(const int32_t* __restrict__ rname, const int32_t* __restrict__ pos, long long cap,
+                             long long key_lo, long long key_hi, unsigned long long* counters) {
+  if (threadIdx.x > 1 || blockIdx.x) return;
+  const long long n = min((long long)counters[0], cap);
+  const long long key = threadIdx.x ? key_hi : key_lo;
+  long long a = 0, b = n;
+  while (a < b) {
+    const long long m = (a + b) >> 1;
+    const long long k = ((long long)rname[m] << 32) | (long long)(uint32_t)pos[m];
+    if (k < key) a = m + 1; else b = m;
+  }
+  counters[2 + threadIdx.x] = (unsigned long long)a;
+}
+
 int ensure_pass(ea_handle* h) {
   if (!h->d_pass) return dmalloc(&h->d_pass, (size_t)h->n);
   return EA_OK;
@@ -1434,8 +1459,11 @@ struct ReportPlan {
 
 // The device pipeline of one report: (threshold) -> window kernel -> window scan -> ordered gather.
 // pass_in_dev: device pass flags for the unthresholded/explicit-pass case (may be null = all TRUE).
+std::mutex g_report_mu[kMaxDevices];   // one report at a time per DEVICE: the launchers set per-function attributes
+                                        // (dynamic shared memory) that two host threads sharing a device would race on
 int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, ea_timing* tm) {
   int rc;
+  std::lock_guard<std::mutex> device_lock(g_report_mu[std::max(0, std::min(h->device, kMaxDevices - 1))]);
   Trace tr("run_report");
   h->n_rows = -1;
   if (tm) memset(tm, 0, sizeof *tm);
@@ -1558,8 +1586,12 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
     } else {
       CU(cudaEventRecord(h->ev[2], h->stream));
     }
+    if (h->own_set) {
+      k_owned_rows<<<1, 32, 0, h->stream>>>(h->d_cols[0], h->d_cols[2], h->cap_rows, h->own_key_lo, h->own_key_hi, h->d_counters);
+      launches++;
+    }
     CU(cudaEventRecord(h->ev[3], h->stream));
-    unsigned long long counters[3] = {0, 0, 0};
+    unsigned long long counters[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(counters, h->d_counters, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->report_n_launches = launches;
@@ -1569,6 +1601,8 @@ int run_report(ea_handle* h, const ReportPlan& rp, const uint8_t* pass_in_dev, e
       continue;
     }
     h->n_rows = (int64_t)counters[0];
+    h->row_first = 0;
+    if (h->own_set) { h->row_first = (int64_t)counters[2]; h->n_rows = std::max<int64_t>(0, (int64_t)counters[3] - (int64_t)counters[2]); }
     tr.mark("kernels");
     if (tm) {
       CU(cudaEventElapsedTime(&tm->total_ms, h->ev[0], h->ev[3]));
@@ -1635,7 +1669,7 @@ int pack_from_device_blob(ea_handle* h, const uint8_t* d_blob, const int64_t* d_
   unsigned f = 0;
   CU(cudaMemcpy(&f, d_flags, 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(&h->npadded, h->d_off + h->n, 8, cudaMemcpyDeviceToHost));
-  if (f) return flags_error(f);
+  if (f & ~(unsigned)F_NONIDENT) return flags_error(f);   // F_NONIDENT is informational (rows reach their strings through templid)
   // true byte total
   {
     int64_t* d_l64; int64_t* d_sum;
@@ -1852,8 +1886,9 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   if (nstr > 0 && !off) return fail(EA_ERR_ARG, "null offsets");
   int rc;
   if ((rc = pick_device(device))) return rc;
-  if (nstr > 0 && off[0] != 0) return fail(EA_ERR_ARG, "string offsets must start at 0");
-  const int64_t total = nstr > 0 ? off[nstr] : 0;
+  if (nstr > 0 && off[0] < 0) return fail(EA_ERR_ARG, "negative string offset");
+  const int64_t base = nstr > 0 ? off[0] : 0;   // string i = blob[off[i], off[i+1]): the offsets need not start at 0 (a shard of a larger blob)
+  const int64_t total = nstr > 0 ? off[nstr] - base : 0;
   if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
   Trace tr("ea_pack_blob");
   ea_handle* h = new ea_handle;
@@ -1918,10 +1953,10 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   int64_t s_begin[kMaxChunks + 1];  // string index range of every chunk
   for (int k = 0; k <= n_chunks; k++) s_begin[k] = nstr * k / n_chunks;
   for (int k = 0; k < n_chunks; k++) {
-    const int64_t b0 = nstr > 0 ? off[s_begin[k]] : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] : 0;
+    const int64_t b0 = nstr > 0 ? off[s_begin[k]] - base : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] - base : 0;
     if (b1 < b0 || b1 > total) { cleanup(); ea_free(h); return fail(EA_ERR_ARG, "string offsets are not ascending"); }
     if (fill && b1 > b0) (*fill)(s_begin[k], s_begin[k + 1]);
-    if (b1 > b0) TRYCU(cudaMemcpyAsync(d_blob + b0, blob + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sc));
+    if (b1 > b0) TRYCU(cudaMemcpyAsync(d_blob + b0, blob + base + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sc));
     TRYCU(cudaEventRecord(ev_chunk[k], sc));
   }
   unsigned f = 0;
@@ -1943,12 +1978,12 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   int64_t tiles_done = 0;
   const int rp_grid = std::max(1, h->sm_count * 8);
   for (int k = 0; k < n_chunks; k++) {
-    const int64_t b0 = nstr > 0 ? off[s_begin[k]] : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] : 0;
+    const int64_t b0 = nstr > 0 ? off[s_begin[k]] - base : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] - base : 0;
     TRYCU(cudaStreamWaitEvent(sk, ev_chunk[k], 0));
     if (b1 > b0) k_validate_domain<<<(int)std::min<int64_t>(((b1 - b0) / 16 + 256) / 256, h->sm_count * 16), 256, 0, sk>>>(d_blob + b0, b1 - b0, d_flags);
     if (by_chunk) {
       const int64_t r0 = std::min(s_begin[k], nrow), r1 = std::min(s_begin[k + 1], nrow);
-      if (r1 > r0) k_repack<<<std::min(grid_for(r1 - r0, 256), rp_grid), 256, 0, sk>>>(d_blob, d_soff, nullptr, r0, r1, h->d_off, h->d_len, h->d_data);
+      if (r1 > r0) k_repack<<<std::min(grid_for(r1 - r0, 256), rp_grid), 256, 0, sk>>>(d_blob - base, d_soff, nullptr, r0, r1, h->d_off, h->d_len, h->d_data);
       if (planar) {  // the tiles whose rows are all repacked by now
         const int64_t t1 = (k == n_chunks - 1 || r1 >= nrow) ? h->pl_tiles : (h->pl_th == 32 ? r1 >> 5 : r1);
         TRY(planar_fill(h, tiles_done, t1, sk));
@@ -1957,7 +1992,7 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
     }
   }
   if (!by_chunk && nrow > 0) {
-    k_repack<<<std::min(grid_for(nrow, 256), rp_grid), 256, 0, sk>>>(d_blob, d_soff, d_templid, 0, nrow, h->d_off, h->d_len, h->d_data);
+    k_repack<<<std::min(grid_for(nrow, 256), rp_grid), 256, 0, sk>>>(d_blob - base, d_soff, d_templid, 0, nrow, h->d_off, h->d_len, h->d_data);
     if (planar) TRY(planar_fill(h, 0, h->pl_tiles, sk));
   }
   TRYCU(cudaMemcpyAsync(&f, d_flags, 4, cudaMemcpyDeviceToHost, sk));
@@ -2059,14 +2094,15 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   *out = nullptr;
   if (nrow != nstr || nrow <= 0) return ea_pack_blob(rname, strand, start, templid, nrow, blob, off, nstr, device, out);
   if (!rname || !strand || !start || !off) return fail(EA_ERR_ARG, "null column");
-  if (off[0] != 0) return fail(EA_ERR_ARG, "string offsets must start at 0");
-  const int64_t total = off[nstr];
+  if (off[0] < 0) return fail(EA_ERR_ARG, "negative string offset");
+  const int64_t total = off[nstr] - off[0];   // the offsets need not start at 0 (a shard of a larger blob)
   if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
   if (nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row/string count");
   int rc;
   if ((rc = pick_device(device))) return rc;
   Trace tr("ea_pack_blob_calls");
   int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  if (g_pack_threads > 0) nt = std::min(nt, g_pack_threads);
   if (const char* e = getenv("EA_HOST_PACK_THREADS")) nt = std::max(1, atoi(e));
   if (nt < 6 && !getenv("EA_HOST_PACK_FORCE"))   // too few cores for the host half to pay: the general packer (all bytes over PCIe)
     return ea_pack_blob(rname, strand, start, templid, nrow, blob, off, nstr, device, out);
@@ -2732,7 +2768,7 @@ int ea_cx_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* p
   int32_t* dst[6] = {rname, strand, pos, context, meth, unmeth};
   if (h->n_rows > 0)
     for (int c = 0; c < 6; c++)
-      if (dst[c]) CU(cudaMemcpyAsync(dst[c], h->d_cols[c], 4 * (size_t)h->n_rows, cudaMemcpyDeviceToHost, h->stream));
+      if (dst[c]) CU(cudaMemcpyAsync(dst[c], h->d_cols[c] + h->row_first, 4 * (size_t)h->n_rows, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   tr.mark("D2H rows");
   return EA_OK;
@@ -2769,7 +2805,8 @@ int ea_cx_report_text(ea_handle* h, const char* const* rname_levels, int32_t n_l
   TRYCU(cudaMemcpyAsync(d_off, off.data(), 4 * off.size(), cudaMemcpyHostToDevice, h->stream));
   TRYCU(cudaMemsetAsync(d_len + n, 0, 8, h->stream));
   const TextLevels lv{d_chars, d_off, n_levels};
-  const ReportCols cols{h->d_cols[0], h->d_cols[1], h->d_cols[2], h->d_cols[3], h->d_cols[4], h->d_cols[5]};
+  const int64_t f0 = h->row_first;
+  const ReportCols cols{h->d_cols[0] + f0, h->d_cols[1] + f0, h->d_cols[2] + f0, h->d_cols[3] + f0, h->d_cols[4] + f0, h->d_cols[5] + f0};
   if (n > 0) k_text_len<<<grid_for(n, 256), 256, 0, h->stream>>>(cols, n, lv, d_len);
   size_t tb = 0;
   TRYCU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_len, d_pos, (int)(n + 1), h->stream));
@@ -2810,12 +2847,22 @@ int ea_cytosine_report(ea_handle* h, const ea_report_params* p, uint8_t* pass_ou
   ReportPlan rp;
   if ((rc = make_plan_from_params(p, 0, &rp))) return rc;
   if ((rc = run_report(h, rp, nullptr, nullptr))) return rc;
-  if (pass_out && h->n > 0) {
-    if (rp.threshold) CU(cudaMemcpyAsync(pass_out, h->d_pass, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
-    else memset(pass_out, 1, (size_t)h->n);
+  const int64_t r0 = h->own_set ? std::min(h->own_row_lo, h->n) : 0;   // a range shard reports the flags of the rows it owns
+  if (pass_out && h->n > r0) {
+    if (rp.threshold) CU(cudaMemcpyAsync(pass_out, h->d_pass + r0, (size_t)(h->n - r0), cudaMemcpyDeviceToHost, h->stream));
+    else memset(pass_out, 1, (size_t)(h->n - r0));
     CU(cudaStreamSynchronize(h->stream));
   }
   *nrow_out = h->n_rows;
+  return EA_OK;
+}
+
+int ea_set_owned_range(ea_handle* h, int64_t key_lo, int64_t key_hi, int64_t own_row_lo) {
+  if (!h) return fail(EA_ERR_ARG, "null handle");
+  if (key_lo < 0) { h->own_set = false; h->own_row_lo = 0; return EA_OK; }
+  if (key_hi < key_lo || own_row_lo < 0 || own_row_lo > h->n) return fail(EA_ERR_ARG, "bad owned range");
+  h->own_set = true; h->own_key_lo = key_lo; h->own_key_hi = key_hi; h->own_row_lo = own_row_lo;
+  h->n_rows = -1;
   return EA_OK;
 }
 
@@ -2965,3 +3012,6 @@ int ea_export_host(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* start
 }
 
 }  // extern "C"
+
+#include "multi.inc"
+#include "scattered.inc"

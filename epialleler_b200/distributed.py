@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .shard import filter_report, merge_reports, plan_shards, slice_bam
+from .shard import Shard, filter_report, merge_reports, plan_shards, plan_shards_native, slice_bam
 
 
 def _lengths(bam):
@@ -17,13 +17,26 @@ def _lengths(bam):
     return (off[1:] - off[:-1])[bam.templid]
 
 
-def shard_report(bam, rank: int, world: int, engine=None, **kw):
-    """This rank's part: (shard, pass flags of its own rows, the report rows it owns)."""
-    if engine is None:
-        from .api import generateCytosineReport
+def local_report(sub, shard: Shard, **kw):
+    """One shard whose rows [row_lo, own_hi) are ALREADY this rank's `sub` (a BamData or DeviceBam holding nothing else):
+    the ownership filter runs on the device (ea_set_owned_range: two binary searches over the ordered report, only the
+    owned rows cross PCIe) and the pass flags come back for the owned rows only.  This is the call a rank makes when it
+    loaded just its own genomic range - no rank ever needs the whole data set."""
+    from .api import generateCytosineReport
+    sub.set_owned(shard.key_lo, shard.key_hi, shard.own_lo - shard.row_lo)
+    own_pass, rep = generateCytosineReport(sub, return_pass=True, **kw)
+    return np.asarray(own_pass), rep
 
-        def engine(sub, **k):
-            return generateCytosineReport(sub, return_pass=True, **k)
+
+def shard_report(bam, rank: int, world: int, engine=None, **kw):
+    """This rank's part of a host `bam` every rank holds: (shard, pass flags of its own rows, the report rows it owns).
+    engine=None runs the library with the device-side ownership filter; a custom engine (the CPU tests) gets the host mask."""
+    if engine is None:
+        sh = plan_shards_native(bam, world)[rank]
+        sub = slice_bam(bam, sh)
+        own_pass, rep = local_report(sub, sh, **kw)
+        sub.close()
+        return sh, own_pass, rep
     sh = plan_shards(bam.rname, bam.start, _lengths(bam), world)[rank]
     sub = slice_bam(bam, sh)
     pass_, rep = engine(sub, **kw)

@@ -77,8 +77,66 @@ def plan_shards(rname, start, length, world: int, weights=None) -> List[Shard]:
     return shards
 
 
+def plan_shards_native(bam, world: int) -> List[Shard]:
+    """The same plan from the library's planner (ea_plan_shards, csrc/multi.inc): no per-row Python temporaries - the cuts
+    are binary searches over the blob offsets and the halo is found by walking back from the cut, so it runs on a
+    billion rows.  Pure host code; identical to plan_shards (tests/test_shard.py)."""
+    import ctypes as C
+
+    from . import _native as N
+    L = N.lib()
+    out = (N.Shard * world)()
+    off = bam.blob()[1]
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    N.check(L.ea_plan_shards(p(bam.rname, C.c_int32), p(bam.start, C.c_int32), p(bam.templid, C.c_int32), bam.nrow, p(off, C.c_int64),
+                             int(off.shape[0] - 1), world, out))
+    return [Shard(r, s.row_lo, s.own_lo, s.own_hi, s.key_lo, s.key_hi) for r, s in enumerate(out)]
+
+
+def plan_shards_windowed(n: int, world: int, fetch, max_len: int, window: int = 1 << 16) -> List[Shard]:
+    """The plan for rows that are NOT materialised anywhere as whole columns (a billion-row data set of which every rank
+    loads only its own range): cuts at equal ROW counts, and only `window` rows around every cut are looked at.
+    fetch(i0, i1) -> (rname, start, length) arrays of rows [i0, i1).  max_len bounds the string lengths (the halo walk
+    stops at the first row that cannot reach the cut).  Equal to plan_shards(..., weights=ones) whenever the run of equal
+    (rname,start) at a cut and the halo fit into the window (asserted)."""
+    cuts = [0]
+    info = {}
+    for r in range(1, world):
+        c = min(max(n * r // world, cuts[-1]), n)
+        if c < n:
+            i0 = max(0, c - window)
+            rn, st, ln = (np.asarray(a, dtype=np.int64) for a in fetch(i0, c + 1))
+            k = (rn << 32) | st
+            first = int(np.searchsorted(k, k[-1], side="left"))
+            assert first > 0 or i0 == 0, "run of equal (rname,start) longer than the window"
+            c = max(i0 + first, cuts[-1])
+            # halo: rows before the cut, same chromosome, reaching past the cut position
+            cut_rn, cut_pos = rn[c - i0], st[c - i0]
+            cand = (rn[:c - i0] == cut_rn) & (st[:c - i0] + ln[:c - i0] > cut_pos)
+            lo = i0 + int(np.argmax(cand)) if cand.any() else c
+            could = (rn[:c - i0] == cut_rn) & (st[:c - i0] + max_len > cut_pos)
+            assert i0 == 0 or not could[0], "halo longer than the window"
+            info[c] = (lo, int(k[c - i0]))
+        cuts.append(c)
+    cuts.append(n)
+    shards = []
+    for r in range(world):
+        own_lo, own_hi = cuts[r], cuts[r + 1]
+        key_lo = KEY_MIN if r == 0 or own_lo >= n else info[own_lo][1]
+        key_hi = KEY_MAX if r == world - 1 or own_hi >= n else info[own_hi][1]
+        row_lo = info[own_lo][0] if (r > 0 and own_lo < n) else own_lo
+        if own_lo >= n:
+            row_lo, key_lo, key_hi = n, KEY_MAX, KEY_MAX
+        shards.append(Shard(r, row_lo, own_lo, own_hi, key_lo, key_hi))
+    for r in range(world - 1):
+        if shards[r + 1].own_lo >= n and shards[r].own_lo < n:
+            shards[r].key_hi = KEY_MAX
+    return shards
+
+
 def filter_report(rep: dict, shard: Shard) -> dict:
-    """Keep the report rows this rank owns."""
+    """Keep the report rows this rank owns (host-side mask: used where the per-shard engine is not the library - the CPU
+    tests; the library filters on the device, ea_set_owned_range)."""
     k = _key(rep["rname"], rep["pos"])
     m = (k >= shard.key_lo) & (k < shard.key_hi)
     out = {c: (v[m] if isinstance(v, np.ndarray) else v) for c, v in rep.items()}

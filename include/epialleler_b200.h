@@ -96,6 +96,13 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
 int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                        int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device,
                        ea_handle** out);
+/* Scattered strings (one heap allocation per template in pageable memory: the reference's std::vector<std::string>,
+ * src/rcpp_read_bam.cpp:185) -> call planes only.  All host threads transpose the strings straight from where they lie
+ * into a small ring of page-locked blocks while the previous block crosses PCIe: nothing is gathered, half the bytes
+ * travel, and a first call pins ~100 MB instead of the whole data set.  Same arguments as ea_pack; same handle kind as
+ * ea_pack_blob_calls.  What the R shim calls for generateCytosineReport. */
+int ea_pack_calls(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                  int64_t nrow, const uint8_t* const* str, const int64_t* len, int64_t nstr, int device, ea_handle** out);
 int ea_has_bytes(const ea_handle* h);            /* 1: byte rows present (ea_pack, ea_pack_blob, ...), 0: call planes only */
 int64_t ea_pack_h2d_bytes(const ea_handle* h);   /* bytes the packer copied host -> device for this handle */
 
@@ -220,6 +227,52 @@ const char* ea_report_kernel(const ea_handle* h);
 int ea_flush_l2(ea_handle* h, int64_t bytes);
 
 /* ---- deterministic synthetic reads (same generator on host and device) ----------------------- */
+
+/* ---- streaming ingestion: what push_template (src/rcpp_read_bam.cpp:61-69) would call instead of
+ * seqxm->emplace_back.  Templates arrive one at a time in FILE order; their bytes go through a ring of page-locked blocks
+ * to the device while the reader keeps decoding.  ea_ingest_finish orders the rows by (rname,start) with a stable sort on
+ * the device - what R/internal.R:195 (setorder) does to the reader's table - packs them, and hands the sorted columns
+ * back (nullable arrays of ea_ingest count entries; templid = template index of every row).  The ingest object is
+ * released by finish or abort. */
+typedef struct ea_ingest ea_ingest;
+int ea_ingest_begin(int device, int64_t expected_templates, ea_ingest** out);
+/* returns the template's index (>= 0) or a negative EA_ERR_* code */
+int64_t ea_ingest_append(ea_ingest* g, int32_t rname, int32_t strand, int32_t start, const uint8_t* bytes, int64_t len);
+int ea_ingest_finish(ea_ingest* g, int32_t* rname_out, int32_t* strand_out, int32_t* start_out, int32_t* templid_out,
+                     ea_handle** out);
+void ea_ingest_abort(ea_ingest* g);
+
+/* ---- range sharding: contiguous genomic ranges, halo rows, no data-path collective ----
+ * key = (int64)rname << 32 | pos.  Shard r packs rows [row_lo, own_hi) (rows [row_lo, own_lo) are the halo: they start
+ * before the cut but reach past it), reports pass flags for rows [own_lo, own_hi) and the report rows with
+ * key_lo <= key < key_hi. */
+typedef struct ea_shard { int64_t row_lo, own_lo, own_hi, key_lo, key_hi; } ea_shard;
+/* Cuts the sorted rows into `world` ranges of about equal bytes, each cut snapped to the first row of its (rname,start)
+ * run.  off/templid/nstr as in ea_pack_blob (templid may be NULL = identity). */
+int ea_plan_shards(const int32_t* rname, const int32_t* start, const int32_t* templid, int64_t nrow, const int64_t* off,
+                   int64_t nstr, int world, ea_shard* out);
+/* Ownership filter ON THE DEVICE for a handle that holds one shard's rows: later ea_cytosine_report / ea_cx_report calls
+ * keep the report rows with key in [key_lo, key_hi) (one contiguous run of the ordered report, found by two binary
+ * searches on the device; only those rows are fetched) and ea_cytosine_report writes the pass flags of rows
+ * [own_row_lo, nrow) to pass_out[0 ..].  key_lo < 0 clears the filter. */
+int ea_set_owned_range(ea_handle* h, int64_t key_lo, int64_t key_hi, int64_t own_row_lo);
+
+/* One process, several devices (what the single-threaded R process calls to use every GPU of the box): plans the shards,
+ * packs shard i on devices[i] (one host thread per device; zero-copy slices of the blob when rows are the strings in file
+ * order), runs the fused report on all devices at once and concatenates the owned rows in genomic order.
+ * calls_only != 0 packs call planes only (ea_pack_blob_calls).  nrow must equal nstr. */
+typedef struct ea_multi ea_multi;
+int ea_pack_multi(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
+                  const uint8_t* blob, const int64_t* off, int64_t nstr, const int* devices, int ndev, int calls_only,
+                  ea_multi** out);
+int ea_multi_ndev(const ea_multi* m);
+ea_handle* ea_multi_handle(ea_multi* m, int i);           /* shard i's handle (owned by m) */
+int ea_multi_shard(const ea_multi* m, int i, ea_shard* out);
+/* pass_out: nrow flags in row order (nullable); nrow_out: rows of the concatenated report */
+int ea_multi_cytosine_report(ea_multi* m, const ea_report_params* p, uint8_t* pass_out, int64_t* nrow_out);
+int ea_multi_report_fetch(ea_multi* m, int32_t* rname, int32_t* strand, int32_t* pos, int32_t* context, int32_t* meth,
+                          int32_t* unmeth);
+void ea_multi_free(ea_multi* m);
 
 #define EA_SYNTH_MAX_CHR 32
 typedef struct ea_synth_cfg {

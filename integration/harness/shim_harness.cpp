@@ -1,0 +1,49 @@
+// Stand-in for the R process around integration/r_shim/rcpp_b200_shim.cpp (R and Rcpp are absent from the build image):
+// it holds the packed templates the way the reference's reader leaves them - a heap std::vector<std::string>, one
+// separately allocated, PAGEABLE string per template (src/rcpp_read_bam.cpp:61-69,185: seqxm->emplace_back) - and makes
+// exactly the calls handle_of() in the shim makes: build the pointer/length tables, then ea_pack_calls (or ea_pack).
+// bench.py times the end-to-end path through it; tests/ check that the handle equals one packed from a blob.
+// Plain C++ (g++), linked against the product's C ABI only.
+#include <cstdint>
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/epialleler_b200.h"
+
+extern "C" {
+
+// what rcpp_read_bam leaves behind: one emplace_back per template
+void* harness_strings_new(const uint8_t* blob, const int64_t* off, int64_t n) {
+  auto* v = new std::vector<std::string>();
+  v->reserve((size_t)n);
+  for (int64_t i = 0; i < n; i++) v->emplace_back(reinterpret_cast<const char*>(blob + off[i]), (size_t)(off[i + 1] - off[i]));
+  return v;
+}
+void harness_strings_free(void* p) { delete static_cast<std::vector<std::string>*>(p); }
+int64_t harness_strings_count(void* p) { return (int64_t)static_cast<std::vector<std::string>*>(p)->size(); }
+
+// handle_of() of the shim: pointer and length tables over the vector, then the packer
+int harness_pack(void* p, const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
+                 int device, int calls_only, ea_handle** out) {
+  auto* seqxm = static_cast<std::vector<std::string>*>(p);
+  const size_t n = seqxm->size();
+  // plain arrays filled by a few threads (no R API in them): a std::vector would zero-fill 2 x 400 MB on one thread first
+  std::unique_ptr<const uint8_t*[]> str(new const uint8_t*[n ? n : 1]);
+  std::unique_ptr<int64_t[]> len(new int64_t[n ? n : 1]);
+  const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+        str[i] = reinterpret_cast<const uint8_t*>((*seqxm)[i].data());
+        len[i] = static_cast<int64_t>((*seqxm)[i].size());
+      }
+    });
+  for (auto& x : th) x.join();
+  return (calls_only ? ea_pack_calls : ea_pack)(rname, strand, start, templid, nrow, str.get(), len.get(), (int64_t)n, device, out);
+}
+
+}  // extern "C"

@@ -9,7 +9,10 @@
 // the three exported R closures (R/RcppExports.R:12-14,28-30,64-66) and the registered native
 // symbols (src/RcppExports.cpp:253-271) keep their names, arity and argument meaning.
 #include <Rcpp.h>
+#include <algorithm>
 #include <cstdio>
+#include <memory>
+#include <thread>
 #include <epialleler_b200.h>
 
 namespace {
@@ -25,30 +28,66 @@ int poll_interrupt() {           // Rcpp::checkUserInterrupt() throws; the C ABI
 
 struct Handle {
   ea_handle* h = nullptr;
+  const void* seqxm = nullptr;   // identity of the strings the handle was packed from
+  R_xlen_t nrow = 0;
+  const int* rname0 = nullptr;   // identity of the columns (a subset / reordered bam.data has other vectors)
+  const int* start0 = nullptr;
   ~Handle() { ea_free(h); }
 };
 
-// The device-resident packed copy hangs on the data.frame as a second external pointer, next to the
-// reference's "seqxm_xptr" (src/rcpp_read_bam.cpp:185): pack once, reuse across reports.
-ea_handle* handle_of(Rcpp::DataFrame& df) {
-  if (df.hasAttribute("b200_xptr")) {
-    Rcpp::XPtr<Handle> p((SEXP)df.attr("b200_xptr"));
-    if (p->h && ea_nrow(p->h) == df.nrows()) return p->h;
-  }
+// Packs bam.data.  need_bytes = false (thresholds, betas, cytosine reports, BED matching): call planes only
+// (ea_pack_calls - the host transposes the reader's strings where they lie, half the bytes cross PCIe);
+// need_bytes = true (lMHL, VCF base frequencies): byte rows too (ea_pack).  The pointer/length tables over the
+// std::vector<std::string> are filled by a few threads (no R API inside them) - integration/harness/shim_harness.cpp is this
+// very code without Rcpp, and what bench.py's end-to-end leg and tests/test_gpu_widen.py run.
+Handle* pack(Rcpp::DataFrame& df, bool need_bytes) {
   Rcpp::XPtr<std::vector<std::string>> seqxm((SEXP)df.attr("seqxm_xptr"));
   Rcpp::IntegerVector rname = df["rname"], strand = df["strand"], start = df["start"], templid = df["templid"];
-  std::vector<const uint8_t*> str(seqxm->size());
-  std::vector<int64_t> len(seqxm->size());
-  for (size_t i = 0; i < seqxm->size(); i++) {
-    str[i] = reinterpret_cast<const uint8_t*>((*seqxm)[i].data());
-    len[i] = static_cast<int64_t>((*seqxm)[i].size());
-  }
+  const size_t n = seqxm->size();
+  std::unique_ptr<const uint8_t*[]> str(new const uint8_t*[n ? n : 1]);
+  std::unique_ptr<int64_t[]> len(new int64_t[n ? n : 1]);
+  const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+        str[i] = reinterpret_cast<const uint8_t*>((*seqxm)[i].data());
+        len[i] = static_cast<int64_t>((*seqxm)[i].size());
+      }
+    });
+  for (auto& x : th) x.join();
   ea_set_poll(poll_interrupt);
   Handle* hd = new Handle;
-  ea_check(ea_pack(rname.begin(), strand.begin(), start.begin(), templid.begin(), df.nrows(), str.data(), len.data(),
-                   static_cast<int64_t>(str.size()), /*device=*/0, &hd->h));
+  hd->seqxm = seqxm.get(); hd->nrow = df.nrows(); hd->rname0 = rname.begin(); hd->start0 = start.begin();
+  const int rc = (need_bytes ? ea_pack : ea_pack_calls)(rname.begin(), strand.begin(), start.begin(), templid.begin(), df.nrows(), str.get(),
+                                                        len.get(), static_cast<int64_t>(n), /*device=*/0, &hd->h);
+  if (rc != EA_OK) { delete hd; ea_check(rc); }
+  return hd;
+}
+
+// The device-resident packed copy hangs on the data.frame as a second external pointer, next to the
+// reference's "seqxm_xptr" (src/rcpp_read_bam.cpp:185): pack once, reuse across reports.  It is reused only for the very
+// same strings AND column vectors (a subset or reordered copy of bam.data has the same seqxm_xptr but other vectors).
+ea_handle* handle_of(Rcpp::DataFrame& df, bool need_bytes = false) {
+  Rcpp::XPtr<std::vector<std::string>> seqxm((SEXP)df.attr("seqxm_xptr"));
+  Rcpp::IntegerVector rname = df["rname"], start = df["start"];
+  if (df.hasAttribute("b200_xptr")) {
+    Rcpp::XPtr<Handle> p((SEXP)df.attr("b200_xptr"));
+    if (p->h && p->seqxm == seqxm.get() && p->nrow == df.nrows() && p->rname0 == rname.begin() && p->start0 == start.begin() &&
+        (!need_bytes || ea_has_bytes(p->h)))
+      return p->h;
+  }
+  Handle* hd = pack(df, need_bytes);
   df.attr("b200_xptr") = Rcpp::XPtr<Handle>(hd, true);
   return hd->h;
+}
+
+// a call that the call planes cannot serve answers EA_ERR_NEEDS_BYTES: pack again with the byte rows and repeat
+template <class F>
+void with_handle(Rcpp::DataFrame& df, F f) {
+  int rc = f(handle_of(df, false));
+  if (rc == EA_ERR_NEEDS_BYTES) rc = f(handle_of(df, true));
+  ea_check(rc);
 }
 
 Rcpp::DataFrame wrap_report(ea_handle* h, int64_t n, Rcpp::DataFrame& df) {
@@ -69,29 +108,28 @@ Rcpp::DataFrame wrap_report(ea_handle* h, int64_t n, Rcpp::DataFrame& df) {
 std::vector<bool> rcpp_threshold_reads(Rcpp::DataFrame& df, const std::string ctx_meth, const std::string ctx_unmeth,
                                        const std::string ooctx_meth, const std::string ooctx_unmeth, const unsigned int min_n_ctx,
                                        const double min_ctx_meth_frac, const double max_ooctx_meth_frac) {
-  ea_handle* h = handle_of(df);
-  std::vector<uint8_t> flags(static_cast<size_t>(ea_nrow(h)) + 1);
-  ea_check(ea_threshold_reads(h, ctx_meth.c_str(), ctx_unmeth.c_str(), ooctx_meth.c_str(), ooctx_unmeth.c_str(), min_n_ctx,
-                              min_ctx_meth_frac, max_ooctx_meth_frac, flags.data()));
+  std::vector<uint8_t> flags(static_cast<size_t>(df.nrows()) + 1);
+  with_handle(df, [&](ea_handle* h) {
+    return ea_threshold_reads(h, ctx_meth.c_str(), ctx_unmeth.c_str(), ooctx_meth.c_str(), ooctx_unmeth.c_str(), min_n_ctx,
+                              min_ctx_meth_frac, max_ooctx_meth_frac, flags.data());
+  });
   return std::vector<bool>(flags.begin(), flags.end() - 1);
 }
 
 // [[Rcpp::export("rcpp_get_xm_beta")]]
 std::vector<double> rcpp_get_xm_beta(Rcpp::DataFrame& df, const std::string ctx_meth, const std::string ctx_unmeth) {
-  ea_handle* h = handle_of(df);
-  std::vector<double> beta(static_cast<size_t>(ea_nrow(h)));
-  ea_check(ea_get_xm_beta(h, ctx_meth.c_str(), ctx_unmeth.c_str(), beta.data()));
+  std::vector<double> beta(static_cast<size_t>(df.nrows()));
+  with_handle(df, [&](ea_handle* h) { return ea_get_xm_beta(h, ctx_meth.c_str(), ctx_unmeth.c_str(), beta.data()); });
   return beta;
 }
 
 // [[Rcpp::export("rcpp_cx_report")]]
 Rcpp::DataFrame rcpp_cx_report(Rcpp::DataFrame& df, Rcpp::LogicalVector& pass, const std::string ctx) {
-  ea_handle* h = handle_of(df);
   std::vector<uint8_t> flags(pass.size());
   for (R_xlen_t i = 0; i < pass.size(); i++) flags[i] = pass[i] != 0;  // NA_LOGICAL counts as TRUE (src/rcpp_cx_report.cpp:118)
   int64_t n = 0;
-  ea_check(ea_cx_report(h, flags.data(), ctx.c_str(), &n));
-  return wrap_report(h, n, df);
+  with_handle(df, [&](ea_handle* h) { return ea_cx_report(h, flags.data(), ctx.c_str(), &n); });
+  return wrap_report(handle_of(df), n, df);
 }
 
 // Optional fourth entry: the fused body of generateCytosineReport (R/generateCytosineReport.R:181-201),
@@ -103,14 +141,13 @@ Rcpp::DataFrame rcpp_cytosine_report_fused(Rcpp::DataFrame& df, const bool thres
                                            const std::string ctx_unmeth, const std::string ooctx_meth, const std::string ooctx_unmeth,
                                            const unsigned int min_n_ctx, const double min_ctx_meth_frac,
                                            const double max_ooctx_meth_frac, const std::string report_ctx) {
-  ea_handle* h = handle_of(df);
   ea_report_params p;
   p.threshold_reads = threshold_reads; p.ctx_meth = ctx_meth.c_str(); p.ctx_unmeth = ctx_unmeth.c_str();
   p.ooctx_meth = ooctx_meth.c_str(); p.ooctx_unmeth = ooctx_unmeth.c_str(); p.min_n_ctx = min_n_ctx;
   p.min_ctx_meth_frac = min_ctx_meth_frac; p.max_ooctx_meth_frac = max_ooctx_meth_frac; p.report_ctx = report_ctx.c_str();
   int64_t n = 0;
-  ea_check(ea_cytosine_report(h, &p, nullptr, &n));
-  return wrap_report(h, n, df);
+  with_handle(df, [&](ea_handle* h) { return ea_cytosine_report(h, &p, nullptr, &n); });
+  return wrap_report(handle_of(df), n, df);
 }
 
 // ---- the siblings that reuse the packed reads; same exported names and signatures as the reference ----
@@ -118,7 +155,7 @@ Rcpp::DataFrame rcpp_cytosine_report_fused(Rcpp::DataFrame& df, const bool thres
 // R/RcppExports.R:40-42, src/rcpp_mhl_report.cpp:46
 // [[Rcpp::export("rcpp_mhl_report")]]
 Rcpp::DataFrame rcpp_mhl_report(Rcpp::DataFrame& df, const std::string ctx, int hmax, const int hmin, const double max_ooctx_meth_frac) {
-  ea_handle* h = handle_of(df);
+  ea_handle* h = handle_of(df, /*need_bytes=*/true);
   int64_t n = 0;
   ea_check(ea_mhl_report(h, ctx.c_str(), hmax, hmin, max_ooctx_meth_frac, &n));
   Rcpp::IntegerVector rname(n), strand(n), pos(n), context(n), coverage(n);
@@ -153,7 +190,7 @@ std::vector<int> rcpp_match_capture(Rcpp::DataFrame& df, Rcpp::DataFrame& bed, c
 // R/RcppExports.R:24-26, src/rcpp_get_base_freqs.cpp:15
 // [[Rcpp::export("rcpp_get_base_freqs")]]
 Rcpp::NumericMatrix rcpp_get_base_freqs(Rcpp::DataFrame& df, std::vector<bool> pass, Rcpp::DataFrame& vcf) {
-  ea_handle* h = handle_of(df);
+  ea_handle* h = handle_of(df, /*need_bytes=*/true);
   Rcpp::IntegerVector chr = vcf["seqnames"], pos = vcf["start"];
   std::vector<uint8_t> flags(pass.begin(), pass.end());
   Rcpp::NumericMatrix res(pos.size(), 20);                                              // column-major, like the library's output

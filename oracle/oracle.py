@@ -316,3 +316,53 @@ class PortCpu(_Cpu):
     PREFIX = "port_"
     SO = PORT_SO
     KIND = "port"
+
+
+# ---- the synthetic workload's rows, regenerated on the host WITHOUT the product library ------------------------------
+SYNTH_SO = os.path.join(HERE, "_build", "libsynth.so")
+_SYNTH_MAX_CHR = 32
+
+
+class SynthCfg(C.Structure):
+    """ea_synth_cfg of include/epialleler_b200.h (a plain C struct; restated so that nothing of the product is imported)."""
+    _fields_ = [("seed", C.c_uint64), ("n_reads", C.c_int64), ("n_chr", C.c_int32), ("len_min", C.c_int32),
+                ("len_max", C.c_int32), ("n_islands", C.c_int32), ("island_len", C.c_int32), ("reserved", C.c_int32),
+                ("chr_len", C.c_int64 * _SYNTH_MAX_CHR)]
+
+
+class HostRows:
+    """What the checkers take: int32 columns + the file-order strings as (blob, off)."""
+
+    def __init__(self, rname, strand, start, blob, off):
+        self.rname, self.strand, self.start = rname, strand, start
+        self.templid = np.arange(rname.shape[0], dtype=np.int32)
+        self._blob, self._off = blob, off
+        self.nrow = int(rname.shape[0])
+
+    def blob(self):
+        return self._blob, self._off
+
+
+def synth_rows(seed, n_reads, chr_len, len_min, len_max=None, n_islands=0, island_len=0, row_begin=0, row_end=None) -> HostRows:
+    """Rows [row_begin, row_end) of the synthetic data set from oracle/_build/libsynth.so, the host build
+    of the repo's generator header.  Bit-identical to ea_synth_host / ea_synth_device (tests/test_oracle.py)."""
+    if not os.path.exists(SYNTH_SO):
+        build(("port",))
+    L = C.CDLL(SYNTH_SO)
+    L.oracle_synth_host.restype = C.c_int
+    L.oracle_synth_host.argtypes = [C.POINTER(SynthCfg), C.c_int64, C.c_int64] + [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]
+    cfg = SynthCfg()
+    cfg.seed, cfg.n_reads, cfg.n_chr, cfg.len_min = seed, n_reads, len(chr_len), len_min
+    cfg.len_max = len_max if len_max is not None else len_min
+    cfg.n_islands, cfg.island_len = n_islands, island_len
+    for i, v in enumerate(chr_len):
+        cfg.chr_len[i] = v
+    row_end = n_reads if row_end is None else row_end
+    n = row_end - row_begin
+    rn, st, sa = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+    off = np.zeros(n + 1, np.int64)
+    if L.oracle_synth_host(C.byref(cfg), row_begin, row_end, _p(rn, C.c_int32), _p(st, C.c_int32), _p(sa, C.c_int32), _p(off, C.c_int64), None):
+        raise ValueError("bad synthetic configuration / row range")
+    blob = np.zeros(max(int(off[-1]), 1), np.uint8)
+    L.oracle_synth_host(C.byref(cfg), row_begin, row_end, None, None, None, _p(off, C.c_int64), _p(blob, C.c_uint8))
+    return HostRows(rn[:n], st[:n], sa[:n], blob[:int(off[-1])], off)

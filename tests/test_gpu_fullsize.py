@@ -17,7 +17,12 @@ import pytest
 import epialleler_b200 as ea
 from epialleler_b200 import _native as N
 from epialleler_b200.api import _params
-from oracle.oracle import PortCpu
+import os
+
+from oracle.oracle import REF_SO, PortCpu, RefCpu
+
+# the compiled reference itself whenever it travelled with the snapshot (oracle/_ref is git-ignored, not gpurun-ignored)
+Checker = RefCpu if os.path.exists(REF_SO) else PortCpu
 
 pytestmark = pytest.mark.gpu
 
@@ -79,7 +84,7 @@ def test_config2_full_size_properties(kernel_policy):
 
     # prefix against the CPU oracle
     host = ea.synth_host(cfg, 0, PREFIX)
-    want_p, want = PortCpu(host).generateCytosineReport(True, "CG", 2, 0.5, 0.1, "CG")
+    want_p, want = Checker(host).generateCytosineReport(True, "CG", 2, 0.5, 0.1, "CG")
     assert np.array_equal(p[:PREFIX], want_p)
     limit = int(host.start[-1])  # rows at positions < start of read PREFIX-1 are complete in the prefix
     k_dev = int(np.searchsorted(rep["pos"], limit, side="left"))
@@ -87,4 +92,26 @@ def test_config2_full_size_properties(kernel_policy):
     assert k_dev == k_cpu and k_dev > 10_000
     for k in ("rname", "strand", "pos", "context", "meth", "unmeth"):
         assert np.array_equal(rep[k][:k_dev], want[k][:k_cpu]), k
-    host.close(); dev.close()
+    host.close()
+
+    # three more windows against the oracle: the middle of the chromosome, a stretch straddling a multiple of every window
+    # size the kernels use (2^24), and the last rows (int32 positions near 2.49e8, the last windows, `hi` clamping).  The
+    # sub-range generator gives rows [a, b); report rows at positions covered ONLY by those rows - from the furthest end of
+    # the rows before a (< start[a] + 150) up to the start of row b-1 - must equal the oracle's on the sub-range.
+    def window(a, b):
+        sub = ea.synth_host(cfg, a, b)
+        wp, w = Checker(sub).generateCytosineReport(True, "CG", 2, 0.5, 0.1, "CG")
+        assert np.array_equal(p[a:b], wp)
+        lo_pos = int(sub.start[0]) + 150 if a > 0 else 0
+        hi_pos = int(sub.start[-1]) if b < READS else CHR1 + 1
+        sel_d = (rep["pos"] >= lo_pos) & (rep["pos"] < hi_pos)
+        sel_c = (w["pos"] >= lo_pos) & (w["pos"] < hi_pos)
+        assert int(sel_c.sum()) > 10_000
+        for k in ("rname", "strand", "pos", "context", "meth", "unmeth"):
+            assert np.array_equal(rep[k][sel_d], w[k][sel_c]), (a, b, k)
+        sub.close()
+    window(READS // 2 - PREFIX // 2, READS // 2 + PREFIX // 2)
+    r_edge = int(np.searchsorted(ea.synth_host(cfg, 3_300_000, 3_500_000).start, 1 << 24)) + 3_300_000   # first row starting beyond position 2^24
+    window(r_edge - PREFIX // 2, r_edge + PREFIX // 2)
+    window(READS - PREFIX, READS)
+    dev.close()

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 CG = ("Z", "z", "XH", "xh", 2, 0.5, 0.1)
 
 
-@pytest.fixture(params=["auto", "vertical", "byte-auto", "lane-group", "thread-per-row-tma", "chunk-per-lane"], autouse=True)
+@pytest.fixture(params=["auto", "vertical", "byte-auto", "lane-group", "thread-per-row-tma", "chunk-per-lane", "long-read"], autouse=True)
 def kernel_policy(request):
     """Every parity test runs with each window kernel: the automatic choice (row-per-lane kernel for one-context
     reports over short 32-byte-multiple rows, else the chunk-per-lane kernel, else the lane-group kernel), the general
@@ -93,9 +93,14 @@ SYNTH = {
     # long reads at ~400x: k_window_vsr with 9 planes per counter; at ~1000x: more rows per window than it takes -> k_window_plr
     "long_reads_400x": dict(seed=13, n_reads=2000, chr_len=[100000], len_min=10000, len_max=30000),
     "long_reads_1000x": dict(seed=14, n_reads=1500, chr_len=[40000], len_min=10000, len_max=30000),
+    # BASELINE configs[4]'s layout in small: 24 chromosomes in hg38's proportions, 150 bp reads at ~40x
+    "genome24": dict(seed=20261021, n_reads=60000, chr_len=[c // 14000 for c in (248956422, 242193529, 198295559, 190214555, 181538259, 170805979,
+                     159345973, 145138636, 138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+                     58617616, 64444167, 46709983, 50818468, 156040895, 57227415)], len_min=150),
 }
 SYNTH_CASES = [(True, "CG", 2, 0.5, 0.1, "CG"), (False, "CG", 2, 0.5, 0.1, "CX"), (True, "CHH", 1, 0.02, 0.9, "CxG"),
-               (True, "CX", 3, 0.04, 0.1, "CHG")]
+               (True, "CX", 3, 0.04, 0.1, "CHG"),
+               (True, "CG", 2, 0.5, 0.1, "CX")]   # BASELINE configs[2]'s exact pair: CG thresholds fused into a three-context report
 
 
 @pytest.mark.parametrize("shape", sorted(SYNTH))

@@ -303,3 +303,18 @@ def test_fisher_exact_host_function_matches_the_oracles():
     # textbook values: Fisher's tea-tasting table and a balanced table
     p = ea.rcpp_fep([3, 5, 0], [1, 5, 0], [1, 5, 0], [3, 5, 0])
     assert abs(p[0] - 34.0 / 70.0) < 1e-12 and p[1] == 1.0 and p[2] == 1.0
+
+
+def test_oracle_side_generator_equals_the_library_generator():
+    """oracle/_build/libsynth.so (the generator header built for the host with g++; what bench.py's reference arm uses so
+    that it never loads the product library) produces the rows ea_synth_host produces, bit for bit, sub-ranges included."""
+    import epialleler_b200 as ea
+    from oracle.oracle import synth_rows
+    for kw, lo, hi in ((dict(seed=20261018, n_reads=5000, chr_len=[300000], len_min=150), 0, None),
+                       (dict(seed=20261019, n_reads=8000, chr_len=[90000, 50000, 20000], len_min=100, len_max=417, n_islands=7, island_len=900), 1234, 6000),
+                       (dict(seed=20261020, n_reads=60, chr_len=[500000, 200000], len_min=10000, len_max=30000), 10, 50)):
+        a = ea.synth_host(ea.synth_config(**kw), lo, hi)
+        b = synth_rows(row_begin=lo, row_end=hi, **kw)
+        for k in ("rname", "strand", "start"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        assert np.array_equal(a.blob()[0], b.blob()[0]) and np.array_equal(a.blob()[1], b.blob()[1])

@@ -64,6 +64,37 @@ def test_shard_plan_properties():
     assert len(plan_shards(np.zeros(0), np.zeros(0), np.zeros(0), 4)) == 4
 
 
+def test_native_planner_equals_python_planner():
+    """ea_plan_shards (binary searches over the offsets + a backward halo walk, no per-row temporaries) == plan_shards."""
+    from epialleler_b200.shard import plan_shards_native
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n, world = int(rng.integers(0, 400)), int(rng.integers(1, 9))
+        rn = rng.integers(1, 4, n).astype(np.int32)
+        st = rng.integers(1, 300, n).astype(np.int32)
+        o = np.lexsort((st, rn))
+        rn, st = rn[o], st[o]
+        ln = rng.integers(0, 60, n).astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(ln)]).astype(np.int64)
+        tid = np.arange(n, dtype=np.int32) if trial % 2 == 0 else rng.permutation(n).astype(np.int32)
+        bam = ea.BamData(rn, np.ones(n, np.int32), st, tid, np.zeros(int(off[-1]), np.uint8), off)
+        want = plan_shards(rn, st, ln[tid], world)
+        got = plan_shards_native(bam, world)
+        assert [(w.row_lo, w.own_lo, w.own_hi, w.key_lo, w.key_hi) for w in want] == [(g.row_lo, g.own_lo, g.own_hi, g.key_lo, g.key_hi) for g in got], (trial, n, world)
+
+
+def test_windowed_planner_equals_python_planner():
+    from epialleler_b200.shard import plan_shards_windowed
+    for cfg in (ea.synth_config(36, 20000, [300000, 100000], 150), ea.synth_config(37, 5000, [c // 30000 for c in (248956422, 242193529, 198295559, 190214555)], 150)):
+        bam = ea.synth_host(cfg)
+        lens = np.diff(bam.blob()[1])
+        fetch = lambda a, b: (bam.rname[a:b], bam.start[a:b], lens[a:b])
+        for world in (1, 2, 3, 8):
+            want = plan_shards(bam.rname, bam.start, lens, world, weights=np.ones(bam.nrow, np.int64))
+            got = plan_shards_windowed(bam.nrow, world, fetch, 150, window=512)
+            assert [(w.row_lo, w.own_lo, w.own_hi, w.key_lo, w.key_hi) for w in want] == [(g.row_lo, g.own_lo, g.own_hi, g.key_lo, g.key_hi) for g in got], world
+
+
 def test_gloo_world_size_2():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
