@@ -215,23 +215,32 @@ def e2e_shim_path(ea, L, host, device, steps):
     page-locked block and device pool (cold)."""
     import torch
     import integration.harness as H
+    from epialleler_b200._native import check as N_check
     t0 = time.perf_counter()
     rs = H.ReaderStrings(host)
     build_s = time.perf_counter() - t0
     L.ea_trim(device)
+    from epialleler_b200.api import _params
+    prm = _params(**THRESH)
+    i32p, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
     times, rows, n_pass, h2d, calls_only = [], 0, 0, 0, True
     for i in range(steps + 1):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         dev = rs.pack(device=device, calls_only=True)
-        pass_flags, rep = ea.generateCytosineReport(dev, return_pass=True, **THRESH)
+        # results land in freshly allocated PAGEABLE arrays, like the R vectors the shim fetches into (wrap_report)
+        pass_flags = np.empty(dev.nrow, np.uint8)
+        nrow = C.c_int64(0)
+        N_check(L.ea_cytosine_report(dev.handle(), C.byref(prm), pass_flags.ctypes.data_as(u8p), C.byref(nrow)))
+        cols = [np.empty(max(nrow.value, 1), np.int32) for _ in range(6)]
+        N_check(L.ea_cx_report_fetch(dev.handle(), *[c.ctypes.data_as(i32p) for c in cols]))
         h2d = int(L.ea_pack_h2d_bytes(dev.handle()))
         calls_only = not bool(L.ea_has_bytes(dev.handle()))
         dev.close()
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t1)
-        rows, n_pass = int(rep["pos"].shape[0]), int(pass_flags.sum())
-        del rep, pass_flags
+        rows, n_pass = int(nrow.value), int(pass_flags.sum())
+        del cols, pass_flags
     rs.close()
     return dict(cold_s=times[0], warm_s=float(np.median(times[1:])) if len(times) > 1 else times[0], rows=rows, n_pass=n_pass, h2d=h2d,
                 calls_only=calls_only, build_strings_s=build_s, steps=steps)
@@ -496,8 +505,8 @@ def run_ours(args):
                            "host_threads": os.environ.get("EA_HOST_PACK_THREADS", str(os.cpu_count())),
                            "what": ("ea_pack_calls through integration/harness: the reader's std::vector<std::string> (one PAGEABLE heap string per template) and pageable int "
                                     "columns -> the shim's handle_of() (pointer tables + ea_pack_calls: host threads transpose the strings where they lie into a ring of "
-                                    "3 page-locked blocks, the blocks cross PCIe) -> ea_cytosine_report -> D2H of pass flags and rows -> ea_free.  cold = first call after "
-                                    "ea_trim() released every cached page-locked block and the device pool"),
+                                    "3 page-locked blocks, the blocks cross PCIe) -> ea_cytosine_report -> ea_cx_report_fetch of pass flags and rows into fresh PAGEABLE arrays (the R "
+                                    "vectors of wrap_report) -> ea_free.  cold = first call after ea_trim() released every cached page-locked block and the device pool"),
                            "from_pinned_blob": None}
         if e2e:
             blob_fig = {"value": tot_e2e_reads / e2e_s, "unit": "reads/s", "seconds_per_step": e2e_s, "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),

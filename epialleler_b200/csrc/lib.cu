@@ -1881,7 +1881,7 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
                    const std::function<void(int64_t, int64_t)>* fill) {
   if (!out) return fail(EA_ERR_ARG, "null out");
   *out = nullptr;
-  if (nrow < 0 || nstr < 0 || nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row/string count");
+  if (nrow < 0 || nstr < 0 || nrow > 0x7FFFFFFEll) return fail(EA_ERR_ARG, "bad row/string count (at most 2^31-2 rows per handle)");
   if (nrow > 0 && (!rname || !strand || !start || !off)) return fail(EA_ERR_ARG, "null column");
   if (nstr > 0 && !off) return fail(EA_ERR_ARG, "null offsets");
   int rc;
@@ -2097,7 +2097,7 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   if (off[0] < 0) return fail(EA_ERR_ARG, "negative string offset");
   const int64_t total = off[nstr] - off[0];   // the offsets need not start at 0 (a shard of a larger blob)
   if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
-  if (nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row/string count");
+  if (nrow > 0x7FFFFFFEll) return fail(EA_ERR_ARG, "bad row/string count (at most 2^31-2 rows per handle)");
   int rc;
   if ((rc = pick_device(device))) return rc;
   Trace tr("ea_pack_blob_calls");
@@ -2350,7 +2350,7 @@ int ea_attach_device(int32_t* d_rname, uint8_t* d_strand, int32_t* d_start, uint
                      int64_t nrow, int device, int take_ownership, ea_handle** out) {
   if (!out) return fail(EA_ERR_ARG, "null out");
   *out = nullptr;
-  if (nrow < 0 || nrow > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row count");
+  if (nrow < 0 || nrow > 0x7FFFFFFEll) return fail(EA_ERR_ARG, "bad row count (at most 2^31-2 rows per handle)");
   if (nrow > 0 && (!d_rname || !d_strand || !d_start || !d_data || !d_off)) return fail(EA_ERR_ARG, "null device pointer");
   int rc;
   if ((rc = pick_device(device))) return rc;
@@ -2900,7 +2900,7 @@ int ea_synth_device(const ea_synth_cfg* cfg, int64_t row_begin, int64_t row_end,
   *out = nullptr;
   easynth::Plan plan;
   if (easynth::make_plan(cfg, &plan)) return fail(EA_ERR_ARG, "bad synthetic configuration");
-  if (row_begin < 0 || row_end < row_begin || row_end > plan.n_reads || row_end - row_begin > 0x7FFFFFFFll) return fail(EA_ERR_ARG, "bad row range");
+  if (row_begin < 0 || row_end < row_begin || row_end > plan.n_reads || row_end - row_begin > 0x7FFFFFFEll) return fail(EA_ERR_ARG, "bad row range");
   int rc;
   if ((rc = pick_device(device))) return rc;
   ea_handle* h = new ea_handle;
