@@ -409,11 +409,12 @@ def rcpp_mhl_report(df, ctx, hmax, hmin, max_ooctx_meth_frac):
     """src/rcpp_mhl_report.cpp:46-228 -> rname, strand, pos, context, coverage (int32), length, lmhl (float64)."""
     L = N.lib()
     nrow = C.c_int64(0)
-    N.check(L.ea_mhl_report(df.handle(), ctx.encode(), int(hmax), int(hmin), float(max_ooctx_meth_frac), C.byref(nrow)))
+    # haplotype contexts made of letter pairs run on the call planes; anything else makes the library ask for the byte rows
+    _on_calls(df, lambda h: N.check(L.ea_mhl_report(h, ctx.encode(), int(hmax), int(hmin), float(max_ooctx_meth_frac), C.byref(nrow))))
     n = nrow.value
     ic = [_host_out(n, np.int32) for _ in range(5)]
     dc = [_host_out(n, np.float64) for _ in range(2)]
-    N.check(L.ea_mhl_report_fetch(df.handle(), *[_p(c, C.c_int32) for c in ic], *[_p(c, C.c_double) for c in dc]))
+    N.check(L.ea_mhl_report_fetch(df.handle(need_bases=False), *[_p(c, C.c_int32) for c in ic], *[_p(c, C.c_double) for c in dc]))
     rep = {k: c[:n] for k, c in zip(("rname", "strand", "pos", "context", "coverage", "length", "lmhl"), ic + dc)}
     rep["levels"] = {"rname": list(df.rname_levels), "strand": list(STRAND_LEVELS), "context": list(CONTEXT_LEVELS)}
     return rep

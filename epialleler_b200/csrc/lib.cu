@@ -39,6 +39,7 @@
 #include "window_mhl.cuh"
 #include "planar.cuh"
 #include "window_vs.cuh"
+#include "window_mhl_pl.cuh"
 #include "synth.h"
 #include "hostpack.h"
 
@@ -2647,7 +2648,6 @@ int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, dou
   int rc;
   CU(cudaSetDevice(h->device));
   h->mhl_rows = -1;
-  NEED_BYTES(h);
   if (h->max_len > 65535) return fail(EA_ERR_ARG, "lMHL report: rows longer than 65535 bytes are not supported (the reference's lookup table ends there)");
   MhlParams prm;
   prm.ctx_mask = 0;
@@ -2682,21 +2682,50 @@ int ea_mhl_report(ea_handle* h, const char* ctx, int32_t hmax, int32_t hmin, dou
     const bool pairs = (prm.ctx_mask & ~pair_bits) == 0 && ((prm.ctx_mask >> 2) & 1u) == ((prm.ctx_mask >> 10) & 1u) &&
                        ((prm.ctx_mask >> 6) & 1u) == ((prm.ctx_mask >> 14) & 1u) && ((prm.ctx_mask >> 7) & 1u) == ((prm.ctx_mask >> 15) & 1u);
     const int cls = pairs ? (int)(((prm.ctx_mask >> 2) & 1u) | (((prm.ctx_mask >> 6) & 1u) << 1) | (((prm.ctx_mask >> 7) & 1u) << 2)) : 0;
-    void (*kern)(Csr, WinTable, MhlParams, MhlOut) = k_window_mhl<0>;
-    switch (cls) {
-      case 1: kern = k_window_mhl<1>; break;
-      case 2: kern = k_window_mhl<2>; break;
-      case 3: kern = k_window_mhl<3>; break;
-      case 4: kern = k_window_mhl<4>; break;
-      case 5: kern = k_window_mhl<5>; break;
-      case 6: kern = k_window_mhl<6>; break;
-      case 7: kern = k_window_mhl<7>; break;
-      default: break;
-    }
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::max(1, std::min<int>(ix->n, h->sm_count * 32));
-    kern<<<grid, kMhlThreads, smem, h->stream>>>(csr_of(h), wt, prm, out);
-    k_scan_windows<<<1, 1024, 0, h->stream>>>(ix->w_cnt, ix->w_dst, ix->n);
+    // letter pairs on rows of at most 1024 positions: the planar kernel (lane per row over the call planes; also serves
+    // handles without byte rows); anything else - and kernel policy 5, which keeps the byte-row kernel tested - reads bytes
+    const bool use_pl = pairs && h->pl_ok && h->pl_th == 32 && g_kernel_policy == 0 && !getenv("EA_MHL_BYTES");
+    if (use_pl) {
+      // every per-position sum of a window is at most (rows over the window) x S(min(longest row, hmax)): below 2^31 the
+      // difference arrays are 32-bit (native shared atomics, 40 KB per CTA)
+      const unsigned long long hbound = std::min<unsigned long long>((unsigned long long)h->max_len, prm.cap);
+      const unsigned long long sbound = hbound < 2 ? hbound : hbound * (hbound + 1) * (hbound + 2) / 6;
+      const bool narrow = (unsigned long long)ix->max_rows * sbound < (1ull << 31) && !getenv("EA_MHL_WIDE");
+      const size_t smem_pl = narrow ? (size_t)2 * 3 * kMhlS * 4 + (size_t)2 * kMhlS * 4 + (size_t)2 * prm.n_cls * kMhlS * 4 : smem;
+      void (*kern)(Planar, WinTable, MhlParams, MhlOut) = nullptr;
+#define EA_MHL_PL(C_) (narrow ? (void (*)(Planar, WinTable, MhlParams, MhlOut))k_window_mhl_pl<C_, int> : (void (*)(Planar, WinTable, MhlParams, MhlOut))k_window_mhl_pl<C_, long long>)
+      switch (cls) {
+        case 1: kern = EA_MHL_PL(1); break;
+        case 2: kern = EA_MHL_PL(2); break;
+        case 3: kern = EA_MHL_PL(3); break;
+        case 4: kern = EA_MHL_PL(4); break;
+        case 5: kern = EA_MHL_PL(5); break;
+        case 6: kern = EA_MHL_PL(6); break;
+        default: kern = EA_MHL_PL(7); break;
+      }
+#undef EA_MHL_PL
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
+      kern<<<grid, kMhlThreads, smem_pl, h->stream>>>(planar_of(h), wt, prm, out);
+      h->report_kernel = narrow ? "k_window_mhl_pl<int> (planar call planes, row per lane, 32-bit difference arrays)" : "k_window_mhl_pl<int64> (planar call planes, row per lane)";
+    } else {
+      NEED_BYTES(h);
+      void (*kern)(Csr, WinTable, MhlParams, MhlOut) = k_window_mhl<0>;
+      switch (cls) {
+        case 1: kern = k_window_mhl<1>; break;
+        case 2: kern = k_window_mhl<2>; break;
+        case 3: kern = k_window_mhl<3>; break;
+        case 4: kern = k_window_mhl<4>; break;
+        case 5: kern = k_window_mhl<5>; break;
+        case 6: kern = k_window_mhl<6>; break;
+        case 7: kern = k_window_mhl<7>; break;
+        default: break;
+      }
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, kMhlThreads, smem, h->stream>>>(csr_of(h), wt, prm, out);
+      h->report_kernel = "k_window_mhl (byte rows, thread per read)";
+    }
+    if ((rc = scan_windows(h, *ix))) return rc;   // multi-block scan beyond a few thousand windows
     MhlCols cols{h->d_mhl_i[0], h->d_mhl_i[1], h->d_mhl_i[2], h->d_mhl_i[3], h->d_mhl_i[4], h->d_mhl_d[0], h->d_mhl_d[1]};
     k_gather_mhl<<<std::max(1, std::min(ix->n / 4 + 1, h->sm_count * 16)), 128, 0, h->stream>>>(
         h->d_mhl_scratch, ix->w_base, ix->w_dst, ix->w_cnt, ix->rname, ix->n, h->mhl_cap, cols);

@@ -73,46 +73,141 @@ __device__ __forceinline__ long long block_exscan_i64(long long v, long long* s_
   return s_warp[warp] + inc - v;
 }
 
-// exclusive block scan of four int64 values at once (three barriers instead of twelve); s_warp: [4][NW]
-template <int NW>
-__device__ __forceinline__ void block_exscan4_i64(long long (&v)[4], long long* s_warp) {
+// exclusive block scan of four values at once (two barriers); s_warp: [4][NW] of long long.  Every warp scans the NW
+// per-warp totals itself with shuffles (one shared load per value instead of NW).
+template <int NW, typename T>
+__device__ __forceinline__ void block_exscan4(T (&v)[4], long long* s_warp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  long long inc[4];
+  T inc[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) inc[j] = v[j];
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const long long o = __shfl_up_sync(0xFFFFFFFFu, inc[j], d);
+      const T o = __shfl_up_sync(0xFFFFFFFFu, inc[j], d);
       if (lane >= d) inc[j] += o;
     }
   __syncthreads();  // protects s_warp against the previous call's readers
   if (lane == 31) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) s_warp[j * NW + warp] = inc[j];
+    for (int j = 0; j < 4; j++) s_warp[j * NW + warp] = (long long)inc[j];
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    long long ex = inc[j] - v[j];
+    const T x = lane < NW ? (T)s_warp[j * NW + lane] : (T)0;
+    T xi = x;
 #pragma unroll
-    for (int w = 0; w < NW; w++) ex += (w < warp) ? s_warp[j * NW + w] : 0ll;
-    v[j] = ex;
+    for (int d = 1; d < NW; d <<= 1) {
+      const T o = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+      if (lane >= d) xi += o;
+    }
+    const T before = __shfl_sync(0xFFFFFFFFu, xi - x, warp);   // sum of the warps in front of this one
+    v[j] = before + inc[j] - v[j];
   }
 }
+template <int NW>
+__device__ __forceinline__ void block_exscan4_i64(long long (&v)[4], long long* s_warp) { block_exscan4<NW, long long>(v, s_warp); }
 
 // bit 0 of every byte of t (t & 0x01010101 == t) gathered into a nibble: bit k = byte k
 __device__ __forceinline__ uint32_t gather4(uint32_t t) { return (t * 0x01020408u) >> 24; }
 
+// shared-memory add on the accumulator type of the difference arrays: int (one native ATOMS.ADD) when the dispatcher has
+// shown that every sum of the window fits 31 bits, else 64-bit
+__device__ __forceinline__ void acc_add(long long* p, long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+__device__ __forceinline__ void acc_add(int* p, long long v) { atomicAdd(p, (int)v); }
+
 // difference-array event: value v becomes active at window-relative position q (clamped to the window start),
 // nothing to do at or beyond the window end
-__device__ __forceinline__ void diff_event(int q, int S, int* dW, long long* dH, long long* dDe, int w, long long hv, long long dv) {
+template <typename ACC>
+__device__ __forceinline__ void diff_event(int q, int S, int* dW, ACC* dH, ACC* dDe, int w, long long hv, long long dv) {
   if (q >= S) return;
   q = max(q, 0);
   atomicAdd(&dW[q], w);
-  atomicAdd(reinterpret_cast<unsigned long long*>(&dH[q]), (unsigned long long)hv);
-  atomicAdd(reinterpret_cast<unsigned long long*>(&dDe[q]), (unsigned long long)dv);
+  acc_add(&dH[q], hv);
+  acc_add(&dDe[q], dv);
+}
+
+// The window's difference arrays -> prefix sums in place, row test, ordered compaction into the scratch rows (shared by the
+// byte-row kernel below and the planar kernel of window_mhl_pl.cuh).  Called by the whole CTA after a barrier.
+template <typename ACC>
+__device__ __forceinline__ void mhl_window_finalize(unsigned char* smem_raw, const MhlParams& prm, const MhlOut& out, int win, int w0,
+                                                    long long* s_scan, uint32_t* s_scan32, long long* s_base_p) {
+  constexpr int S = kMhlS;
+  constexpr int PER = S / kMhlThreads;
+  const int NCLS = prm.n_cls;
+  ACC* const L64 = reinterpret_cast<ACC*>(smem_raw);
+  int* const dWb = reinterpret_cast<int*>(L64 + 2 * 3 * S);
+  uint32_t* const Tb = reinterpret_cast<uint32_t*>(dWb + 2 * S);
+  long long& s_base = *s_base_p;
+  // ---- finalize: the four difference arrays of each strand become their prefix sums IN PLACE (every thread owns
+  //      PER consecutive positions), then the row test and the ordered compaction read them back ----
+  const int q0 = threadIdx.x * PER;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    int* const pw = dWb + s * S + q0;
+    ACC* const ph = L64 + (s * 3 + 0) * S + q0;
+    ACC* const pd = L64 + (s * 3 + 1) * S + q0;
+    ACC* const pn = L64 + (s * 3 + 2) * S + q0;
+    ACC rw = 0, rh = 0, rd = 0, rn = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { rw += pw[k]; rh += ph[k]; rd += pd[k]; rn += pn[k]; }
+    ACC ex[4] = {rw, rh, rd, rn};
+    block_exscan4<kMhlWarps, ACC>(ex, s_scan);
+    rw = ex[0]; rh = ex[1]; rd = ex[2]; rn = ex[3];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      rw += pw[k]; pw[k] = (int)rw;
+      rh += ph[k]; ph[k] = rh;
+      rd += pd[k]; pd[k] = rd;
+      rn += pn[k]; pn[k] = rn;
+    }
+  }
+  uint32_t flags = 0;   // bit 2k+s
+  uint32_t which = 0;   // 2 bits per (k,s): class of the row
+#pragma unroll
+  for (int k = 0; k < PER; k++)
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int cv = dWb[s * S + q0 + k];
+      if (cv <= 0) continue;
+      const uint32_t half = (uint32_t)cv >> 1;
+#pragma unroll
+      for (int cls = 0; cls < 3; cls++) {
+        const uint32_t code = cls == 0 ? 2u : (cls == 1 ? 6u : 7u);
+        if (!((prm.ctx_mask >> code) & 1u)) continue;
+        if (Tb[(s * NCLS + prm.slot[cls]) * S + q0 + k] > half) { flags |= 1u << (2 * k + s); which |= (uint32_t)cls << (2 * (2 * k + s)); }
+      }
+    }
+  uint32_t nrows_u;
+  const int my_off = (int)block_exscan_u32<kMhlWarps>((uint32_t)__popc(flags), &nrows_u, s_scan32);
+  const int nrows_total = (int)nrows_u;
+  if (threadIdx.x == 0) {
+    const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
+    s_base = (long long)bb;
+    out.w_base[win] = (long long)bb;
+    out.w_cnt[win] = nrows_total;
+  }
+  __syncthreads();
+  const long long wbase = s_base;
+  if (flags && wbase + nrows_total <= out.cap) {
+    MhlRow* dst = out.scratch + wbase + my_off;
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (!((flags >> (2 * k + s)) & 1u)) continue;
+        const int cls = (which >> (2 * (2 * k + s))) & 3;
+        const int code = cls == 0 ? 2 : (cls == 1 ? 6 : 7);
+        const int c = (int)Tb[(s * NCLS + prm.slot[cls]) * S + q0 + k];
+        MhlRow rrow;
+        rrow.pos = w0 + q0 + k; rrow.strand_ctx = (s + 1) | (code << 8); rrow.coverage = c; rrow.pad = 0;
+        rrow.length = (double)(unsigned long long)L64[(s * 3 + 0) * S + q0 + k] / (double)c;                                            // (double)uint64 / int, :97
+        rrow.lmhl = (double)(unsigned long long)L64[(s * 3 + 2) * S + q0 + k] / (double)(unsigned long long)L64[(s * 3 + 1) * S + q0 + k];  // :98
+        *dst++ = rrow;
+      }
+  }
 }
 
 // PAIRS: `ctx` is a union of the letter pairs Hh / Xx / Zz (what generateMhlReport passes, R/generateMhlReport.R:178-180):
@@ -308,73 +403,7 @@ k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
     }
     __syncthreads();
 
-    // ---- finalize: the four difference arrays of each strand become their prefix sums IN PLACE (every thread owns
-    //      PER consecutive positions), then the row test and the ordered compaction read them back ----
-    const int q0 = threadIdx.x * PER;
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      int* const pw = dWb + s * S + q0;
-      long long* const ph = L64 + (s * 3 + 0) * S + q0;
-      long long* const pd = L64 + (s * 3 + 1) * S + q0;
-      long long* const pn = L64 + (s * 3 + 2) * S + q0;
-      int rw = 0; long long rh = 0, rd = 0, rn = 0;
-#pragma unroll
-      for (int k = 0; k < PER; k++) { rw += pw[k]; rh += ph[k]; rd += pd[k]; rn += pn[k]; }
-      long long ex[4] = {(long long)rw, rh, rd, rn};
-      block_exscan4_i64<kMhlWarps>(ex, s_scan);
-      rw = (int)ex[0]; rh = ex[1]; rd = ex[2]; rn = ex[3];
-#pragma unroll
-      for (int k = 0; k < PER; k++) {
-        rw += pw[k]; pw[k] = rw;
-        rh += ph[k]; ph[k] = rh;
-        rd += pd[k]; pd[k] = rd;
-        rn += pn[k]; pn[k] = rn;
-      }
-    }
-    uint32_t flags = 0;   // bit 2k+s
-    uint32_t which = 0;   // 2 bits per (k,s): class of the row
-#pragma unroll
-    for (int k = 0; k < PER; k++)
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const int cv = dWb[s * S + q0 + k];
-        if (cv <= 0) continue;
-        const uint32_t half = (uint32_t)cv >> 1;
-#pragma unroll
-        for (int cls = 0; cls < 3; cls++) {
-          const uint32_t code = cls == 0 ? 2u : (cls == 1 ? 6u : 7u);
-          if (!((prm.ctx_mask >> code) & 1u)) continue;
-          if (Tb[(s * NCLS + prm.slot[cls]) * S + q0 + k] > half) { flags |= 1u << (2 * k + s); which |= (uint32_t)cls << (2 * (2 * k + s)); }
-        }
-      }
-    uint32_t nrows_u;
-    const int my_off = (int)block_exscan_u32<kMhlWarps>((uint32_t)__popc(flags), &nrows_u, s_scan32);
-    const int nrows_total = (int)nrows_u;
-    if (threadIdx.x == 0) {
-      const unsigned long long bb = nrows_total ? atomicAdd(out.cursor, (unsigned long long)nrows_total) : 0ull;
-      s_base = (long long)bb;
-      out.w_base[win] = (long long)bb;
-      out.w_cnt[win] = nrows_total;
-    }
-    __syncthreads();
-    const long long wbase = s_base;
-    if (flags && wbase + nrows_total <= out.cap) {
-      MhlRow* dst = out.scratch + wbase + my_off;
-#pragma unroll
-      for (int k = 0; k < PER; k++)
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          if (!((flags >> (2 * k + s)) & 1u)) continue;
-          const int cls = (which >> (2 * (2 * k + s))) & 3;
-          const int code = cls == 0 ? 2 : (cls == 1 ? 6 : 7);
-          const int c = (int)Tb[(s * NCLS + prm.slot[cls]) * S + q0 + k];
-          MhlRow rrow;
-          rrow.pos = w0 + q0 + k; rrow.strand_ctx = (s + 1) | (code << 8); rrow.coverage = c; rrow.pad = 0;
-          rrow.length = (double)(unsigned long long)L64[(s * 3 + 0) * S + q0 + k] / (double)c;                                            // (double)uint64 / int, :97
-          rrow.lmhl = (double)(unsigned long long)L64[(s * 3 + 2) * S + q0 + k] / (double)(unsigned long long)L64[(s * 3 + 1) * S + q0 + k];  // :98
-          *dst++ = rrow;
-        }
-    }
+    mhl_window_finalize<long long>(smem_raw, prm, out, win, w0, s_scan, s_scan32, &s_base);
   }
 }
 

@@ -395,8 +395,8 @@ from helpers import MHL_CASES, assert_mhl_equal  # noqa: E402
 
 @pytest.mark.parametrize("name", golden_names())
 def test_mhl_report_golden_vectors(name, kernel_policy):
-    if kernel_policy != "auto":
-        pytest.skip("the lMHL report has one kernel")
+    if kernel_policy not in ("auto", "byte-auto"):
+        pytest.skip("the lMHL report has two kernels: planar call planes (auto) and byte rows (byte-auto)")
     bam, z = load_golden(name)
     for cname, hctx, hmax, hmin, moo in MHL_CASES:
         rep = ea.generateMhlReport(bam, haplotype_context=hctx, max_haplotype_window=hmax, min_haplotype_length=hmin, max_outofcontext_beta=moo)
@@ -405,8 +405,8 @@ def test_mhl_report_golden_vectors(name, kernel_policy):
 
 
 def test_mhl_report_identity_and_synthetic(kernel_policy):
-    if kernel_policy != "auto":
-        pytest.skip("the lMHL report has one kernel")
+    if kernel_policy not in ("auto", "byte-auto"):
+        pytest.skip("the lMHL report has two kernels: planar call planes (auto) and byte rows (byte-auto)")
     # inst/unitTests/test_generateMhlReport.R:7-12: window 1 == meth/(meth+unmeth) of the unthresholded CG report, identical()
     bam, _ = load_golden("capture")
     m1 = ea.generateMhlReport(bam, max_haplotype_window=1)
@@ -416,7 +416,7 @@ def test_mhl_report_identity_and_synthetic(kernel_policy):
     for shape in ("wgbs150", "pe_merged", "capture_islands", "tiny_reads", "long_reads"):
         host = ea.synth_host(ea.synth_config(**SYNTH[shape]))
         oracle = PortCpu(host)
-        for hctx, hmax, hmin, moo in (("CG", 0, 0, 0.1), ("CX", 2, 3, 0.6), ("CHG", 0, 1, 1.0)):
+        for hctx, hmax, hmin, moo in (("CG", 0, 0, 0.1), ("CX", 2, 3, 0.6), ("CHG", 0, 1, 1.0), ("CxG", 5, 0, 0.4), ("CHH", 0, 2, 0.9)):
             want = oracle.generateMhlReport(hctx, hmax, hmin, moo)
             got = ea.generateMhlReport(host, haplotype_context=hctx, max_haplotype_window=hmax, min_haplotype_length=hmin, max_outofcontext_beta=moo)
             assert want["pos"].shape[0] > 0
