@@ -343,7 +343,7 @@ def run_ours(args):
     if world == 1 and not args.no_e2e:
         host = ea.synth_host(cfg)
         if not args.no_shim:
-            shim = e2e_shim_path(ea, L, host, local, max(1, min(args.steps, 3)))
+            shim = e2e_shim_path(ea, L, host, local, max(1, min(args.steps, 5)))
         e2e = e2e_pinned_blob(ea, L, host, local, max(1, min(args.steps, 5)), barrier)
         del host
         L.ea_trim(local)
@@ -490,6 +490,9 @@ def run_ours(args):
         }
         if two_pass:
             line["two_pass_variant"] = two_pass
+        if world > 1:
+            line["scaling_note"] = ("weak scaling of configs[4] at %d reads per GPU; the 1-GPU point of THIS workload is other_configs.cfg5_shard of the N=1 line "
+                                    "(rows [0, 125 M) of the same data set on one GPU) - the N=1 headline value is configs[1], a different shape" % int(tot_reads / world))
         if halo is not None:
             line["halo"] = {"rows_total": int(tot_halo), "bytes_total": int(tot_halo * READ_LEN), "cuts": world - 1,
                             "what": ("rows that start before a cut and reach past it, packed on both neighbours (zero communication); the measured alternatives "

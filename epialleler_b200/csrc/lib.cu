@@ -84,6 +84,12 @@ struct Trace {
 // packs and frees tens of GB per call, and plain cudaMalloc/cudaFree of such blocks costs tens to hundreds of milliseconds
 // (measured, EA_TRACE) while the pool hands the cached blocks back in microseconds.  ea_trim() returns the cached memory to
 // the driver.  Allocation is made synchronous here (the callers' work runs on other streams).
+// Result copy into CALLER memory.  Page-locked destinations (ea_host_alloc, cudaHostRegister) take the copy as it is.
+// Pageable ones - R vectors, numpy arrays: what every binding passes - would be staged by the driver through small bounce
+// buffers at a few GB/s with the fresh destination pages first touched one by one; instead the data crosses PCIe in 16 MB
+// pieces into two page-locked blocks from the library's cache while a few host threads copy the previous piece out (and
+// first-touch the destination's pages in parallel).  Returns after the data has landed.  Defined below ea_host_free.
+cudaError_t d2h_result(void* dst, const void* src, size_t bytes, cudaStream_t s);
 constexpr int kMaxDevices = 64;
 cudaMemPool_t g_pools[kMaxDevices] = {};
 std::mutex g_pool_mu;
@@ -1740,6 +1746,53 @@ __global__ void k_synth_bytes(easynth::Plan plan, int64_t row_begin, int64_t n, 
 
 }  // namespace
 
+namespace {
+cudaError_t d2h_result(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  constexpr size_t kPiece = 16u << 20;
+  if (bytes == 0) return cudaSuccess;
+  bool pageable = false;
+  if (bytes >= 2 * kPiece && !getenv("EA_NO_STAGED_D2H")) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, dst) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+  }
+  if (!pageable) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(s);
+  }
+  uint8_t* buf[2] = {static_cast<uint8_t*>(ea_host_alloc(kPiece)), static_cast<uint8_t*>(ea_host_alloc(kPiece))};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaError_t e = (buf[0] && buf[1]) ? cudaSuccess : cudaErrorMemoryAllocation;
+  for (auto& x : ev) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming | cudaEventBlockingSync);
+  const size_t n_pieces = (bytes + kPiece - 1) / kPiece;
+  const int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency() / 2, 8u));
+  auto copy_out = [&](size_t k) {   // piece k: staging block -> destination, nt threads
+    const size_t o = k * kPiece, n = std::min(kPiece, bytes - o);
+    const uint8_t* from = buf[k & 1];
+    uint8_t* to = static_cast<uint8_t*>(dst) + o;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back([=]() { memcpy(to + n * t / nt, from + n * t / nt, n * (t + 1) / nt - n * t / nt); });
+    memcpy(to, from, n / nt);
+    for (auto& x : th) x.join();
+  };
+  for (size_t k = 0; k < n_pieces && e == cudaSuccess; k++) {
+    const size_t o = k * kPiece, n = std::min(kPiece, bytes - o);
+    e = cudaMemcpyAsync(buf[k & 1], static_cast<const uint8_t*>(src) + o, n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[k & 1], s);
+    if (k > 0 && e == cudaSuccess) {   // piece k is on its way: copy piece k-1 out meanwhile
+      e = cudaEventSynchronize(ev[(k - 1) & 1]);
+      if (e == cudaSuccess) copy_out(k - 1);
+    }
+  }
+  if (e == cudaSuccess) e = cudaEventSynchronize(ev[(n_pieces - 1) & 1]);
+  if (e == cudaSuccess) copy_out(n_pieces - 1);
+  else cudaStreamSynchronize(s);
+  for (auto& x : ev) if (x) cudaEventDestroy(x);
+  ea_host_free(buf[0]); ea_host_free(buf[1]);
+  return e;
+}
+}  // namespace
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -2385,7 +2438,7 @@ int ea_threshold_reads(ea_handle* h, const char* ctx_meth, const char* ctx_unmet
   ThrParams tp{min_n_ctx, min_ctx_meth_frac, max_ooctx_meth_frac};
   CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
   if ((rc = launch_threshold(h, spec, tp, h->d_pass, nullptr, h->d_counters + 1))) return rc;
-  if (h->n > 0) CU(cudaMemcpyAsync(pass_out, h->d_pass, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (h->n > 0) CU(d2h_result(pass_out, h->d_pass, (size_t)h->n, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return EA_OK;
 }
@@ -2399,7 +2452,7 @@ int ea_get_xm_beta(ea_handle* h, const char* ctx_meth, const char* ctx_unmeth, d
   parse_beta_letters(ctx_meth, ctx_unmeth, &spec);
   ThrParams tp{0, 0.0, 0.0};
   if ((rc = launch_threshold(h, spec, tp, nullptr, h->d_beta, nullptr))) return rc;
-  if (h->n > 0) CU(cudaMemcpyAsync(beta_out, h->d_beta, 8 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (h->n > 0) CU(d2h_result(beta_out, h->d_beta, 8 * (size_t)h->n, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return EA_OK;
 }
@@ -2471,7 +2524,7 @@ int ea_match_target(ea_handle* h, int mode, const int32_t* bed_chr, const int32_
   CU(cudaSetDevice(h->device));
   if ((rc = match_on_device(h, mode, bed_chr, bed_start, bed_end, nbed, param))) return rc;
   if (match_out && h->n > 0) {
-    CU(cudaMemcpyAsync(match_out, h->d_match, 4 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(d2h_result(match_out, h->d_match, 4 * (size_t)h->n, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
   return EA_OK;
@@ -2542,7 +2595,7 @@ int ea_base_freqs(ea_handle* h, const uint8_t* pass, const int32_t* vcf_chr, con
   }
   k_counts_to_double<<<grid_for((int64_t)cells, 256), 256, 0, h->stream>>>(d_counts, (int64_t)cells, d_out);
   TRYCU(cudaGetLastError());
-  TRYCU(cudaMemcpyAsync(freqs_out, d_out, 8 * cells, cudaMemcpyDeviceToHost, h->stream));
+  TRYCU(d2h_result(freqs_out, d_out, 8 * cells, h->stream));
   TRYCU(cudaStreamSynchronize(h->stream));
 #undef TRY
 #undef TRYCU
@@ -2761,9 +2814,9 @@ int ea_mhl_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* 
   double* dd[2] = {length, lmhl};
   if (h->mhl_rows > 0) {
     for (int c = 0; c < 5; c++)
-      if (di[c]) CU(cudaMemcpyAsync(di[c], h->d_mhl_i[c], 4 * (size_t)h->mhl_rows, cudaMemcpyDeviceToHost, h->stream));
+      if (di[c]) CU(d2h_result(di[c], h->d_mhl_i[c], 4 * (size_t)h->mhl_rows, h->stream));
     for (int c = 0; c < 2; c++)
-      if (dd[c]) CU(cudaMemcpyAsync(dd[c], h->d_mhl_d[c], 8 * (size_t)h->mhl_rows, cudaMemcpyDeviceToHost, h->stream));
+      if (dd[c]) CU(d2h_result(dd[c], h->d_mhl_d[c], 8 * (size_t)h->mhl_rows, h->stream));
   }
   CU(cudaStreamSynchronize(h->stream));
   return EA_OK;
@@ -2797,7 +2850,7 @@ int ea_cx_report_fetch(ea_handle* h, int32_t* rname, int32_t* strand, int32_t* p
   int32_t* dst[6] = {rname, strand, pos, context, meth, unmeth};
   if (h->n_rows > 0)
     for (int c = 0; c < 6; c++)
-      if (dst[c]) CU(cudaMemcpyAsync(dst[c], h->d_cols[c] + h->row_first, 4 * (size_t)h->n_rows, cudaMemcpyDeviceToHost, h->stream));
+      if (dst[c]) CU(d2h_result(dst[c], h->d_cols[c] + h->row_first, 4 * (size_t)h->n_rows, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   tr.mark("D2H rows");
   return EA_OK;
@@ -2863,7 +2916,7 @@ int ea_cx_report_text_fetch(ea_handle* h, char* out) {
   CU(cudaSetDevice(h->device));
   if (h->text_bytes > 0) {
     if (!out) return fail(EA_ERR_ARG, "null output buffer");
-    CU(cudaMemcpyAsync(out, h->d_text, (size_t)h->text_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(d2h_result(out, h->d_text, (size_t)h->text_bytes, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
   return EA_OK;
@@ -2878,7 +2931,7 @@ int ea_cytosine_report(ea_handle* h, const ea_report_params* p, uint8_t* pass_ou
   if ((rc = run_report(h, rp, nullptr, nullptr))) return rc;
   const int64_t r0 = h->own_set ? std::min(h->own_row_lo, h->n) : 0;   // a range shard reports the flags of the rows it owns
   if (pass_out && h->n > r0) {
-    if (rp.threshold) CU(cudaMemcpyAsync(pass_out, h->d_pass + r0, (size_t)(h->n - r0), cudaMemcpyDeviceToHost, h->stream));
+    if (rp.threshold) CU(d2h_result(pass_out, h->d_pass + r0, (size_t)(h->n - r0), h->stream));
     else memset(pass_out, 1, (size_t)(h->n - r0));
     CU(cudaStreamSynchronize(h->stream));
   }

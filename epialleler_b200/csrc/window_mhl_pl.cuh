@@ -65,64 +65,67 @@ k_window_mhl_pl(Planar pl, WinTable wt, MhlParams prm, MhlOut out) {
         ou += __popc(ooc & v.w);
       }
       const bool keep = mine && len > 0 && rel0 + len > 0 && !((int)h < prm.hmin || (double)om / (double)(om + ou) > prm.max_ooctx);
-      if (keep) {
-        const long long hv = (long long)h;
-        const long long dv = (long long)mhl_S(h < prm.cap ? h : prm.cap);
-        int* const dW = dWb + s * S;
-        ACC* const dH = L64 + (s * 3 + 0) * S;
-        ACC* const dDe = L64 + (s * 3 + 1) * S;
-        ACC* const dNu = L64 + (s * 3 + 2) * S;
-        uint32_t* const T = Tb + s * NCLS * S;
-        const int nu = (len + 31) >> 5;
-        uint32_t covb = 0, msz = 0;
-        int ms = 0, me = 0;
-        auto close_stretch = [&]() {  // +-S(min(size, hmax)) around the non-'-' pieces of [ms, me] (both ends are calls)
-          const long long nv = (long long)mhl_S(msz < prm.cap ? msz : prm.cap);
-          uint32_t carry = 0;
-          for (int ju = ms >> 5; ju <= (me >> 5); ju++) {
-            const uint4 v = __ldg(src + ju * 32);
-            const int b0 = ju == (ms >> 5) ? (ms & 31) : 0, b1 = ju == (me >> 5) ? (me & 31) : 31;
-            const uint32_t span = (FULL << b0) & (FULL >> (31 - b1));
-            const uint32_t sp = ~(v.x & v.y & ~v.z & v.w) & span;
-            for (uint32_t tr = (sp ^ ((sp << 1) | carry)) & span; tr; tr &= tr - 1u) {
-              const int k = __ffs(tr) - 1;
-              const int q = rel0 + 32 * ju + k;
-              if (q < S) acc_add(&dNu[max(q, 0)], ((sp >> k) & 1u) ? nv : -nv);
-            }
-            carry = sp >> 31;
-          }
-          if (rel0 + me + 1 < S) acc_add(&dNu[max(rel0 + me + 1, 0)], -nv);
-          msz = 0;
-        };
-        // ---- 2. events, unit by unit (the second read of the row's units hits L2) ----
-        for (int j = 0; j < nu; j++) {
-          const uint4 v = ldg_plunit(src + j * 32);
-          const int kmax = min(32, len - 32 * j);
-          const uint32_t valid = kmax >= 32 ? FULL : ((1u << kmax) - 1u);
-          const uint32_t t2 = (~v.x & v.y & ~v.z) & sel2, t6 = (~v.x & v.y & v.z) & sel6, t7 = (v.x & v.y & v.z) & sel7;
-          const uint32_t call = (t2 | t6 | t7) & valid;
-          const uint32_t nd = ~(v.x & v.y & ~v.z & v.w) & valid;
-          const int base = rel0 + 32 * j;
-          for (uint32_t tr = (nd ^ ((nd << 1) | covb)) & valid; tr; tr &= tr - 1u) {  // coverage transitions
+      const long long hv = (long long)h;
+      const long long dv = (long long)mhl_S(h < prm.cap ? h : prm.cap);
+      int* const dW = dWb + s * S;
+      ACC* const dH = L64 + (s * 3 + 0) * S;
+      ACC* const dDe = L64 + (s * 3 + 1) * S;
+      ACC* const dNu = L64 + (s * 3 + 2) * S;
+      uint32_t* const T = Tb + s * NCLS * S;
+      const int nu = keep ? (len + 31) >> 5 : 0;
+      uint32_t covb = 0, msz = 0;
+      int ms = 0, me = 0;
+      auto close_stretch = [&]() {  // +-S(min(size, hmax)) around the non-'-' pieces of [ms, me] (both ends are calls)
+        const long long nv = (long long)mhl_S(msz < prm.cap ? msz : prm.cap);
+        uint32_t carry = 0;
+        for (int ju = ms >> 5; ju <= (me >> 5); ju++) {
+          const uint4 v = __ldg(src + ju * 32);
+          const int b0 = ju == (ms >> 5) ? (ms & 31) : 0, b1 = ju == (me >> 5) ? (me & 31) : 31;
+          const uint32_t span = (FULL << b0) & (FULL >> (31 - b1));
+          const uint32_t sp = ~(v.x & v.y & ~v.z & v.w) & span;
+          for (uint32_t tr = (sp ^ ((sp << 1) | carry)) & span; tr; tr &= tr - 1u) {
             const int k = __ffs(tr) - 1;
-            const bool on = (nd >> k) & 1u;
-            diff_event(base + k, S, dW, dH, dDe, on ? 1 : -1, on ? hv : -hv, on ? dv : -dv);
+            const int q = rel0 + 32 * ju + k;
+            if (q < S) acc_add(&dNu[max(q, 0)], ((sp >> k) & 1u) ? nv : -nv);
           }
-          covb = (nd >> (kmax - 1)) & 1u;
-          if (CLS & 1) for (uint32_t m = t2 & valid; m; m &= m - 1u) { const int q = base + __ffs(m) - 1; if ((unsigned)q < (unsigned)S) atomicAdd(&T[prm.slot[0] * S + q], 1u); }
-          if (CLS & 2) for (uint32_t m = t6 & valid; m; m &= m - 1u) { const int q = base + __ffs(m) - 1; if ((unsigned)q < (unsigned)S) atomicAdd(&T[prm.slot[1] * S + q], 1u); }
-          if (CLS & 4) for (uint32_t m = t7 & valid; m; m &= m - 1u) { const int q = base + __ffs(m) - 1; if ((unsigned)q < (unsigned)S) atomicAdd(&T[prm.slot[2] * S + q], 1u); }
-          for (uint32_t m = call; m; m &= m - 1u) {   // methylated stretches over the context's calls in position order
-            const int k = __ffs(m) - 1;
-            if (!((v.w >> k) & 1u)) {
-              if (!msz) ms = 32 * j + k;
-              me = 32 * j + k; msz++;
-            } else if (msz) close_stretch();
-          }
+          carry = sp >> 31;
         }
-        if (covb) diff_event(rel0 + len, S, dW, dH, dDe, -1, -hv, -dv);
-        if (msz) close_stretch();
+        if (rel0 + me + 1 < S) acc_add(&dNu[max(rel0 + me + 1, 0)], -nv);
+        msz = 0;
+      };
+      // ---- 2. events, unit by unit (the second read of the row's units hits L2).  The unit loop is WARP-UNIFORM (the tile's
+      //      unit rows) and every per-lane loop is followed by __syncwarp(): lanes that leave a data-dependent loop early do
+      //      not reconverge on their own, and the rest of the sweep would run on a third of the lanes ----
+      for (int j = 0; j < nu_t; j++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (j < nu) v = ldg_plunit(src + j * 32);
+        const int kmax = min(32, len - 32 * j);
+        const uint32_t valid = j < nu ? (kmax >= 32 ? FULL : ((1u << kmax) - 1u)) : 0u;
+        const uint32_t t2 = (~v.x & v.y & ~v.z) & sel2, t6 = (~v.x & v.y & v.z) & sel6, t7 = (v.x & v.y & v.z) & sel7;
+        const uint32_t call = (t2 | t6 | t7) & valid;
+        const uint32_t nd = ~(v.x & v.y & ~v.z & v.w) & valid;
+        const int base = rel0 + 32 * j;
+        for (uint32_t tr = (nd ^ ((nd << 1) | covb)) & valid; tr; tr &= tr - 1u) {  // coverage transitions
+          const int k = __ffs(tr) - 1;
+          const bool on = (nd >> k) & 1u;
+          diff_event(base + k, S, dW, dH, dDe, on ? 1 : -1, on ? hv : -hv, on ? dv : -dv);
+        }
+        __syncwarp();
+        if (j < nu) covb = (nd >> (kmax - 1)) & 1u;
+        if (CLS & 1) { for (uint32_t m = t2 & valid; m; m &= m - 1u) { const int q = base + __ffs(m) - 1; if ((unsigned)q < (unsigned)S) atomicAdd(&T[prm.slot[0] * S + q], 1u); } __syncwarp(); }
+        if (CLS & 2) { for (uint32_t m = t6 & valid; m; m &= m - 1u) { const int q = base + __ffs(m) - 1; if ((unsigned)q < (unsigned)S) atomicAdd(&T[prm.slot[1] * S + q], 1u); } __syncwarp(); }
+        if (CLS & 4) { for (uint32_t m = t7 & valid; m; m &= m - 1u) { const int q = base + __ffs(m) - 1; if ((unsigned)q < (unsigned)S) atomicAdd(&T[prm.slot[2] * S + q], 1u); } __syncwarp(); }
+        for (uint32_t m = call; m; m &= m - 1u) {   // methylated stretches over the context's calls in position order
+          const int k = __ffs(m) - 1;
+          if (!((v.w >> k) & 1u)) {
+            if (!msz) ms = 32 * j + k;
+            me = 32 * j + k; msz++;
+          } else if (msz) close_stretch();
+        }
+        __syncwarp();
       }
+      if (covb) diff_event(rel0 + len, S, dW, dH, dDe, -1, -hv, -dv);
+      if (msz) close_stretch();
       __syncwarp();
     }
     __syncthreads();

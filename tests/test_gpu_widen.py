@@ -239,3 +239,30 @@ def test_ingest_synthetic_shuffled_and_spanning_blocks(monkeypatch):
     g = ea.Ingest(0)
     g.append(1, 1, 5, b"\xfc")
     g.abort()
+
+
+def test_large_results_into_pageable_memory(monkeypatch):
+    """Results of more than 32 MB fetched into PAGEABLE caller memory (what every binding passes) go through the staged copy
+    (two page-locked blocks, host threads copying out): the bytes must equal the direct copy and the oracle's values."""
+    cfg = ea.synth_config(50, 4_500_000, [45_000_000], 150)
+    dev = ea.synth_device(cfg)
+    beta = ea.rcpp_get_xm_beta(dev, "Z", "z")          # 36 MB of doubles into a plain numpy array
+    monkeypatch.setenv("EA_NO_STAGED_D2H", "1")
+    beta_direct = ea.rcpp_get_xm_beta(dev, "Z", "z")
+    assert np.array_equal(beta, beta_direct, equal_nan=True)
+    host = ea.synth_host(cfg, 4_400_000, 4_500_000)     # the last rows against the oracle (tail piece of the staged copy)
+    assert np.array_equal(beta[4_400_000:], PortCpu(host).rcpp_get_xm_beta("Z", "z"))
+    monkeypatch.delenv("EA_NO_STAGED_D2H")
+    # report columns and flags into pageable arrays through the C ABI directly
+    from epialleler_b200.api import _params
+    L = N.lib()
+    prm = _params(False, "CG", 2, 0.5, 0.1, "CX")
+    nrow = C.c_int64(0)
+    N.check(L.ea_cytosine_report(dev.handle(), C.byref(prm), None, C.byref(nrow)))
+    assert nrow.value * 4 > (32 << 20)
+    cols = [np.empty(nrow.value, np.int32) for _ in range(6)]
+    N.check(L.ea_cx_report_fetch(dev.handle(), *[c.ctypes.data_as(C.POINTER(C.c_int32)) for c in cols]))
+    rep = ea.generateCytosineReport(dev, threshold_reads=False, report_context="CX")   # page-locked result blocks
+    for c, k in zip(cols, COLS):
+        assert np.array_equal(c, rep[k]), k
+    dev.close()
