@@ -208,7 +208,7 @@ def run_other_configs(ea, L, N, args, peak, device):
     return out
 
 
-def e2e_shim_path(ea, L, host, device, steps):
+def e2e_shim_path(ea, L, host, device, steps, warm=3):
     """End to end through the boundary R binds: the reader's std::vector<std::string> (one PAGEABLE heap string per
     template, integration/harness) + pageable int columns -> handle_of() of the shim (pointer tables, ea_pack_calls) ->
     ea_cytosine_report -> fetch into fresh host arrays -> ea_free.  Runs FIRST in the process: the first call is a real cold
@@ -223,7 +223,9 @@ def e2e_shim_path(ea, L, host, device, steps):
     prm = _params(**THRESH)
     i32p, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
     times, rows, n_pass, h2d, calls_only = [], 0, 0, 0, True
-    for i in range(steps + 1):
+    # call 0 = the cold call; then `warm` untimed calls (a GPU that sat idle while the host prepared the strings takes a few
+    # seconds of work before its allocations and copies run at speed - measured: 0.6-1.4 s per call in that phase); then `steps`
+    for i in range(1 + warm + steps):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         dev = rs.pack(device=device, calls_only=True)
@@ -241,8 +243,8 @@ def e2e_shim_path(ea, L, host, device, steps):
         rows, n_pass = int(nrow.value), int(pass_flags.sum())
         del cols, pass_flags
     rs.close()
-    return dict(cold_s=times[0], warm_s=float(np.median(times[1:])) if len(times) > 1 else times[0], rows=rows, n_pass=n_pass, h2d=h2d,
-                calls_only=calls_only, build_strings_s=build_s, steps=steps)
+    return dict(cold_s=times[0], warm_s=float(np.median(times[1 + warm:])), warmup_s=[round(t, 4) for t in times[1:1 + warm]],
+                all_s=[round(t, 4) for t in times[1 + warm:]], rows=rows, n_pass=n_pass, h2d=h2d, calls_only=calls_only, build_strings_s=build_s, steps=steps, warm=warm)
 
 
 def e2e_pinned_blob(ea, L, host, device, steps, barrier, owned=None):
@@ -500,13 +502,14 @@ def run_ours(args):
         if shim:  # the path the R shim calls is the headline e2e; the pinned-blob figure rides along
             line["e2e"] = {"value": tot_reads / shim["warm_s"], "unit": "reads/s", "h2d_bytes_per_step": shim["h2d"], "d2h_bytes_per_step": int(own_reads + 24 * shim["rows"]),
                            "seconds_per_step": shim["warm_s"], "cold_first_call_seconds": shim["cold_s"], "cold_first_call_reads_per_s": tot_reads / shim["cold_s"],
-                           "steps": shim["steps"], "pinned_host_memory": False, "calls_only": shim["calls_only"],
+                           "steps": shim["steps"], "warmup": shim["warm"], "warmup_seconds": shim["warmup_s"], "step_seconds": shim["all_s"],
+                           "pinned_host_memory": False, "calls_only": shim["calls_only"],
                            "host_threads": os.environ.get("EA_HOST_PACK_THREADS", str(os.cpu_count())),
                            "what": ("ea_pack_calls through integration/harness: the reader's std::vector<std::string> (one PAGEABLE heap string per template) and pageable int "
                                     "columns -> the shim's handle_of() (pointer tables + ea_pack_calls: host threads transpose the strings where they lie into a ring of "
                                     "3 page-locked blocks, the blocks cross PCIe) -> ea_cytosine_report -> ea_cx_report_fetch of pass flags and rows into fresh PAGEABLE arrays (the R "
                                     "vectors of wrap_report) -> ea_free.  The leg runs first in the process: cold = the process's first call (no cached page-locked block, empty device "
-                                    "pool, kernels not yet loaded); seconds_per_step = median of the following calls"),
+                                    "pool, kernels not yet loaded, GPU idle since start-up); then `warmup` untimed calls; seconds_per_step = median of the `steps` calls after them"),
                            "from_pinned_blob": None}
         if e2e:
             blob_fig = {"value": tot_e2e_reads / e2e_s, "unit": "reads/s", "seconds_per_step": e2e_s, "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
