@@ -90,6 +90,18 @@ __attribute__((target("avx2"))) static inline void unit_avx2_fast(const uint8_t*
   _mm_stream_si128(dst, _mm_set_epi32((int)d, (int)c, (int)b, (int)a));   // written once, read by the DMA engine only
 }
 
+// the row's LAST, partial unit (n < 32 valid positions) of a row of at least 32 bytes: load the 32 bytes that END at the
+// row's end - always inside the string - and shift the plane words down, instead of copying the tail into a scratch block
+__attribute__((target("avx2"))) static inline void unit_avx2_tail(const uint8_t* row_end, int n, __m128i* dst) {
+  const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(row_end - 32));
+  const int sh = 32 - n;
+  const uint32_t a = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 7)) >> sh;
+  const uint32_t b = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6)) >> sh;
+  const uint32_t c = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5)) >> sh;
+  const uint32_t d = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 4)) >> sh;
+  _mm_stream_si128(dst, _mm_set_epi32((int)d, (int)c, (int)b, (int)a));
+}
+
 __attribute__((target("avx2"))) static void pack_tiles_avx2(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst) {
   // a full 32-byte load at or below safe_end stays inside the blob; scattered strings: only full units are loaded directly
   const uint8_t* const safe_end = job.str ? nullptr : job.blob + job.off[job.n] - 32;
@@ -110,6 +122,7 @@ __attribute__((target("avx2"))) static void pack_tiles_avx2(const Job& job, cons
         const uint8_t* p = row[l] + 32 * j;
         if (n <= 0) { _mm_stream_si128(tile + j * 32 + l, _mm_setzero_si128()); continue; }
         if (safe_end ? p <= safe_end : n >= 32) { unit_avx2_fast(p, n, tile + j * 32 + l); continue; }
+        if (len[l] >= 32) { unit_avx2_tail(row[l] + len[l], n, tile + j * 32 + l); continue; }
         alignas(32) uint8_t tmp[32] = {0};
         memcpy(tmp, p, (size_t)(n < 32 ? n : 32));
         unit_avx2_fast(tmp, n, tile + j * 32 + l);
