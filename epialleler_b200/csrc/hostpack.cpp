@@ -65,7 +65,13 @@ unsigned scan_rows(const Job& job, int64_t t0, int64_t t1, uint32_t* ls, int32_t
     int mx = 0;
     const int64_t r1 = (t * 32 + 32 < job.n) ? t * 32 + 32 : job.n;
     for (int64_t r = t * 32; r < r1; r++) {
-      if (job.templid && job.templid[r] != (int32_t)r) flags |= kNotIdentity;
+      if (job.str) {   // scattered strings: any in-range templid is fine
+        const int64_t t = job.sidx(r);
+        if (t < 0 || t >= job.nstr) { flags |= kBadTemplid; ls[r] = 0; continue; }
+        if (job.len[t] > 0 && !job.str[t]) { flags |= kNullString; ls[r] = 0; continue; }
+      } else if (job.templid && job.templid[r] != (int32_t)r) {
+        flags |= kNotIdentity;
+      }
       const int64_t l = job.row_len(r);
       if (l < 0 || l > 0x7FFFFFF0ll) { flags |= kBadLength; ls[r] = 0; continue; }
       const int32_t s = job.strand[r];

@@ -10,14 +10,18 @@ struct Job {
   const int32_t* strand;    // 1 '+', 2 '-'
   const int32_t* templid;   // nullptr or the identity
   int64_t n;
-  // scattered form (ea_pack_calls: the reference's std::vector<std::string>): row r = str[r][0 .. len[r]); blob/off unused
+  // scattered form (ea_pack_calls: the reference's std::vector<std::string>): row r = string t = templid[r] (or r), i.e.
+  // str[t][0 .. len[t]); blob/off unused.  Rows need NOT be the strings in file order here (paired-end data: templates are
+  // read in name order and the table is sorted by coordinate afterwards) - every row is fetched through its pointer anyway.
   const uint8_t* const* str = nullptr;
   const int64_t* len = nullptr;
-  const uint8_t* row_ptr(int64_t r) const { return str ? str[r] : blob + off[r]; }
-  int64_t row_len(int64_t r) const { return str ? len[r] : off[r + 1] - off[r]; }
+  int64_t nstr = 0;
+  int64_t sidx(int64_t r) const { return templid ? (int64_t)templid[r] : r; }
+  const uint8_t* row_ptr(int64_t r) const { return str ? str[sidx(r)] : blob + off[r]; }
+  int64_t row_len(int64_t r) const { return str ? len[sidx(r)] : off[r + 1] - off[r]; }
 };
 
-enum : unsigned { kNotIdentity = 1u, kBadLength = 2u, kBadStrand = 4u, kBadCode = 8u };
+enum : unsigned { kNotIdentity = 1u, kBadLength = 2u, kBadStrand = 4u, kBadCode = 8u, kBadTemplid = 16u, kNullString = 32u };
 
 // pass 1 over the rows of tiles [t0, t1) (tiles of 32 rows): ls[r] = length | (strand == '-') << 31, tile_nu[t] = unit rows
 // of tile t (max over its rows of ceil(length / 32)); returns the OR of the flags above

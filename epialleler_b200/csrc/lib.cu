@@ -1921,9 +1921,11 @@ int ea_device(const ea_handle* h) { return h ? h->device : -1; }
 // fill (optional): called with a range of strings right before their chunk of the blob is sent - ea_pack gathers the
 // scattered strings of chunk k into the page-locked blob while chunk k-1 is on its way to the device.
 namespace {
+// fill (ea_pack): the caller's strings are scattered; fill(s0, s1, dst) gathers strings [s0, s1) back to back into dst, one
+// of `kRing` page-locked blocks the implementation cycles through (a block is refilled once its previous copy has landed)
 int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                    int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out,
-                   const std::function<void(int64_t, int64_t)>* fill);
+                   const std::function<void(int64_t, int64_t, uint8_t*)>* fill);
 }
 int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                  int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out) {
@@ -1932,7 +1934,7 @@ int ea_pack_blob(const int32_t* rname, const int32_t* strand, const int32_t* sta
 namespace {
 int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                    int64_t nrow, const uint8_t* blob, const int64_t* off, int64_t nstr, int device, ea_handle** out,
-                   const std::function<void(int64_t, int64_t)>* fill) {
+                   const std::function<void(int64_t, int64_t, uint8_t*)>* fill) {
   if (!out) return fail(EA_ERR_ARG, "null out");
   *out = nullptr;
   if (nrow < 0 || nstr < 0 || nrow > 0x7FFFFFFEll) return fail(EA_ERR_ARG, "bad row/string count (at most 2^31-2 rows per handle)");
@@ -1943,19 +1945,26 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   if (nstr > 0 && off[0] < 0) return fail(EA_ERR_ARG, "negative string offset");
   const int64_t base = nstr > 0 ? off[0] : 0;   // string i = blob[off[i], off[i+1]): the offsets need not start at 0 (a shard of a larger blob)
   const int64_t total = nstr > 0 ? off[nstr] - base : 0;
-  if (total < 0 || (total > 0 && !blob)) return fail(EA_ERR_ARG, "bad string blob");
+  if (total < 0 || (total > 0 && !blob && !fill)) return fail(EA_ERR_ARG, "bad string blob");
   Trace tr("ea_pack_blob");
   ea_handle* h = new ea_handle;
   h->device = device; h->n = nrow;
-  constexpr int kMaxChunks = 32;
-  int64_t chunk_bytes = 256ll << 20;  // ~5 ms of PCIe 5 x16 per chunk; EA_PACK_CHUNK_MB overrides (tests)
+  // chunks of whole strings: ~256 MB (~5 ms of PCIe 5 x16) from a caller's blob, at most 32 of them; ~64 MB when the strings
+  // are gathered through the ring of page-locked blocks (a first call then pins 200 MB, not the whole data set);
+  // EA_PACK_CHUNK_MB overrides (tests)
+  const int kMaxChunks = fill ? 4096 : 32;
+  constexpr int kRing = 3;
+  int64_t chunk_bytes = fill ? 64ll << 20 : 256ll << 20;
   if (const char* e = getenv("EA_PACK_CHUNK_MB")) chunk_bytes = std::max<int64_t>(1, atoll(e)) << 20;
   const int n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)kMaxChunks, total / chunk_bytes + 1, std::max<int64_t>(nstr, 1)}));
   int32_t *d_strand32 = nullptr, *d_templid = nullptr; int64_t *d_soff = nullptr, *d_padded = nullptr; uint8_t* d_blob = nullptr;
   unsigned* d_flags = nullptr; void* d_tmp = nullptr;
   cudaStream_t sc = nullptr, sk = nullptr;
-  cudaEvent_t ev_meta = nullptr, ev_chunk[kMaxChunks] = {};
+  cudaEvent_t ev_meta = nullptr;
+  std::vector<cudaEvent_t> ev_chunk((size_t)n_chunks, nullptr);
+  uint8_t* ring[kRing] = {};
   auto cleanup = [&]() {
+    for (auto& p : ring) ea_host_free(p);
     FreeScope fs;
     pool_free(d_strand32); pool_free(d_templid); pool_free(d_soff); pool_free(d_blob); pool_free(d_flags); pool_free(d_padded); pool_free(d_tmp);
     if (sc) cudaStreamDestroy(sc);
@@ -2004,13 +2013,23 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
     k_lens_from_templid<<<grid_for(nrow, 256), 256, 0, sk>>>(d_soff, d_templid, nrow, nstr, h->d_len, d_padded, d_flags);
   }
   TRYCU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_padded, h->d_off, (int)(nrow + 1), sk));
-  int64_t s_begin[kMaxChunks + 1];  // string index range of every chunk
-  for (int k = 0; k <= n_chunks; k++) s_begin[k] = nstr * k / n_chunks;
+  std::vector<int64_t> s_begin((size_t)n_chunks + 1);  // string index range of every chunk
+  for (int k = 0; k <= n_chunks; k++) s_begin[(size_t)k] = nstr * k / n_chunks;
+  if (fill) {
+    int64_t slot = 1;
+    for (int k = 0; k < n_chunks; k++) slot = std::max(slot, off[s_begin[(size_t)k + 1]] - off[s_begin[(size_t)k]]);
+    for (auto& p : ring) { p = static_cast<uint8_t*>(ea_host_alloc((size_t)slot)); if (!p) { cleanup(); ea_free(h); return EA_ERR_CUDA; } }
+  }
   for (int k = 0; k < n_chunks; k++) {
     const int64_t b0 = nstr > 0 ? off[s_begin[k]] - base : 0, b1 = nstr > 0 ? off[s_begin[k + 1]] - base : 0;
     if (b1 < b0 || b1 > total) { cleanup(); ea_free(h); return fail(EA_ERR_ARG, "string offsets are not ascending"); }
-    if (fill && b1 > b0) (*fill)(s_begin[k], s_begin[k + 1]);
-    if (b1 > b0) TRYCU(cudaMemcpyAsync(d_blob + b0, blob + base + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sc));
+    const uint8_t* src = blob ? blob + base + b0 : nullptr;
+    if (fill && b1 > b0) {
+      if (k >= kRing) TRYCU(cudaEventSynchronize(ev_chunk[(size_t)(k - kRing)]));   // the block's previous copy has landed
+      (*fill)(s_begin[k], s_begin[k + 1], ring[k % kRing]);
+      src = ring[k % kRing];
+    }
+    if (b1 > b0) TRYCU(cudaMemcpyAsync(d_blob + b0, src, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sc));
     TRYCU(cudaEventRecord(ev_chunk[k], sc));
   }
   unsigned f = 0;
@@ -2369,35 +2388,30 @@ int ea_pack(const int32_t* rname, const int32_t* strand, const int32_t* start, c
   if (!out) return fail(EA_ERR_ARG, "null out");
   *out = nullptr;
   if (nstr < 0 || (nstr > 0 && (!str || !len))) return fail(EA_ERR_ARG, "bad string table");
-  // gather the scattered strings (std::vector<std::string> in the reference) into one pinned blob
   std::vector<int64_t> off((size_t)nstr + 1, 0);
   for (int64_t i = 0; i < nstr; i++) {
     if (len[i] < 0) return fail(EA_ERR_ARG, "negative string length");
     off[(size_t)i + 1] = off[(size_t)i] + len[i];
   }
-  const int64_t total = off[(size_t)nstr];
   int rc;
   if ((rc = pick_device(device))) return rc;
-  // the gather target is a page-locked block from the library's cache (ea_host_alloc): the H2D copy of ea_pack_blob then
-  // overlaps with the repack, and a second pack of similar size does not pay cudaHostAlloc again
-  uint8_t* blob = static_cast<uint8_t*>(ea_host_alloc((size_t)std::max<int64_t>(total, 1)));
-  if (!blob) return EA_ERR_CUDA;
+  // the strings are gathered chunk by chunk into a ring of three page-locked blocks (pack_blob_impl), chunk k while chunk
+  // k-1 crosses PCIe: the H2D copies run at PCIe speed and a first call pins ~200 MB instead of the whole data set
   const int nt_max = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)std::thread::hardware_concurrency(), 16));
-  const std::function<void(int64_t, int64_t)> gather = [&](int64_t s0, int64_t s1) {  // strings [s0, s1) -> their place in the blob
-    const int64_t bytes = off[(size_t)s1] - off[(size_t)s0];
+  const std::function<void(int64_t, int64_t, uint8_t*)> gather = [&](int64_t s0, int64_t s1, uint8_t* dst) {  // strings [s0, s1) back to back
+    const int64_t b0 = off[(size_t)s0], bytes = off[(size_t)s1] - b0;
     const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt_max, bytes / (4 << 20) + 1));
     auto work = [&](int t) {
       for (int64_t i = s0 + (s1 - s0) * t / nt; i < s0 + (s1 - s0) * (t + 1) / nt; i++)
-        if (len[i]) memcpy(blob + off[(size_t)i], str[i], (size_t)len[i]);
+        if (len[i]) memcpy(dst + (off[(size_t)i] - b0), str[i], (size_t)len[i]);
     };
     if (nt == 1) { work(0); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back(work, t);
     for (auto& x : th) x.join();
   };
-  rc = pack_blob_impl(rname, strand, start, templid, nrow, blob, off.data(), nstr, device, out, &gather);
-  ea_host_free(blob);
-  return rc;
+  for (int64_t i = 0; i < nstr; i++) if (len[i] > 0 && !str[i]) return fail(EA_ERR_ARG, "null string %lld", (long long)i);
+  return pack_blob_impl(rname, strand, start, templid, nrow, nullptr, off.data(), nstr, device, out, &gather);
 }
 
 int ea_attach_device(int32_t* d_rname, uint8_t* d_strand, int32_t* d_start, uint8_t* d_data, int64_t* d_off,

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 int main() {
@@ -18,7 +19,7 @@ int main() {
   std::vector<const uint8_t*> sp(n); std::vector<int64_t> sl(n);
   for (int64_t i = 0; i < n; i++) { sp[i] = (const uint8_t*)strs[i].data(); sl[i] = strs[i].size(); }
   eahp::Job jb{blob.data(), off.data(), strand.data(), nullptr, n};
-  eahp::Job js{nullptr, nullptr, strand.data(), nullptr, n}; js.str = sp.data(); js.len = sl.data();
+  eahp::Job js{nullptr, nullptr, strand.data(), nullptr, n}; js.str = sp.data(); js.len = sl.data(); js.nstr = n;
   const int64_t nt = (n + 31) / 32;
   std::vector<uint32_t> ls(n), ls2(n); std::vector<int32_t> nu(nt), nu2(nt);
   eahp::scan_rows(jb, 0, nt, ls.data(), nu.data()); eahp::scan_rows(js, 0, nt, ls2.data(), nu2.data());
@@ -27,6 +28,21 @@ int main() {
   void *a, *b; posix_memalign(&a, 64, toff[nt] * 512 + 64); posix_memalign(&b, 64, toff[nt] * 512 + 64);
   memset(a, 0xAA, toff[nt] * 512); memset(b, 0x55, toff[nt] * 512);
   eahp::pack_tiles(jb, toff.data(), 0, nt, (uint8_t*)a); eahp::pack_tiles(js, toff.data(), 0, nt, (uint8_t*)b);
-  printf("%s\n", memcmp(a, b, toff[nt] * 512) == 0 ? "scattered == blob: OK" : "MISMATCH");
-  return memcmp(a, b, toff[nt] * 512) != 0;
+  if (memcmp(a, b, toff[nt] * 512) != 0) { printf("MISMATCH\n"); return 1; }
+  // rows that reach their strings through templid (paired-end data): strings stored in a shuffled order
+  std::vector<int32_t> perm(n); for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+  for (int64_t i = n - 1; i > 0; i--) std::swap(perm[i], perm[rand() % (i + 1)]);
+  std::vector<const uint8_t*> sp2(n); std::vector<int64_t> sl2(n);
+  for (int64_t r = 0; r < n; r++) { sp2[perm[r]] = sp[r]; sl2[perm[r]] = sl[r]; }   // string perm[r] holds row r's bytes
+  eahp::Job jt{nullptr, nullptr, strand.data(), perm.data(), n}; jt.str = sp2.data(); jt.len = sl2.data(); jt.nstr = n;
+  std::vector<uint32_t> ls3(n); std::vector<int32_t> nu3(nt);
+  const unsigned f3 = eahp::scan_rows(jt, 0, nt, ls3.data(), nu3.data());
+  if (f3 || ls3 != ls || nu3 != nu) { printf("templid scan mismatch (flags %u)\n", f3); return 1; }
+  memset(b, 0x33, toff[nt] * 512);
+  eahp::pack_tiles(jt, toff.data(), 0, nt, (uint8_t*)b);
+  if (memcmp(a, b, toff[nt] * 512) != 0) { printf("templid MISMATCH\n"); return 1; }
+  perm[7] = (int32_t)n;   // out of range
+  if (!(eahp::scan_rows(jt, 0, 1, ls3.data(), nu3.data()) & eahp::kBadTemplid)) { printf("bad templid not flagged\n"); return 1; }
+  printf("scattered == blob, templid followed: OK\n");
+  return 0;
 }

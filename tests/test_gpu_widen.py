@@ -180,15 +180,26 @@ def test_pack_calls_rejects_bad_input_and_falls_back(monkeypatch):
         rs.pack(calls_only=True)
     assert e.value.code == N.EA_ERR_DOMAIN
     rs.close()
-    # rows that are not the strings in file order: the general packer takes over (byte rows present)
-    gold, _ = load_golden("amplicon010meth")
-    rs = H.ReaderStrings(gold)
-    dev = rs.pack(calls_only=True)
-    want_pass, want = oracle(gold)
-    got_pass, got = ea.generateCytosineReport(dev, return_pass=True)
-    assert np.array_equal(got_pass, want_pass)
-    assert_report_equal(got, want, "fixture through ea_pack_calls")
-    dev.close(); rs.close()
+    # rows that are not the strings in file order (paired-end data: templid is a permutation) stay on the fast path
+    for name in ("amplicon010meth", "capture"):
+        gold, _ = load_golden(name)
+        rs = H.ReaderStrings(gold)
+        dev = rs.pack(calls_only=True)
+        assert not N.lib().ea_has_bytes(dev.handle())
+        for kw in KW_SETS:
+            want_pass, want = oracle(gold, **kw)
+            got_pass, got = ea.generateCytosineReport(dev, return_pass=True, **kw)
+            assert np.array_equal(got_pass, want_pass), (name, kw)
+            assert_report_equal(got, want, "%s through ea_pack_calls %s" % (name, kw))
+        dev.close(); rs.close()
+    # a templid outside the strings is rejected like the reference's seqxm->at() would throw
+    bad_tid = bam.templid.copy()
+    bad_tid[17] = bam.nrow + 5
+    rs = H.ReaderStrings(ea.BamData(bam.rname, bam.strand, bam.start, bad_tid, blob, off))
+    with pytest.raises(ea.EaError) as e:
+        rs.pack(calls_only=True)
+    assert e.value.code == N.EA_ERR_ARG
+    rs.close()
 
 
 @pytest.mark.parametrize("name", ["amplicon010meth", "capture"])
