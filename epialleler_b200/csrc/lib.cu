@@ -127,6 +127,33 @@ cudaError_t pool_malloc(void** p, size_t bytes) {
 template <class T>
 cudaError_t pool_malloc(T** p, size_t bytes) { return pool_malloc(reinterpret_cast<void**>(p), bytes); }
 
+// Growing the pool is what costs: a handle is some twenty blocks, and when they are all NEW memory the allocations of one
+// call add up to 0.3-1 s - and the pool keeps growing over the following calls, a stall here and there, until it happens to
+// hold a fitting block for every request (measured: 250-270 ms per pack+report+free with a warm pool, 270-1070 ms after
+// ea_trim()).  The packers therefore say up front what the handle will need: if the pool's free bytes fall short, ONE block
+// of the deficit is allocated and freed again - everything after it is carved out of cached memory.
+void pool_reserve(size_t want_free) {
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) != cudaSuccess || ea_pool(dev, &pool) != cudaSuccess) { cudaGetLastError(); return; }
+  uint64_t reserved = 0, used = 0;
+  if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess ||
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) { cudaGetLastError(); return; }
+  const uint64_t have = reserved > used ? reserved - used : 0;
+  if (have >= want_free) return;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return; }
+  const size_t deficit = std::min<size_t>(want_free - have, free_b / 2);   // never more than half of what the device has left
+  if (deficit < (64u << 20)) return;
+  void* p = nullptr;
+  if (cudaMallocFromPoolAsync(&p, deficit, pool, cudaStreamPerThread) == cudaSuccess) {
+    cudaFreeAsync(p, cudaStreamPerThread);
+    cudaStreamSynchronize(cudaStreamPerThread);
+  } else {
+    cudaGetLastError();
+  }
+}
+
 // Freeing a block that any stream may still use needs a device-wide synchronisation first (like cudaFree).  Code that
 // frees many blocks in a row opens a FreeScope: the first pool_free inside it synchronises, the others only free.
 thread_local int g_free_scope_depth = 0;
@@ -1947,6 +1974,9 @@ int pack_blob_impl(const int32_t* rname, const int32_t* strand, const int32_t* s
   const int64_t total = nstr > 0 ? off[nstr] - base : 0;
   if (total < 0 || (total > 0 && !blob && !fill)) return fail(EA_ERR_ARG, "bad string blob");
   Trace tr("ea_pack_blob");
+  // tight copy + padded rows + call planes + ~80 bytes per row of columns, keys, index scratch and report rows
+  if (!getenv("EA_NO_POOL_RESERVE")) pool_reserve((size_t)((double)total * 2.7) + (size_t)nrow * 64 + (64u << 20));
+  tr.mark("pool reserve");
   ea_handle* h = new ea_handle;
   h->device = device; h->n = nrow;
   // chunks of whole strings: ~256 MB (~5 ms of PCIe 5 x16) from a caller's blob, at most 32 of them; ~64 MB when the strings
@@ -2174,6 +2204,9 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
   int rc;
   if ((rc = pick_device(device))) return rc;
   Trace tr("ea_pack_blob_calls");
+  // call planes (half the bytes, ragged tiles up to ~1.6x) + four raw chunks + ~80 bytes per row
+  if (!getenv("EA_NO_POOL_RESERVE")) pool_reserve((size_t)((double)total * 0.85) + (size_t)nrow * 48 + (832u << 20));
+  tr.mark("pool reserve");
   int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
   if (g_pack_threads > 0) nt = std::min(nt, g_pack_threads);
   if (const char* e = getenv("EA_HOST_PACK_THREADS")) nt = std::max(1, atoi(e));

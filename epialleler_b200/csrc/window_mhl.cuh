@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(kMhlThreads, 3)
 k_window_mhl(Csr csr, WinTable wt, MhlParams prm, MhlOut out) {
   constexpr bool PAIRS = CLS != 0;
   constexpr int S = kMhlS;
-  constexpr int PER = S / kMhlThreads;  // 4
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ long long s_scan[4 * kMhlWarps];
   __shared__ uint32_t s_scan32[kMhlWarps + 1];
