@@ -228,7 +228,7 @@ def e2e_shim_path(ea, L, host, device, steps, warm=3):
     for i in range(1 + warm + steps):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        dev = rs.pack(device=device, calls_only=True)
+        dev = rs.pack(device=device, calls_only=True, records=True)
         # results land in freshly allocated PAGEABLE arrays, like the R vectors the shim fetches into (wrap_report)
         pass_flags = np.empty(dev.nrow, np.uint8)
         nrow = C.c_int64(0)
@@ -505,9 +505,9 @@ def run_ours(args):
                            "steps": shim["steps"], "warmup": shim["warm"], "warmup_seconds": shim["warmup_s"], "step_seconds": shim["all_s"],
                            "pinned_host_memory": False, "calls_only": shim["calls_only"],
                            "host_threads": os.environ.get("EA_HOST_PACK_THREADS", str(os.cpu_count())),
-                           "what": ("ea_pack_calls through integration/harness: the reader's std::vector<std::string> (one PAGEABLE heap string per template) and pageable int "
-                                    "columns -> the shim's handle_of() (pointer tables + ea_pack_calls: host threads transpose the strings where they lie into a ring of "
-                                    "3 page-locked blocks, the blocks cross PCIe) -> ea_cytosine_report -> ea_cx_report_fetch of pass flags and rows into fresh PAGEABLE arrays (the R "
+                           "what": ("ea_pack_calls_records through integration/harness: the reader's std::vector<std::string> (one PAGEABLE heap string per template) and pageable int "
+                                    "columns -> the shim's handle_of() (the vector's std::string objects are handed over as a record array, no pointer tables; host threads "
+                                    "transpose the strings where they lie into a ring of 3 page-locked blocks, the blocks cross PCIe) -> ea_cytosine_report -> ea_cx_report_fetch of pass flags and rows into fresh PAGEABLE arrays (the R "
                                     "vectors of wrap_report) -> ea_free.  The leg runs first in the process: cold = the process's first call (no cached page-locked block, empty device "
                                     "pool, kernels not yet loaded, GPU idle since start-up); then `warmup` untimed calls; seconds_per_step = median of the `steps` calls after them"),
                            "from_pinned_blob": None}

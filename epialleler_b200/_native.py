@@ -92,6 +92,7 @@ SIGNATURES = {
     "ea_synth_host": (C.c_int, [C.POINTER(SynthCfg), C.c_int64, C.c_int64, _I32P, _I32P, _I32P, _I64P, _U8P]),
     "ea_export_host": (C.c_int, [_H, _I32P, _I32P, _I32P, _I64P, _U8P]),
     "ea_pack_calls": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_void_p), _I64P, C.c_int64, C.c_int, C.POINTER(_H)]),
+    "ea_pack_calls_records": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_H)]),
     "ea_ingest_begin": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_H)]),
     "ea_ingest_append": (C.c_int64, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "ea_ingest_finish": (C.c_int, [_H, _I32P, _I32P, _I32P, _I32P, C.POINTER(_H)]),

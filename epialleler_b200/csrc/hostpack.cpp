@@ -65,10 +65,10 @@ unsigned scan_rows(const Job& job, int64_t t0, int64_t t1, uint32_t* ls, int32_t
     int mx = 0;
     const int64_t r1 = (t * 32 + 32 < job.n) ? t * 32 + 32 : job.n;
     for (int64_t r = t * 32; r < r1; r++) {
-      if (job.str) {   // scattered strings: any in-range templid is fine
+      if (job.scattered()) {   // scattered strings: any in-range templid is fine
         const int64_t t = job.sidx(r);
         if (t < 0 || t >= job.nstr) { flags |= kBadTemplid; ls[r] = 0; continue; }
-        if (job.len[t] > 0 && !job.str[t]) { flags |= kNullString; ls[r] = 0; continue; }
+        if (job.len_at(t) > 0 && !job.ptr_at(t)) { flags |= kNullString; ls[r] = 0; continue; }
       } else if (job.templid && job.templid[r] != (int32_t)r) {
         flags |= kNotIdentity;
       }
@@ -110,7 +110,7 @@ __attribute__((target("avx2"))) static inline void unit_avx2_tail(const uint8_t*
 
 __attribute__((target("avx2"))) static void pack_tiles_avx2(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst) {
   // a full 32-byte load at or below safe_end stays inside the blob; scattered strings: only full units are loaded directly
-  const uint8_t* const safe_end = job.str ? nullptr : job.blob + job.off[job.n] - 32;
+  const uint8_t* const safe_end = job.scattered() ? nullptr : job.blob + job.off[job.n] - 32;
   static const uint8_t kNone[1] = {0};
   for (int64_t t = t0; t < t1; t++) {
     __m128i* tile = reinterpret_cast<__m128i*>(dst + (toff[t] - toff[t0]) * 512);

@@ -10,15 +10,23 @@ struct Job {
   const int32_t* strand;    // 1 '+', 2 '-'
   const int32_t* templid;   // nullptr or the identity
   int64_t n;
-  // scattered form (ea_pack_calls: the reference's std::vector<std::string>): row r = string t = templid[r] (or r), i.e.
-  // str[t][0 .. len[t]); blob/off unused.  Rows need NOT be the strings in file order here (paired-end data: templates are
-  // read in name order and the table is sorted by coordinate afterwards) - every row is fetched through its pointer anyway.
+  // scattered form (ea_pack_calls: the reference's std::vector<std::string>): row r = string t = templid[r] (or r).  Rows
+  // need NOT be the strings in file order here (paired-end data: templates are read in name order and the table is sorted
+  // by coordinate afterwards) - every row is fetched through its pointer anyway.  Two ways to say where string t lies:
+  //   tables  : str[t] / len[t]
+  //   records : an array of fixed-size records (the std::string objects themselves), string t's data pointer at
+  //             rec + t * stride + ptr_off and its length (size_t) at rec + t * stride + len_off - no tables to build
   const uint8_t* const* str = nullptr;
   const int64_t* len = nullptr;
+  const uint8_t* rec = nullptr;
+  int64_t stride = 0, ptr_off = 0, len_off = 0;
   int64_t nstr = 0;
+  bool scattered() const { return str != nullptr || rec != nullptr; }
   int64_t sidx(int64_t r) const { return templid ? (int64_t)templid[r] : r; }
-  const uint8_t* row_ptr(int64_t r) const { return str ? str[sidx(r)] : blob + off[r]; }
-  int64_t row_len(int64_t r) const { return str ? len[sidx(r)] : off[r + 1] - off[r]; }
+  const uint8_t* ptr_at(int64_t t) const { return rec ? *reinterpret_cast<const uint8_t* const*>(rec + t * stride + ptr_off) : str[t]; }
+  int64_t len_at(int64_t t) const { return rec ? (int64_t)*reinterpret_cast<const uint64_t*>(rec + t * stride + len_off) : len[t]; }
+  const uint8_t* row_ptr(int64_t r) const { return scattered() ? ptr_at(sidx(r)) : blob + off[r]; }
+  int64_t row_len(int64_t r) const { return scattered() ? len_at(sidx(r)) : off[r + 1] - off[r]; }
 };
 
 enum : unsigned { kNotIdentity = 1u, kBadLength = 2u, kBadStrand = 4u, kBadCode = 8u, kBadTemplid = 16u, kNullString = 32u };

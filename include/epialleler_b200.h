@@ -103,6 +103,12 @@ int ea_pack_blob_calls(const int32_t* rname, const int32_t* strand, const int32_
  * ea_pack_blob_calls.  What the R shim calls for generateCytosineReport. */
 int ea_pack_calls(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
                   int64_t nrow, const uint8_t* const* str, const int64_t* len, int64_t nstr, int device, ea_handle** out);
+/* The same without pointer tables: `records` = nstr fixed-size records (the std::string OBJECTS of the reader's vector) with
+ * the data pointer at ptr_offset and the length (size_t) at len_offset inside each record of `stride` bytes.  The binding
+ * finds the two offsets of its standard library with a probe string (integration/harness/shim_harness.cpp). */
+int ea_pack_calls_records(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid,
+                          int64_t nrow, const void* records, int64_t nstr, int64_t stride, int64_t ptr_offset, int64_t len_offset,
+                          int device, ea_handle** out);
 int ea_has_bytes(const ea_handle* h);            /* 1: byte rows present (ea_pack, ea_pack_blob, ...), 0: call planes only */
 int64_t ea_pack_h2d_bytes(const ea_handle* h);   /* bytes the packer copied host -> device for this handle */
 

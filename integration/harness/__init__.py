@@ -25,6 +25,8 @@ def lib():
         L.harness_strings_count.argtypes = [C.c_void_p]
         L.harness_pack.restype = C.c_int
         L.harness_pack.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.harness_pack_records.restype = C.c_int
+        L.harness_pack_records.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
 
@@ -41,12 +43,19 @@ class ReaderStrings:
         self.cols = [np.array(getattr(bam, k), dtype=np.int32, copy=True) for k in ("rname", "strand", "start", "templid")]
         self.nrow = int(self.cols[0].shape[0])
 
-    def pack(self, device=0, calls_only=True):
-        """handle_of() of the shim -> epialleler_b200.api.DeviceBam"""
+    def pack(self, device=0, calls_only=True, records=False):
+        """handle_of() of the shim -> epialleler_b200.api.DeviceBam.  records=True: the table-free call
+        (ea_pack_calls_records on the vector's std::string objects); else pointer/length tables + ea_pack_calls / ea_pack."""
         from epialleler_b200 import _native as N
         from epialleler_b200.api import DeviceBam
         h = C.c_void_p()
-        N.check(lib().harness_pack(self._v, *[c.ctypes.data for c in self.cols], self.nrow, device, 1 if calls_only else 0, C.byref(h)))
+        if records and calls_only:
+            rc = lib().harness_pack_records(self._v, *[c.ctypes.data for c in self.cols], self.nrow, device, C.byref(h))
+            if rc == -1000:
+                raise RuntimeError("std::string layout not understood by the probe")
+            N.check(rc)
+        else:
+            N.check(lib().harness_pack(self._v, *[c.ctypes.data for c in self.cols], self.nrow, device, 1 if calls_only else 0, C.byref(h)))
         return DeviceBam(h, device)
 
     def close(self):

@@ -6,6 +6,7 @@
 // Plain C++ (g++), linked against the product's C ABI only.
 #include <cstdint>
 #include <algorithm>
+#include <initializer_list>
 #include <memory>
 #include <string>
 #include <thread>
@@ -24,6 +25,35 @@ void* harness_strings_new(const uint8_t* blob, const int64_t* off, int64_t n) {
 }
 void harness_strings_free(void* p) { delete static_cast<std::vector<std::string>*>(p); }
 int64_t harness_strings_count(void* p) { return (int64_t)static_cast<std::vector<std::string>*>(p)->size(); }
+
+// Where a std::string keeps its data pointer and its length, found with probe strings (libstdc++: 0 and 8 in a 32-byte
+// object; the probe makes no assumption).  false: layout not understood - use the pointer tables.
+static bool string_layout(int64_t* ptr_off, int64_t* len_off) {
+  static_assert(sizeof(std::string) % 8 == 0, "unexpected std::string size");
+  int64_t po = -1, lo = -1;
+  for (size_t n : {(size_t)100, (size_t)3, (size_t)7777}) {   // heap, short-string and large probes must agree
+    std::string probe(n, 'x');
+    const unsigned char* raw = reinterpret_cast<const unsigned char*>(&probe);
+    int64_t p = -1, l = -1;
+    for (size_t o = 0; o + 8 <= sizeof(std::string); o += 8) {
+      if (p < 0 && *reinterpret_cast<const char* const*>(raw + o) == probe.data()) p = (int64_t)o;
+      else if (l < 0 && *reinterpret_cast<const size_t*>(raw + o) == n) l = (int64_t)o;
+    }
+    if (p < 0 || l < 0 || (po >= 0 && (p != po || l != lo))) return false;
+    po = p; lo = l;
+  }
+  *ptr_off = po; *len_off = lo;
+  return true;
+}
+
+// handle_of() of the shim, table-free form: the vector's std::string objects ARE the record array
+int harness_pack_records(void* p, const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
+                         int device, ea_handle** out) {
+  auto* seqxm = static_cast<std::vector<std::string>*>(p);
+  int64_t po, lo;
+  if (!string_layout(&po, &lo)) return -1000;
+  return ea_pack_calls_records(rname, strand, start, templid, nrow, seqxm->data(), (int64_t)seqxm->size(), (int64_t)sizeof(std::string), po, lo, device, out);
+}
 
 // handle_of() of the shim: pointer and length tables over the vector, then the packer
 int harness_pack(void* p, const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,

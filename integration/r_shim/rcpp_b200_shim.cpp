@@ -11,6 +11,7 @@
 #include <Rcpp.h>
 #include <algorithm>
 #include <cstdio>
+#include <initializer_list>
 #include <memory>
 #include <thread>
 #include <epialleler_b200.h>
@@ -35,32 +36,58 @@ struct Handle {
   ~Handle() { ea_free(h); }
 };
 
-// Packs bam.data.  need_bytes = false (thresholds, betas, cytosine reports, BED matching): call planes only
-// (ea_pack_calls - the host transposes the reader's strings where they lie, half the bytes cross PCIe);
+// Packs bam.data.  need_bytes = false (thresholds, betas, cytosine reports, BED matching, lMHL): call planes only
+// (ea_pack_calls_records / ea_pack_calls - the host transposes the reader's strings where they lie, half the bytes cross PCIe);
 // need_bytes = true (lMHL, VCF base frequencies): byte rows too (ea_pack).  The pointer/length tables over the
 // std::vector<std::string> are filled by a few threads (no R API inside them) - integration/harness/shim_harness.cpp is this
 // very code without Rcpp, and what bench.py's end-to-end leg and tests/test_gpu_widen.py run.
+// Where this standard library's std::string keeps its data pointer and its length (probe strings; libstdc++: 0 and 8).
+bool string_layout(int64_t* ptr_off, int64_t* len_off) {
+  int64_t po = -1, lo = -1;
+  for (size_t n : {(size_t)100, (size_t)3, (size_t)7777}) {
+    std::string probe(n, 'x');
+    const unsigned char* raw = reinterpret_cast<const unsigned char*>(&probe);
+    int64_t p = -1, l = -1;
+    for (size_t o = 0; o + 8 <= sizeof(std::string); o += 8) {
+      if (p < 0 && *reinterpret_cast<const char* const*>(raw + o) == probe.data()) p = (int64_t)o;
+      else if (l < 0 && *reinterpret_cast<const size_t*>(raw + o) == n) l = (int64_t)o;
+    }
+    if (p < 0 || l < 0 || (po >= 0 && (p != po || l != lo))) return false;
+    po = p; lo = l;
+  }
+  *ptr_off = po; *len_off = lo;
+  return true;
+}
+
 Handle* pack(Rcpp::DataFrame& df, bool need_bytes) {
   Rcpp::XPtr<std::vector<std::string>> seqxm((SEXP)df.attr("seqxm_xptr"));
   Rcpp::IntegerVector rname = df["rname"], strand = df["strand"], start = df["start"], templid = df["templid"];
   const size_t n = seqxm->size();
-  std::unique_ptr<const uint8_t*[]> str(new const uint8_t*[n ? n : 1]);
-  std::unique_ptr<int64_t[]> len(new int64_t[n ? n : 1]);
-  const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
-  std::vector<std::thread> th;
-  for (unsigned t = 0; t < nt; t++)
-    th.emplace_back([&, t]() {
-      for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
-        str[i] = reinterpret_cast<const uint8_t*>((*seqxm)[i].data());
-        len[i] = static_cast<int64_t>((*seqxm)[i].size());
-      }
-    });
-  for (auto& x : th) x.join();
   ea_set_poll(poll_interrupt);
   Handle* hd = new Handle;
   hd->seqxm = seqxm.get(); hd->nrow = df.nrows(); hd->rname0 = rname.begin(); hd->start0 = start.begin();
-  const int rc = (need_bytes ? ea_pack : ea_pack_calls)(rname.begin(), strand.begin(), start.begin(), templid.begin(), df.nrows(), str.get(),
-                                                        len.get(), static_cast<int64_t>(n), /*device=*/0, &hd->h);
+  int rc;
+  int64_t po, lo;
+  if (!need_bytes && sizeof(std::string) % 8 == 0 && string_layout(&po, &lo)) {
+    // the vector's std::string objects are handed over as they are: no pointer tables (55 ms per 50 M strings)
+    rc = ea_pack_calls_records(rname.begin(), strand.begin(), start.begin(), templid.begin(), df.nrows(), seqxm->data(),
+                               static_cast<int64_t>(n), static_cast<int64_t>(sizeof(std::string)), po, lo, /*device=*/0, &hd->h);
+  } else {
+    std::unique_ptr<const uint8_t*[]> str(new const uint8_t*[n ? n : 1]);
+    std::unique_ptr<int64_t[]> len(new int64_t[n ? n : 1]);
+    const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+      th.emplace_back([&, t]() {
+        for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+          str[i] = reinterpret_cast<const uint8_t*>((*seqxm)[i].data());
+          len[i] = static_cast<int64_t>((*seqxm)[i].size());
+        }
+      });
+    for (auto& x : th) x.join();
+    rc = (need_bytes ? ea_pack : ea_pack_calls)(rname.begin(), strand.begin(), start.begin(), templid.begin(), df.nrows(), str.get(),
+                                                len.get(), static_cast<int64_t>(n), /*device=*/0, &hd->h);
+  }
   if (rc != EA_OK) { delete hd; ea_check(rc); }
   return hd;
 }

@@ -41,6 +41,16 @@ int main() {
   memset(b, 0x33, toff[nt] * 512);
   eahp::pack_tiles(jt, toff.data(), 0, nt, (uint8_t*)b);
   if (memcmp(a, b, toff[nt] * 512) != 0) { printf("templid MISMATCH\n"); return 1; }
+  // record-array form: the std::string objects themselves (libstdc++: data pointer at 0, length at 8)
+  if (sizeof(std::string) == 32 && *reinterpret_cast<const char* const*>(&strs[5]) == strs[5].data()) {
+    eahp::Job jr{nullptr, nullptr, strand.data(), nullptr, n};
+    jr.rec = reinterpret_cast<const uint8_t*>(strs.data()); jr.stride = sizeof(std::string); jr.ptr_off = 0; jr.len_off = 8; jr.nstr = n;
+    std::vector<uint32_t> ls4(n); std::vector<int32_t> nu4(nt);
+    if (eahp::scan_rows(jr, 0, nt, ls4.data(), nu4.data()) || ls4 != ls || nu4 != nu) { printf("records scan mismatch\n"); return 1; }
+    memset(b, 0x77, toff[nt] * 512);
+    eahp::pack_tiles(jr, toff.data(), 0, nt, (uint8_t*)b);
+    if (memcmp(a, b, toff[nt] * 512) != 0) { printf("records MISMATCH\n"); return 1; }
+  }
   perm[7] = (int32_t)n;   // out of range
   if (!(eahp::scan_rows(jt, 0, 1, ls3.data(), nu3.data()) & eahp::kBadTemplid)) { printf("bad templid not flagged\n"); return 1; }
   printf("scattered == blob, templid followed: OK\n");

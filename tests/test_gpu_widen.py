@@ -151,15 +151,16 @@ def test_pack_calls_from_reader_strings(threads, monkeypatch):
     monkeypatch.setenv("EA_PACK_CHUNK_MB", "1")
     for name, bam in shapes():
         rs = H.ReaderStrings(bam)
-        dev = rs.pack(calls_only=True)
-        assert not N.lib().ea_has_bytes(dev.handle()) and dev.nrow == bam.nrow and dev.nbytes == int(bam.blob()[1][-1])
-        for kw in KW_SETS[:2]:
-            want_pass, want = oracle(bam, **kw)
-            got_pass, got = ea.generateCytosineReport(dev, return_pass=True, **kw)
-            assert np.array_equal(got_pass, want_pass), (name, kw)
-            assert_report_equal(got, want, "%s ea_pack_calls %s" % (name, kw))
-        assert np.array_equal(ea.rcpp_get_xm_beta(dev, "Z", "z"), PortCpu(bam).rcpp_get_xm_beta("Z", "z"))
-        dev.close()
+        for records in (False, True):   # pointer tables / the table-free call on the std::string objects themselves
+            dev = rs.pack(calls_only=True, records=records)
+            assert not N.lib().ea_has_bytes(dev.handle()) and dev.nrow == bam.nrow and dev.nbytes == int(bam.blob()[1][-1])
+            for kw in KW_SETS[:2]:
+                want_pass, want = oracle(bam, **kw)
+                got_pass, got = ea.generateCytosineReport(dev, return_pass=True, **kw)
+                assert np.array_equal(got_pass, want_pass), (name, kw)
+                assert_report_equal(got, want, "%s ea_pack_calls %s records=%s" % (name, kw, records))
+            assert np.array_equal(ea.rcpp_get_xm_beta(dev, "Z", "z"), PortCpu(bam).rcpp_get_xm_beta("Z", "z"))
+            dev.close()
         dev2 = rs.pack(calls_only=False)   # ea_pack: byte rows too
         assert N.lib().ea_has_bytes(dev2.handle())
         want_pass, want = oracle(bam)
@@ -184,14 +185,16 @@ def test_pack_calls_rejects_bad_input_and_falls_back(monkeypatch):
     for name in ("amplicon010meth", "capture"):
         gold, _ = load_golden(name)
         rs = H.ReaderStrings(gold)
-        dev = rs.pack(calls_only=True)
-        assert not N.lib().ea_has_bytes(dev.handle())
-        for kw in KW_SETS:
-            want_pass, want = oracle(gold, **kw)
-            got_pass, got = ea.generateCytosineReport(dev, return_pass=True, **kw)
-            assert np.array_equal(got_pass, want_pass), (name, kw)
-            assert_report_equal(got, want, "%s through ea_pack_calls %s" % (name, kw))
-        dev.close(); rs.close()
+        for records in (False, True):
+            dev = rs.pack(calls_only=True, records=records)
+            assert not N.lib().ea_has_bytes(dev.handle())
+            for kw in KW_SETS:
+                want_pass, want = oracle(gold, **kw)
+                got_pass, got = ea.generateCytosineReport(dev, return_pass=True, **kw)
+                assert np.array_equal(got_pass, want_pass), (name, kw)
+                assert_report_equal(got, want, "%s through ea_pack_calls %s" % (name, kw))
+            dev.close()
+        rs.close()
     # a templid outside the strings is rejected like the reference's seqxm->at() would throw
     bad_tid = bam.templid.copy()
     bad_tid[17] = bam.nrow + 5
@@ -250,6 +253,10 @@ def test_ingest_synthetic_shuffled_and_spanning_blocks(monkeypatch):
     g = ea.Ingest(0)
     g.append(1, 1, 5, b"\xfc")
     g.abort()
+    dev, cols = ea.Ingest(0).finish()   # no templates at all
+    assert dev.nrow == 0 and cols["rname"].shape[0] == 0
+    assert ea.generateCytosineReport(dev)["pos"].shape[0] == 0
+    dev.close()
 
 
 def test_large_results_into_pageable_memory(monkeypatch):

@@ -21,14 +21,15 @@ t0 = time.perf_counter()
 rs = H.ReaderStrings(host)
 print("build heap strings %.2f s" % (time.perf_counter() - t0), flush=True)
 L.ea_trim(0)
-for i in range(4):
+for i in range(8):
+    records = i >= 4   # calls 4-7: the table-free call (ea_pack_calls_records)
     torch.cuda.synchronize()
     t = [time.perf_counter()]
-    d = rs.pack(calls_only=True); t.append(time.perf_counter())
+    d = rs.pack(calls_only=True, records=records); t.append(time.perf_counter())
     p, rep = ea.generateCytosineReport(d, return_pass=True); t.append(time.perf_counter())
     d.close(); torch.cuda.synchronize(); t.append(time.perf_counter())
     del p, rep
-    print("call %d: pack %.1f ms  report+fetch %.1f ms  free %.1f ms  total %.1f ms" % (i, *(1e3 * (b - a) for a, b in zip(t, t[1:])), 1e3 * (t[-1] - t[0])), flush=True)
+    print("%s call %d: pack %.1f ms  report+fetch %.1f ms  free %.1f ms  total %.1f ms" % ("records" if records else "tables ", i, *(1e3 * (b - a) for a, b in zip(t, t[1:])), 1e3 * (t[-1] - t[0])), flush=True)
 
 # ---- the same with results fetched into PAGEABLE arrays (what the R shim's wrap_report does) ----
 import ctypes as C  # noqa: E402
