@@ -296,7 +296,7 @@ def generateCytosineReport(bam, report_file=None, threshold_reads=True, threshol
     p = _params(threshold_reads, threshold_context, min_context_sites, min_context_beta, max_outofcontext_beta, report_context)
     nrow = C.c_int64(0)
     if isinstance(bam, MultiBam):
-        return bam._report(p, report_file, return_pass)
+        return bam._report(p, (report_file, gzip) if report_file is not None else None, return_pass)
     n_flags = getattr(bam, "n_owned", bam.nrow)   # a range shard reports the flags of the rows it owns
     pass_out = _host_out(n_flags, np.uint8) if return_pass else None
     _on_calls(bam, lambda h: N.check(L.ea_cytosine_report(h, C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow))))
@@ -342,11 +342,12 @@ class MultiBam:
 
     def _report(self, p, report_file, return_pass):
         L = N.lib()
-        if report_file is not None:
-            raise NotImplementedError("report_file with several devices: fetch the report and write it")
         nrow = C.c_int64(0)
         pass_out = _host_out(self.nrow, np.uint8) if return_pass else None
         N.check(L.ea_multi_cytosine_report(self._m, C.byref(p), _p(pass_out, C.c_uint8) if return_pass else None, C.byref(nrow)))
+        if report_file is not None:   # every shard formats the rows it owns on its device; the pieces are the file, in genomic order
+            _write_report_text(self.report_text(), report_file[0], report_file[1])
+            return None
         n = nrow.value
         cols = [_host_out(n, np.int32) for _ in range(6)]
         N.check(L.ea_multi_report_fetch(self._m, *[_p(c, C.c_int32) for c in cols]))
@@ -355,6 +356,23 @@ class MultiBam:
         if return_pass:
             return pass_out[:self.nrow].view(np.bool_), rep
         return rep
+
+    def report_text(self, header=True):
+        """The last report as the bytes .writeReport would put into the file: shard i's owned rows formatted on device i
+        (ea_cx_report_text honours the ownership filter), concatenated in genomic order."""
+        L = N.lib()
+        names = [str(x).encode() for x in self.rname_levels]
+        arr = (C.c_char_p * max(len(names), 1))(*names)
+        parts = []
+        for i in range(L.ea_multi_ndev(self._m)):
+            h = L.ea_multi_handle(self._m, i)
+            nbytes = C.c_int64(0)
+            N.check(L.ea_cx_report_text(h, arr, len(names), 1 if (header and i == 0) else 0, C.byref(nbytes)))
+            out = np.empty(max(nbytes.value, 1), np.uint8)
+            if nbytes.value:
+                N.check(L.ea_cx_report_text_fetch(h, out.ctypes.data_as(C.c_void_p)))
+            parts.append(out[:nbytes.value])
+        return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
 
     def close(self):
         if self._m is not None:

@@ -92,6 +92,20 @@ def test_pack_multi_equals_single(ndev_shards):
         bam.close()
 
 
+def test_pack_multi_report_file(tmp_path):
+    """report_file with several shards: every device formats the rows it owns; the concatenation is the single-device file."""
+    bam = ea.synth_host(ea.synth_config(51, 20000, [90000, 60000, 30000], 150))
+    bam.rname_levels = ["chr1", "chr2", "chrX"]
+    one, many = str(tmp_path / "one.tsv"), str(tmp_path / "many.tsv.gz")
+    ea.generateCytosineReport(bam, report_file=one, report_context="CX")
+    mb = ea.MultiBam(bam, [0, 0, 0, 0])
+    ea.generateCytosineReport(mb, report_file=many, report_context="CX", gzip=True)
+    import gzip
+    assert gzip.open(many, "rb").read() == open(one, "rb").read()
+    assert open(one, "rb").read().count(b"\n") > 1000
+    mb.close(); bam.close()
+
+
 def test_pack_multi_shuffled_templid_and_errors():
     bam0 = ea.synth_host(ea.synth_config(46, 9000, [70000, 30000], 60, 300))
     blob, off = bam0.blob()
