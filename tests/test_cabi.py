@@ -74,3 +74,21 @@ def test_synth_host_is_deterministic_sorted_and_in_domain():
     sub = ea.synth_host(cfg, 1000, 1100)
     o = a.blob()[1]
     assert np.array_equal(sub.blob()[0], a.blob()[0][o[1000]:o[1100]]) and np.array_equal(sub.start, a.start[1000:1100])
+
+
+def test_reference_arm_runs_without_the_product_library():
+    """bench.py --impl reference: the compiled reference (or the C port) on rows from the oracle's own generator build; the
+    line carries the contract's keys and the process maps no library of the product."""
+    import json
+    import subprocess
+    import sys
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--ref-rows', '20000'];"
+            "runpy.run_path('bench.py', run_name='__main__');"
+            "print('MAPPED', [l.split()[-1] for l in open('/proc/self/maps') if 'libepialleler_b200' in l], file=sys.stderr)")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["cores"] == 1
+    assert "MAPPED []" in out.stderr, out.stderr[-500:]
