@@ -57,6 +57,7 @@ SIGNATURES = {
     "ea_last_error": (C.c_char_p, []),
     "ea_device_count": (C.c_int, []),
     "ea_set_poll": (None, [C.c_void_p]),
+    "ea_set_handle_poll": (None, [_H, C.c_void_p]),
     "ea_set_kernel_policy": (C.c_int, [C.c_int]),
     "ea_report_kernel": (C.c_char_p, [_H]),
     "ea_mhl_report": (C.c_int, [_H, C.c_char_p, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_int64)]),

@@ -68,7 +68,8 @@ int fail(int code, const char* fmt, ...) {
 
 #define POLL()                                                                   \
   do {                                                                           \
-    if (g_poll && g_poll()) return fail(EA_ERR_INTERRUPT, "interrupted by caller"); \
+    ea_poll_fn poll_ = h->poll ? h->poll : g_poll;   /* the handle's own callback wins over the process-wide one */ \
+    if (poll_ && poll_()) return fail(EA_ERR_INTERRUPT, "interrupted by caller"); \
   } while (0)
 
 // EA_TRACE=1: wall-clock stage marks on stderr (each mark synchronizes the device; diagnostics only)
@@ -263,6 +264,7 @@ struct ea_handle {
   void* d_flush = nullptr;
   int64_t flush_bytes = 0;
   int sm_count = 148;
+  ea_poll_fn poll = nullptr;       // per-handle interrupt poll (ea_set_handle_poll); null = the process-wide one
 };
 
 namespace {
@@ -1833,6 +1835,7 @@ int ea_device_count(void) {
   return n;
 }
 void ea_set_poll(ea_poll_fn fn) { g_poll = fn; }
+void ea_set_handle_poll(ea_handle* h, ea_poll_fn fn) { if (h) h->poll = fn; }
 int ea_set_kernel_policy(int policy) { const int old = g_kernel_policy; if (policy >= 0) g_kernel_policy = policy; return old; }
 
 void ea_free(ea_handle* h) {

@@ -62,7 +62,8 @@ typedef int (*ea_poll_fn)(void);
 int ea_version(void);
 const char* ea_last_error(void);
 int ea_device_count(void);
-void ea_set_poll(ea_poll_fn fn);
+void ea_set_poll(ea_poll_fn fn);                         /* process-wide */
+void ea_set_handle_poll(ea_handle* h, ea_poll_fn fn);    /* this handle only; wins over the process-wide callback */
 /* Kernel choice for the report: 0 automatic (default: the row-per-lane kernel for one-context reports over rows of at
  * most 256 bytes that are multiples of 32 bytes, else the chunk-per-lane kernel for reads up to 1 KB, else the long-read
  * kernel (flags from the stand-alone threshold pass), else - more than 32767 rows over one window - the general

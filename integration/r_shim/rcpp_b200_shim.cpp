@@ -63,7 +63,6 @@ Handle* pack(Rcpp::DataFrame& df, bool need_bytes) {
   Rcpp::XPtr<std::vector<std::string>> seqxm((SEXP)df.attr("seqxm_xptr"));
   Rcpp::IntegerVector rname = df["rname"], strand = df["strand"], start = df["start"], templid = df["templid"];
   const size_t n = seqxm->size();
-  ea_set_poll(poll_interrupt);
   Handle* hd = new Handle;
   hd->seqxm = seqxm.get(); hd->nrow = df.nrows(); hd->rname0 = rname.begin(); hd->start0 = start.begin();
   int rc;
@@ -89,6 +88,7 @@ Handle* pack(Rcpp::DataFrame& df, bool need_bytes) {
                                                 len.get(), static_cast<int64_t>(n), /*device=*/0, &hd->h);
   }
   if (rc != EA_OK) { delete hd; ea_check(rc); }
+  ea_set_handle_poll(hd->h, poll_interrupt);   // per handle: other users of the library in the process keep theirs
   return hd;
 }
 

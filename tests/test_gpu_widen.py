@@ -298,3 +298,30 @@ def test_large_results_into_pageable_memory(monkeypatch):
     for c, k in zip(cols, COLS):
         assert np.array_equal(c, rep[k]), k
     dev.close()
+
+
+def test_interrupt_poll_process_wide_and_per_handle():
+    """The poll callback (the reference polls Rcpp::checkUserInterrupt, src/rcpp_cx_report.cpp:110): a non-zero answer aborts
+    the report with EA_ERR_INTERRUPT; a handle's own callback wins over the process-wide one and leaves other handles alone."""
+    L = N.lib()
+    POLL = C.CFUNCTYPE(C.c_int)
+    stop, go = POLL(lambda: 1), POLL(lambda: 0)
+    a = ea.synth_host(ea.synth_config(52, 3000, [30000], 150))
+    b = ea.synth_host(ea.synth_config(53, 3000, [30000], 150))
+    want = ea.generateCytosineReport(a)
+    try:
+        L.ea_set_handle_poll(a.handle(need_bases=False), C.cast(stop, C.c_void_p))
+        with pytest.raises(ea.EaError) as e:
+            ea.generateCytosineReport(a)
+        assert e.value.code == N.EA_ERR_INTERRUPT
+        assert ea.generateCytosineReport(b)["pos"].shape[0] > 0          # another handle is not affected
+        L.ea_set_poll(C.cast(stop, C.c_void_p))                          # process-wide: b stops, a's own callback decides for a
+        L.ea_set_handle_poll(a.handle(need_bases=False), C.cast(go, C.c_void_p))
+        with pytest.raises(ea.EaError):
+            ea.generateCytosineReport(b)
+        assert_report_equal(ea.generateCytosineReport(a), want, "per-handle poll wins")
+    finally:
+        L.ea_set_poll(None)
+        L.ea_set_handle_poll(a.handle(need_bases=False), None)
+    assert_report_equal(ea.generateCytosineReport(a), want, "poll cleared")
+    a.close(); b.close()
