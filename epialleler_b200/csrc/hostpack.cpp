@@ -9,6 +9,7 @@
 #include <immintrin.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 namespace eahp {
@@ -138,7 +139,71 @@ __attribute__((target("avx2"))) static void pack_tiles_avx2(const Job& job, cons
   _mm_sfence();
 }
 
+// AVX-512 + VBMI + GFNI: 64 positions (two units) per step.  A masked load takes the bytes (nothing beyond the row is
+// touched, masked-out bytes read as code 0), GF2P8AFFINE with the data as the MATRIX operand transposes every 8 x 8 bit block
+// (byte m of a qword = bit m of its eight bytes, after a byte reversal inside the qwords that puts position k at bit k), and
+// one VPERMB gathers the four low planes of both units: bytes 0-15 = unit 0 {A,B,C,D}, bytes 16-31 = unit 1.
+#define EA_HP_512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi,gfni")))
+EA_HP_512 static inline __m256i planes64(const uint8_t* p, int n /* valid bytes, 1..64 */) {
+  alignas(64) static const uint8_t kRev[64] = {7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8,
+                                               7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8};
+  alignas(64) static const uint8_t kIdx[64] = {0, 8, 16, 24, 1, 9, 17, 25, 2, 10, 18, 26, 3, 11, 19, 27, 32, 40, 48, 56, 33, 41, 49, 57, 34, 42, 50, 58, 35, 43, 51, 59};
+  const __mmask64 k = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+  __m512i v = _mm512_maskz_loadu_epi8(k, p);
+  v = _mm512_shuffle_epi8(v, _mm512_load_si512(kRev));
+  const __m512i t = _mm512_gf2p8affine_epi64_epi8(_mm512_set1_epi64((long long)0x8040201008040201ull), v, 0);
+  return _mm512_castsi512_si256(_mm512_permutexvar_epi8(_mm512_load_si512(kIdx), t));
+}
+
+EA_HP_512 static void pack_tiles_avx512(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst) {
+  static const uint8_t kNone[1] = {0};
+  for (int64_t t = t0; t < t1; t++) {
+    __m128i* tile = reinterpret_cast<__m128i*>(dst + (toff[t] - toff[t0]) * 512);
+    const int nu_t = (int)(toff[t + 1] - toff[t]);
+    const uint8_t* row[32];
+    int len[32];
+    for (int l = 0; l < 32; l++) {
+      const int64_t r = t * 32 + l;
+      if (r < job.n) { row[l] = job.row_ptr(r); len[l] = (int)job.row_len(r); }
+      else { row[l] = kNone; len[l] = 0; }
+    }
+    for (int j = 0; j < nu_t; j += 2) {   // two unit rows of the tile per step (1 KB written front to back)
+      const bool two = j + 1 < nu_t;
+      for (int l = 0; l < 32; l++) {
+        const int n = len[l] - 32 * j;
+        __m256i w = _mm256_setzero_si256();
+        if (n > 0) w = planes64(row[l] + 32 * j, n < 64 ? n : 64);
+        _mm_stream_si128(tile + j * 32 + l, _mm256_castsi256_si128(w));
+        if (two) _mm_stream_si128(tile + (j + 1) * 32 + l, _mm256_extracti128_si256(w, 1));
+      }
+    }
+  }
+  _mm_sfence();
+}
+
+EA_HP_512 static void pack_rows_avx512(const Job& job, const int64_t* uoff, int64_t r0, int64_t r1, uint8_t* dst) {
+  for (int64_t r = r0; r < r1; r++) {
+    const int64_t len = job.row_len(r);
+    const uint8_t* row = job.row_ptr(r);
+    uint8_t* d = dst + (uoff[r] - uoff[r0]) * 16;
+    const int64_t nu = (len + 31) >> 5;
+    for (int64_t j = 0; j < nu; j += 2) {
+      const int64_t n = len - 32 * j;
+      const __m256i w = planes64(row + 32 * j, (int)(n < 64 ? n : 64));
+      if (j + 1 < nu) _mm256_storeu_si256(reinterpret_cast<__m256i*>(d + j * 16), w);
+      else _mm_storeu_si128(reinterpret_cast<__m128i*>(d + j * 16), _mm256_castsi256_si128(w));
+    }
+  }
+}
+
+static bool have_avx512() {
+  static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+                        __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("gfni") && !getenv("EA_NO_AVX512");
+  return v;
+}
+
 unsigned pack_tiles(const Job& job, const int64_t* toff, int64_t t0, int64_t t1, uint8_t* dst) {
+  if (have_avx512() && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) { pack_tiles_avx512(job, toff, t0, t1, dst); return 0u; }
   if (have_avx2() && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) { pack_tiles_avx2(job, toff, t0, t1, dst); return 0u; }
   bool ok = true;
   for (int64_t t = t0; t < t1; t++) {
@@ -164,6 +229,7 @@ unsigned pack_tiles(const Job& job, const int64_t* toff, int64_t t0, int64_t t1,
 }
 
 unsigned pack_rows(const Job& job, const int64_t* uoff, int64_t r0, int64_t r1, uint8_t* dst) {
+  if (have_avx512()) { pack_rows_avx512(job, uoff, r0, r1, dst); return 0u; }   // the device validates the planes it receives
   const bool avx2 = have_avx2();
   bool ok = true;
   for (int64_t r = r0; r < r1; r++) {

@@ -29,6 +29,30 @@ int main() {
   memset(a, 0xAA, toff[nt] * 512); memset(b, 0x55, toff[nt] * 512);
   eahp::pack_tiles(jb, toff.data(), 0, nt, (uint8_t*)a); eahp::pack_tiles(js, toff.data(), 0, nt, (uint8_t*)b);
   if (memcmp(a, b, toff[nt] * 512) != 0) { printf("MISMATCH\n"); return 1; }
+  // whatever SIMD path the library picked (AVX-512 + GFNI, AVX2, scalar) against a plain restatement of the layout:
+  // unit j of row l of tile t = 16 bytes at ((toff[t] + j) * 32 + l) * 16, plane b bit k = bit b of the code at position 32 j + k
+  {
+    const uint32_t* units = (const uint32_t*)a;
+    for (int64_t r = 0; r < n; r++) {
+      const int64_t t = r / 32, l = r % 32;
+      for (int64_t j = 0; j < toff[t + 1] - toff[t]; j++) {
+        uint32_t want[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 32; k++) { const int64_t pos = 32 * j + k; if (pos < (int64_t)strs[r].size()) for (int pb = 0; pb < 4; pb++) want[pb] |= (uint32_t)(((uint8_t)strs[r][pos] >> pb) & 1) << k; }
+        if (memcmp(units + ((toff[t] + j) * 32 + l) * 4, want, 16) != 0) { printf("plane mismatch at row %lld unit %lld\n", (long long)r, (long long)j); return 1; }
+      }
+    }
+    // the long-read layout (units of a row contiguous)
+    std::vector<int64_t> uoff(n + 1, 0); for (int64_t r = 0; r < n; r++) uoff[r + 1] = uoff[r] + ((int64_t)strs[r].size() + 31) / 32;
+    std::vector<uint32_t> rows_out((size_t)uoff[n] * 4 + 16, 0xDEADBEEFu);
+    eahp::pack_rows(js, uoff.data(), 0, n, (uint8_t*)rows_out.data());
+    for (int64_t r = 0; r < n; r++)
+      for (int64_t j = 0; j < uoff[r + 1] - uoff[r]; j++) {
+        uint32_t want[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 32; k++) { const int64_t pos = 32 * j + k; if (pos < (int64_t)strs[r].size()) for (int pb = 0; pb < 4; pb++) want[pb] |= (uint32_t)(((uint8_t)strs[r][pos] >> pb) & 1) << k; }
+        if (memcmp(rows_out.data() + (uoff[r] + j) * 4, want, 16) != 0) { printf("row-layout mismatch at row %lld unit %lld\n", (long long)r, (long long)j); return 1; }
+      }
+    if (rows_out[(size_t)uoff[n] * 4] != 0xDEADBEEFu) { printf("pack_rows wrote past its end\n"); return 1; }
+  }
   // rows that reach their strings through templid (paired-end data): strings stored in a shuffled order
   std::vector<int32_t> perm(n); for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
   for (int64_t i = n - 1; i > 0; i--) std::swap(perm[i], perm[rand() % (i + 1)]);
