@@ -101,6 +101,7 @@ SIGNATURES = {
     "ea_plan_shards": (C.c_int, [_I32P, _I32P, _I32P, C.c_int64, _I64P, C.c_int64, C.c_int, C.POINTER(Shard)]),
     "ea_set_owned_range": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64]),
     "ea_pack_multi": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, _U8P, _I64P, C.c_int64, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(_H)]),
+    "ea_pack_multi_records": (C.c_int, [_I32P, _I32P, _I32P, _I32P, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int), C.c_int, C.POINTER(_H)]),
     "ea_multi_ndev": (C.c_int, [_H]),
     "ea_multi_handle": (_H, [_H, C.c_int]),
     "ea_multi_shard": (C.c_int, [_H, C.c_int, C.POINTER(Shard)]),

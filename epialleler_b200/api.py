@@ -327,9 +327,16 @@ class MultiBam:
                                 bam.nrow, _p(blob, C.c_uint8), _p(off, C.c_int64), bam.nstr, dv, len(self.devices), 1 if calls_only else 0, C.byref(m)))
         self._m = m
 
+    @classmethod
+    def from_handle(cls, m, nrow, devices, rname_levels=()):
+        """Wraps an ea_multi* packed elsewhere (ea_pack_multi_records through the shim / integration/harness)."""
+        self = cls.__new__(cls)
+        self.bam, self._nrow, self.rname_levels, self.devices, self._m = None, int(nrow), list(rname_levels), list(devices), m
+        return self
+
     @property
     def nrow(self):
-        return self.bam.nrow
+        return self.bam.nrow if self.bam is not None else self._nrow
 
     def shards(self):
         L = N.lib()

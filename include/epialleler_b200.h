@@ -272,6 +272,10 @@ typedef struct ea_multi ea_multi;
 int ea_pack_multi(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
                   const uint8_t* blob, const int64_t* off, int64_t nstr, const int* devices, int ndev, int calls_only,
                   ea_multi** out);
+/* The same from the reader's scattered strings, described as ea_pack_calls_records describes them (call planes only). */
+int ea_pack_multi_records(const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
+                          const void* records, int64_t nstr, int64_t stride, int64_t ptr_offset, int64_t len_offset,
+                          const int* devices, int ndev, ea_multi** out);
 int ea_multi_ndev(const ea_multi* m);
 ea_handle* ea_multi_handle(ea_multi* m, int i);           /* shard i's handle (owned by m) */
 int ea_multi_shard(const ea_multi* m, int i, ea_shard* out);

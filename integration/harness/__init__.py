@@ -27,6 +27,8 @@ def lib():
         L.harness_pack.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.harness_pack_records.restype = C.c_int
         L.harness_pack_records.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+        L.harness_pack_multi_records.restype = C.c_int
+        L.harness_pack_multi_records.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
 
@@ -57,6 +59,18 @@ class ReaderStrings:
         else:
             N.check(lib().harness_pack(self._v, *[c.ctypes.data for c in self.cols], self.nrow, device, 1 if calls_only else 0, C.byref(h)))
         return DeviceBam(h, device)
+
+    def pack_multi(self, devices, rname_levels=()):
+        """the shim's multi-GPU pack (ea_pack_multi_records) -> epialleler_b200.api.MultiBam"""
+        from epialleler_b200 import _native as N
+        from epialleler_b200.api import MultiBam
+        dv = (C.c_int * len(devices))(*devices)
+        m = C.c_void_p()
+        rc = lib().harness_pack_multi_records(self._v, *[c.ctypes.data for c in self.cols], self.nrow, dv, len(devices), C.byref(m))
+        if rc == -1000:
+            raise RuntimeError("std::string layout not understood by the probe")
+        N.check(rc)
+        return MultiBam.from_handle(m, self.nrow, list(devices), rname_levels)
 
     def close(self):
         if self._v and _lib is not None:

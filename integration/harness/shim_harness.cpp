@@ -55,6 +55,15 @@ int harness_pack_records(void* p, const int32_t* rname, const int32_t* strand, c
   return ea_pack_calls_records(rname, strand, start, templid, nrow, seqxm->data(), (int64_t)seqxm->size(), (int64_t)sizeof(std::string), po, lo, device, out);
 }
 
+// the shim's multi-GPU pack: the same record array, cut into range shards, one device each
+int harness_pack_multi_records(void* p, const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
+                               const int* devices, int ndev, ea_multi** out) {
+  auto* seqxm = static_cast<std::vector<std::string>*>(p);
+  int64_t po, lo;
+  if (!string_layout(&po, &lo)) return -1000;
+  return ea_pack_multi_records(rname, strand, start, templid, nrow, seqxm->data(), (int64_t)seqxm->size(), (int64_t)sizeof(std::string), po, lo, devices, ndev, out);
+}
+
 // handle_of() of the shim: pointer and length tables over the vector, then the packer
 int harness_pack(void* p, const int32_t* rname, const int32_t* strand, const int32_t* start, const int32_t* templid, int64_t nrow,
                  int device, int calls_only, ea_handle** out) {

@@ -177,6 +177,42 @@ Rcpp::DataFrame rcpp_cytosine_report_fused(Rcpp::DataFrame& df, const bool thres
   return wrap_report(handle_of(df), n, df);
 }
 
+// Optional fifth entry: the same on several GPUs of the box from the one R process.  The rows are cut into contiguous genomic
+// ranges with halo rows (ea_pack_multi_records plans them), every device packs and reports its range at once, the owned rows
+// come back concatenated in genomic order - identical to the single-device report.  R side:
+//   cx.report <- rcpp_cytosine_report_fused_multi(bam, devices = 0:7, threshold.reads, ..., report.ctx)
+// [[Rcpp::export("rcpp_cytosine_report_fused_multi")]]
+Rcpp::DataFrame rcpp_cytosine_report_fused_multi(Rcpp::DataFrame& df, Rcpp::IntegerVector devices, const bool threshold_reads,
+                                                 const std::string ctx_meth, const std::string ctx_unmeth, const std::string ooctx_meth,
+                                                 const std::string ooctx_unmeth, const unsigned int min_n_ctx, const double min_ctx_meth_frac,
+                                                 const double max_ooctx_meth_frac, const std::string report_ctx) {
+  Rcpp::XPtr<std::vector<std::string>> seqxm((SEXP)df.attr("seqxm_xptr"));
+  Rcpp::IntegerVector rname = df["rname"], strand = df["strand"], start = df["start"], templid = df["templid"];
+  int64_t po, lo;
+  if (!string_layout(&po, &lo)) Rcpp::stop("epialleler_b200: std::string layout not understood");
+  std::vector<int> dev(devices.begin(), devices.end());
+  ea_multi* m = nullptr;
+  ea_check(ea_pack_multi_records(rname.begin(), strand.begin(), start.begin(), templid.begin(), df.nrows(), seqxm->data(),
+                                 static_cast<int64_t>(seqxm->size()), static_cast<int64_t>(sizeof(std::string)), po, lo, dev.data(),
+                                 static_cast<int>(dev.size()), &m));
+  ea_report_params p;
+  p.threshold_reads = threshold_reads; p.ctx_meth = ctx_meth.c_str(); p.ctx_unmeth = ctx_unmeth.c_str();
+  p.ooctx_meth = ooctx_meth.c_str(); p.ooctx_unmeth = ooctx_unmeth.c_str(); p.min_n_ctx = min_n_ctx;
+  p.min_ctx_meth_frac = min_ctx_meth_frac; p.max_ooctx_meth_frac = max_ooctx_meth_frac; p.report_ctx = report_ctx.c_str();
+  int64_t n = 0;
+  int rc = ea_multi_cytosine_report(m, &p, nullptr, &n);
+  Rcpp::IntegerVector o_rname(n), o_strand(n), pos(n), context(n), meth(n), unmeth(n);
+  if (rc == EA_OK) rc = ea_multi_report_fetch(m, o_rname.begin(), o_strand.begin(), pos.begin(), context.begin(), meth.begin(), unmeth.begin());
+  ea_multi_free(m);
+  ea_check(rc);
+  o_rname.attr("class") = "factor";   o_rname.attr("levels") = rname.attr("levels");
+  o_strand.attr("class") = "factor";  o_strand.attr("levels") = strand.attr("levels");
+  context.attr("class") = "factor";
+  context.attr("levels") = Rcpp::CharacterVector::create("NA1", "CHH", "NA3", "NA4", "NA5", "CHG", "CG");
+  return Rcpp::DataFrame::create(Rcpp::Named("rname") = o_rname, Rcpp::Named("strand") = o_strand, Rcpp::Named("pos") = pos,
+                                 Rcpp::Named("context") = context, Rcpp::Named("meth") = meth, Rcpp::Named("unmeth") = unmeth);
+}
+
 // ---- the siblings that reuse the packed reads; same exported names and signatures as the reference ----
 
 // R/RcppExports.R:40-42, src/rcpp_mhl_report.cpp:46

@@ -92,6 +92,27 @@ def test_pack_multi_equals_single(ndev_shards):
         bam.close()
 
 
+def test_pack_multi_from_reader_strings(monkeypatch):
+    """ea_pack_multi_records: the reader's heap strings cut into range shards, one device (here: one shared device) each -
+    rows in file order and rows that reach their strings through templid (paired-end fixtures)."""
+    monkeypatch.setenv("EA_HOST_PACK_FORCE", "1")
+    cases = [ea.synth_host(ea.synth_config(54, 30000, [c // 14000 for c in HG38], 150)), ea.synth_host(ea.synth_config(55, 9000, [70000, 30000], 60, 300)),
+             load_golden("capture")[0], load_golden("amplicon010meth")[0]]
+    for bam in cases:
+        rs = H.ReaderStrings(bam)
+        for nsh in (1, 3, 7):
+            mb = rs.pack_multi([0] * nsh)
+            sh = mb.shards()
+            assert sh[0].own_lo == 0 and sh[-1].own_hi == bam.nrow and all(a.own_hi == b.own_lo for a, b in zip(sh, sh[1:]))
+            for kw in KW_SETS[:2]:
+                want_pass, want = oracle(bam, **kw)
+                got_pass, got = ea.generateCytosineReport(mb, return_pass=True, **kw)
+                assert np.array_equal(got_pass, want_pass), (nsh, kw)
+                assert_report_equal(got, want, "multi from reader strings x%d %s" % (nsh, kw))
+            mb.close()
+        rs.close(); bam.close()
+
+
 def test_pack_multi_report_file(tmp_path):
     """report_file with several shards: every device formats the rows it owns; the concatenation is the single-device file."""
     bam = ea.synth_host(ea.synth_config(51, 20000, [90000, 60000, 30000], 150))
