@@ -83,6 +83,27 @@ def test_native_planner_equals_python_planner():
         assert [(w.row_lo, w.own_lo, w.own_hi, w.key_lo, w.key_hi) for w in want] == [(g.row_lo, g.own_lo, g.own_hi, g.key_lo, g.key_hi) for g in got], (trial, n, world)
 
 
+def test_native_planner_many_pieces():
+    """Rows that reach their strings through templid: the native planner sums PIECES of the rows and scans inside the piece a
+    cut falls into (no per-row prefix array) - several pieces, zero-length strings, ties at the cuts."""
+    from epialleler_b200.shard import plan_shards_native
+    rng = np.random.default_rng(1)
+    n = 300_000
+    rn = np.sort(rng.integers(1, 4, n)).astype(np.int32)
+    st = rng.integers(1, 5000, n).astype(np.int32)
+    o = np.lexsort((st, rn))
+    rn, st = rn[o], st[o]
+    ln = rng.integers(0, 40, n).astype(np.int64)
+    ln[rng.random(n) < 0.3] = 0
+    off = np.concatenate([[0], np.cumsum(ln)]).astype(np.int64)
+    tid = rng.permutation(n).astype(np.int32)
+    bam = ea.BamData(rn, np.ones(n, np.int32), st, tid, np.zeros(int(off[-1]), np.uint8), off)
+    for world in (2, 5, 8):
+        want = plan_shards(rn, st, ln[tid], world)
+        got = plan_shards_native(bam, world)
+        assert [(w.row_lo, w.own_lo, w.own_hi, w.key_lo, w.key_hi) for w in want] == [(g.row_lo, g.own_lo, g.own_hi, g.key_lo, g.key_hi) for g in got], world
+
+
 def test_windowed_planner_equals_python_planner():
     from epialleler_b200.shard import plan_shards_windowed
     for cfg in (ea.synth_config(36, 20000, [300000, 100000], 150), ea.synth_config(37, 5000, [c // 30000 for c in (248956422, 242193529, 198295559, 190214555)], 150)):

@@ -54,5 +54,31 @@ for k in [d for d in (1, 2, 4, 8) if d <= ndev]:
     med = np.median(np.asarray(times), axis=0)
     out["runs"].append({"devices": k, "pack_s": float(med[0]), "report_fetch_s": float(med[1]), "total_s": float(med[2]), "reads_per_s": reads / float(med[2]),
                         "rows": int(rep["pos"].shape[0]), "halo_rows": [int(s.own_lo - s.row_lo) for s in sh], "crc": c})
+# the same through the shim's calls: the reader's heap std::strings (pageable), ea_pack_multi_records
+import integration.harness as H  # noqa: E402
+rs = H.ReaderStrings(bam)
+out["from_reader_strings"] = []
+for k in [d for d in (1, 2, 4, 8) if d <= ndev]:
+    times = []
+    for i in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mb = rs.pack_multi(list(range(k)))
+        t1 = time.perf_counter()
+        p, rep = ea.generateCytosineReport(mb, return_pass=True)
+        t2 = time.perf_counter()
+        mb.close()
+        for d in range(k):
+            torch.cuda.synchronize(d)
+        t3 = time.perf_counter()
+        if i:
+            times.append((t1 - t0, t2 - t1, t3 - t0))
+    c = zlib.crc32(np.ascontiguousarray(p).view(np.uint8))
+    for col in ("rname", "strand", "pos", "context", "meth", "unmeth"):
+        c = zlib.crc32(np.ascontiguousarray(rep[col]).view(np.uint8), c)
+    crcs.add(c)
+    med = np.median(np.asarray(times), axis=0)
+    out["from_reader_strings"].append({"devices": k, "pack_s": float(med[0]), "report_fetch_s": float(med[1]), "total_s": float(med[2]),
+                                       "reads_per_s": reads / float(med[2]), "rows": int(rep["pos"].shape[0]), "crc": c})
 out["identical_across_device_counts"] = len(crcs) == 1
 print(json.dumps(out, indent=1))
