@@ -104,6 +104,37 @@ def test_native_planner_many_pieces():
         assert [(w.row_lo, w.own_lo, w.own_hi, w.key_lo, w.key_hi) for w in want] == [(g.row_lo, g.own_lo, g.own_hi, g.key_lo, g.key_hi) for g in got], world
 
 
+def test_native_planner_on_a_slice_of_a_larger_blob_and_degenerate_inputs():
+    """Offsets that do not start at 0 (a shard of a larger blob is planned where it lies), more shards than rows, one shard,
+    no rows; a templid outside the strings is an error."""
+    import ctypes as C
+
+    from epialleler_b200 import _native as N
+    L = N.lib()
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rng = np.random.default_rng(2)
+    n = 5000
+    rn = np.ones(n, np.int32)
+    st = np.sort(rng.integers(1, 100000, n)).astype(np.int32)
+    ln = rng.integers(1, 200, n).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(ln)]).astype(np.int64)
+    lo, hi = 1200, 4100
+    for world in (1, 2, 6):
+        want = plan_shards(rn[lo:hi], st[lo:hi], ln[lo:hi], world)
+        out = (N.Shard * world)()
+        N.check(L.ea_plan_shards(p(rn[lo:], C.c_int32), p(st[lo:], C.c_int32), None, hi - lo, p(off[lo:], C.c_int64), hi - lo, world, out))
+        assert [(w.row_lo, w.own_lo, w.own_hi, w.key_lo, w.key_hi) for w in want] == [(g.row_lo, g.own_lo, g.own_hi, g.key_lo, g.key_hi) for g in out], world
+    for nrow, world in ((3, 8), (0, 4), (1, 1)):
+        want = plan_shards(rn[:nrow], st[:nrow], ln[:nrow], world)
+        out = (N.Shard * world)()
+        N.check(L.ea_plan_shards(p(rn, C.c_int32), p(st, C.c_int32), None, nrow, p(off, C.c_int64), nrow, world, out))
+        assert [(w.row_lo, w.own_lo, w.own_hi, w.key_lo, w.key_hi) for w in want] == [(g.row_lo, g.own_lo, g.own_hi, g.key_lo, g.key_hi) for g in out], (nrow, world)
+    bad = np.arange(n, dtype=np.int32)
+    bad[10] = n + 3
+    out = (N.Shard * 2)()
+    assert L.ea_plan_shards(p(rn, C.c_int32), p(st, C.c_int32), p(bad, C.c_int32), n, p(off, C.c_int64), n, 2, out) == N.EA_ERR_ARG
+
+
 def test_windowed_planner_equals_python_planner():
     from epialleler_b200.shard import plan_shards_windowed
     for cfg in (ea.synth_config(36, 20000, [300000, 100000], 150), ea.synth_config(37, 5000, [c // 30000 for c in (248956422, 242193529, 198295559, 190214555)], 150)):
